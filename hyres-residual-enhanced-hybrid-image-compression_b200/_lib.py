@@ -1,0 +1,110 @@
+"""ctypes binding of ``csrc/libhyres_b200.so`` (the C-ABI declared in include/hyres_b200.h).
+
+The library is the product: if it is missing or the device is not sm_100 the
+package raises -- there is no CPU or PyTorch fallback behind these calls.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libhyres_b200.so")
+
+HYRES_CONV, HYRES_DECONV_K5S2 = 0, 1
+EPI_LINEAR, EPI_ADD, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_PIXSCALE = range(6)
+ACT_NONE, ACT_RELU, ACT_PRELU, ACT_CLAMP01 = range(4)
+
+
+class HyresError(RuntimeError):
+    pass
+
+
+class ConvIO(C.Structure):
+    _fields_ = [
+        ("x0", C.c_void_p), ("x1", C.c_void_p),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("epi", C.c_int), ("act", C.c_int), ("slope", C.c_float),
+        ("aux0", C.c_void_p), ("ld_aux0", C.c_int),
+        ("aux1", C.c_void_p), ("ld_aux1", C.c_int),
+        ("pixscale", C.c_void_p),
+        ("out_bf16", C.c_void_p), ("ld_out", C.c_int),
+        ("out_sq", C.c_void_p), ("ld_sq", C.c_int),
+        ("out_f32", C.c_void_p),
+        ("f32_sb", C.c_int64), ("f32_sh", C.c_int64), ("f32_sw", C.c_int64), ("f32_sc", C.c_int64),
+        ("mt_hint", C.c_int),
+    ]
+
+
+_lib = None
+
+_vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+
+# name -> (restype, argtypes); mirrors include/hyres_b200.h one to one.
+SIGNATURES = {
+    "hyres_version": (_i, []),
+    "hyres_device_check": (_i, [_i]),
+    "hyres_last_error": (C.c_char_p, []),
+    "hyres_conv_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hyres_conv_update": (_i, [_vp, _vp, _vp]),
+    "hyres_conv_destroy": (None, [_vp]),
+    "hyres_conv_macs_per_pos": (_i64, [_vp]),
+    "hyres_conv_out_size": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
+    "hyres_conv_run": (_i, [_vp, C.POINTER(ConvIO), _vp]),
+    "hyres_residual_im2col5s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hyres_addback_im2col3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hyres_final_clamp": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "hyres_gc_quant_pass": (_i, [_vp, _vp, _i, _i, _u64, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_gc_merge_likelihood": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_gc_symbols": (_i, [_vp, _vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_gc_indexes": (_i, [_vp, _vp, _i, _f, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_gc_dequant": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_add_to_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "hyres_eb_forward": (_i, [_vp, _vp, _vp, _i, _u64, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_eb_dequant": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_refine_se_pool": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_refine_se_scale_down": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hyres_refine_up_concat_stats": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_refine_spatial_att": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hyres_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_nhwc_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_nhwc_bf16_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_reduce_sqdiff": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "hyres_reduce_log2": (_i, [_vp, _i64, _vp, _vp]),
+    "hyres_pmf_to_quantized_cdf": (_i, [_vp, _i, _i, _vp]),
+    "hyres_rans_encode_bound": (_i64, [_i64]),
+    "hyres_rans_encode": (_i, [_vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    "hyres_rans_decode": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
+    "hyres_rans_encode_batch": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "hyres_rans_decode_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
+}
+
+
+def lib():
+    """Load the shared library (once) and declare every prototype."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise HyresError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                "(the hot path has no fallback implementation)"
+            )
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name, None)
+            if fn is None:  # reported by missing_symbols(); calling it raises AttributeError
+                continue
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def missing_symbols():
+    """Names declared in include/hyres_b200.h that the built library does not export."""
+    handle = lib()
+    return [n for n in SIGNATURES if not hasattr(handle, n)]
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().hyres_last_error().decode(errors="replace")
+        raise HyresError(f"{what} failed with code {rc}: {msg}")

@@ -1,0 +1,699 @@
+// Implicit-GEMM convolution for the HyRES codec on Blackwell tensor cores.
+//
+// Replaces every nn.Conv2d / nn.ConvTranspose2d of the reference hot path
+// (models/checkerboard.py:35-88, models/layers/attention.py:16-47,
+// models/layers/enhancement.py:60-85, compressai GDN / ResidualBottleneckBlock).
+//
+// Design (B200-first, not a cuDNN translation):
+//  * activations NHWC bf16, weights packed K-major bf16, fp32 accumulation in TMEM;
+//  * one CTA owns a (16*MT) x 8 patch of output positions of one image and BN output
+//    channels: MT accumulators of 128 x BN fp32 in tensor memory;
+//  * A operand: TMA loads a *halo patch* [(16*MT+halo) rows][8 cols][64 ch] once per
+//    (kernel column, 64-channel chunk); every vertical tap of that column is the same
+//    patch shifted by whole rows = 1 KB, so the UMMA descriptor just moves its start
+//    address (stays 1024 B aligned -> canonical SWIZZLE_128B K-major layout).  Image
+//    borders are the TMA out-of-bounds zero fill: no padding pass, no predication;
+//  * stride-2 convs read plain NHWC through a 5-D view (2C, W/2, 2, H/2, B): the
+//    parity of a tap selects the inner offset / parity coordinate, so they are stride-1
+//    patch loads too.  Transposed convs are 4 sub-pixel phases (9/6/6/4 taps) writing
+//    interleaved output positions (grid.z = phase);
+//  * B operand: [BN][64] weight tiles streamed through their own mbarrier ring;
+//  * warp roles: warps 0-3 epilogue (TMEM lane == output position), warp 4 TMA
+//    producer, warp 5 TMEM allocator + single-thread tcgen05.mma issuer;
+//  * fused epilogues: bias, ReLU/PReLU/clamp, residual add, attention gate,
+//    GDN/IGDN normalisation, per-pixel scale; bf16 / fp32 / squared outputs.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "host_util.h"
+#include "hyres_b200.h"
+
+namespace {
+
+constexpr int kTileW = 8;     // output columns per tile
+constexpr int kSubH = 16;     // output rows per 128-row accumulator
+constexpr int kMaxTaps = 5;   // vertical taps per patch
+constexpr int kThreads = 192;
+
+struct TapGroup {
+  int32_t src;      // 0: x0, 1: x1
+  int32_t c_off;    // inner (channel) coordinate of the box
+  int32_t dw;       // column coordinate offset relative to the tile origin
+  int32_t dh;       // row coordinate offset of the patch start
+  int32_t hpar;     // coordinate along the parity dimension (stride-2 view)
+  int32_t ntaps;    // B tiles consumed against this patch
+  int32_t kslot0;   // first 64-wide K slot in the packed weights
+  int32_t tap_row[kMaxTaps];  // row shift (in patch rows) of each tap
+};
+
+struct alignas(64) ConvParams {
+  CUtensorMap mapA0;
+  CUtensorMap mapA1;
+  CUtensorMap mapB;
+  const TapGroup* groups;
+  int32_t ph_begin[4];
+  int32_t ph_count[4];
+  int32_t tiles_w, tiles_h;  // tiles per image
+  int32_t OHv, OWv;          // extent of the iterated output grid (per phase for deconv)
+  int32_t OH, OW;            // true output extent
+  int32_t out_mul;           // 1, or 2 for transposed conv
+  int32_t MT, BN, NA, NB;
+  int32_t a_stage_bytes, b_stage_bytes, patch_rows;
+  int32_t tmem_cols;
+  int32_t cout;              // live output channels
+  int32_t epi, act;
+  float slope;
+  const float* bias;
+  const __nv_bfloat16* aux0;
+  const __nv_bfloat16* aux1;
+  const float* pixscale;
+  int32_t ld_aux0, ld_aux1;
+  __nv_bfloat16* out_bf16;
+  __nv_bfloat16* out_sq;
+  int32_t ld_out, ld_sq;
+  float* out_f32;
+  long long f32_sb, f32_sh, f32_sw, f32_sc;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == HYRES_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == HYRES_ACT_PRELU) return v >= 0.f ? v : v * slope;
+  if (act == HYRES_ACT_CLAMP01) return fminf(fmaxf(v, 0.f), 1.f);
+  return v;
+}
+
+__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* p, float (&f)[16]) {
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f[2 * i] = hy::bf16_lo(u[i]);
+    f[2 * i + 1] = hy::bf16_hi(u[i]);
+  }
+}
+
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const float (&f)[16]) {
+  uint4 a, b;
+  a.x = hy::pack_bf16(f[0], f[1]);
+  a.y = hy::pack_bf16(f[2], f[3]);
+  a.z = hy::pack_bf16(f[4], f[5]);
+  a.w = hy::pack_bf16(f[6], f[7]);
+  b.x = hy::pack_bf16(f[8], f[9]);
+  b.y = hy::pack_bf16(f[10], f[11]);
+  b.z = hy::pack_bf16(f[12], f[13]);
+  b.w = hy::pack_bf16(f[14], f[15]);
+  reinterpret_cast<uint4*>(p)[0] = a;
+  reinterpret_cast<uint4*>(p)[1] = b;
+}
+
+__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = a_base + p.NA * p.a_stage_bytes;
+  const uint32_t bar_base = b_base + p.NB * p.b_stage_bytes;
+  // barrier slots (8 B each): a_full[NA] a_empty[NA] b_full[NB] b_empty[NB] acc_full ; tmem slot
+  const uint32_t a_full = bar_base;
+  const uint32_t a_empty = a_full + 8 * p.NA;
+  const uint32_t b_full = a_empty + 8 * p.NA;
+  const uint32_t b_empty = b_full + 8 * p.NB;
+  const uint32_t acc_full = b_empty + 8 * p.NB;
+  const uint32_t tmem_slot = acc_full + 8;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int b_img = blockIdx.x / tiles_per_img;
+  const int t_in = blockIdx.x - b_img * tiles_per_img;
+  const int th = t_in / p.tiles_w;
+  const int tw = t_in - th * p.tiles_w;
+  const int h0 = th * (kSubH * p.MT);
+  const int w0 = tw * kTileW;
+  const int n0 = blockIdx.y * p.BN;
+  const int phase = blockIdx.z;
+  const int g_begin = p.ph_begin[phase];
+  const int g_count = p.ph_count[phase];
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.NA; ++i) {
+      hy::mbar_init(a_full + 8 * i, 1);
+      hy::mbar_init(a_empty + 8 * i, 1);
+    }
+    for (int i = 0; i < p.NB; ++i) {
+      hy::mbar_init(b_full + 8 * i, 1);
+      hy::mbar_init(b_empty + 8 * i, 1);
+    }
+    hy::mbar_init(acc_full, 1);
+    hy::mbar_fence_init();
+  }
+  if (warp == 4 && lane == 0) {
+    hy::tma_prefetch_desc(&p.mapA0);
+    hy::tma_prefetch_desc(&p.mapA1);
+    hy::tma_prefetch_desc(&p.mapB);
+  }
+  if (warp == 5) {
+    hy::tmem_alloc(tmem_slot, p.tmem_cols);
+    hy::tmem_relinquish();
+  }
+  hy::tc_fence_before();
+  __syncthreads();
+  hy::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t a_bytes = p.patch_rows * (kTileW * 128);
+      for (int g = 0; g < g_count; ++g) {
+        const TapGroup tg = p.groups[g_begin + g];
+        hy::mbar_wait(a_empty + 8 * sa, pa ^ 1u);
+        hy::mbar_arrive_expect_tx(a_full + 8 * sa, a_bytes);
+        hy::tma_load_5d(a_base + sa * p.a_stage_bytes, tg.src ? &p.mapA1 : &p.mapA0,
+                        a_full + 8 * sa, tg.c_off, w0 + tg.dw, tg.hpar, h0 + tg.dh, b_img);
+        for (int t = 0; t < tg.ntaps; ++t) {
+          hy::mbar_wait(b_empty + 8 * sb, pb ^ 1u);
+          hy::mbar_arrive_expect_tx(b_full + 8 * sb, p.b_stage_bytes);
+          hy::tma_load_2d(b_base + sb * p.b_stage_bytes, &p.mapB, b_full + 8 * sb,
+                          (tg.kslot0 + t) * 64, n0);
+          if (++sb == p.NB) { sb = 0; pb ^= 1u; }
+        }
+        if (++sa == p.NA) { sa = 0; pa ^= 1u; }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = hy::umma_idesc_bf16(128, p.BN);
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      uint32_t first = 0;  // becomes 1 after the first k-step (accumulate flag)
+      for (int g = 0; g < g_count; ++g) {
+        const TapGroup tg = p.groups[g_begin + g];
+        hy::mbar_wait(a_full + 8 * sa, pa);
+        hy::tc_fence_after();
+        const uint32_t a_stage = a_base + sa * p.a_stage_bytes;
+        for (int t = 0; t < tg.ntaps; ++t) {
+          hy::mbar_wait(b_full + 8 * sb, pb);
+          hy::tc_fence_after();
+          const uint32_t b_stage = b_base + sb * p.b_stage_bytes;
+          const uint32_t a_tap = a_stage + tg.tap_row[t] * (kTileW * 128);
+          for (int sub = 0; sub < p.MT; ++sub) {
+            const uint32_t a_sub = a_tap + sub * (kSubH * kTileW * 128);
+            const uint32_t d_tmem = tmem_base + sub * p.BN;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              hy::umma_bf16(d_tmem, hy::umma_desc_sw128(a_sub + k * 32),
+                            hy::umma_desc_sw128(b_stage + k * 32), idesc, first | (uint32_t)k);
+            }
+          }
+          first = 1;
+          hy::umma_commit(b_empty + 8 * sb);
+          if (++sb == p.NB) { sb = 0; pb ^= 1u; }
+        }
+        hy::umma_commit(a_empty + 8 * sa);
+        if (++sa == p.NA) { sa = 0; pa ^= 1u; }
+      }
+      hy::umma_commit(acc_full);
+    }
+  } else {
+    // ===================== epilogue (warps 0-3) =====================
+    hy::mbar_wait(acc_full, 0);
+    hy::tc_fence_after();
+    const int row = warp * 32 + lane;  // TMEM lane == tile row
+    const int ti = row >> 3;
+    const int tj = row & 7;
+    const int ph_p = phase >> 1, ph_q = phase & 1;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int sub = 0; sub < p.MT; ++sub) {
+      const int hv = h0 + sub * kSubH + ti;
+      const int wv = w0 + tj;
+      const bool valid = (hv < p.OHv) && (wv < p.OWv);
+      const int oh = hv * p.out_mul + ph_p;
+      const int ow = wv * p.out_mul + ph_q;
+      const long long opix = (static_cast<long long>(b_img) * p.OH + oh) * p.OW + ow;
+      float ps = 1.f;
+      if (valid && p.epi == HYRES_EPI_PIXSCALE) ps = __ldg(p.pixscale + opix);
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t r[16];
+        hy::tmem_ld16(t_lane + sub * p.BN + c0, r);
+        hy::tmem_ld_wait();
+        const int n = n0 + c0;
+        if (!valid || n >= p.cout) continue;
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        const bool full16 = (n + 16 <= p.cout);
+        if (p.epi == HYRES_EPI_PIXSCALE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= ps;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);  // bias padded to BN multiple
+        if (p.epi == HYRES_EPI_ADD) {
+          float a[16];
+          load16_bf16(p.aux0 + opix * p.ld_aux0 + n, a);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += a[i];
+        } else if (p.epi == HYRES_EPI_GATE) {
+          float a[16], x[16];
+          load16_bf16(p.aux1 + opix * p.ld_aux1 + n, a);
+          load16_bf16(p.aux0 + opix * p.ld_aux0 + n, x);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = a[i] * (1.f / (1.f + __expf(-v[i]))) + x[i];
+        } else if (p.epi == HYRES_EPI_GDN) {
+          float x[16];
+          load16_bf16(p.aux0 + opix * p.ld_aux0 + n, x);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = x[i] * rsqrtf(v[i]);
+        } else if (p.epi == HYRES_EPI_IGDN) {
+          float x[16];
+          load16_bf16(p.aux0 + opix * p.ld_aux0 + n, x);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = x[i] * sqrtf(v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act, p.slope);
+
+        if (p.out_bf16) {
+          __nv_bfloat16* o = p.out_bf16 + opix * p.ld_out + n;
+          if (full16) {
+            store16_bf16(o, v);
+          } else {
+            for (int i = 0; i < 16 && n + i < p.cout; ++i) o[i] = __float2bfloat16_rn(v[i]);
+          }
+        }
+        if (p.out_sq) {
+          __nv_bfloat16* o = p.out_sq + opix * p.ld_sq + n;
+          float s[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            // square of the *stored* (bf16-rounded) activation: the GDN operand is x^2 of
+            // the tensor the next layer sees.
+            const float xb = __bfloat162float(__float2bfloat16_rn(v[i]));
+            s[i] = xb * xb;
+          }
+          if (full16) {
+            store16_bf16(o, s);
+          } else {
+            for (int i = 0; i < 16 && n + i < p.cout; ++i) o[i] = __float2bfloat16_rn(s[i]);
+          }
+        }
+        if (p.out_f32) {
+          float* o = p.out_f32 + b_img * p.f32_sb + oh * p.f32_sh + ow * p.f32_sw + n * p.f32_sc;
+          if (full16 && p.f32_sc == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            for (int i = 0; i < 16 && n + i < p.cout; ++i) o[i * p.f32_sc] = v[i];
+          }
+        }
+      }
+    }
+  }
+
+  hy::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    hy::tc_fence_after();
+    hy::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int choose_bn(int cout) {
+  if (cout <= 16) return 16;
+  int pad = (cout + 15) / 16 * 16;
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (pad % bn == 0) return bn;
+  return 16;
+}
+
+}  // namespace
+
+struct hyres_conv {
+  int kind, cin0, cin1, w_cin_total, cout, R, S, stride, pad, dil;
+  int BN, cout_pad, ktot, nphase, extra_rows;
+  int ph_begin[4], ph_count[4];
+  std::vector<TapGroup> groups;
+  std::vector<uint8_t> tap_mask;
+  // k-slot -> (src, chunk, r, s) for weight packing
+  struct Slot { int src, chunk, r, s; };
+  std::vector<Slot> slots;
+  TapGroup* d_groups = nullptr;
+  __nv_bfloat16* d_w = nullptr;
+  float* d_bias = nullptr;
+  int64_t macs_per_pos = 0;
+};
+
+namespace {
+
+void build_plan(hyres_conv* c) {
+  c->groups.clear();
+  c->slots.clear();
+  auto live = [&](int r, int s) { return c->tap_mask.empty() || c->tap_mask[r * c->S + s] != 0; };
+  const int nsrc = c->cin1 > 0 ? 2 : 1;
+  int extra = 0;
+  auto add_group = [&](int src, int c_off, int dw, int hpar, const std::vector<std::pair<int, int>>& taps,
+                       int chunk, int s) {
+    // taps: (row offset in view rows, r)
+    if (taps.empty()) return;
+    int mn = taps[0].first, mx = taps[0].first;
+    for (auto& t : taps) { mn = std::min(mn, t.first); mx = std::max(mx, t.first); }
+    TapGroup g{};
+    g.src = src; g.c_off = c_off; g.dw = dw; g.dh = mn; g.hpar = hpar;
+    g.ntaps = static_cast<int>(taps.size());
+    g.kslot0 = static_cast<int>(c->slots.size());
+    for (size_t i = 0; i < taps.size(); ++i) {
+      g.tap_row[i] = taps[i].first - mn;
+      c->slots.push_back({src, chunk, taps[i].second, s});
+    }
+    extra = std::max(extra, mx - mn);
+    c->groups.push_back(g);
+  };
+  if (c->kind == HYRES_CONV && c->stride == 1) {
+    c->nphase = 1;
+    c->ph_begin[0] = 0;
+    for (int src = 0; src < nsrc; ++src) {
+      const int cin = src ? c->cin1 : c->cin0;
+      for (int ch = 0; ch < (cin + 63) / 64; ++ch)
+        for (int s = 0; s < c->S; ++s) {
+          std::vector<std::pair<int, int>> taps;
+          for (int r = 0; r < c->R; ++r)
+            if (live(r, s)) taps.push_back({r * c->dil - c->pad, r});
+          add_group(src, ch * 64, s * c->dil - c->pad, 0, taps, ch, s);
+        }
+    }
+    c->ph_count[0] = static_cast<int>(c->groups.size());
+  } else if (c->kind == HYRES_CONV && c->stride == 2) {
+    c->nphase = 1;
+    c->ph_begin[0] = 0;
+    for (int ch = 0; ch < (c->cin0 + 63) / 64; ++ch)
+      for (int s = 0; s < c->S; ++s) {
+        const int ds = s - c->pad;
+        const int q = ds & 1;
+        const int wq = (ds - q) / 2;
+        for (int par = 0; par < 2; ++par) {
+          std::vector<std::pair<int, int>> taps;
+          for (int r = 0; r < c->R; ++r) {
+            const int dr = r - c->pad;
+            if ((dr & 1) != par || !live(r, s)) continue;
+            taps.push_back({(dr - par) / 2, r});
+          }
+          add_group(0, q * c->cin0 + ch * 64, wq, par, taps, ch, s);
+        }
+      }
+    c->ph_count[0] = static_cast<int>(c->groups.size());
+  } else {  // HYRES_DECONV_K5S2
+    c->nphase = 4;
+    for (int ph = 0; ph < 4; ++ph) {
+      const int pp = ph >> 1, qq = ph & 1;
+      c->ph_begin[ph] = static_cast<int>(c->groups.size());
+      for (int ch = 0; ch < (c->cin0 + 63) / 64; ++ch)
+        for (int s = qq; s < 5; s += 2) {
+          std::vector<std::pair<int, int>> taps;
+          for (int r = pp; r < 5; r += 2) taps.push_back({(pp + 2 - r) / 2, r});
+          add_group(0, ch * 64, (qq + 2 - s) / 2, 0, taps, ch, s);
+        }
+      c->ph_count[ph] = static_cast<int>(c->groups.size()) - c->ph_begin[ph];
+    }
+  }
+  c->extra_rows = extra;
+  c->ktot = static_cast<int>(c->slots.size()) * 64;
+  c->macs_per_pos = static_cast<int64_t>(c->ktot) * c->cout_pad / (c->nphase);
+}
+
+void pack_weights(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16>& out) {
+  out.assign(static_cast<size_t>(c->cout_pad) * c->ktot, __float2bfloat16(0.f));
+  const int RS = c->R * c->S;
+  for (size_t ks = 0; ks < c->slots.size(); ++ks) {
+    const auto& sl = c->slots[ks];
+    const int cin_src = sl.src ? c->cin1 : c->cin0;
+    const int cbase = (sl.src ? c->cin0 : 0) + sl.chunk * 64;
+    for (int cc = 0; cc < 64; ++cc) {
+      if (sl.chunk * 64 + cc >= cin_src) break;
+      const int ci = cbase + cc;
+      for (int n = 0; n < c->cout; ++n) {
+        float v;
+        if (c->kind == HYRES_DECONV_K5S2)
+          v = w[(static_cast<size_t>(ci) * c->cout + n) * RS + sl.r * c->S + sl.s];
+        else
+          v = w[(static_cast<size_t>(n) * c->w_cin_total + ci) * RS + sl.r * c->S + sl.s];
+        out[static_cast<size_t>(n) * c->ktot + ks * 64 + cc] = __float2bfloat16(v);
+      }
+    }
+  }
+}
+
+int upload_weights(hyres_conv* c, const float* weight, const float* bias) {
+  std::vector<__nv_bfloat16> packed;
+  pack_weights(c, weight, packed);
+  HY_CUDA(cudaMemcpy(c->d_w, packed.data(), packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  std::vector<float> b(c->cout_pad, 0.f);
+  if (bias) std::copy(bias, bias + c->cout, b.begin());
+  HY_CUDA(cudaMemcpy(c->d_bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return HYRES_OK;
+}
+
+int encode_act_map(CUtensorMap* m, const void* ptr, int C, int B, int H, int W, int stride2, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return hy_fail(HYRES_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[5], strides[4];
+  const cuuint64_t es = 2;
+  if (!stride2) {
+    dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = B;
+    strides[0] = C * es; strides[1] = (cuuint64_t)W * C * es; strides[2] = (cuuint64_t)W * C * es;
+    strides[3] = (cuuint64_t)H * W * C * es;
+  } else {
+    dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = B;
+    strides[0] = 2 * C * es; strides[1] = (cuuint64_t)W * C * es; strides[2] = 2ull * W * C * es;
+    strides[3] = (cuuint64_t)H * W * C * es;
+  }
+  cuuint32_t box[5] = {64, (cuuint32_t)kTileW, 1, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(act C=%d B=%d H=%d W=%d s2=%d rows=%d) -> %d", C, B, H, W,
+             stride2, box_rows, (int)r);
+    return hy_fail(HYRES_ERR_DRIVER, msg);
+  }
+  return HYRES_OK;
+}
+
+int encode_w_map(CUtensorMap* m, const void* ptr, int ktot, int cout_pad, int bn) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return hy_fail(HYRES_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)cout_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)ktot * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)bn};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(weights ktot=%d cout=%d bn=%d) -> %d", ktot, cout_pad, bn, (int)r);
+    return hy_fail(HYRES_ERR_DRIVER, msg);
+  }
+  return HYRES_OK;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout, int R, int S,
+                      int stride, int pad, int dil, const float* weight, const float* bias,
+                      const uint8_t* tap_mask) {
+  if (!out || !weight) return hy_fail(HYRES_ERR_ARG, "conv_create: null argument");
+  if (kind != HYRES_CONV && kind != HYRES_DECONV_K5S2) return hy_fail(HYRES_ERR_ARG, "conv_create: bad kind");
+  if (cin0 <= 0 || cin1 < 0 || cout <= 0 || (cin0 % 8) || (cin1 % 8))
+    return hy_fail(HYRES_ERR_ARG, "conv_create: channel counts must be positive multiples of 8");
+  if (kind == HYRES_DECONV_K5S2) {
+    if (R != 5 || S != 5 || cin1 != 0) return hy_fail(HYRES_ERR_UNSUPPORTED, "deconv: only k5 s2 p2 op1");
+    stride = 2; pad = 2; dil = 1;
+  } else {
+    if (stride != 1 && stride != 2) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv: stride must be 1 or 2");
+    if (stride == 2 && (dil != 1 || cin1 != 0 || pad != R / 2 || R != S))
+      return hy_fail(HYRES_ERR_UNSUPPORTED, "conv stride 2: needs dil=1, pad=k/2, one input");
+    if (R > kMaxTaps || S > 7 || dil < 1) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv: kernel too large");
+    if (stride == 1 && 2 * pad != dil * (R - 1))
+      return hy_fail(HYRES_ERR_UNSUPPORTED, "conv stride 1: only 'same' padding");
+  }
+  if (cin1 > 0 && (cin0 % 64)) return hy_fail(HYRES_ERR_UNSUPPORTED, "two-input conv: cin0 must be a multiple of 64");
+  hyres_conv* c = new hyres_conv();
+  c->kind = kind; c->cin0 = cin0; c->cin1 = cin1;
+  c->w_cin_total = w_cin_total > 0 ? w_cin_total : cin0 + cin1;
+  c->cout = cout; c->R = R; c->S = S; c->stride = stride; c->pad = pad; c->dil = dil;
+  if (tap_mask) c->tap_mask.assign(tap_mask, tap_mask + R * S);
+  c->BN = choose_bn(cout);
+  c->cout_pad = (cout + c->BN - 1) / c->BN * c->BN;
+  build_plan(c);
+  if (c->groups.empty()) { delete c; return hy_fail(HYRES_ERR_ARG, "conv_create: no live taps"); }
+  cudaError_t e;
+  e = cudaMalloc(&c->d_groups, c->groups.size() * sizeof(TapGroup));
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_groups, c->groups.data(), c->groups.size() * sizeof(TapGroup), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_w, static_cast<size_t>(c->cout_pad) * c->ktot * sizeof(__nv_bfloat16));
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_bias, c->cout_pad * sizeof(float));
+  if (e != cudaSuccess) { hyres_conv_destroy(c); return hy_fail(HYRES_ERR_CUDA, cudaGetErrorString(e)); }
+  int rc = upload_weights(c, weight, bias);
+  if (rc != HYRES_OK) { hyres_conv_destroy(c); return rc; }
+  *out = c;
+  return HYRES_OK;
+}
+
+int hyres_conv_update(hyres_conv* c, const float* weight, const float* bias) {
+  if (!c || !weight) return hy_fail(HYRES_ERR_ARG, "conv_update: null argument");
+  return upload_weights(c, weight, bias);
+}
+
+void hyres_conv_destroy(hyres_conv* c) {
+  if (!c) return;
+  if (c->d_groups) cudaFree(c->d_groups);
+  if (c->d_w) cudaFree(c->d_w);
+  if (c->d_bias) cudaFree(c->d_bias);
+  delete c;
+}
+
+int64_t hyres_conv_macs_per_pos(const hyres_conv* c) { return c ? c->macs_per_pos : 0; }
+
+int hyres_conv_out_size(const hyres_conv* c, int H, int W, int* OH, int* OW) {
+  if (!c || !OH || !OW) return hy_fail(HYRES_ERR_ARG, "conv_out_size: null argument");
+  if (c->kind == HYRES_DECONV_K5S2) { *OH = 2 * H; *OW = 2 * W; }
+  else if (c->stride == 2) { *OH = H / 2; *OW = W / 2; }
+  else { *OH = H; *OW = W; }
+  return HYRES_OK;
+}
+
+int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
+  if (!c || !io || !io->x0) return hy_fail(HYRES_ERR_ARG, "conv_run: null argument");
+  if (c->cin1 > 0 && !io->x1) return hy_fail(HYRES_ERR_ARG, "conv_run: second input missing");
+  if (io->B <= 0 || io->H <= 0 || io->W <= 0) return hy_fail(HYRES_ERR_ARG, "conv_run: empty input");
+  if (c->kind == HYRES_CONV && c->stride == 2 && ((io->H | io->W) & 1))
+    return hy_fail(HYRES_ERR_ARG, "conv_run: stride-2 conv needs even H and W");
+  if ((io->epi == HYRES_EPI_ADD || io->epi == HYRES_EPI_GDN || io->epi == HYRES_EPI_IGDN || io->epi == HYRES_EPI_GATE) && !io->aux0)
+    return hy_fail(HYRES_ERR_ARG, "conv_run: aux0 missing for epilogue");
+  if (io->epi == HYRES_EPI_GATE && !io->aux1) return hy_fail(HYRES_ERR_ARG, "conv_run: aux1 missing for gate");
+  if (io->epi == HYRES_EPI_PIXSCALE && !io->pixscale) return hy_fail(HYRES_ERR_ARG, "conv_run: pixscale missing");
+  if (io->aux0 && (io->ld_aux0 % 8)) return hy_fail(HYRES_ERR_ARG, "conv_run: ld_aux0 must be a multiple of 8");
+  if (io->aux1 && (io->ld_aux1 % 8)) return hy_fail(HYRES_ERR_ARG, "conv_run: ld_aux1 must be a multiple of 8");
+  if (io->out_bf16 && (io->ld_out % 8)) return hy_fail(HYRES_ERR_ARG, "conv_run: ld_out must be a multiple of 8");
+  if (io->out_sq && (io->ld_sq % 8)) return hy_fail(HYRES_ERR_ARG, "conv_run: ld_sq must be a multiple of 8");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+  ConvParams p;
+  memset(&p, 0, sizeof p);
+  int OH, OW;
+  hyres_conv_out_size(c, io->H, io->W, &OH, &OW);
+  p.OH = OH; p.OW = OW;
+  p.out_mul = c->kind == HYRES_DECONV_K5S2 ? 2 : 1;
+  p.OHv = OH / p.out_mul; p.OWv = OW / p.out_mul;
+  p.BN = c->BN;
+  // sub-tiles per CTA: as many as TMEM allows while keeping >= 2 waves of CTAs
+  int mt = io->mt_hint;
+  if (mt != 1 && mt != 2 && mt != 4) {
+    mt = 4;
+    while (mt > 1) {
+      const long long ctas = static_cast<long long>(io->B) * ((p.OHv + kSubH * mt - 1) / (kSubH * mt)) *
+                             ((p.OWv + kTileW - 1) / kTileW) * (c->cout_pad / c->BN) * c->nphase;
+      if (mt * c->BN <= 512 && ctas >= 2LL * num_sms()) break;
+      mt >>= 1;
+    }
+  }
+  while (mt > 1 && mt * c->BN > 512) mt >>= 1;
+  p.MT = mt;
+  p.patch_rows = kSubH * mt + c->extra_rows;
+  if (p.patch_rows > 256) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: patch too tall");
+  p.a_stage_bytes = p.patch_rows * kTileW * 128;
+  p.b_stage_bytes = c->BN * 128;
+  p.NA = 2;
+  p.NB = 4;
+  auto smem_need = [&]() { return p.NA * p.a_stage_bytes + p.NB * p.b_stage_bytes + 256 + 1024; };
+  while (smem_need() > 227 * 1024 && p.NB > 2) --p.NB;
+  if (smem_need() > 227 * 1024) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: tile does not fit shared memory");
+  int cols = 32;
+  while (cols < mt * c->BN) cols <<= 1;
+  p.tmem_cols = cols;
+  p.tiles_w = (p.OWv + kTileW - 1) / kTileW;
+  p.tiles_h = (p.OHv + kSubH * mt - 1) / (kSubH * mt);
+  for (int i = 0; i < 4; ++i) { p.ph_begin[i] = c->ph_begin[i]; p.ph_count[i] = c->ph_count[i]; }
+  p.groups = c->d_groups;
+  p.cout = c->cout;
+  p.epi = io->epi; p.act = io->act; p.slope = io->slope;
+  p.bias = c->d_bias;
+  p.aux0 = static_cast<const __nv_bfloat16*>(io->aux0); p.ld_aux0 = io->ld_aux0;
+  p.aux1 = static_cast<const __nv_bfloat16*>(io->aux1); p.ld_aux1 = io->ld_aux1;
+  p.pixscale = io->pixscale;
+  p.out_bf16 = static_cast<__nv_bfloat16*>(io->out_bf16); p.ld_out = io->ld_out;
+  p.out_sq = static_cast<__nv_bfloat16*>(io->out_sq); p.ld_sq = io->ld_sq;
+  p.out_f32 = io->out_f32;
+  p.f32_sb = io->f32_sb; p.f32_sh = io->f32_sh; p.f32_sw = io->f32_sw; p.f32_sc = io->f32_sc;
+
+  const int s2 = (c->kind == HYRES_CONV && c->stride == 2) ? 1 : 0;
+  int rc = encode_act_map(&p.mapA0, io->x0, c->cin0, io->B, io->H, io->W, s2, p.patch_rows);
+  if (rc != HYRES_OK) return rc;
+  if (c->cin1 > 0) rc = encode_act_map(&p.mapA1, io->x1, c->cin1, io->B, io->H, io->W, 0, p.patch_rows);
+  else p.mapA1 = p.mapA0;
+  if (rc != HYRES_OK) return rc;
+  rc = encode_w_map(&p.mapB, c->d_w, c->ktot, c->cout_pad, c->BN);
+  if (rc != HYRES_OK) return rc;
+
+  const int smem = smem_need();
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    HY_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = 227 * 1024;
+  }
+  dim3 grid(static_cast<unsigned>(io->B * p.tiles_w * p.tiles_h), c->cout_pad / c->BN, c->nphase);
+  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,232 @@
+/*
+ * hyres_b200.h — C-ABI of the B200-native HyRES residual-codec hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch / C++ types.
+ * Every entry point returns 0 on success or a negative HYRES_ERR_* code; no
+ * exception crosses the boundary. Device pointers are raw CUDA device
+ * addresses; `stream` is a cudaStream_t passed as void*.
+ *
+ * Each group of entry points cites the reference interface it replaces
+ * (paths relative to the upstream repository, tmkhang1999/HyRES-...):
+ *
+ *   hyres_conv_*            nn.Conv2d / nn.ConvTranspose2d call sites of
+ *                           models/checkerboard.py:35-88 (g_a, g_s, h_a, h_s,
+ *                           context_prediction, param_aggregation),
+ *                           models/layers/attention.py:16-47 (ResidualUnit, gate),
+ *                           models/layers/enhancement.py:60-85 (MultiScaleRefine),
+ *                           compressai GDN (conv2d(x^2, gamma, beta)) and
+ *                           ResidualBottleneckBlock.
+ *   hyres_residual_*        models/hyres.py:48,62,66-67,96,127,131-132
+ *   hyres_gc_*              models/checkerboard.py:106-142,149-165 +
+ *                           compressai GaussianConditional.{quantize,
+ *                           _likelihood,build_indexes,dequantize}
+ *   hyres_eb_*              compressai EntropyBottleneck.{forward,compress,
+ *                           decompress} via models/checkerboard.py:96-101,172-173,206
+ *   hyres_refine_*          models/layers/enhancement.py:15-21,36-40,87-112
+ *   hyres_reduce_*          src/losses/rd_loss.py:23-26,39
+ *   hyres_rans_*, hyres_pmf_to_quantized_cdf
+ *                           compressai.ans.{RansEncoder.encode_with_indexes,
+ *                           RansDecoder.decode_with_indexes} and
+ *                           compressai._CXX.pmf_to_quantized_cdf, reached from
+ *                           models/checkerboard.py:159-165,172-173,206,261-267
+ */
+#ifndef HYRES_B200_H
+#define HYRES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYRES_OK 0
+#define HYRES_ERR_ARG -1
+#define HYRES_ERR_CUDA -2
+#define HYRES_ERR_DRIVER -3
+#define HYRES_ERR_UNSUPPORTED -4
+#define HYRES_ERR_STATE -5
+
+/* Library / device probes. hyres_device_check returns HYRES_OK only on an
+ * sm_100 device; there is no CPU fallback behind any compute entry point. */
+int hyres_version(void);
+int hyres_device_check(int device);
+const char* hyres_last_error(void);
+
+/* ------------------------------------------------------------------------- */
+/* Implicit-GEMM convolution on tcgen05 tensor cores (NHWC bf16, fp32 accum). */
+/* ------------------------------------------------------------------------- */
+
+typedef struct hyres_conv hyres_conv;
+
+/* kind */
+#define HYRES_CONV 0        /* nn.Conv2d, weight [Cout][Cin][R][S]                         */
+#define HYRES_DECONV_K5S2 1 /* nn.ConvTranspose2d(k=5,s=2,p=2,output_padding=1),
+                               weight [Cin][Cout][5][5] (compressai `deconv`)              */
+
+/* epilogue modes: v = f(acc + bias) */
+#define HYRES_EPI_LINEAR 0   /* v = acc + bias                                             */
+#define HYRES_EPI_ADD 1      /* v = acc + bias + aux0           (residual skip)            */
+#define HYRES_EPI_GATE 2     /* v = aux1 * sigmoid(acc+bias) + aux0  (AttentionBlock)      */
+#define HYRES_EPI_GDN 3      /* v = aux0 * rsqrt(acc + bias)    (GDN; input is x^2)        */
+#define HYRES_EPI_IGDN 4     /* v = aux0 * sqrt(acc + bias)     (inverse GDN)              */
+#define HYRES_EPI_PIXSCALE 5 /* v = acc * pixscale[pixel] + bias (spatial attention)       */
+
+/* activation applied after the epilogue mode */
+#define HYRES_ACT_NONE 0
+#define HYRES_ACT_RELU 1
+#define HYRES_ACT_PRELU 2   /* single-slope PReLU */
+#define HYRES_ACT_CLAMP01 3
+
+/* Create a layer: packs `weight` (host fp32, PyTorch layout) into the K-major
+ * bf16 B operand, uploads it with `bias` (host fp32, may be NULL) and builds the
+ * tap table. `w_cin_total` is the Cin extent of the weight array; the layer
+ * consumes its first cin0+cin1 input channels (cin1 > 0: a second input tensor
+ * is concatenated along channels). `tap_mask` (R*S bytes, may be NULL) drops
+ * taps whose entry is 0 (checkerboard context conv). */
+int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout,
+                      int R, int S, int stride, int pad, int dil, const float* weight,
+                      const float* bias, const uint8_t* tap_mask);
+/* Re-pack new weights into an existing layer (same geometry). */
+int hyres_conv_update(hyres_conv* c, const float* weight, const float* bias);
+void hyres_conv_destroy(hyres_conv* c);
+/* MACs per output position the packed layer executes (padded K and N included). */
+int64_t hyres_conv_macs_per_pos(const hyres_conv* c);
+
+typedef struct {
+  const void* x0; /* bf16 NHWC [B,H,W,cin0] */
+  const void* x1; /* bf16 NHWC [B,H,W,cin1] or NULL */
+  int B, H, W;    /* input extent */
+  int epi, act;
+  float slope;
+  const void* aux0; /* bf16 NHWC at output resolution, channel stride ld_aux0 */
+  int ld_aux0;
+  const void* aux1;
+  int ld_aux1;
+  const float* pixscale; /* fp32 [B,OH,OW] */
+  void* out_bf16;        /* bf16 NHWC, channel stride ld_out (>= cout), may be NULL */
+  int ld_out;
+  void* out_sq; /* bf16 NHWC of v*v (GDN operand), may be NULL */
+  int ld_sq;
+  float* out_f32; /* fp32, arbitrary strides (elements), may be NULL */
+  int64_t f32_sb, f32_sh, f32_sw, f32_sc;
+  int mt_hint; /* 0 = auto; else force 1/2/4 sub-tiles per CTA */
+} hyres_conv_io;
+
+int hyres_conv_out_size(const hyres_conv* c, int H, int W, int* OH, int* OW);
+int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Memory-bound kernels                                                       */
+/* ------------------------------------------------------------------------- */
+
+/* residual = x - jpeg (fp32 NCHW out, may be NULL) and the 5x5/stride-2 im2col
+ * of the residual as bf16 [B,H/2,W/2,128] (k = (r*5+s)*3+c, 75 live) that feeds
+ * g_a.0 as a 1x1 GEMM. jpeg may be NULL (x is already the residual).
+ * models/hyres.py:48,96 + models/checkerboard.py:36 */
+int hyres_residual_im2col5s2(const float* x, const float* jpeg, float* residual, void* a_out,
+                             int B, int H, int W, void* stream);
+/* x0 = jpeg + r_hat (fp32 NCHW out) and the 3x3 im2col of x0 as bf16
+ * [B,H,W,64] (k = (r*3+s)*3+c, 27 live) feeding refine.conv_in.
+ * models/hyres.py:62,127 + models/layers/enhancement.py:60 */
+int hyres_addback_im2col3(const float* jpeg, const float* r_hat, float* x0, void* a_out, int B,
+                          int H, int W, void* stream);
+/* x_hat = clamp(x0 + refined, 0, 1), all fp32 NCHW. models/hyres.py:66-67,131-132 */
+int hyres_final_clamp(const float* x0, const float* refined, float* x_hat, int64_t n, void* stream);
+
+/* GaussianConditional / checkerboard quantiser. y: fp32 NHWC [B,h,w,M];
+ * params: fp32 NHWC [B,h,w,2M] with scales in channels [0,M) and means in
+ * [M,2M) (models/checkerboard.py:118). pass 0 = anchor, 1 = non-anchor.
+ * mode 0: STE/round (eval), mode 1: additive uniform noise (seeded Philox). */
+int hyres_gc_quant_pass(const float* y, const float* params, int pass, int mode, uint64_t seed,
+                        float* yq_f32, void* yq_bf16, int B, int h, int w, int M, void* stream);
+/* y_hat = yq_a + yq_na (bf16 NHWC out); likelihoods of `y` under
+ * (scales_a+scales_na, means_a+means_na) written fp32 NCHW [B,M,h,w];
+ * partial sums of log2(lik) accumulated (deterministically) into *sum_log2
+ * (double, device). models/checkerboard.py:136-142 */
+int hyres_gc_merge_likelihood(const float* y, const float* params_a, const float* params_na,
+                              const float* yq_a, const float* yq_na, int mode, uint64_t seed,
+                              void* y_hat_bf16, float* lik_nchw, double* sum_log2, int B, int h,
+                              int w, int M, void* stream);
+/* symbols = int32(round(y_part - mean)), indexes = bucketize(max(scale, bound)),
+ * both written in (B,M,h,w) order; yq = symbol + mean (dequantize).
+ * models/checkerboard.py:159-161 */
+int hyres_gc_symbols(const float* y, const float* params, int pass, const float* scale_table,
+                     int n_scales, float scale_bound, int32_t* symbols, int32_t* indexes,
+                     float* yq_f32, void* yq_bf16, int B, int h, int w, int M, void* stream);
+/* decoder side: indexes from scales only. models/checkerboard.py:163-165 */
+int hyres_gc_indexes(const float* params, const float* scale_table, int n_scales,
+                     float scale_bound, int32_t* indexes, int B, int h, int w, int M, void* stream);
+/* decoder side: yq = float(symbol) + mean; symbols in (B,M,h,w) order. */
+int hyres_gc_dequant(const int32_t* symbols, const float* params, float* yq_f32, void* yq_bf16,
+                     int B, int h, int w, int M, void* stream);
+/* y_hat = a + b (fp32 NHWC in, bf16 NHWC out). models/checkerboard.py:234 */
+int hyres_add_to_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
+
+/* EntropyBottleneck. z: fp32 NHWC [B,h,w,C]. `eb_params`: fp32 [C][58] =
+ * softplus(matrices) (3,9,9,9,3), biases (3,3,3,3,1), tanh(factors) (3,3,3,3);
+ * medians fp32 [C]. mode 0: dequantize (round about the median), 1: noise.
+ * z_hat written bf16 NHWC (+ fp32 NCHW optional), likelihood fp32 NCHW,
+ * symbols int32 (B,C,h,w) optional. */
+int hyres_eb_forward(const float* z, const float* eb_params, const float* medians, int mode,
+                     uint64_t seed, float lik_bound, void* zhat_bf16, float* zhat_nchw,
+                     float* lik_nchw, int32_t* symbols, double* sum_log2, int B, int h, int w,
+                     int C, void* stream);
+/* z_hat = float(symbol) + median, symbols (B,C,h,w) -> bf16 NHWC. */
+int hyres_eb_dequant(const int32_t* symbols, const float* medians, void* zhat_bf16, int B, int h,
+                     int w, int C, void* stream);
+
+/* MultiScaleRefine memory ops (feat: bf16 NHWC, C=64). */
+int hyres_refine_se_pool(const void* feat, float* pooled /*[B,C]*/, int B, int H, int W, int C,
+                         void* stream);
+int hyres_refine_se_scale_down(const void* feat, const float* pooled, const float* fc1,
+                               const float* fc2, int C, int Cr, void* feat_s, void* feat_h,
+                               void* feat_q, int B, int H, int W, void* stream);
+int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi /*[B,H,W,3C]*/,
+                                 float* stats /*[B,H,W,2]*/, int B, int H, int W, int C,
+                                 void* stream);
+int hyres_refine_spatial_att(const float* stats, const float* w7x7, float* att /*[B,H,W]*/,
+                             int B, int H, int W, void* stream);
+
+/* layout helpers */
+int hyres_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W,
+                                void* stream);
+int hyres_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W, void* stream);
+int hyres_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H, int W,
+                                void* stream);
+
+/* sum((a-b)^2) and sum(log2(x)) accumulated into a device double. */
+int hyres_reduce_sqdiff(const float* a, const float* b, int64_t n, double* out, void* stream);
+int hyres_reduce_log2(const float* x, int64_t n, double* out, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Entropy coder (host). Byte-identical to compressai's rANS64 interface.      */
+/* ------------------------------------------------------------------------- */
+
+/* compressai._CXX.pmf_to_quantized_cdf: out has n+1 entries. */
+int hyres_pmf_to_quantized_cdf(const float* pmf, int n, int precision, uint32_t* out);
+
+/* RansEncoder.encode_with_indexes. cdfs: [n_cdfs][cdf_stride] int32. Writes at most
+ * out_cap bytes; *out_len receives the length (HYRES_ERR_ARG if out_cap too small;
+ * 4*(n_symbols_incl_bypass)+8 always suffices, see hyres_rans_encode_bound). */
+int64_t hyres_rans_encode_bound(int64_t n);
+int hyres_rans_encode(const int32_t* symbols, const int32_t* indexes, int64_t n,
+                      const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                      const int32_t* offsets, uint8_t* out, int64_t out_cap, int64_t* out_len);
+/* RansDecoder.decode_with_indexes. */
+int hyres_rans_decode(const uint8_t* in, int64_t in_len, const int32_t* indexes, int64_t n,
+                      const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                      const int32_t* offsets, int32_t* symbols_out);
+/* Batched variants: `count` independent strings coded on up to `threads` host threads. */
+int hyres_rans_encode_batch(int count, const int32_t* const* symbols, const int32_t* const* indexes,
+                            const int64_t* n, const int32_t* cdfs, int n_cdfs, int cdf_stride,
+                            const int32_t* cdf_sizes, const int32_t* offsets, uint8_t* const* out,
+                            const int64_t* out_cap, int64_t* out_len, int threads);
+int hyres_rans_decode_batch(int count, const uint8_t* const* in, const int64_t* in_len,
+                            const int32_t* const* indexes, const int64_t* n, const int32_t* cdfs,
+                            int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                            const int32_t* offsets, int32_t* const* symbols_out, int threads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYRES_B200_H */
