@@ -4,3 +4,7 @@ Import name: ``hyres_b200`` (a shim package at the repository root extends its
 ``__path__`` to this directory, whose hyphenated name is not importable).
 """
 from . import _lib  # noqa: F401
+from .models import (LightWeightCheckerboard, RateDistortionLoss, ResidualJPEGCompression,  # noqa: F401
+                     get_scale_table)
+from .layers import AttentionBlock, CheckboardMaskedConv2d, MultiScaleRefine, conv1x1, conv3x3  # noqa: F401
+from .jpeg import TurboJPEGCompression  # noqa: F401

@@ -60,7 +60,7 @@ SIGNATURES = {
     "hyres_add_to_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hyres_eb_forward": (_i, [_vp, _vp, _vp, _i, _u64, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_eb_dequant": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "hyres_refine_se_pool": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_refine_se_pool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_se_scale_down": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_refine_up_concat_stats": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_spatial_att": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -1,0 +1,128 @@
+"""Host entropy coder of the product path (csrc/rans.cpp through the C-ABI).
+
+Mirrors the pybind11 interface the reference crosses
+(``compressai.ans.RansEncoder().encode_with_indexes`` / ``RansDecoder().decode_with_indexes``
+and ``compressai._CXX.pmf_to_quantized_cdf``; reached from
+models/checkerboard.py:159-165,172-173,206,261-267) but takes flat int32 numpy arrays
+instead of Python lists, and adds batched calls that code independent strings in parallel.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib as L
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+def pmf_to_quantized_cdf(pmf, precision=16):
+    """-> int32 numpy array with len(pmf)+1 entries; raises ValueError on an invalid pmf."""
+    p = np.ascontiguousarray(np.asarray(pmf, dtype=np.float32)).ravel()
+    out = np.zeros(p.size + 1, dtype=np.uint32)
+    rc = L.lib().hyres_pmf_to_quantized_cdf(p.ctypes.data, p.size, int(precision), out.ctypes.data)
+    if rc != 0:
+        raise ValueError("Invalid `pmf`: " + L.lib().hyres_last_error().decode())
+    return out.astype(np.int32)
+
+
+class CdfTables:
+    """Flat view of an entropy model's ``_quantized_cdf`` / ``_cdf_length`` / ``_offset`` buffers."""
+
+    def __init__(self, quantized_cdf, cdf_length, offset):
+        self.cdf = _i32(quantized_cdf)
+        if self.cdf.ndim != 2:
+            raise ValueError(f"Invalid CDF size {self.cdf.shape}")
+        self.sizes = _i32(cdf_length).ravel()
+        self.offsets = _i32(offset).ravel()
+        if self.sizes.size != self.cdf.shape[0] or self.offsets.size != self.cdf.shape[0]:
+            raise ValueError("cdf_length / offset do not match the CDF table")
+
+
+def encode_with_indexes(symbols, indexes, tables):
+    s, ix = _i32(symbols).ravel(), _i32(indexes).ravel()
+    if s.size != ix.size:
+        raise ValueError("`symbols` and `indexes` should have the same size.")
+    lib = L.lib()
+    cap = int(lib.hyres_rans_encode_bound(s.size))
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_int64(0)
+    t = tables
+    rc = lib.hyres_rans_encode(s.ctypes.data, ix.ctypes.data, s.size, t.cdf.ctypes.data, t.cdf.shape[0], t.cdf.shape[1],
+                               t.sizes.ctypes.data, t.offsets.ctypes.data, out.ctypes.data, cap, C.byref(n))
+    if rc != 0 and n.value > cap:
+        cap = n.value
+        out = np.empty(cap, dtype=np.uint8)
+        rc = lib.hyres_rans_encode(s.ctypes.data, ix.ctypes.data, s.size, t.cdf.ctypes.data, t.cdf.shape[0],
+                                   t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data, out.ctypes.data, cap,
+                                   C.byref(n))
+    L.check(rc, "hyres_rans_encode")
+    return out[: n.value].tobytes()
+
+
+def decode_with_indexes(string, indexes, tables):
+    ix = _i32(indexes).ravel()
+    buf = np.frombuffer(string, dtype=np.uint8)
+    out = np.empty(ix.size, dtype=np.int32)
+    t = tables
+    L.check(L.lib().hyres_rans_decode(buf.ctypes.data, buf.size, ix.ctypes.data, ix.size, t.cdf.ctypes.data,
+                                      t.cdf.shape[0], t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data,
+                                      out.ctypes.data), "hyres_rans_decode")
+    return out
+
+
+def _threads(n):
+    return max(1, min(n, os.cpu_count() or 1))
+
+
+def encode_batch(symbols, indexes, tables, threads=None):
+    """symbols / indexes: int32 arrays [count, n] (rows = independent strings) -> list of bytes."""
+    s, ix = _i32(symbols), _i32(indexes)
+    if s.shape != ix.shape or s.ndim != 2:
+        raise ValueError("`symbols` and `indexes` should be [count, n] arrays of the same size.")
+    count, n = s.shape
+    if count == 0:
+        return []
+    lib = L.lib()
+    cap = int(lib.hyres_rans_encode_bound(n))
+    t = tables
+    while True:
+        out = np.empty((count, cap), dtype=np.uint8)
+        sp = (C.c_void_p * count)(*[s[i].ctypes.data for i in range(count)])
+        ip = (C.c_void_p * count)(*[ix[i].ctypes.data for i in range(count)])
+        op = (C.c_void_p * count)(*[out[i].ctypes.data for i in range(count)])
+        ns = np.full(count, n, dtype=np.int64)
+        caps = np.full(count, cap, dtype=np.int64)
+        lens = np.zeros(count, dtype=np.int64)
+        rc = lib.hyres_rans_encode_batch(count, sp, ip, ns.ctypes.data, t.cdf.ctypes.data, t.cdf.shape[0],
+                                         t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data, op,
+                                         caps.ctypes.data, lens.ctypes.data, _threads(threads or count))
+        if rc != 0 and lens.max() > cap:
+            cap = int(lens.max())
+            continue
+        L.check(rc, "hyres_rans_encode_batch")
+        return [out[i, : lens[i]].tobytes() for i in range(count)]
+
+
+def decode_batch(strings, indexes, tables, threads=None):
+    """strings: list of bytes; indexes int32 [count, n] -> int32 [count, n]."""
+    ix = _i32(indexes)
+    count, n = ix.shape
+    if len(strings) != count:
+        raise ValueError("Invalid strings or indexes parameters")
+    if count == 0:
+        return np.empty((0, n), dtype=np.int32)
+    bufs = [np.frombuffer(s, dtype=np.uint8) for s in strings]
+    out = np.empty((count, n), dtype=np.int32)
+    bp = (C.c_void_p * count)(*[b.ctypes.data for b in bufs])
+    ip = (C.c_void_p * count)(*[ix[i].ctypes.data for i in range(count)])
+    op = (C.c_void_p * count)(*[out[i].ctypes.data for i in range(count)])
+    lens = np.array([b.size for b in bufs], dtype=np.int64)
+    ns = np.full(count, n, dtype=np.int64)
+    t = tables
+    L.check(L.lib().hyres_rans_decode_batch(count, bp, lens.ctypes.data, ip, ns.ctypes.data, t.cdf.ctypes.data,
+                                            t.cdf.shape[0], t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data,
+                                            op, _threads(threads or count)), "hyres_rans_decode_batch")
+    return out

@@ -635,17 +635,11 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   p.out_mul = c->kind == HYRES_DECONV_K5S2 ? 2 : 1;
   p.OHv = OH / p.out_mul; p.OWv = OW / p.out_mul;
   p.BN = c->BN;
-  // sub-tiles per CTA: as many as TMEM allows while keeping >= 2 waves of CTAs
+  // sub-tiles per CTA.  Measured on B200 (tools/check_conv.py, 4x256x384 maps): one 128-row
+  // accumulator per CTA with 2-3 co-resident CTAs per SM beats taller tiles, whose epilogue
+  // is not overlapped with another CTA's main loop.
   int mt = io->mt_hint;
-  if (mt != 1 && mt != 2 && mt != 4) {
-    mt = 4;
-    while (mt > 1) {
-      const long long ctas = static_cast<long long>(io->B) * ((p.OHv + kSubH * mt - 1) / (kSubH * mt)) *
-                             ((p.OWv + kTileW - 1) / kTileW) * (c->cout_pad / c->BN) * c->nphase;
-      if (mt * c->BN <= 512 && ctas >= 2LL * num_sms()) break;
-      mt >>= 1;
-    }
-  }
+  if (mt != 1 && mt != 2 && mt != 4) mt = 1;
   while (mt > 1 && mt * c->BN > 512) mt >>= 1;
   p.MT = mt;
   p.patch_rows = kSubH * mt + c->extra_rows;

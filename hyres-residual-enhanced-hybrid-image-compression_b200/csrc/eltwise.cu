@@ -1,0 +1,278 @@
+// HBM-bound kernels of the HyRES hot path: residual / add-back / clamp, im2col for the
+// two 3-channel convolutions, NHWC<->NCHW layout changes, and loss reductions.
+// All are coalesced and vectorised; none stages through shared memory unless it
+// transposes.  Reference call sites are cited per entry point in include/hyres_b200.h.
+#include <cstdint>
+
+#include "common.cuh"
+#include "host_util.h"
+#include "hyres_b200.h"
+
+namespace {
+
+constexpr int kBlock = 256;
+
+inline int grid_for(int64_t n, int per_block, int cap = 148 * 16) {
+  int64_t g = (n + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return static_cast<int>(g);
+}
+
+// out = a - b  or  a + b   (fp32, float4 body + scalar tail)
+template <int SIGN>
+__global__ void addsub_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
+                              int64_t n) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i);
+    const float4 y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    float4 r;
+    r.x = SIGN > 0 ? x.x + y.x : x.x - y.x;
+    r.y = SIGN > 0 ? x.y + y.y : x.y - y.y;
+    r.z = SIGN > 0 ? x.z + y.z : x.z - y.z;
+    r.w = SIGN > 0 ? x.w + y.w : x.w - y.w;
+    reinterpret_cast<float4*>(o)[i] = r;
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    o[i] = SIGN > 0 ? a[i] + b[i] : a[i] - b[i];
+}
+
+__global__ void final_clamp_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
+                                   int64_t n) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i);
+    const float4 y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    float4 r;
+    r.x = fminf(fmaxf(x.x + y.x, 0.f), 1.f);
+    r.y = fminf(fmaxf(x.y + y.y, 0.f), 1.f);
+    r.z = fminf(fmaxf(x.z + y.z, 0.f), 1.f);
+    r.w = fminf(fmaxf(x.w + y.w, 0.f), 1.f);
+    reinterpret_cast<float4*>(o)[i] = r;
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    o[i] = fminf(fmaxf(a[i] + b[i], 0.f), 1.f);
+}
+
+// im2col of a 3-channel fp32 NCHW image into bf16 rows of KPAD entries:
+//   A[b, i, j, (r*K + s)*3 + c] = x[b, c, i*STRIDE + r - PAD, j*STRIDE + s - PAD]  (0 outside)
+// One thread writes 8 consecutive k (16 B), so a warp writes 512 contiguous bytes.
+template <int K, int STRIDE, int PAD, int KPAD>
+__global__ void im2col3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int H, int W,
+                               int OH, int OW) {
+  constexpr int G = KPAD / 8;
+  const int64_t total = static_cast<int64_t>(B) * OH * OW * G;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int64_t plane = static_cast<int64_t>(H) * W;
+  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total; t += stride) {
+    const int g = static_cast<int>(t % G);
+    int64_t pix = t / G;
+    const int j = static_cast<int>(pix % OW);
+    pix /= OW;
+    const int i = static_cast<int>(pix % OH);
+    const int b = static_cast<int>(pix / OH);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = g * 8 + e;
+      float val = 0.f;
+      if (k < K * K * 3) {
+        const int c = k % 3;
+        const int rs = k / 3;
+        const int r = rs / K, s = rs % K;
+        const int ih = i * STRIDE + r - PAD, iw = j * STRIDE + s - PAD;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+          val = __ldg(x + (static_cast<int64_t>(b) * 3 + c) * plane + static_cast<int64_t>(ih) * W + iw);
+      }
+      v[e] = val;
+    }
+    uint4 o;
+    o.x = hy::pack_bf16(v[0], v[1]);
+    o.y = hy::pack_bf16(v[2], v[3]);
+    o.z = hy::pack_bf16(v[4], v[5]);
+    o.w = hy::pack_bf16(v[6], v[7]);
+    reinterpret_cast<uint4*>(a)[t] = o;
+  }
+}
+
+// [B][C][HW] fp32 -> [B][HW][C] bf16 and the reverse directions, 32x32 tiles through smem.
+template <typename TIn, typename TOut>
+__global__ void transpose_tiles(const TIn* __restrict__ in, TOut* __restrict__ out, int rows, int cols) {
+  // in: [batch][rows][cols] -> out: [batch][cols][rows]
+  __shared__ float tile[32][33];
+  const int64_t boff = static_cast<int64_t>(blockIdx.z) * rows * cols;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int r = r0 + dy, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[dy][threadIdx.x] = static_cast<float>(in[boff + static_cast<int64_t>(r) * cols + c]);
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += blockDim.y) {
+    const int c = c0 + dy, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[boff + static_cast<int64_t>(c) * rows + r] = static_cast<TOut>(tile[threadIdx.x][dy]);
+  }
+}
+
+__global__ void add_to_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                   __nv_bfloat16* __restrict__ o, int64_t n) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i);
+    const float4 y = __ldg(reinterpret_cast<const float4*>(b) + i);
+    uint2 r;
+    r.x = hy::pack_bf16(x.x + y.x, x.y + y.y);
+    r.y = hy::pack_bf16(x.z + y.z, x.w + y.w);
+    reinterpret_cast<uint2*>(o)[i] = r;
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    o[i] = __float2bfloat16_rn(a[i] + b[i]);
+}
+
+__device__ __forceinline__ void block_accumulate(double v, double* out) {
+  __shared__ double part[kBlock / 32];
+  v = hy::warp_sum_d(v);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double s = threadIdx.x < kBlock / 32 ? part[threadIdx.x] : 0.0;
+    s = hy::warp_sum_d(s);
+    if (threadIdx.x == 0) atomicAdd(out, s);
+  }
+}
+
+__global__ void sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, double* out) {
+  float acc = 0.f;
+  double dacc = 0.0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int it = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const float d = __ldg(a + i) - __ldg(b + i);
+    acc = fmaf(d, d, acc);
+    if ((++it & 63) == 0) { dacc += acc; acc = 0.f; }
+  }
+  block_accumulate(dacc + acc, out);
+}
+
+__global__ void log2_kernel(const float* __restrict__ x, int64_t n, double* out) {
+  float acc = 0.f;
+  double dacc = 0.0;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int it = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    acc += log2f(__ldg(x + i));
+    if ((++it & 63) == 0) { dacc += acc; acc = 0.f; }
+  }
+  block_accumulate(dacc + acc, out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int hyres_residual_im2col5s2(const float* x, const float* jpeg, float* residual, void* a_out, int B, int H, int W,
+                             void* stream_v) {
+  if (!x || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return hy_fail(HYRES_ERR_ARG, "residual_im2col5s2: bad argument");
+  if (jpeg && !residual) return hy_fail(HYRES_ERR_ARG, "residual_im2col5s2: residual buffer required with jpeg");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  const int64_t n = static_cast<int64_t>(B) * 3 * H * W;
+  const float* src = x;
+  if (jpeg) {
+    addsub_kernel<-1><<<grid_for(n, kBlock * 4), kBlock, 0, st>>>(x, jpeg, residual, n);
+    src = residual;
+  }
+  if (a_out) {
+    const int64_t t = static_cast<int64_t>(B) * (H / 2) * (W / 2) * 16;
+    im2col3_kernel<5, 2, 2, 128><<<grid_for(t, kBlock, 148 * 32), kBlock, 0, st>>>(
+        src, static_cast<__nv_bfloat16*>(a_out), B, H, W, H / 2, W / 2);
+  }
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_addback_im2col3(const float* jpeg, const float* r_hat, float* x0, void* a_out, int B, int H, int W,
+                          void* stream_v) {
+  if (!r_hat || B <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "addback_im2col3: bad argument");
+  if (jpeg && !x0) return hy_fail(HYRES_ERR_ARG, "addback_im2col3: x0 buffer required with jpeg");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  const int64_t n = static_cast<int64_t>(B) * 3 * H * W;
+  const float* src = r_hat;
+  if (jpeg) {
+    addsub_kernel<1><<<grid_for(n, kBlock * 4), kBlock, 0, st>>>(jpeg, r_hat, x0, n);
+    src = x0;
+  }
+  if (a_out) {
+    const int64_t t = static_cast<int64_t>(B) * H * W * 8;
+    im2col3_kernel<3, 1, 1, 64><<<grid_for(t, kBlock, 148 * 32), kBlock, 0, st>>>(
+        src, static_cast<__nv_bfloat16*>(a_out), B, H, W, H, W);
+  }
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_final_clamp(const float* x0, const float* refined, float* x_hat, int64_t n, void* stream_v) {
+  if (!x0 || !refined || !x_hat || n < 0) return hy_fail(HYRES_ERR_ARG, "final_clamp: bad argument");
+  if (n == 0) return HYRES_OK;
+  final_clamp_kernel<<<grid_for(n, kBlock * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(x0, refined, x_hat, n);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_add_to_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream_v) {
+  if (!a || !b || !out_bf16 || n < 0) return hy_fail(HYRES_ERR_ARG, "add_to_bf16: bad argument");
+  if (n == 0) return HYRES_OK;
+  add_to_bf16_kernel<<<grid_for(n, kBlock * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      a, b, static_cast<__nv_bfloat16*>(out_bf16), n);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W, void* stream_v) {
+  if (!in || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "nchw_to_nhwc: bad argument");
+  const int hw = H * W;
+  dim3 grid((hw + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  transpose_tiles<float, __nv_bfloat16><<<grid, block, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      in, static_cast<__nv_bfloat16*>(out), C, hw);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int W, void* stream_v) {
+  if (!in || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "nhwc_to_nchw: bad argument");
+  const int hw = H * W;
+  dim3 grid((C + 31) / 32, (hw + 31) / 32, B), block(32, 8);
+  transpose_tiles<float, float><<<grid, block, 0, static_cast<cudaStream_t>(stream_v)>>>(in, out, hw, C);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H, int W, void* stream_v) {
+  if (!in || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "nhwc_bf16_to_nchw: bad argument");
+  const int hw = H * W;
+  dim3 grid((C + 31) / 32, (hw + 31) / 32, B), block(32, 8);
+  transpose_tiles<__nv_bfloat16, float><<<grid, block, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      static_cast<const __nv_bfloat16*>(in), out, hw, C);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_reduce_sqdiff(const float* a, const float* b, int64_t n, double* out, void* stream_v) {
+  if (!a || !b || !out || n < 0) return hy_fail(HYRES_ERR_ARG, "reduce_sqdiff: bad argument");
+  if (n == 0) return HYRES_OK;
+  sqdiff_kernel<<<grid_for(n, kBlock * 8, 148 * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(a, b, n, out);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_reduce_log2(const float* x, int64_t n, double* out, void* stream_v) {
+  if (!x || !out || n < 0) return hy_fail(HYRES_ERR_ARG, "reduce_log2: bad argument");
+  if (n == 0) return HYRES_OK;
+  log2_kernel<<<grid_for(n, kBlock * 8, 148 * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(x, n, out);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,405 @@
+"""Drop-in model API of the B200 hot path.
+
+``LightWeightCheckerboard`` and ``ResidualJPEGCompression`` keep the reference's constructor
+arguments, method names, dict keys, attribute paths and state-dict keys
+(models/checkerboard.py:24-283, models/hyres.py:9-181) while every tensor operation runs in
+the sm_100a kernels behind include/hyres_b200.h.  There is no CPU or eager-PyTorch path:
+inputs must live on a CUDA sm_100 device and the shared library must be built.
+
+Reference quirks reproduced on purpose:
+  Q1  anchor / non-anchor tensors are zero-filled full-size tensors; every position of both
+      passes is quantised and entropy-coded (2x the textbook symbol count);
+  Q2  likelihoods use scales_a + scales_na and means_a + means_na at every position;
+  Q3  ``decompress`` clamps the decoded residual to [0,1], ``forward`` does not;
+  Q4  dead taps of the checkerboard conv are masked (here: never packed; ``weight.data`` is
+      masked once at construction / load so the state dict matches the reference's after a call).
+Deliberate deviation: ``ResidualJPEGCompression.load_state_dict`` strips the ``refine.`` prefix
+before loading the refine block (the reference passes the prefixed keys through, which raises
+for any checkpoint that contains them -- models/hyres.py:150-162).
+"""
+import math
+import time
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .engine import CodecEngine, RefineEngine
+from .entropy import EntropyBottleneck, GaussianConditional
+from .jpeg import TurboJPEGCompression
+from .layers import (AttentionBlock, CheckboardMaskedConv2d, GDN, MultiScaleRefine, Quantizer,
+                     ResidualBottleneckBlock, conv, conv1x1, conv3x3, deconv)
+
+SCALES_MIN, SCALES_MAX, SCALES_LEVELS = 0.11, 256, 64
+
+
+def get_scale_table(min=SCALES_MIN, max=SCALES_MAX, levels=SCALES_LEVELS):
+    return torch.exp(torch.linspace(math.log(min), math.log(max), levels))
+
+
+_LEGACY_EB = {"_matrix": "matrices.", "_bias": "biases.", "_factor": "factors."}
+
+
+def _rename_legacy_eb_keys(state_dict):
+    """compressai <= 1.1 checkpoints name the EntropyBottleneck parameters _matrix{i} / _bias{i} / _factor{i}."""
+    out = {}
+    for k, v in state_dict.items():
+        head, _, leaf = k.rpartition(".")
+        for old, new in _LEGACY_EB.items():
+            if leaf.startswith(old) and leaf[len(old):].isdigit():
+                leaf = new + leaf[len(old):]
+        out[(head + "." if head else "") + leaf] = v
+    return out
+
+
+def _resize_buffers(module, module_name, names, state_dict):
+    """Give the CDF buffers the checkpoint's shapes before nn.Module.load_state_dict copies into them."""
+    for name in names:
+        key = f"{module_name}.{name}" if module_name else name
+        if key in state_dict:
+            new = state_dict[key]
+            cur = module._buffers.get(name)
+            dev = cur.device if cur is not None else new.device
+            if cur is None or cur.numel() == 0 or cur.shape != new.shape:
+                module._buffers[name] = torch.zeros(new.size(), dtype=new.dtype, device=dev)
+
+
+def _require_cuda(x, what):
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise RuntimeError(f"{what}: input must be a CUDA tensor -- the B200 hot path has no CPU fallback")
+    _lib.check(_lib.lib().hyres_device_check(x.device.index if x.device.index is not None else torch.cuda.current_device()),
+               "hyres_device_check")
+
+
+class CompressionModel(nn.Module):
+    def aux_loss(self):
+        return sum(m.loss() for m in self.modules() if isinstance(m, EntropyBottleneck))
+
+    def update(self, scale_table=None, force=False, update_quantiles=False):
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = False
+        for _, module in self.named_modules():
+            if isinstance(module, EntropyBottleneck):
+                updated |= module.update(force=force)
+            if isinstance(module, GaussianConditional):
+                updated |= module.update_scale_table(scale_table, force=force)
+        return updated
+
+    def load_state_dict(self, state_dict, strict=True):
+        state_dict = _rename_legacy_eb_keys(state_dict)
+        for name, module in self.named_modules():
+            if not any(x.startswith(name) for x in state_dict.keys()):
+                continue
+            if isinstance(module, EntropyBottleneck):
+                _resize_buffers(module, name, ["_quantized_cdf", "_offset", "_cdf_length"], state_dict)
+            if isinstance(module, GaussianConditional):
+                _resize_buffers(module, name, ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        return nn.Module.load_state_dict(self, state_dict, strict=strict)
+
+
+class LightWeightCheckerboard(CompressionModel):
+    def __init__(self, N=128, M=192):
+        super().__init__()
+        self.N, self.M = N, M
+        self.entropy_bottleneck = EntropyBottleneck(N)
+        self.gaussian_conditional = GaussianConditional(None)
+        self.quantizer = Quantizer()
+        self.g_a = nn.Sequential(
+            conv(3, N), GDN(N), ResidualBottleneckBlock(N, N), AttentionBlock(N), conv(N, N), GDN(N),
+            ResidualBottleneckBlock(N, N), conv(N, M), AttentionBlock(M))
+        self.g_s = nn.Sequential(
+            AttentionBlock(M), deconv(M, N), ResidualBottleneckBlock(N, N), GDN(N, inverse=True), deconv(N, N),
+            AttentionBlock(N), ResidualBottleneckBlock(N, N), GDN(N, inverse=True), deconv(N, 3))
+        self.h_a = nn.Sequential(conv3x3(M, N), nn.ReLU(inplace=True), conv(N, N), nn.ReLU(inplace=True), conv(N, N))
+        self.h_s = nn.Sequential(deconv(N, N), nn.ReLU(inplace=True), deconv(N, N * 3 // 2), nn.ReLU(inplace=True),
+                                 conv3x3(N * 3 // 2, 2 * M))
+        self.context_prediction = CheckboardMaskedConv2d(M, 2 * M, kernel_size=5, padding=2, stride=1)
+        self.param_aggregation = nn.Sequential(conv1x1(4 * M, 640), nn.ReLU(inplace=True), conv1x1(640, 512),
+                                               nn.ReLU(inplace=True), conv1x1(512, 2 * M))
+        self._engine = None
+        self._noise_calls = 0
+
+    # -- engine plumbing --
+    def engine(self):
+        if self._engine is None:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("move the model to a CUDA sm_100 device first (model.cuda()); no CPU fallback")
+            with torch.no_grad():  # Q4: masked taps are zero in the stored weights
+                self.context_prediction.weight.data *= self.context_prediction.mask
+            self._engine = CodecEngine(self)
+        self._engine.sync()
+        return self._engine
+
+    def _seed(self):
+        self._noise_calls += 1
+        return (int(torch.initial_seed()) * 1000003 + self._noise_calls) & ((1 << 62) - 1)
+
+    def _scale_table(self, dev):
+        t = self.gaussian_conditional.scale_table
+        if t.numel() == 0:
+            raise ValueError("Uninitialized CDFs. Run update() first")
+        return t.to(dev, torch.float32).contiguous()
+
+    @staticmethod
+    def _check_input(x):
+        if x.dim() != 4 or x.size(1) != 3:
+            raise ValueError(f"expected a [B,3,H,W] tensor, got {tuple(x.shape)}")
+        if x.size(2) % 32 or x.size(3) % 32:
+            raise ValueError("H and W must be multiples of 32 (the reference never pads)")
+
+    # -- forward (models/checkerboard.py:90-147) --
+    def forward(self, x, noisequant=False, stats=None):
+        """-> {"x_hat": [B,3,H,W], "likelihoods": {"y": [B,M,H/8,W/8], "z": [B,N,H/32,W/32]}}.
+
+        ``stats``: optional 2-element CUDA double tensor accumulating sum(log2 lik_y), sum(log2 lik_z)
+        inside the likelihood kernels (used by the fused RD loss)."""
+        _require_cuda(x, "forward")
+        self._check_input(x)
+        eng = self.engine()
+        x = x.contiguous().float()
+        training = self.training
+        _, a = ops.residual_im2col5s2(x)
+        y16, y32 = eng.g_a(a)
+        z32 = eng.h_a(y16)
+        ebp, med = eng.eb_params()
+        eb = ops.eb_forward(z32, ebp, med, lik_noise=training, out_noise=training and noisequant, seed=self._seed(),
+                            lik_bound=self.entropy_bottleneck.likelihood_bound,
+                            sum_log2=None if stats is None else stats[1:2])
+        latent = eng.h_s(eb["zhat_bf16"])
+        pa = eng.head(latent)
+        yqa32, yqa16 = ops.gc_quant_pass(y32, pa, 0, noise=noisequant, seed=self._seed())
+        ctx = eng.context(yqa16)
+        pna = eng.head(latent, ctx)
+        yqna32, _ = ops.gc_quant_pass(y32, pna, 1, noise=noisequant, seed=self._seed(), want_bf16=False)
+        y_hat16, lik_y = ops.gc_merge_likelihood(y32, pa, pna, yqa32, yqna32, noise=training, seed=self._seed(),
+                                                 sum_log2=None if stats is None else stats[0:1])
+        x_hat = eng.g_s(y_hat16)
+        return {"x_hat": x_hat, "likelihoods": {"y": lik_y, "z": eb["lik"]}}
+
+    # -- symbols of both passes (GPU part of compress) --
+    def encode_symbols(self, x):
+        """GPU front-end of ``compress``: returns the integer streams the entropy coder consumes,
+        all int32 CUDA tensors in (B,C,h,w) order, plus the shapes."""
+        _require_cuda(x, "compress")
+        self._check_input(x)
+        eng = self.engine()
+        x = x.contiguous().float()
+        table = self._scale_table(x.device)
+        bound = float(self.gaussian_conditional.scale_bound.item())
+        _, a = ops.residual_im2col5s2(x)
+        y16, y32 = eng.g_a(a)
+        z32 = eng.h_a(y16)
+        ebp, med = eng.eb_params()
+        eb = ops.eb_forward(z32, ebp, med, want_lik=False, want_symbols=True)
+        latent = eng.h_s(eb["zhat_bf16"])
+        pa = eng.head(latent)
+        sym_a, idx_a, _, yqa16 = ops.gc_symbols(y32, pa, 0, table, bound, want_f32=False)
+        ctx = eng.context(yqa16)
+        pna = eng.head(latent, ctx)
+        sym_na, idx_na, _, _ = ops.gc_symbols(y32, pna, 1, table, bound, want_f32=False, want_bf16=False)
+        return {"sym_z": eb["symbols"], "sym_a": sym_a, "idx_a": idx_a, "sym_na": sym_na, "idx_na": idx_na,
+                "y": y32, "z": z32, "params_a": pa, "params_na": pna}
+
+    # -- compress (models/checkerboard.py:167-198) --
+    def compress(self, x):
+        start_time = time.time()
+        s = self.encode_symbols(x)
+        gc, ebm = self.gaussian_conditional, self.entropy_bottleneck
+        z_strings = ebm.encode_symbols(s["sym_z"], ebm._build_indexes(s["sym_z"].size()))
+        anchor_strings = gc.encode_symbols(s["sym_a"], s["idx_a"])
+        non_anchor_strings = gc.encode_symbols(s["sym_na"], s["idx_na"])
+        return {"strings": [[anchor_strings, non_anchor_strings], z_strings],
+                "shape": torch.Size(s["sym_z"].shape[-2:]), "time": time.time() - start_time}
+
+    # -- decompress (models/checkerboard.py:200-240) --
+    def decompress(self, strings, shape):
+        start_time = time.time()
+        eng = self.engine()
+        dev = next(self.parameters()).device
+        gc, ebm = self.gaussian_conditional, self.entropy_bottleneck
+        table = self._scale_table(dev)
+        bound = float(gc.scale_bound.item())
+        B = len(strings[1])
+        out_size = (B, ebm._quantized_cdf.size(0), int(shape[0]), int(shape[1]))
+        sym_z = ebm.decode_symbols(strings[1], ebm._build_indexes(out_size)).to(dev)
+        _, med = eng.eb_params()
+        latent = eng.h_s(ops.eb_dequant(sym_z.contiguous(), med))
+        pa = eng.head(latent)
+        idx_a = ops.gc_indexes(pa, table, self.M, bound)
+        sym_a = gc.decode_symbols(strings[0][0], idx_a).to(dev)
+        yqa32, yqa16 = ops.gc_dequant(sym_a.contiguous(), pa)
+        ctx = eng.context(yqa16)
+        pna = eng.head(latent, ctx)
+        idx_na = ops.gc_indexes(pna, table, self.M, bound)
+        sym_na = gc.decode_symbols(strings[0][1], idx_na).to(dev)
+        yqna32, _ = ops.gc_dequant(sym_na.contiguous(), pna, want_bf16=False)
+        y_hat16 = ops.add_to_bf16(yqa32, yqna32)
+        x_hat = eng.g_s(y_hat16, clamp=True)  # Q3
+        return {"x_hat": x_hat, "time": time.time() - start_time}
+
+    def inference(self, x):
+        c = self.compress(x)
+        d = self.decompress(c["strings"], c["shape"])
+        return {"x_hat": d["x_hat"], "time": {"compression": c["time"], "decompression": d["time"],
+                                              "total": c["time"] + d["time"]}}
+
+    def update(self, scale_table=None, force=False, **kwargs):
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= super().update(force=force)
+        return updated
+
+    def load_state_dict(self, state_dict, **kwargs):
+        state_dict = _rename_legacy_eb_keys(state_dict)
+        _resize_buffers(self.gaussian_conditional, "gaussian_conditional",
+                        ["_quantized_cdf", "_offset", "_cdf_length", "scale_table"], state_dict)
+        out = super().load_state_dict(state_dict)
+        if self._engine is not None:
+            self._engine.sync(force=True)
+        return out
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._engine = None  # device / dtype moved: rebuild the packed layers lazily
+        return out
+
+    @classmethod
+    def from_state_dict(cls, state_dict):
+        net = cls()
+        net.load_state_dict(state_dict)
+        return net
+
+
+class ResidualJPEGCompression(CompressionModel):
+    def __init__(self, base_model=None, jpeg_quality=1, se_reduction=1, **kwargs):
+        super().__init__()
+        self.jpeg = TurboJPEGCompression(quality=jpeg_quality)
+        self.residual_model = base_model if base_model is not None else LightWeightCheckerboard(**kwargs)
+        self.refine = MultiScaleRefine(in_channels=3, mid_channels=64)
+        self._refine_engine = None
+
+    def refine_engine(self):
+        if self._refine_engine is None:
+            self._refine_engine = RefineEngine(self.refine)
+        self._refine_engine.sync()
+        return self._refine_engine
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._refine_engine = None
+        return out
+
+    def _reconstruct(self, jpeg_decoded, residual_hat):
+        x0, a = ops.addback_im2col3(residual_hat, jpeg_decoded)
+        refined = self.refine_engine()(a)
+        return ops.final_clamp(x0, refined)
+
+    # -- forward (models/hyres.py:23-77) --
+    def forward(self, x, noisequant=False, jpeg=None, stats=None):
+        """``jpeg=(jpeg_decoded, jpeg_bpp)`` injects the JPEG stage's result (tensor on any device);
+        by default the CPU JPEG round trip of the reference runs here."""
+        device = next(self.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("move the model to a CUDA sm_100 device first; the B200 hot path has no CPU fallback")
+        if jpeg is None:
+            jpeg_decoded_cpu, jpeg_bpp = self.jpeg(x.cpu() if x.is_cuda else x)
+        else:
+            jpeg_decoded_cpu, jpeg_bpp = jpeg
+        jpeg_decoded = jpeg_decoded_cpu.to(device, torch.float32).contiguous()
+        xd = x.to(device, torch.float32).contiguous()
+        self.residual_model._check_input(xd)
+        residual, _ = ops.residual_im2col5s2(xd, jpeg_decoded)
+        res = self.residual_model(residual, noisequant=noisequant, stats=stats)
+        residual_hat = res["x_hat"]
+        x_hat = self._reconstruct(jpeg_decoded, residual_hat)
+        return {"x_hat": x_hat, "likelihoods": res["likelihoods"],
+                "jpeg_bpp_loss": torch.tensor(jpeg_bpp, device=device), "jpeg_decoded": jpeg_decoded,
+                "residual": residual, "residual_hat": residual_hat}
+
+    # -- compress / decompress (models/hyres.py:79-134) --
+    def compress(self, x, jpeg_buffers=None):
+        device = next(self.parameters()).device
+        if jpeg_buffers is None:
+            jpeg_buffers = self.jpeg.compress(x)
+        jpeg_decoded = self.jpeg.decompress(jpeg_buffers, device).float().contiguous()
+        xd = x.to(device, torch.float32).contiguous()
+        residual, _ = ops.residual_im2col5s2(xd, jpeg_decoded)
+        out = self.residual_model.compress(residual)
+        out["jpeg_buffers"] = jpeg_buffers
+        return out
+
+    def decompress(self, compressed_data):
+        jpeg_buffers = compressed_data["jpeg_buffers"]
+        strings, shape = compressed_data["strings"], compressed_data["shape"]
+        device = next(self.parameters()).device
+        jpeg_decoded = self.jpeg.decompress(jpeg_buffers, device).float().contiguous()
+        result = self.residual_model.decompress(strings, shape)
+        result["x_hat"] = self._reconstruct(jpeg_decoded, result["x_hat"])
+        return result
+
+    def load_state_dict(self, state_dict, **kwargs):
+        residual_sd, refine_sd, se_sd, rest = {}, {}, {}, {}
+        for key, value in state_dict.items():
+            if key.startswith("residual_model."):
+                residual_sd[key[len("residual_model."):]] = value
+            elif key.startswith("se_block."):
+                se_sd[key] = value
+            elif key.startswith("refine."):
+                refine_sd[key[len("refine."):]] = value
+            else:
+                rest[key] = value
+        if residual_sd:
+            self.residual_model.load_state_dict(residual_sd)
+        if se_sd:
+            self.se_block.load_state_dict(se_sd)  # no such attribute: AttributeError, as in the reference
+        if refine_sd:
+            self.refine.load_state_dict(refine_sd)
+            if self._refine_engine is not None:
+                self._refine_engine.sync(force=True)
+        if rest:
+            nn.Module.load_state_dict(self, rest, **kwargs)
+
+    @classmethod
+    def from_state_dict(cls, state_dict, jpeg_quality=None):
+        kwargs = {}
+        if jpeg_quality is not None:
+            kwargs["jpeg_quality"] = jpeg_quality
+        net = cls(**kwargs)
+        net.load_state_dict(state_dict)
+        return net
+
+    def update(self, scale_table=None, force=False, **kwargs):
+        return self.residual_model.update(scale_table=scale_table, force=force, **kwargs)
+
+
+class RateDistortionLoss(nn.Module):
+    """src/losses/rd_loss.py:18-44 without the VGG term (alpha = 0, as train.sh sets): the three
+    reductions (sum log2 lik_y, sum log2 lik_z, sum squared error) run as fused device reductions."""
+
+    def __init__(self, lmbda=0.004):
+        super().__init__()
+        self.lmbda = lmbda
+
+    def forward(self, output, target, stats=None):
+        N, _, H, W = target.size()
+        num_pixels = N * H * W
+        dev = output["x_hat"].device
+        acc = torch.zeros(3, dtype=torch.float64, device=dev)
+        if stats is not None:
+            acc[0:2] = stats
+        else:
+            ops.reduce_log2(output["likelihoods"]["y"].contiguous(), acc[0:1])
+            ops.reduce_log2(output["likelihoods"]["z"].contiguous(), acc[1:2])
+        ops.reduce_sqdiff(output["x_hat"].contiguous(), target.to(dev, torch.float32).contiguous(), acc[2:3])
+        out = {}
+        out["y_bpp_loss"] = (-acc[0] / num_pixels).float()
+        out["z_bpp_loss"] = (-acc[1] / num_pixels).float()
+        out["residual_bpp_loss"] = out["y_bpp_loss"] + out["z_bpp_loss"]
+        jpeg_bpp = output.get("jpeg_bpp_loss", torch.zeros((), device=dev))
+        out["bpp_loss"] = out["residual_bpp_loss"] + jpeg_bpp
+        out["mse_loss"] = (acc[2] / output["x_hat"].numel()).float() * 255 ** 2
+        out["loss"] = self.lmbda * out["mse_loss"] + out["bpp_loss"]
+        return out

@@ -158,3 +158,205 @@ class ConvLayer:
             raise ValueError(f"{name}: expected [B={B},OH={OH},OW={OW},C] channel-contiguous, got {tuple(t.shape)}")
         if t.stride(1) != OW * t.stride(2) or t.stride(0) != OH * OW * t.stride(2):
             raise ValueError(f"{name}: pixel stride must be uniform (a channel slice of a dense NHWC tensor)")
+
+
+# --------------------------------------------------------------------------------------
+# memory-bound kernels
+# --------------------------------------------------------------------------------------
+def _f32c(t, name):
+    if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected contiguous CUDA fp32 tensor")
+    return t
+
+
+def residual_im2col5s2(x, jpeg=None, want_residual=True):
+    """x, jpeg: fp32 NCHW [B,3,H,W].  Returns (residual fp32 NCHW or x, A bf16 [B,H/2,W/2,128])."""
+    _f32c(x, "x")
+    B, C, H, W = x.shape
+    if C != 3:
+        raise ValueError("expected 3 channels")
+    res = None
+    if jpeg is not None:
+        _f32c(jpeg, "jpeg")
+        res = torch.empty_like(x)
+    a = torch.empty((B, H // 2, W // 2, 128), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().hyres_residual_im2col5s2(_ptr(x), _ptr(jpeg), _ptr(res), _ptr(a), B, H, W, _stream()),
+            "hyres_residual_im2col5s2")
+    return (res if res is not None else x), a
+
+
+def addback_im2col3(r_hat, jpeg=None):
+    """x0 = jpeg + r_hat (or r_hat), A bf16 [B,H,W,64] = 3x3 im2col of x0."""
+    _f32c(r_hat, "r_hat")
+    B, C, H, W = r_hat.shape
+    x0 = None
+    if jpeg is not None:
+        _f32c(jpeg, "jpeg")
+        x0 = torch.empty_like(r_hat)
+    a = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=r_hat.device)
+    L.check(L.lib().hyres_addback_im2col3(_ptr(jpeg), _ptr(r_hat), _ptr(x0), _ptr(a), B, H, W, _stream()),
+            "hyres_addback_im2col3")
+    return (x0 if x0 is not None else r_hat), a
+
+
+def final_clamp(x0, refined):
+    _f32c(x0, "x0"), _f32c(refined, "refined")
+    out = torch.empty_like(x0)
+    L.check(L.lib().hyres_final_clamp(_ptr(x0), _ptr(refined), _ptr(out), x0.numel(), _stream()), "hyres_final_clamp")
+    return out
+
+
+def gc_quant_pass(y, params, pass_id, noise=False, seed=0, want_f32=True, want_bf16=True):
+    """y fp32 NHWC [B,h,w,M]; params fp32 NHWC [B,h,w,2M] -> (yq fp32 NHWC, yq bf16 NHWC)."""
+    _f32c(y, "y")
+    B, h, w, M = y.shape
+    if params is not None:
+        _f32c(params, "params")
+    o32 = torch.empty_like(y) if want_f32 else None
+    o16 = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    L.check(L.lib().hyres_gc_quant_pass(_ptr(y), _ptr(params), pass_id, 1 if noise else 0, seed, _ptr(o32), _ptr(o16),
+                                        B, h, w, M, _stream()), "hyres_gc_quant_pass")
+    return o32, o16
+
+
+def gc_merge_likelihood(y, params_a, params_na, yq_a, yq_na, noise=False, seed=0, want_lik=True, sum_log2=None):
+    """-> (y_hat bf16 NHWC, lik fp32 NCHW).  sum_log2: optional 1-element CUDA double accumulator."""
+    B, h, w, M = y.shape
+    y_hat = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if yq_a is not None else None
+    lik = torch.empty((B, M, h, w), dtype=torch.float32, device=y.device) if want_lik else None
+    L.check(L.lib().hyres_gc_merge_likelihood(_ptr(y), _ptr(params_a), _ptr(params_na), _ptr(yq_a), _ptr(yq_na),
+                                              1 if noise else 0, seed, _ptr(y_hat), _ptr(lik), _ptr(sum_log2), B, h,
+                                              w, M, _stream()), "hyres_gc_merge_likelihood")
+    return y_hat, lik
+
+
+def gc_symbols(y, params, pass_id, scale_table, scale_bound=0.11, want_f32=True, want_bf16=True):
+    """-> (symbols int32 [B,M,h,w], indexes int32 [B,M,h,w], yq fp32 NHWC, yq bf16 NHWC)"""
+    _f32c(y, "y"), _f32c(params, "params"), _f32c(scale_table, "scale_table")
+    B, h, w, M = y.shape
+    sym = torch.empty((B, M, h, w), dtype=torch.int32, device=y.device)
+    idx = torch.empty((B, M, h, w), dtype=torch.int32, device=y.device)
+    o32 = torch.empty_like(y) if want_f32 else None
+    o16 = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    L.check(L.lib().hyres_gc_symbols(_ptr(y), _ptr(params), pass_id, _ptr(scale_table), scale_table.numel(),
+                                     float(scale_bound), _ptr(sym), _ptr(idx), _ptr(o32), _ptr(o16), B, h, w, M,
+                                     _stream()), "hyres_gc_symbols")
+    return sym, idx, o32, o16
+
+
+def gc_indexes(params, scale_table, M, scale_bound=0.11):
+    _f32c(params, "params")
+    B, h, w, _ = params.shape
+    idx = torch.empty((B, M, h, w), dtype=torch.int32, device=params.device)
+    L.check(L.lib().hyres_gc_indexes(_ptr(params), _ptr(scale_table), scale_table.numel(), float(scale_bound),
+                                     _ptr(idx), B, h, w, M, _stream()), "hyres_gc_indexes")
+    return idx
+
+
+def gc_dequant(symbols, params, want_f32=True, want_bf16=True):
+    """symbols int32 [B,M,h,w] (+ means from params NHWC) -> (yq fp32 NHWC, yq bf16 NHWC)"""
+    B, M, h, w = symbols.shape
+    dev = symbols.device
+    o32 = torch.empty((B, h, w, M), dtype=torch.float32, device=dev) if want_f32 else None
+    o16 = torch.empty((B, h, w, M), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    L.check(L.lib().hyres_gc_dequant(_ptr(symbols), _ptr(params), _ptr(o32), _ptr(o16), B, h, w, M, _stream()),
+            "hyres_gc_dequant")
+    return o32, o16
+
+
+def add_to_bf16(a, b):
+    out = torch.empty(a.shape, dtype=torch.bfloat16, device=a.device)
+    L.check(L.lib().hyres_add_to_bf16(_ptr(a), _ptr(b), _ptr(out), a.numel(), _stream()), "hyres_add_to_bf16")
+    return out
+
+
+def eb_forward(z, eb_params, medians, lik_noise=False, out_noise=False, seed=0, lik_bound=1e-9, want_zhat_nchw=False,
+               want_lik=True, want_symbols=False, sum_log2=None):
+    """z fp32 NHWC [B,h,w,C] -> dict(zhat_bf16 NHWC, zhat_nchw, lik NCHW, symbols [B,C,h,w])"""
+    _f32c(z, "z")
+    B, h, w, Cc = z.shape
+    dev = z.device
+    zh16 = torch.empty(z.shape, dtype=torch.bfloat16, device=dev)
+    zh32 = torch.empty((B, Cc, h, w), dtype=torch.float32, device=dev) if want_zhat_nchw else None
+    lik = torch.empty((B, Cc, h, w), dtype=torch.float32, device=dev) if want_lik else None
+    sym = torch.empty((B, Cc, h, w), dtype=torch.int32, device=dev) if want_symbols else None
+    mode = (1 if lik_noise else 0) | (2 if out_noise else 0)
+    L.check(L.lib().hyres_eb_forward(_ptr(z), _ptr(eb_params), _ptr(medians), mode, seed, float(lik_bound), _ptr(zh16),
+                                     _ptr(zh32), _ptr(lik), _ptr(sym), _ptr(sum_log2), B, h, w, Cc, _stream()),
+            "hyres_eb_forward")
+    return dict(zhat_bf16=zh16, zhat_nchw=zh32, lik=lik, symbols=sym)
+
+
+def eb_dequant(symbols, medians):
+    B, Cc, h, w = symbols.shape
+    out = torch.empty((B, h, w, Cc), dtype=torch.bfloat16, device=symbols.device)
+    L.check(L.lib().hyres_eb_dequant(_ptr(symbols), _ptr(medians), _ptr(out), B, h, w, Cc, _stream()),
+            "hyres_eb_dequant")
+    return out
+
+
+def refine_se_scale_down(feat, fc1, fc2):
+    """feat bf16 NHWC [B,H,W,64] -> (feat*se bf16, half-res, quarter-res, pooled fp32 [B,64])"""
+    _chk_nhwc(feat, "feat")
+    B, H, W, Cc = feat.shape
+    dev = feat.device
+    scratch = torch.empty((B * 64 * Cc,), dtype=torch.float32, device=dev)
+    pooled = torch.empty((B, Cc), dtype=torch.float32, device=dev)
+    lib = L.lib()
+    L.check(lib.hyres_refine_se_pool(_ptr(feat), _ptr(scratch), _ptr(pooled), B, H, W, Cc, _stream()),
+            "hyres_refine_se_pool")
+    fs = torch.empty_like(feat)
+    fh = torch.empty((B, H // 2, W // 2, Cc), dtype=torch.bfloat16, device=dev)
+    fq = torch.empty((B, H // 4, W // 4, Cc), dtype=torch.bfloat16, device=dev)
+    L.check(lib.hyres_refine_se_scale_down(_ptr(feat), _ptr(pooled), _ptr(fc1), _ptr(fc2), Cc, fc1.shape[0], _ptr(fs),
+                                           _ptr(fh), _ptr(fq), B, H, W, _stream()), "hyres_refine_se_scale_down")
+    return fs, fh, fq, pooled
+
+
+def refine_up_concat_stats(f2, f3, multi):
+    """multi bf16 [B,H,W,192] holds branch 1 in [..., :64]; fills [64:192] and returns stats [B,H,W,2]."""
+    B, H, W, C3 = multi.shape
+    stats = torch.empty((B, H, W, 2), dtype=torch.float32, device=multi.device)
+    L.check(L.lib().hyres_refine_up_concat_stats(_ptr(f2), _ptr(f3), _ptr(multi), _ptr(stats), B, H, W, C3 // 3,
+                                                 _stream()), "hyres_refine_up_concat_stats")
+    return stats
+
+
+def refine_spatial_att(stats, w7):
+    B, H, W, _ = stats.shape
+    att = torch.empty((B, H, W), dtype=torch.float32, device=stats.device)
+    L.check(L.lib().hyres_refine_spatial_att(_ptr(stats), _ptr(w7), _ptr(att), B, H, W, _stream()),
+            "hyres_refine_spatial_att")
+    return att
+
+
+def nchw_f32_to_nhwc_bf16(x):
+    _f32c(x, "x")
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, H, W, Cc), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().hyres_nchw_f32_to_nhwc_bf16(_ptr(x), _ptr(out), B, Cc, H, W, _stream()))
+    return out
+
+
+def nhwc_to_nchw_f32(x):
+    _f32c(x, "x")
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    L.check(L.lib().hyres_nhwc_to_nchw_f32(_ptr(x), _ptr(out), B, Cc, H, W, _stream()))
+    return out
+
+
+def nhwc_bf16_to_nchw_f32(x):
+    _chk_nhwc(x, "x")
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, Cc, H, W), dtype=torch.float32, device=x.device)
+    L.check(L.lib().hyres_nhwc_bf16_to_nchw_f32(_ptr(x), _ptr(out), B, Cc, H, W, _stream()))
+    return out
+
+
+def reduce_sqdiff(a, b, out):
+    L.check(L.lib().hyres_reduce_sqdiff(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream()), "hyres_reduce_sqdiff")
+
+
+def reduce_log2(x, out):
+    L.check(L.lib().hyres_reduce_log2(_ptr(x), x.numel(), _ptr(out), _stream()), "hyres_reduce_log2")

@@ -176,8 +176,9 @@ int hyres_eb_dequant(const int32_t* symbols, const float* medians, void* zhat_bf
                      int w, int C, void* stream);
 
 /* MultiScaleRefine memory ops (feat: bf16 NHWC, C=64). */
-int hyres_refine_se_pool(const void* feat, float* pooled /*[B,C]*/, int B, int H, int W, int C,
-                         void* stream);
+/* scratch: fp32 [B*64*C] partial sums (two-stage, fixed-order reduction). */
+int hyres_refine_se_pool(const void* feat, float* scratch, float* pooled /*[B,C]*/, int B, int H,
+                         int W, int C, void* stream);
 int hyres_refine_se_scale_down(const void* feat, const float* pooled, const float* fc1,
                                const float* fc2, int C, int Cr, void* feat_s, void* feat_h,
                                void* feat_q, int B, int H, int W, void* stream);
