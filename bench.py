@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Headline benchmark of the HyRES residual-codec hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): full ResidualJPEGCompression forward + rate-distortion loss on
+a batch of 16 synthetic 768x512 images per GPU (N=128, M=192, random-init weights, seed 1926).
+One step = one pass of the hot path over one batch.  The JPEG round trip is a third-party CPU
+boundary (libjpeg-turbo) on both arms: it runs once at set-up and its output (`jpeg_decoded`,
+`jpeg_bpp`) is an input of every step.
+
+  value : Mpixel/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
+  e2e   : Mpixel/s through the public API with pinned HOST inputs, H2D copies and the D2H read of
+          the loss inside the timed region
+  roofline     : the tcgen05 implicit-GEMM convolution kernel (tensor bound), canonical
+                 algorithmic FLOPs of the step / summed CUDA-event time of its launches
+  cpu_baseline : the CPU oracle (the reference's PyTorch semantics, fp32) on a bounded sample
+
+`--impl reference` times that CPU path alone, on every host core, for the driver's ratio.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, BATCH = 512, 768, 16
+LMBDA = 0.008
+# canonical algorithmic work, BASELINE.md section 3 (1 MAC = 2 FLOP; masked conv = 12 taps;
+# anchor pass of the parameter head K = 384)
+MAC_PER_PX_CONV = 483_234  # codec forward 370 624 + MultiScaleRefine 112 610
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))), hbm=float(d["hbm_gbs"]),
+                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md, sustained)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return None
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_step_factory(sample_images, threads):
+    """The reference's CPU path (oracle restatement, fp32, reference semantics) on a bounded sample."""
+    import torch
+    from oracle import hyres_oracle as O
+    torch.set_num_threads(threads)
+    net = O.make_model(seed=1926, wrapper=True)
+    crit = O.RateDistortionLoss(lmbda=LMBDA)
+    x = O.synthetic_image(sample_images, H, W)
+    jpeg = net.jpeg(x)
+
+    def step():
+        with torch.no_grad(), O.precision("fp32"):
+            out = net(x, jpeg=jpeg)
+            return float(crit(out, x)["loss"])
+    return step, sample_images * H * W
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's own CPU implementation of the path (here: the oracle port,
+    because compressai is not installable -- DESIGN.md section 3), all host threads, rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample_images = 1
+    step, px = oracle_step_factory(sample_images, cores)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = px / dt / 1e6
+    sample = f"{sample_images} synthetic {W}x{H} image per step (of the {BATCH}-image batch), full forward + RD loss, fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": "hyres_forward_mpixel_per_s", "value": v, "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n):
+    return {"workload": "BASELINE.json configs[1]: ResidualJPEGCompression (JPEG q=1 stage injected + residual codec "
+                        "N=128 M=192 + MultiScaleRefine) forward + RD loss, batch 16 of 768x512 synthetic images per GPU",
+            "batch_per_gpu": BATCH, "height": H, "width": W, "global_batch": BATCH * n, "lambda": LMBDA,
+            "sharding": "by image, no data-path collective; 4-double statistics all-reduce",
+            "l2": "inputs + activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
+            "weights": "random init, seed 1926"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import hyres_b200
+    from hyres_b200 import _lib, dist as D, ops, synthetic
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA sm_100 device: the hot path has no CPU fallback")
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.lib()
+    _lib.check(lib.hyres_device_check(local), "hyres_device_check")
+
+    torch.manual_seed(1926)
+    net = hyres_b200.ResidualJPEGCompression(jpeg_quality=1)
+    net.update(force=True)
+    net = net.to(dev).eval()
+    crit = hyres_b200.RateDistortionLoss(lmbda=LMBDA)
+
+    x_host = synthetic.synthetic_image(BATCH, H, W, seed=1926 + rank).pin_memory()
+    jd, jpeg_bpp = net.jpeg(x_host)  # third-party CPU boundary, outside the timed region
+    jd_host = jd.contiguous().pin_memory()
+    x_dev, jd_dev = x_host.to(dev), jd_host.to(dev)
+    px_step = BATCH * H * W
+    stats = torch.zeros(2, dtype=torch.float64, device=dev)
+
+    def step_resident():
+        stats.zero_()
+        out = net(x_dev, jpeg=(jd_dev, jpeg_bpp), stats=stats)
+        return crit(out, x_dev, stats=stats)
+
+    def step_e2e():
+        stats.zero_()
+        xd = x_host.to(dev, non_blocking=True)  # src/utils/engine.py:36: the batch moves to the device once
+        out = net(xd, jpeg=(jd_host, jpeg_bpp), stats=stats)
+        lo = crit(out, xd, stats=stats)
+        return torch.stack([lo["loss"].double(), lo["bpp_loss"].double(), lo["mse_loss"].double()]).cpu()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_resident()
+        barrier()
+        sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+        sampler.start()
+        l0 = lib.hyres_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            lo = step_resident()
+        e1.record()
+        barrier()
+        ms_local = e0.elapsed_time(e1) / args.steps
+        launches = (lib.hyres_launch_count() - l0) // args.steps
+        clocks = sampler.stop()
+        ms = D.max_over_ranks(ms_local, dev)
+        loss_val = float(lo["loss"])
+
+        # ---- end to end through the public API with host buffers ----
+        for _ in range(2):
+            step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            res = step_e2e()
+        torch.cuda.synchronize()
+        e2e_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, dev)
+        h2d = x_host.numel() * 4 + jd_host.numel() * 4  # x + jpeg_decoded, fp32
+        d2h = res.numel() * 8
+
+        # ---- roofline of the dominant kernel: per-launch CUDA events around every conv launch ----
+        conv_ms, conv_n = None, 0
+        if rank == 0:
+            ops.ConvLayer.profile_begin()
+            step_resident()
+            torch.cuda.synchronize()
+            conv_ms, conv_n = ops.ConvLayer.profile_end()
+
+    if rank != 0:
+        torch.distributed.destroy_process_group()
+        return
+    peaks = load_peaks()
+    value = world * px_step / (ms * 1e-3) / 1e6
+    flops_step = 2.0 * MAC_PER_PX_CONV * px_step
+    achieved = flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms else None
+    line = {
+        "metric": "hyres_forward_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+        "e2e": {"value": world * px_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches) * args.steps,
+        "gpu_launches_per_step": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all %d launches of one step)" % conv_n,
+                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["tflops"] if achieved else None, "traffic": None,
+                     "peak_source": peaks["source"], "conv_ms_per_step": conv_ms,
+                     "conv_share_of_step": conv_ms / ms_local if conv_ms else None,
+                     "step_tflops": flops_step / (ms * 1e-3) / 1e12,
+                     "step_frac": flops_step / (ms * 1e-3) / 1e12 / peaks["tflops"]},
+        "loss": loss_val,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        step, px = oracle_step_factory(1, cores)
+        step()
+        t0 = time.perf_counter()
+        n = 3
+        for _ in range(n):
+            step()
+        dt = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                                "sample": f"1 synthetic {W}x{H} image (1/16 of the batch), full forward + RD loss, "
+                                          f"fp32 oracle, mean of {n} after 1 warm-up"}
+    print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

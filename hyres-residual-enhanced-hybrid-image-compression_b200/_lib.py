@@ -43,6 +43,7 @@ SIGNATURES = {
     "hyres_version": (_i, []),
     "hyres_device_check": (_i, [_i]),
     "hyres_last_error": (C.c_char_p, []),
+    "hyres_launch_count": (C.c_longlong, []),
     "hyres_conv_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hyres_conv_update": (_i, [_vp, _vp, _vp]),
     "hyres_conv_destroy": (None, [_vp]),

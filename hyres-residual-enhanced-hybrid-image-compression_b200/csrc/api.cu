@@ -5,7 +5,12 @@
 #include "host_util.h"
 #include "hyres_b200.h"
 
+#include <atomic>
+
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void hy_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int hy_fail(int code, const char* msg) {
   snprintf(g_err, sizeof g_err, "%s", msg ? msg : "");
@@ -15,6 +20,8 @@ int hy_fail(int code, const char* msg) {
 extern "C" {
 
 int hyres_version(void) { return 100; }
+
+long long hyres_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* hyres_last_error(void) { return g_err; }
 

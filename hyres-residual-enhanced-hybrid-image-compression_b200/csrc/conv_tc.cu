@@ -685,6 +685,7 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
     smem_set = 227 * 1024;
   }
   dim3 grid(static_cast<unsigned>(io->B * p.tiles_w * p.tiles_h), c->cout_pad / c->BN, c->nphase);
+  hy_count_launch();
   conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;

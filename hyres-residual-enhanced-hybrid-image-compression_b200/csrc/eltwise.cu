@@ -181,11 +181,13 @@ int hyres_residual_im2col5s2(const float* x, const float* jpeg, float* residual,
   const int64_t n = static_cast<int64_t>(B) * 3 * H * W;
   const float* src = x;
   if (jpeg) {
+    hy_count_launch();
     addsub_kernel<-1><<<grid_for(n, kBlock * 4), kBlock, 0, st>>>(x, jpeg, residual, n);
     src = residual;
   }
   if (a_out) {
     const int64_t t = static_cast<int64_t>(B) * (H / 2) * (W / 2) * 16;
+    hy_count_launch();
     im2col3_kernel<5, 2, 2, 128><<<grid_for(t, kBlock, 148 * 32), kBlock, 0, st>>>(
         src, static_cast<__nv_bfloat16*>(a_out), B, H, W, H / 2, W / 2);
   }
@@ -201,11 +203,13 @@ int hyres_addback_im2col3(const float* jpeg, const float* r_hat, float* x0, void
   const int64_t n = static_cast<int64_t>(B) * 3 * H * W;
   const float* src = r_hat;
   if (jpeg) {
+    hy_count_launch();
     addsub_kernel<1><<<grid_for(n, kBlock * 4), kBlock, 0, st>>>(jpeg, r_hat, x0, n);
     src = x0;
   }
   if (a_out) {
     const int64_t t = static_cast<int64_t>(B) * H * W * 8;
+    hy_count_launch();
     im2col3_kernel<3, 1, 1, 64><<<grid_for(t, kBlock, 148 * 32), kBlock, 0, st>>>(
         src, static_cast<__nv_bfloat16*>(a_out), B, H, W, H, W);
   }
@@ -216,6 +220,7 @@ int hyres_addback_im2col3(const float* jpeg, const float* r_hat, float* x0, void
 int hyres_final_clamp(const float* x0, const float* refined, float* x_hat, int64_t n, void* stream_v) {
   if (!x0 || !refined || !x_hat || n < 0) return hy_fail(HYRES_ERR_ARG, "final_clamp: bad argument");
   if (n == 0) return HYRES_OK;
+  hy_count_launch();
   final_clamp_kernel<<<grid_for(n, kBlock * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(x0, refined, x_hat, n);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
@@ -224,6 +229,7 @@ int hyres_final_clamp(const float* x0, const float* refined, float* x_hat, int64
 int hyres_add_to_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream_v) {
   if (!a || !b || !out_bf16 || n < 0) return hy_fail(HYRES_ERR_ARG, "add_to_bf16: bad argument");
   if (n == 0) return HYRES_OK;
+  hy_count_launch();
   add_to_bf16_kernel<<<grid_for(n, kBlock * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(
       a, b, static_cast<__nv_bfloat16*>(out_bf16), n);
   HY_CUDA(cudaGetLastError());
@@ -234,6 +240,7 @@ int hyres_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H,
   if (!in || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "nchw_to_nhwc: bad argument");
   const int hw = H * W;
   dim3 grid((hw + 31) / 32, (C + 31) / 32, B), block(32, 8);
+  hy_count_launch();
   transpose_tiles<float, __nv_bfloat16><<<grid, block, 0, static_cast<cudaStream_t>(stream_v)>>>(
       in, static_cast<__nv_bfloat16*>(out), C, hw);
   HY_CUDA(cudaGetLastError());
@@ -244,6 +251,7 @@ int hyres_nhwc_to_nchw_f32(const float* in, float* out, int B, int C, int H, int
   if (!in || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "nhwc_to_nchw: bad argument");
   const int hw = H * W;
   dim3 grid((C + 31) / 32, (hw + 31) / 32, B), block(32, 8);
+  hy_count_launch();
   transpose_tiles<float, float><<<grid, block, 0, static_cast<cudaStream_t>(stream_v)>>>(in, out, hw, C);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
@@ -253,6 +261,7 @@ int hyres_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H,
   if (!in || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "nhwc_bf16_to_nchw: bad argument");
   const int hw = H * W;
   dim3 grid((C + 31) / 32, (hw + 31) / 32, B), block(32, 8);
+  hy_count_launch();
   transpose_tiles<__nv_bfloat16, float><<<grid, block, 0, static_cast<cudaStream_t>(stream_v)>>>(
       static_cast<const __nv_bfloat16*>(in), out, hw, C);
   HY_CUDA(cudaGetLastError());
@@ -262,6 +271,7 @@ int hyres_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H,
 int hyres_reduce_sqdiff(const float* a, const float* b, int64_t n, double* out, void* stream_v) {
   if (!a || !b || !out || n < 0) return hy_fail(HYRES_ERR_ARG, "reduce_sqdiff: bad argument");
   if (n == 0) return HYRES_OK;
+  hy_count_launch();
   sqdiff_kernel<<<grid_for(n, kBlock * 8, 148 * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(a, b, n, out);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
@@ -270,6 +280,7 @@ int hyres_reduce_sqdiff(const float* a, const float* b, int64_t n, double* out, 
 int hyres_reduce_log2(const float* x, int64_t n, double* out, void* stream_v) {
   if (!x || !out || n < 0) return hy_fail(HYRES_ERR_ARG, "reduce_log2: bad argument");
   if (n == 0) return HYRES_OK;
+  hy_count_launch();
   log2_kernel<<<grid_for(n, kBlock * 8, 148 * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(x, n, out);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;

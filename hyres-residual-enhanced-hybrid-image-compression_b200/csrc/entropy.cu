@@ -349,6 +349,7 @@ int hyres_gc_quant_pass(const float* y, const float* params, int pass, int mode,
   const int64_t npix = static_cast<int64_t>(B) * h * w;
   const int64_t total = npix * (M / 4);
   int grid = static_cast<int>(std::min<int64_t>((total + kThreads - 1) / kThreads, 148 * 16));
+  hy_count_launch();
   gc_quant_pass_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
       y, params, pass, mode, seed, yq_f32, static_cast<__nv_bfloat16*>(yq_bf16), npix, h, w, M);
   HY_CUDA(cudaGetLastError());
@@ -366,6 +367,7 @@ int hyres_gc_merge_likelihood(const float* y, const float* params_a, const float
   int rc = set_smem(reinterpret_cast<const void*>(gc_merge_likelihood_kernel), smem);
   if (rc) return rc;
   dim3 grid((hw + kPix - 1) / kPix, B);
+  hy_count_launch();
   gc_merge_likelihood_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       y, params_a, params_na, yq_a, yq_na, mode, seed, static_cast<__nv_bfloat16*>(y_hat_bf16), lik_nchw, sum_log2,
       hw, M, 0.11f, 1e-9f);
@@ -382,6 +384,7 @@ int hyres_gc_symbols(const float* y, const float* params, int pass, const float*
   int rc = set_smem(reinterpret_cast<const void*>(gc_symbols_kernel), smem);
   if (rc) return rc;
   dim3 grid((h * w + kPix - 1) / kPix, B);
+  hy_count_launch();
   gc_symbols_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       y, params, pass, scale_table, n_scales, scale_bound, symbols, indexes, yq_f32,
       static_cast<__nv_bfloat16*>(yq_bf16), h, w, M);
@@ -397,6 +400,7 @@ int hyres_gc_indexes(const float* params, const float* scale_table, int n_scales
   int rc = set_smem(reinterpret_cast<const void*>(gc_symbols_kernel), smem);
   if (rc) return rc;
   dim3 grid((h * w + kPix - 1) / kPix, B);
+  hy_count_launch();
   gc_symbols_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       nullptr, params, 0, scale_table, n_scales, scale_bound, nullptr, indexes, nullptr, nullptr, h, w, M);
   HY_CUDA(cudaGetLastError());
@@ -411,6 +415,7 @@ int hyres_gc_dequant(const int32_t* symbols, const float* params, float* yq_f32,
   int rc = set_smem(reinterpret_cast<const void*>(gc_dequant_kernel), smem);
   if (rc) return rc;
   dim3 grid((h * w + kPix - 1) / kPix, B);
+  hy_count_launch();
   gc_dequant_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       symbols, params, yq_f32, static_cast<__nv_bfloat16*>(yq_bf16), h * w, M);
   HY_CUDA(cudaGetLastError());
@@ -426,6 +431,7 @@ int hyres_eb_forward(const float* z, const float* eb_params, const float* median
   int rc = set_smem(reinterpret_cast<const void*>(eb_forward_kernel), smem);
   if (rc) return rc;
   dim3 grid((h * w + kPix - 1) / kPix, B);
+  hy_count_launch();
   eb_forward_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       z, reinterpret_cast<const EbChan*>(eb_params), medians, mode, seed, lik_bound,
       static_cast<__nv_bfloat16*>(zhat_bf16), zhat_nchw, lik_nchw, symbols, sum_log2, h * w, C);
@@ -441,6 +447,7 @@ int hyres_eb_dequant(const int32_t* symbols, const float* medians, void* zhat_bf
   int rc = set_smem(reinterpret_cast<const void*>(eb_dequant_kernel), smem);
   if (rc) return rc;
   dim3 grid((h * w + kPix - 1) / kPix, B);
+  hy_count_launch();
   eb_dequant_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       symbols, medians, static_cast<__nv_bfloat16*>(zhat_bf16), h * w, C);
   HY_CUDA(cudaGetLastError());

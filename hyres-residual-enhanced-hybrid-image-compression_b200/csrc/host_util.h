@@ -5,6 +5,8 @@
 #include <cuda_runtime.h>
 
 int hy_fail(int code, const char* msg);
+// Every kernel launch of the library is counted (hyres_launch_count): bench.py reports it.
+void hy_count_launch();
 
 #define HY_CUDA(expr)                                                   \
   do {                                                                  \

@@ -260,7 +260,9 @@ int hyres_refine_se_pool(const void* feat, float* scratch, float* pooled, int B,
   if (!feat || !scratch || !pooled || B <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "se_pool: bad argument");
   if (C != 64) return hy_fail(HYRES_ERR_UNSUPPORTED, "se_pool: C must be 64");
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  hy_count_launch();
   se_pool_partial<<<dim3(kPoolBlocks, B), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(feat), scratch, H * W);
+  hy_count_launch();
   se_pool_final<<<B, 64, 0, st>>>(scratch, pooled, H * W);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
@@ -275,6 +277,7 @@ int hyres_refine_se_scale_down(const void* feat, const float* pooled, const floa
   if ((H & 3) || (W & 3)) return hy_fail(HYRES_ERR_ARG, "se_scale_down: H and W must be multiples of 4");
   const int64_t nblk = static_cast<int64_t>(H / 4) * (W / 4) * 8;
   int gx = static_cast<int>(std::min<int64_t>((nblk + kThreads - 1) / kThreads, 148 * 8));
+  hy_count_launch();
   se_scale_down_kernel<<<dim3(gx, B), kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
       static_cast<const __nv_bfloat16*>(feat), pooled, fc1, fc2, Cr, static_cast<__nv_bfloat16*>(feat_s),
       static_cast<__nv_bfloat16*>(feat_h), static_cast<__nv_bfloat16*>(feat_q), H, W);
@@ -289,6 +292,7 @@ int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi, fl
   if ((H & 3) || (W & 3)) return hy_fail(HYRES_ERR_ARG, "up_concat_stats: H and W must be multiples of 4");
   const int64_t npix = static_cast<int64_t>(B) * H * W;
   int gx = static_cast<int>(std::min<int64_t>((npix * 8 + kThreads - 1) / kThreads, 148 * 16));
+  hy_count_launch();
   up_concat_stats_kernel<<<gx, kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
       static_cast<const __nv_bfloat16*>(f2), static_cast<const __nv_bfloat16*>(f3), static_cast<__nv_bfloat16*>(multi),
       stats, H, W, npix);
@@ -299,6 +303,7 @@ int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi, fl
 int hyres_refine_spatial_att(const float* stats, const float* w7x7, float* att, int B, int H, int W, void* stream_v) {
   if (!stats || !w7x7 || !att || B <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "spatial_att: bad argument");
   dim3 grid((W + 31) / 32, (H + 7) / 8, B);
+  hy_count_launch();
   spatial_att_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_v)>>>(stats, w7x7, att, H, W);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;

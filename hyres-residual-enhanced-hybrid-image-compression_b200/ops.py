@@ -30,6 +30,20 @@ def _chk_nhwc(t, name, dtype=torch.bfloat16):
 class ConvLayer:
     """One packed convolution layer (weights live in the library, bf16 K-major)."""
 
+    _prof = None  # list of (start, end) CUDA events while profile_begin() is active
+
+    @classmethod
+    def profile_begin(cls):
+        """Bracket every conv launch with CUDA events on the launch stream (bench.py roofline)."""
+        cls._prof = []
+
+    @classmethod
+    def profile_end(cls):
+        """-> (summed device milliseconds of the conv launches, number of launches)."""
+        ev, cls._prof = cls._prof or [], None
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev), len(ev)
+
     def __init__(self, weight, bias=None, kind=HYRES_CONV, stride=1, pad=0, dil=1, cin0=None,
                  cin1=0, tap_mask=None):
         w = weight.detach().to("cpu", torch.float32).contiguous()
@@ -147,7 +161,14 @@ class ConvLayer:
             io.f32_sb, io.f32_sh, io.f32_sw, io.f32_sc = view.stride()
         io.mt_hint = mt
         keep += [o16, osq, o32]
-        L.check(L.lib().hyres_conv_run(self._h, C.byref(io), _stream()), "hyres_conv_run")
+        if ConvLayer._prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            L.check(L.lib().hyres_conv_run(self._h, C.byref(io), _stream()), "hyres_conv_run")
+            e1.record()
+            ConvLayer._prof.append((e0, e1))
+        else:
+            L.check(L.lib().hyres_conv_run(self._h, C.byref(io), _stream()), "hyres_conv_run")
         return o16, osq, o32
 
     @staticmethod

@@ -51,6 +51,9 @@ extern "C" {
 int hyres_version(void);
 int hyres_device_check(int device);
 const char* hyres_last_error(void);
+/* Number of CUDA kernels this library has launched since it was loaded (host-side count;
+ * launches replayed from a captured CUDA graph are counted once, at capture). */
+long long hyres_launch_count(void);
 
 /* ------------------------------------------------------------------------- */
 /* Implicit-GEMM convolution on tcgen05 tensor cores (NHWC bf16, fp32 accum). */

@@ -1,0 +1,44 @@
+"""tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu through hyres_conv_run) against a torch fp32
+convolution of the same bf16-rounded operands.  Tolerances: fp32 outputs 2e-4 of the output
+range (accumulation order only), bf16 outputs 1e-2 (one bf16 rounding of the result)."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import check_conv  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("idx", range(len(check_conv.CASES)), ids=[c["name"] for c in check_conv.CASES])
+def test_conv_case(build_lib, idx):
+    case = dict(check_conv.CASES[idx])
+    check_conv.CASES[idx] = {k: v for k, v in case.items() if k != "perf"}  # correctness only
+    try:
+        r = check_conv.run_case(idx)
+    finally:
+        check_conv.CASES[idx] = case
+    assert r["ok"], r
+
+
+def test_conv_argument_errors(build_lib):
+    import torch
+    from hyres_b200 import _lib, ops
+    w = torch.randn(64, 64, 3, 3)
+    with pytest.raises(_lib.HyresError):
+        ops.ConvLayer(w, None, stride=3, pad=1)  # unsupported stride
+    with pytest.raises(_lib.HyresError):
+        ops.ConvLayer(torch.randn(64, 60, 1, 1), None)  # channels not a multiple of 8
+    layer = ops.ConvLayer(w, None, stride=1, pad=1)
+    with pytest.raises(ValueError):
+        layer(torch.zeros(1, 8, 8, 32, dtype=torch.bfloat16, device="cuda"))  # wrong channel count
+    with pytest.raises(ValueError):
+        layer(torch.zeros(1, 8, 8, 64, dtype=torch.float32, device="cuda"))  # wrong dtype
+    x = torch.zeros(1, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(_lib.HyresError):
+        layer(x, epi=ops.EPI_ADD)  # epilogue operand missing
+    o, _, _ = layer(x)
+    torch.cuda.synchronize()
+    assert o.shape == (1, 8, 8, 64) and float(o.abs().max()) == 0.0

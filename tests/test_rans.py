@@ -1,0 +1,132 @@
+"""Entropy coder: the product's C++ coder (csrc/rans.cpp, host code behind the C-ABI) against the
+plain-C oracle and the committed known-answer vector; round-trip properties; error paths.
+CPU only (the coder is host code on both sides)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from conftest import load_golden
+
+
+@pytest.fixture(scope="module")
+def tables(build_lib, oracle_net):
+    from hyres_b200 import coder
+    gc = oracle_net.residual_model.gaussian_conditional
+    return coder.CdfTables(gc._quantized_cdf.numpy(), gc._cdf_length.numpy(), gc._offset.numpy())
+
+
+def test_known_answer_vector(build_lib, oracle, tables):
+    from hyres_b200 import coder
+    g = load_golden("rans_kat")
+    sym, idx, want = g["symbols"].astype(np.int32), g["indexes"].astype(np.int32), g["string"].tobytes()
+    # tables regenerated here must be the fixture's
+    assert (tables.sizes == g["cdf_length"]).all() and (tables.offsets == g["offset"]).all()
+    assert (tables.cdf[0, :16] == g["cdf_row0"]).all() and (tables.cdf[63, :8] == g["cdf_row63_head"]).all()
+    assert oracle.rans_encode_with_indexes(sym, idx, tables.cdf, tables.sizes, tables.offsets) == want
+    mine = coder.encode_with_indexes(sym, idx, tables)
+    assert mine == want
+    assert len(mine) % 4 == 0 and len(mine) >= 8
+    assert (coder.decode_with_indexes(want, idx, tables) == sym).all()
+    assert (oracle.rans_decode_with_indexes(mine, idx, tables.cdf, tables.sizes, tables.offsets) == sym).all()
+
+
+def test_empty_input_is_the_flushed_state(build_lib, oracle, tables):
+    from hyres_b200 import coder
+    e = np.zeros(0, dtype=np.int32)
+    mine = coder.encode_with_indexes(e, e, tables)
+    assert mine == oracle.rans_encode_with_indexes(e, e, tables.cdf, tables.sizes, tables.offsets)
+    assert mine == (1 << 31).to_bytes(8, "little")
+    assert coder.decode_with_indexes(mine, e, tables).size == 0
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 700), st.floats(0.2, 40.0), st.booleans())
+def test_roundtrip_and_byte_identity(build_lib, oracle, tables, seed, n, spread, escapes):
+    from hyres_b200 import coder
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, 64, size=n).astype(np.int32)
+    sym = np.round(rng.standard_normal(n) * spread).astype(np.int32)
+    if escapes:
+        k = rng.integers(0, n, size=max(1, n // 9))
+        sym[k] += rng.integers(-70000, 70000, size=k.size).astype(np.int32)
+    want = oracle.rans_encode_with_indexes(sym, idx, tables.cdf, tables.sizes, tables.offsets)
+    mine = coder.encode_with_indexes(sym, idx, tables)
+    assert mine == want
+    assert (coder.decode_with_indexes(mine, idx, tables) == sym).all()
+
+
+def test_batch_matches_single(build_lib, tables):
+    from hyres_b200 import coder
+    rng = np.random.default_rng(7)
+    count, n = 5, 3000
+    idx = rng.integers(0, 64, size=(count, n)).astype(np.int32)
+    sym = np.round(rng.standard_normal((count, n)) * 3).astype(np.int32)
+    sym[2, ::50] = 9999
+    strings = coder.encode_batch(sym, idx, tables, threads=3)
+    assert strings == [coder.encode_with_indexes(sym[i], idx[i], tables) for i in range(count)]
+    assert (coder.decode_batch(strings, idx, tables, threads=2) == sym).all()
+    assert coder.encode_batch(sym[:0], idx[:0], tables) == []
+
+
+def test_pmf_to_quantized_cdf_matches_oracle(build_lib, oracle):
+    from hyres_b200 import coder
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 17, 300, 3133):
+        p = rng.random(n).astype(np.float32) ** 6  # many tiny bins -> exercises the steal loop
+        p /= p.sum()
+        got = coder.pmf_to_quantized_cdf(p)
+        want = oracle.pmf_to_quantized_cdf(p).numpy()
+        assert (got == want).all()
+        assert got[0] == 0 and got[-1] == 65536 and (np.diff(got) > 0).all()
+    with pytest.raises(ValueError):
+        coder.pmf_to_quantized_cdf(np.array([0.5, -0.1, 0.6], dtype=np.float32))
+    with pytest.raises(ValueError):
+        coder.pmf_to_quantized_cdf(np.array([0.5, np.nan], dtype=np.float32))
+
+
+def test_error_paths(build_lib, tables):
+    from hyres_b200 import _lib, coder
+    sym = np.zeros(8, dtype=np.int32)
+    bad_idx = np.full(8, 64, dtype=np.int32)  # out-of-range CDF row
+    with pytest.raises(_lib.HyresError):
+        coder.encode_with_indexes(sym, bad_idx, tables)
+    with pytest.raises(ValueError):
+        coder.encode_with_indexes(sym, np.zeros(7, dtype=np.int32), tables)
+    with pytest.raises(_lib.HyresError):  # a stream shorter than the 8-byte flushed state
+        coder.decode_with_indexes(b"\x00\x01\x02", np.zeros(4, dtype=np.int32), tables)
+    # output capacity too small: HYRES_ERR_ARG and the needed length reported
+    lib = _lib.lib()
+    s = np.arange(100, dtype=np.int32) % 5
+    ix = np.zeros(100, dtype=np.int32)
+    out = np.empty(4, dtype=np.uint8)
+    n = C.c_int64(0)
+    rc = lib.hyres_rans_encode(s.ctypes.data, ix.ctypes.data, s.size, tables.cdf.ctypes.data, tables.cdf.shape[0],
+                               tables.cdf.shape[1], tables.sizes.ctypes.data, tables.offsets.ctypes.data,
+                               out.ctypes.data, 4, C.byref(n))
+    assert rc == -1 and n.value > 4
+
+
+def test_entropy_model_string_api(build_lib, oracle_net):
+    """EntropyModel.encode_symbols / decode_symbols keep compressai's argument checks."""
+    import torch
+    import hyres_b200
+    gc = hyres_b200.models.GaussianConditional(None)
+    with pytest.raises(ValueError, match="Uninitialized CDFs"):
+        gc.encode_symbols(torch.zeros(1, 4, dtype=torch.int32), torch.zeros(1, 4, dtype=torch.int32))
+    gc.update_scale_table(hyres_b200.get_scale_table())
+    ogc = oracle_net.residual_model.gaussian_conditional
+    assert torch.equal(gc._quantized_cdf, ogc._quantized_cdf)
+    assert torch.equal(gc._cdf_length, ogc._cdf_length) and torch.equal(gc._offset, ogc._offset)
+    with pytest.raises(ValueError):
+        gc.encode_symbols(torch.zeros(4, dtype=torch.int32), torch.zeros(4, dtype=torch.int32))
+    with pytest.raises(ValueError):
+        gc.encode_symbols(torch.zeros(1, 4, dtype=torch.int32), torch.zeros(1, 5, dtype=torch.int32))
+    sym = torch.randint(-5, 6, (2, 3, 4, 4), dtype=torch.int32)
+    idx = torch.randint(0, 64, (2, 3, 4, 4), dtype=torch.int32)
+    strings = gc.encode_symbols(sym, idx)
+    assert len(strings) == 2 and all(isinstance(s, bytes) for s in strings)
+    assert torch.equal(gc.decode_symbols(strings, idx), sym)
+    with pytest.raises(ValueError):
+        gc.decode_symbols(strings[:1], idx)
