@@ -112,7 +112,7 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const float (&f)[
   reinterpret_cast<uint4*>(p)[1] = b;
 }
 
-__global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+__global__ void __launch_bounds__(kThreads, 3) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -228,57 +228,98 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
     }
   } else {
     // ===================== epilogue (warps 0-3) =====================
-    hy::mbar_wait(acc_full, 0);
-    hy::tc_fence_after();
+    // Software-pipelined over 16-column chunks: the TMEM load and the global loads of the
+    // epilogue operands (skip / gate / GDN inputs) of chunk c+1 are in flight while chunk c is
+    // finished and stored, and the first chunk's operands are requested before the
+    // accumulator is complete, so one global-load latency is exposed per tile, not per chunk.
     const int row = warp * 32 + lane;  // TMEM lane == tile row
     const int ti = row >> 3;
     const int tj = row & 7;
     const int ph_p = phase >> 1, ph_q = phase & 1;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    for (int sub = 0; sub < p.MT; ++sub) {
+    const bool need0 = p.epi == HYRES_EPI_ADD || p.epi == HYRES_EPI_GATE || p.epi == HYRES_EPI_GDN ||
+                       p.epi == HYRES_EPI_IGDN;
+    const bool need1 = p.epi == HYRES_EPI_GATE;
+    const int nchunk = p.BN >> 4;
+    const int total = p.MT * nchunk;
+    auto geom = [&](int it, long long& opix, int& oh, int& ow, bool& valid, int& n) {
+      const int sub = it / nchunk;
       const int hv = h0 + sub * kSubH + ti;
       const int wv = w0 + tj;
-      const bool valid = (hv < p.OHv) && (wv < p.OWv);
-      const int oh = hv * p.out_mul + ph_p;
-      const int ow = wv * p.out_mul + ph_q;
-      const long long opix = (static_cast<long long>(b_img) * p.OH + oh) * p.OW + ow;
-      float ps = 1.f;
-      if (valid && p.epi == HYRES_EPI_PIXSCALE) ps = __ldg(p.pixscale + opix);
-      for (int c0 = 0; c0 < p.BN; c0 += 16) {
-        uint32_t r[16];
-        hy::tmem_ld16(t_lane + sub * p.BN + c0, r);
-        hy::tmem_ld_wait();
-        const int n = n0 + c0;
-        if (!valid || n >= p.cout) continue;
+      n = n0 + (it - sub * nchunk) * 16;
+      valid = (hv < p.OHv) && (wv < p.OWv) && (n < p.cout);
+      oh = hv * p.out_mul + ph_p;
+      ow = wv * p.out_mul + ph_q;
+      opix = (static_cast<long long>(b_img) * p.OH + oh) * p.OW + ow;
+    };
+    auto fetch_aux = [&](int it, uint4 (&x0)[2], uint4 (&x1)[2]) {
+      long long opix; int oh, ow, n; bool valid;
+      geom(it, opix, oh, ow, valid, n);
+      if (!valid) return;
+      if (need0) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.aux0 + opix * p.ld_aux0 + n);
+        x0[0] = __ldg(q); x0[1] = __ldg(q + 1);
+      }
+      if (need1) {
+        const uint4* q = reinterpret_cast<const uint4*>(p.aux1 + opix * p.ld_aux1 + n);
+        x1[0] = __ldg(q); x1[1] = __ldg(q + 1);
+      }
+    };
+    auto unpack = [](const uint4 (&x)[2], float (&f)[16]) {
+      const uint32_t u[8] = {x[0].x, x[0].y, x[0].z, x[0].w, x[1].x, x[1].y, x[1].z, x[1].w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { f[2 * i] = hy::bf16_lo(u[i]); f[2 * i + 1] = hy::bf16_hi(u[i]); }
+    };
+    uint4 a0c[2] = {}, a1c[2] = {}, a0n[2] = {}, a1n[2] = {};
+    uint32_t rc[16];
+    fetch_aux(0, a0c, a1c);
+    hy::mbar_wait(acc_full, 0);
+    hy::tc_fence_after();
+    hy::tmem_ld16(t_lane, rc);
+    hy::tmem_ld_fence(rc);
+    for (int it = 0; it < total; ++it) {
+      if (it + 1 < total) {
+        fetch_aux(it + 1, a0n, a1n);
+      }
+      long long opix; int oh, ow, n; bool valid;
+      geom(it, opix, oh, ow, valid, n);
+      if (valid) {
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rc[i]);
         const bool full16 = (n + 16 <= p.cout);
         if (p.epi == HYRES_EPI_PIXSCALE) {
+          const float ps = __ldg(p.pixscale + opix);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] *= ps;
         }
+        {
+          const float4* bq = reinterpret_cast<const float4*>(p.bias + n);  // bias padded to BN multiple
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);  // bias padded to BN multiple
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = __ldg(bq + i);
+            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+          }
+        }
         if (p.epi == HYRES_EPI_ADD) {
           float a[16];
-          load16_bf16(p.aux0 + opix * p.ld_aux0 + n, a);
+          unpack(a0c, a);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += a[i];
         } else if (p.epi == HYRES_EPI_GATE) {
           float a[16], x[16];
-          load16_bf16(p.aux1 + opix * p.ld_aux1 + n, a);
-          load16_bf16(p.aux0 + opix * p.ld_aux0 + n, x);
+          unpack(a1c, a);
+          unpack(a0c, x);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = a[i] * (1.f / (1.f + __expf(-v[i]))) + x[i];
         } else if (p.epi == HYRES_EPI_GDN) {
           float x[16];
-          load16_bf16(p.aux0 + opix * p.ld_aux0 + n, x);
+          unpack(a0c, x);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = x[i] * rsqrtf(v[i]);
         } else if (p.epi == HYRES_EPI_IGDN) {
           float x[16];
-          load16_bf16(p.aux0 + opix * p.ld_aux0 + n, x);
+          unpack(a0c, x);
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = x[i] * sqrtf(v[i]);
         }
@@ -319,6 +360,12 @@ __global__ void __launch_bounds__(kThreads) conv_tc_kernel(const __grid_constant
             for (int i = 0; i < 16 && n + i < p.cout; ++i) o[i * p.f32_sc] = v[i];
           }
         }
+      }
+      if (it + 1 < total) {
+        const int sub1 = (it + 1) / nchunk;
+        hy::tmem_ld16(t_lane + sub1 * p.BN + (it + 1 - sub1 * nchunk) * 16, rc);
+        hy::tmem_ld_fence(rc);
+        a0c[0] = a0n[0]; a0c[1] = a0n[1]; a1c[0] = a1n[0]; a1c[1] = a1n[1];
       }
     }
   }
@@ -646,8 +693,17 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   if (p.patch_rows > 256) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: patch too tall");
   p.a_stage_bytes = p.patch_rows * kTileW * 128;
   p.b_stage_bytes = c->BN * 128;
-  p.NA = 2;
-  p.NB = 4;
+  // ring depths sized by what one tile actually consumes: small layers then fit several
+  // CTAs per SM, which is what hides the load -> MMA -> epilogue latency chain of a tile.
+  int max_groups = 0, max_btiles = 0;
+  for (int ph = 0; ph < c->nphase; ++ph) {
+    max_groups = std::max(max_groups, c->ph_count[ph]);
+    int bt = 0;
+    for (int g = 0; g < c->ph_count[ph]; ++g) bt += c->groups[c->ph_begin[ph] + g].ntaps;
+    max_btiles = std::max(max_btiles, bt);
+  }
+  p.NA = std::min(2, max_groups);
+  p.NB = std::min(4, max_btiles);
   auto smem_need = [&]() { return p.NA * p.a_stage_bytes + p.NB * p.b_stage_bytes + 256 + 1024; };
   while (smem_need() > 227 * 1024 && p.NB > 2) --p.NB;
   if (smem_need() > 227 * 1024) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: tile does not fit shared memory");

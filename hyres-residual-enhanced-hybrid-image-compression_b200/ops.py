@@ -31,17 +31,20 @@ class ConvLayer:
     """One packed convolution layer (weights live in the library, bf16 K-major)."""
 
     _prof = None  # list of (start, end) CUDA events while profile_begin() is active
+    _prof_info = []
 
     @classmethod
     def profile_begin(cls):
         """Bracket every conv launch with CUDA events on the launch stream (bench.py roofline)."""
         cls._prof = []
+        cls._prof_info = []
 
     @classmethod
     def profile_end(cls):
         """-> (summed device milliseconds of the conv launches, number of launches)."""
         ev, cls._prof = cls._prof or [], None
         torch.cuda.synchronize()
+        cls.last_profile = [dict(info, ms=a.elapsed_time(b)) for (a, b), info in zip(ev, cls._prof_info)]
         return sum(a.elapsed_time(b) for a, b in ev), len(ev)
 
     def __init__(self, weight, bias=None, kind=HYRES_CONV, stride=1, pad=0, dil=1, cin0=None,
@@ -167,6 +170,9 @@ class ConvLayer:
             L.check(L.lib().hyres_conv_run(self._h, C.byref(io), _stream()), "hyres_conv_run")
             e1.record()
             ConvLayer._prof.append((e0, e1))
+            ConvLayer._prof_info.append(dict(kind=self.kind, cin=self.cin0 + self.cin1, cout=self.cout, k=self.R,
+                                             stride=self.stride, dil=self.dil, B=B, H=H, W=W, OH=OH, OW=OW,
+                                             epi=epi, f32=o32 is not None, sq=osq is not None))
         else:
             L.check(L.lib().hyres_conv_run(self._h, C.byref(io), _stream()), "hyres_conv_run")
         return o16, osq, o32
