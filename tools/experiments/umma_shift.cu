@@ -7,10 +7,10 @@
 #include <vector>
 #include "common.cuh"
 
-constexpr int kRows = 256;  // rows in the smem A buffer (64 bf16 = 128 B each)
+constexpr int kRows = 320;  // rows in the smem A buffer (64 bf16 = 128 B each)
 
 __global__ void __launch_bounds__(128) k(const __nv_bfloat16* a_lin, const __nv_bfloat16* b_lin, float* out,
-                                        int shift, int use_base_off) {
+                                        int shift, int use_base_off, int sbo_rows) {
   extern __shared__ uint8_t raw[];
   const uint32_t base = (hy::smem_u32(raw) + 1023u) & ~1023u;
   uint8_t* gen = raw + (base - hy::smem_u32(raw));
@@ -39,6 +39,8 @@ __global__ void __launch_bounds__(128) k(const __nv_bfloat16* a_lin, const __nv_
     const uint32_t a0 = a_s + shift * 128;
     for (int kk = 0; kk < 4; ++kk) {
       uint64_t ad = hy::umma_desc_sw128(a0 + kk * 32);
+      // 8-row groups sbo_rows*128 B apart (8 = dense; 10 = a patch that is 10 positions wide)
+      ad = (ad & ~(static_cast<uint64_t>(0x3fff) << 32)) | (static_cast<uint64_t>((sbo_rows * 128) >> 4) << 32);
       if (use_base_off) ad |= static_cast<uint64_t>((a0 >> 7) & 7) << 49;
       hy::umma_bf16(tmem, ad, hy::umma_desc_sw128(b_s + kk * 32), idesc, kk ? 1u : 0u);
     }
@@ -72,9 +74,11 @@ int main() {
   const int smem = kRows * 128 + 64 * 128 + 1024 + 64;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   std::vector<float> out(128 * 64);
+  for (int sbo = 8; sbo <= 10; sbo += 2)
   for (int ubo = 0; ubo < 2; ++ubo)
-    for (int shift = 0; shift < 18; ++shift) {
-      k<<<1, 128, smem>>>(da, db, dout, shift, ubo);
+    for (int shift = 0; shift < 23; ++shift) {
+      if (sbo == 10 && ubo == 1) continue;
+      k<<<1, 128, smem>>>(da, db, dout, shift, ubo, sbo);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("base_off=%d shift=%d CUDA error %s\n", ubo, shift, cudaGetErrorString(e)); return 1; }
       cudaMemcpy(out.data(), dout, out.size() * 4, cudaMemcpyDeviceToHost);
@@ -82,10 +86,11 @@ int main() {
       for (int m = 0; m < 128; ++m)
         for (int n = 0; n < 64; ++n) {
           float ref = 0;
-          for (int c = 0; c < 64; ++c) ref += __bfloat162float(a[(m + shift) * 64 + c]) * __bfloat162float(b[n * 64 + c]);
+          const int row = shift + (m >> 3) * sbo + (m & 7);
+          for (int c = 0; c < 64; ++c) ref += __bfloat162float(a[row * 64 + c]) * __bfloat162float(b[n * 64 + c]);
           if (ref != out[m * 64 + n]) ++bad;
         }
-      printf("base_off=%d shift=%2d mismatches=%d\n", ubo, shift, bad);
+      printf("sbo_rows=%d base_off=%d shift=%2d mismatches=%d\n", sbo, ubo, shift, bad);
     }
   return 0;
 }
