@@ -34,6 +34,15 @@ class ConvIO(C.Structure):
     ]
 
 
+class RuIO(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("ld_x", C.c_int),
+        ("out", C.c_void_p), ("ld_out", C.c_int),
+        ("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+        ("final_relu", C.c_int),
+    ]
+
+
 _lib = None
 
 _vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
@@ -50,6 +59,8 @@ SIGNATURES = {
     "hyres_conv_macs_per_pos": (_i64, [_vp]),
     "hyres_conv_out_size": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "hyres_conv_run": (_i, [_vp, C.POINTER(ConvIO), _vp]),
+    "hyres_ru_supported": (_i, [_vp, _vp, _vp]),
+    "hyres_ru_run": (_i, [_vp, _vp, _vp, C.POINTER(RuIO), _vp]),
     "hyres_residual_im2col5s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_addback_im2col3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_final_clamp": (_i, [_vp, _vp, _vp, _i64, _vp]),

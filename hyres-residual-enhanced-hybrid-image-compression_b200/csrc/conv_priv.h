@@ -1,0 +1,63 @@
+// Private (library-internal) view of a packed convolution layer, shared by the generic
+// implicit-GEMM kernel (conv_tc.cu) and the fused ResidualUnit kernel (ru_fused.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <vector>
+
+constexpr int kMaxTaps = 5;   // vertical taps per patch
+
+struct TapGroup {
+  int32_t src;      // 0: x0, 1: x1
+  int32_t c_off;    // inner (channel) coordinate of the box
+  int32_t dw;       // column coordinate offset relative to the tile origin
+  int32_t dh;       // row coordinate offset of the patch start
+  int32_t hpar;     // coordinate along the parity dimension (stride-2 view)
+  int32_t ntaps;    // B tiles consumed against this patch
+  int32_t kslot0;   // first 64-wide K slot in the packed weights
+  int32_t tap_row[kMaxTaps];  // row shift (in patch rows) of each tap
+};
+
+struct hyres_conv {
+  int kind, cin0, cin1, w_cin_total, cout, R, S, stride, pad, dil;
+  int BN, cout_pad, ktot, nphase, extra_rows;
+  int ph_begin[4], ph_count[4];
+  std::vector<TapGroup> groups;
+  std::vector<uint8_t> tap_mask;
+  // k-slot -> (src, chunk, r, s) for weight packing
+  struct Slot { int src, chunk, r, s; };
+  std::vector<Slot> slots;
+  TapGroup* d_groups = nullptr;
+  __nv_bfloat16* d_w = nullptr;
+  float* d_bias = nullptr;
+  int64_t macs_per_pos = 0;
+};
+
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+
+// [cout_pad][ktot] K-major bf16 weights -> 2-D map, box = 64 k-elements x `rows` output channels, SWIZZLE_128B.
+int encode_w_map(CUtensorMap* m, const void* ptr, int ktot, int cout_pad, int rows);
+int num_sms();

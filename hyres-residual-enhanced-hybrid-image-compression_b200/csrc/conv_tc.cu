@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "conv_priv.h"
 #include "host_util.h"
 #include "hyres_b200.h"
 
@@ -37,19 +38,7 @@ namespace {
 
 constexpr int kTileW = 8;     // output columns per tile
 constexpr int kSubH = 16;     // output rows per 128-row accumulator
-constexpr int kMaxTaps = 5;   // vertical taps per patch
 constexpr int kThreads = 192;
-
-struct TapGroup {
-  int32_t src;      // 0: x0, 1: x1
-  int32_t c_off;    // inner (channel) coordinate of the box
-  int32_t dw;       // column coordinate offset relative to the tile origin
-  int32_t dh;       // row coordinate offset of the patch start
-  int32_t hpar;     // coordinate along the parity dimension (stride-2 view)
-  int32_t ntaps;    // B tiles consumed against this patch
-  int32_t kslot0;   // first 64-wide K slot in the packed weights
-  int32_t tap_row[kMaxTaps];  // row shift (in patch rows) of each tap
-};
 
 struct alignas(64) ConvParams {
   CUtensorMap mapA0;
@@ -382,24 +371,6 @@ __global__ void __launch_bounds__(kThreads, 3) conv_tc_kernel(const __grid_const
 // host side
 // ----------------------------------------------------------------------------
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
 int choose_bn(int cout) {
   if (cout <= 16) return 16;
   int pad = (cout + 15) / 16 * 16;
@@ -409,21 +380,6 @@ int choose_bn(int cout) {
 }
 
 }  // namespace
-
-struct hyres_conv {
-  int kind, cin0, cin1, w_cin_total, cout, R, S, stride, pad, dil;
-  int BN, cout_pad, ktot, nphase, extra_rows;
-  int ph_begin[4], ph_count[4];
-  std::vector<TapGroup> groups;
-  std::vector<uint8_t> tap_mask;
-  // k-slot -> (src, chunk, r, s) for weight packing
-  struct Slot { int src, chunk, r, s; };
-  std::vector<Slot> slots;
-  TapGroup* d_groups = nullptr;
-  __nv_bfloat16* d_w = nullptr;
-  float* d_bias = nullptr;
-  int64_t macs_per_pos = 0;
-};
 
 namespace {
 
@@ -562,6 +518,8 @@ int encode_act_map(CUtensorMap* m, const void* ptr, int C, int B, int H, int W, 
   return HYRES_OK;
 }
 
+}  // namespace
+
 int encode_w_map(CUtensorMap* m, const void* ptr, int ktot, int cout_pad, int bn) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return hy_fail(HYRES_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
@@ -590,8 +548,6 @@ int num_sms() {
   }
   return n;
 }
-
-}  // namespace
 
 extern "C" {
 

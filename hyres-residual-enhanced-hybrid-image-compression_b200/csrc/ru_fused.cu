@@ -1,0 +1,441 @@
+// Fused bottleneck residual unit on Blackwell tensor cores:
+//
+//     out = [ReLU]( x + conv1x1_{64->128}( ReLU( conv3x3_{64->64}( ReLU( conv1x1_{128->64}(x) ))))) )
+//
+// i.e. the reference's ResidualUnit (models/layers/attention.py:16-33, final ReLU) and
+// compressai's ResidualBottleneckBlock (models/checkerboard.py:38,42,51,55, no final ReLU)
+// at C = 128.  These 16 blocks are 40 % of the MACs of the codec and, launched as three
+// convolutions each, are bound by HBM round trips of the two 64-channel intermediates and by
+// per-tile latency.  Here one persistent CTA per SM keeps all three weight matrices (104 KB)
+// resident in shared memory and walks 16x8 output tiles:
+//
+//   TMA   x halo patch 18x10 positions x 128 ch (two 64-ch SWIZZLE_128B chunks, image borders
+//         zero-filled by the TMA unit), double buffered;
+//   G1    tcgen05.mma  [180(->256) x 128] . W1^T -> TMEM (2 x 64 columns)
+//   E1    TMEM -> +bias, ReLU, zero outside the image, bf16 -> smem patch t1 [180][64] (swizzled)
+//   G2    nine taps, each ONE descriptor on the same t1 patch: start row (r*10+s), 8-row
+//         groups 10 rows (1280 B) apart -> TMEM (64 columns).  No im2col, no duplicate of t1.
+//   E2    TMEM -> +bias, ReLU, bf16 -> smem t2 [128][64]
+//   G3    tcgen05.mma  [128 x 64] . W3^T -> TMEM (128 columns)
+//   E3    TMEM -> +bias + skip (centre of the x patch, still in smem) [ReLU] -> bf16 staged
+//         over the x buffer -> TMA store (clipped at the image edge by the TMA unit).
+//
+// HBM traffic is the algorithmic minimum (read x once + halo, write out once); the next
+// tile's TMA load and the previous tile's TMA store overlap the three GEMMs.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "conv_priv.h"
+#include "host_util.h"
+#include "hyres_b200.h"
+
+namespace {
+
+constexpr int kTH = 16, kTW = 8;        // output tile
+constexpr int kPW = 10;                 // patch width (positions)
+constexpr int kNP = 180;                // patch positions (18 x 10)
+constexpr int kThreads = 224;           // warps 0-3 epilogue, 4 TMA load, 5 MMA, 6 TMA store
+
+// shared-memory map (bytes from the 1024-aligned base)
+constexpr uint32_t kW1 = 0;             // [2 k-chunks][64 n][128 B]
+constexpr uint32_t kW2 = 16384;         // [9 taps][64 n][128 B]
+constexpr uint32_t kW3 = 90112;         // [128 n][128 B]
+constexpr uint32_t kWBytes = 106496;
+constexpr uint32_t kX0 = 106496;        // 2 buffers x 2 chunks
+constexpr uint32_t kXChunk = 23552;     // 180 rows x 128 B, padded to a multiple of 1024
+constexpr uint32_t kXStride = 2 * kXChunk;
+constexpr uint32_t kXBytes = kNP * 128; // bytes one TMA chunk load delivers
+constexpr uint32_t kS = kX0 + 2 * kXStride;  // t1 patch, then t2
+constexpr uint32_t kBars = kS + kXChunk;
+constexpr uint32_t kBias = kBars + 256;
+constexpr uint32_t kSmemUsed = kBias + 1024;
+
+enum { W_FULL = 0, X_FULL = 1, X_EMPTY = 3, G1_DONE = 5, T1_READY = 6, G2_DONE = 7, T2_READY = 8, G3_DONE = 9,
+       ACC_FREE = 10, STAGED = 11, NUM_BARS = 12 };
+
+struct alignas(64) RuParams {
+  CUtensorMap mapX, mapOut, mapW1, mapW2, mapW3;
+  const float* b1;
+  const float* b2;
+  const float* b3;
+  int32_t H, W, tiles_w, tiles_per_img, ntiles, final_relu;
+};
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// 32 accumulator columns -> (+bias) ReLU -> 32 bf16 in q[0..3]; `keep` = 0 zeroes the row.
+__device__ __forceinline__ void bias_relu_pack32(const uint32_t (&r)[32], uint32_t bias_addr, bool keep, uint4 (&q)[4]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 ba = lds_f4(bias_addr + g * 32);
+    const float4 bb = lds_f4(bias_addr + g * 32 + 16);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+    v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w;
+    v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = keep ? fmaxf(v[i], 0.f) : 0.f;
+    q[g].x = hy::pack_bf16(v[0], v[1]);
+    q[g].y = hy::pack_bf16(v[2], v[3]);
+    q[g].z = hy::pack_bf16(v[4], v[5]);
+    q[g].w = hy::pack_bf16(v[6], v[7]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_constant__ RuParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto bar = [&](int i) { return base + kBars + 8u * i; };
+  const uint32_t tmem_slot = base + kBars + 128;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    hy::mbar_init(bar(W_FULL), 1);
+    for (int i = 0; i < 2; ++i) {
+      hy::mbar_init(bar(X_FULL + i), 1);
+      hy::mbar_init(bar(X_EMPTY + i), 1);
+    }
+    hy::mbar_init(bar(G1_DONE), 1);
+    hy::mbar_init(bar(G2_DONE), 1);
+    hy::mbar_init(bar(G3_DONE), 1);
+    hy::mbar_init(bar(T1_READY), 128);
+    hy::mbar_init(bar(T2_READY), 128);
+    hy::mbar_init(bar(ACC_FREE), 128);
+    hy::mbar_init(bar(STAGED), 128);
+    hy::mbar_fence_init();
+  }
+  {
+    // biases -> smem: b1 [64] | b2 [64] | b3 [128]
+    float* sb = reinterpret_cast<float*>(smem_raw + (base - hy::smem_u32(smem_raw)) + kBias);
+    for (int i = threadIdx.x; i < 256; i += kThreads)
+      sb[i] = i < 64 ? __ldg(p.b1 + i) : (i < 128 ? __ldg(p.b2 + i - 64) : __ldg(p.b3 + i - 128));
+  }
+  if (warp == 4 && lane == 0) {
+    hy::tma_prefetch_desc(&p.mapX);
+    hy::tma_prefetch_desc(&p.mapW1);
+    hy::tma_prefetch_desc(&p.mapW2);
+    hy::tma_prefetch_desc(&p.mapW3);
+  }
+  if (warp == 6 && lane == 0) hy::tma_prefetch_desc(&p.mapOut);
+  if (warp == 5) {
+    hy::tmem_alloc(tmem_slot, 256);
+    hy::tmem_relinquish();
+  }
+  hy::tc_fence_before();
+  __syncthreads();
+  hy::tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto tile_origin = [&](int t, int& b_img, int& h0, int& w0) {
+    b_img = t / p.tiles_per_img;
+    const int rem = t - b_img * p.tiles_per_img;
+    const int th = rem / p.tiles_w;
+    h0 = th * kTH;
+    w0 = (rem - th * p.tiles_w) * kTW;
+  };
+
+  if (warp == 4) {
+    // ============================ TMA load producer ============================
+    if (lane == 0) {
+      hy::mbar_arrive_expect_tx(bar(W_FULL), kWBytes);
+      hy::tma_load_2d(base + kW1, &p.mapW1, bar(W_FULL), 0, 0);
+      hy::tma_load_2d(base + kW1 + 8192, &p.mapW1, bar(W_FULL), 64, 0);
+      for (int s = 0; s < 9; ++s) hy::tma_load_2d(base + kW2 + s * 8192, &p.mapW2, bar(W_FULL), s * 64, 0);
+      hy::tma_load_2d(base + kW3, &p.mapW3, bar(W_FULL), 0, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        int b_img, h0, w0;
+        tile_origin(t, b_img, h0, w0);
+        hy::mbar_wait(bar(X_EMPTY + b), ph ^ 1u);
+        hy::mbar_arrive_expect_tx(bar(X_FULL + b), 2 * kXBytes);
+        const uint32_t xb = base + kX0 + b * kXStride;
+        hy::tma_load_4d(xb, &p.mapX, bar(X_FULL + b), 0, w0 - 1, h0 - 1, b_img);
+        hy::tma_load_4d(xb + kXChunk, &p.mapX, bar(X_FULL + b), 64, w0 - 1, h0 - 1, b_img);
+      }
+    }
+  } else if (warp == 5) {
+    // ============================ MMA issuer ============================
+    if (lane == 0) {
+      const uint32_t idesc64 = hy::umma_idesc_bf16(128, 64);
+      const uint32_t idesc128 = hy::umma_idesc_bf16(128, 128);
+      hy::mbar_wait(bar(W_FULL), 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        const uint32_t ph = it & 1;
+        const uint32_t xb = base + kX0 + b * kXStride;
+        hy::mbar_wait(bar(X_FULL + b), (it >> 1) & 1);
+        if (it > 0) hy::mbar_wait(bar(ACC_FREE), (it - 1) & 1);  // E3 of the previous tile drained columns [0,128)
+        hy::tc_fence_after();
+        // G1: t1 = x . W1^T over the 180-position patch (2 blocks of 128 rows; rows >= 180 unused)
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              hy::umma_bf16(tmem_base + blk * 64, hy::umma_desc_sw128(xb + kc * kXChunk + blk * 16384 + k * 32),
+                            hy::umma_desc_sw128(base + kW1 + kc * 8192 + k * 32), idesc64, (kc | k) ? 1u : 0u);
+        hy::umma_commit(bar(G1_DONE));
+        // G2: 3x3 over the t1 patch in smem; tap (r,s) = start row r*10+s, row groups 1280 B apart
+        hy::mbar_wait(bar(T1_READY), ph);
+        hy::tc_fence_after();
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              hy::umma_bf16(tmem_base + 128,
+                            hy::umma_desc_sw128(base + kS + (r * kPW + s) * 128 + k * 32, kPW * 128),
+                            hy::umma_desc_sw128(base + kW2 + (s * 3 + r) * 8192 + k * 32), idesc64,
+                            (s | r | k) ? 1u : 0u);
+        hy::umma_commit(bar(G2_DONE));
+        // G3: 1x1 expand
+        hy::mbar_wait(bar(T2_READY), ph);
+        hy::tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          hy::umma_bf16(tmem_base, hy::umma_desc_sw128(base + kS + k * 32),
+                        hy::umma_desc_sw128(base + kW3 + k * 32), idesc128, k ? 1u : 0u);
+        hy::umma_commit(bar(G3_DONE));
+      }
+    }
+  } else if (warp == 6) {
+    // ============================ TMA store ============================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+        const int b = it & 1;
+        int b_img, h0, w0;
+        tile_origin(t, b_img, h0, w0);
+        const uint32_t xb = base + kX0 + b * kXStride;
+        hy::mbar_wait(bar(STAGED), it & 1);
+        hy::tma_store_4d(&p.mapOut, xb, 0, w0, h0, b_img);
+        hy::tma_store_4d(&p.mapOut, xb + kXChunk, 64, w0, h0, b_img);
+        hy::tma_store_commit();
+        hy::tma_store_wait_read<0>();           // smem of this x buffer may be refilled
+        hy::mbar_arrive(bar(X_EMPTY + b));
+      }
+      hy::tma_store_wait_all<0>();
+    }
+  } else {
+    // ============================ epilogue warps 0-3 ============================
+    const int tid = threadIdx.x;  // TMEM lane == GEMM row
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t sbias = base + kBias;
+    const int ti = tid >> 3, tj = tid & 7;
+    const int pc = (ti + 1) * kPW + tj + 1;  // this thread's output position inside the x patch
+    int it = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+      const int b = it & 1;
+      const uint32_t ph = it & 1;
+      int b_img, h0, w0;
+      tile_origin(t, b_img, h0, w0);
+      const uint32_t xb = base + kX0 + b * kXStride;
+      uint32_t ra[32], rb[32];
+      uint4 q[4];
+
+      // ---- E1: t1 patch ----
+      hy::mbar_wait(bar(G1_DONE), ph);
+      hy::tc_fence_after();
+#pragma unroll
+      for (int blk = 0; blk < 2; ++blk) {
+        if (blk == 1 && warp >= 2) break;  // rows 192.. do not exist (warp-uniform)
+        const int pp = blk * 128 + tid;
+        const int pr = pp / kPW, pq = pp - pr * kPW;
+        const int hh = h0 - 1 + pr, ww = w0 - 1 + pq;
+        const bool live = pp < kNP;
+        const bool keep = live && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;  // conv2 zero-pads t1, not x
+        const uint32_t row = base + kS + pp * 128;
+        const uint32_t sw = pp & 7;
+        hy::tmem_ld32(t_lane + blk * 64, ra);
+        hy::tmem_ld_fence32(ra);
+        hy::tmem_ld32(t_lane + blk * 64 + 32, rb);
+        bias_relu_pack32(ra, sbias, keep, q);
+        if (live) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) sts128(row + ((g ^ sw) << 4), q[g]);
+        }
+        hy::tmem_ld_fence32(rb);
+        bias_relu_pack32(rb, sbias + 128, keep, q);
+        if (live) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) sts128(row + (((4 + g) ^ sw) << 4), q[g]);
+        }
+      }
+      hy::fence_async_smem();
+      hy::tc_fence_before();
+      hy::mbar_arrive(bar(T1_READY));
+
+      // ---- E2: t2 ----
+      hy::mbar_wait(bar(G2_DONE), ph);
+      hy::tc_fence_after();
+      {
+        const uint32_t row = base + kS + tid * 128;
+        const uint32_t sw = tid & 7;
+        hy::tmem_ld32(t_lane + 128, ra);
+        hy::tmem_ld_fence32(ra);
+        hy::tmem_ld32(t_lane + 128 + 32, rb);
+        bias_relu_pack32(ra, sbias + 256, true, q);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sts128(row + ((g ^ sw) << 4), q[g]);
+        hy::tmem_ld_fence32(rb);
+        bias_relu_pack32(rb, sbias + 256 + 128, true, q);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sts128(row + (((4 + g) ^ sw) << 4), q[g]);
+      }
+      hy::fence_async_smem();
+      hy::tc_fence_before();
+      hy::mbar_arrive(bar(T2_READY));
+
+      // ---- E3: + bias + skip, stage over the x buffer, hand to the store warp ----
+      hy::mbar_wait(bar(G3_DONE), ph);
+      hy::mbar_wait(bar(X_FULL + b), (it >> 1) & 1);  // (already complete) acquire the TMA-written patch
+      hy::tc_fence_after();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t skip_row = xb + h * kXChunk + pc * 128;
+        const uint32_t skip_sw = pc & 7;
+        uint4 o[8];
+        hy::tmem_ld32(t_lane + h * 64, ra);
+        hy::tmem_ld_fence32(ra);
+        hy::tmem_ld32(t_lane + h * 64 + 32, rb);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half == 1) hy::tmem_ld_fence32(rb);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int j = half * 4 + g;  // 16-byte chunk (8 channels) of the 64-channel row
+            const uint4 sk = lds128(skip_row + ((j ^ skip_sw) << 4));
+            const uint32_t bias_addr = sbias + 512 + (h * 64 + j * 8) * 4;
+            const float4 ba = lds_f4(bias_addr), bb = lds_f4(bias_addr + 16);
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(half ? rb[g * 8 + i] : ra[g * 8 + i]);
+            v[0] += ba.x + hy::bf16_lo(sk.x); v[1] += ba.y + hy::bf16_hi(sk.x);
+            v[2] += ba.z + hy::bf16_lo(sk.y); v[3] += ba.w + hy::bf16_hi(sk.y);
+            v[4] += bb.x + hy::bf16_lo(sk.z); v[5] += bb.y + hy::bf16_hi(sk.z);
+            v[6] += bb.z + hy::bf16_lo(sk.w); v[7] += bb.w + hy::bf16_hi(sk.w);
+            if (p.final_relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            o[j].x = hy::pack_bf16(v[0], v[1]);
+            o[j].y = hy::pack_bf16(v[2], v[3]);
+            o[j].z = hy::pack_bf16(v[4], v[5]);
+            o[j].w = hy::pack_bf16(v[6], v[7]);
+          }
+        }
+        if (h == 1) {
+          hy::tc_fence_before();
+          hy::mbar_arrive(bar(ACC_FREE));  // TMEM columns [0,128) may be overwritten by the next G1
+        }
+        // the staging rows overlap other threads' skip rows of this chunk: all reads first
+        hy::named_bar_sync(1, 128);
+        const uint32_t st_row = xb + h * kXChunk + tid * 128;
+        const uint32_t st_sw = tid & 7;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sts128(st_row + ((j ^ st_sw) << 4), o[j]);
+      }
+      hy::fence_async_smem();
+      hy::mbar_arrive(bar(STAGED));
+    }
+  }
+
+  hy::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    hy::tc_fence_after();
+    hy::tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int encode_act4d(CUtensorMap* m, const void* ptr, int C, int ld, int B, int H, int W, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return hy_fail(HYRES_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled(ru act C=%d ld=%d B=%d H=%d W=%d) -> %d", C, ld, B, H, W, (int)r);
+    return hy_fail(HYRES_ERR_DRIVER, msg);
+  }
+  return HYRES_OK;
+}
+
+bool is_conv(const hyres_conv* c, int cin, int cout, int k) {
+  return c && c->kind == HYRES_CONV && c->cin0 == cin && c->cin1 == 0 && c->cout == cout && c->R == k && c->S == k &&
+         c->stride == 1 && c->dil == 1 && c->pad == k / 2 && c->tap_mask.empty();
+}
+
+}  // namespace
+
+extern "C" {
+
+int hyres_ru_supported(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c3) {
+  return is_conv(c1, 128, 64, 1) && is_conv(c2, 64, 64, 3) && is_conv(c3, 64, 128, 1) ? 1 : 0;
+}
+
+int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c3, const hyres_ru_io* io,
+                 void* stream_v) {
+  if (!io || !io->x || !io->out) return hy_fail(HYRES_ERR_ARG, "ru_run: null argument");
+  if (!hyres_ru_supported(c1, c2, c3))
+    return hy_fail(HYRES_ERR_UNSUPPORTED, "ru_run: needs 1x1 128->64, 3x3 64->64 (stride 1, pad 1), 1x1 64->128");
+  if (io->B <= 0 || io->H <= 0 || io->W <= 0) return hy_fail(HYRES_ERR_ARG, "ru_run: empty input");
+  if (io->ld_x < 128 || io->ld_out < 128 || (io->ld_x % 8) || (io->ld_out % 8))
+    return hy_fail(HYRES_ERR_ARG, "ru_run: channel strides must be >= 128 and multiples of 8");
+  if (io->x == io->out) return hy_fail(HYRES_ERR_ARG, "ru_run: in-place operation is not supported (halo reads)");
+  RuParams p;
+  memset(&p, 0, sizeof p);
+  int rc = encode_act4d(&p.mapX, io->x, 128, io->ld_x, io->B, io->H, io->W, kPW, kTH + 2);
+  if (rc != HYRES_OK) return rc;
+  rc = encode_act4d(&p.mapOut, io->out, 128, io->ld_out, io->B, io->H, io->W, kTW, kTH);
+  if (rc != HYRES_OK) return rc;
+  if ((rc = encode_w_map(&p.mapW1, c1->d_w, c1->ktot, c1->cout_pad, 64)) != HYRES_OK) return rc;
+  if ((rc = encode_w_map(&p.mapW2, c2->d_w, c2->ktot, c2->cout_pad, 64)) != HYRES_OK) return rc;
+  if ((rc = encode_w_map(&p.mapW3, c3->d_w, c3->ktot, c3->cout_pad, 128)) != HYRES_OK) return rc;
+  p.b1 = c1->d_bias; p.b2 = c2->d_bias; p.b3 = c3->d_bias;
+  p.H = io->H; p.W = io->W;
+  p.tiles_w = (io->W + kTW - 1) / kTW;
+  p.tiles_per_img = p.tiles_w * ((io->H + kTH - 1) / kTH);
+  p.ntiles = p.tiles_per_img * io->B;
+  p.final_relu = io->final_relu ? 1 : 0;
+  const int smem = kSmemUsed + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const int grid = std::min(p.ntiles, num_sms());
+  hy_count_launch();
+  ru_fused_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+}  // extern "C"

@@ -66,11 +66,14 @@ class _RU:
     def __init__(self, c1, c2, c3, final_relu):
         self.c1, self.c2, self.c3 = _conv(c1), _conv(c2), _conv(c3)
         self.final_act = ACT_RELU if final_relu else ACT_NONE
+        self.fused = ops.ru_supported(self.c1.layer, self.c2.layer, self.c3.layer)
 
     def layers(self):
         return [self.c1, self.c2, self.c3]
 
     def __call__(self, x, out_sq=False):
+        if self.fused and not out_sq:
+            return ops.ru_fused(x, self.c1.layer, self.c2.layer, self.c3.layer, self.final_act == ACT_RELU)
         a, _, _ = self.c1(x, act=ACT_RELU)
         b, _, _ = self.c2(a, act=ACT_RELU)
         o, sq, _ = self.c3(b, epi=EPI_ADD, aux0=x, act=self.final_act, out_sq=out_sq)

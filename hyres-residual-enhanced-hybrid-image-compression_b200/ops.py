@@ -187,6 +187,33 @@ class ConvLayer:
             raise ValueError(f"{name}: pixel stride must be uniform (a channel slice of a dense NHWC tensor)")
 
 
+def ru_supported(c1, c2, c3):
+    """True when the three layers form the C=128 bottleneck the fused kernel implements."""
+    return bool(L.lib().hyres_ru_supported(c1._h, c2._h, c3._h))
+
+
+def ru_fused(x, c1, c2, c3, final_relu, out=None):
+    """out = [ReLU](x + c3(ReLU(c2(ReLU(c1(x)))))) in one persistent kernel (csrc/ru_fused.cu)."""
+    _chk_nhwc(x, "x")
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    io = L.RuIO()
+    io.x, io.ld_x, io.out, io.ld_out = x.data_ptr(), x.stride(2), out.data_ptr(), out.stride(2)
+    io.B, io.H, io.W, io.final_relu = B, H, W, 1 if final_relu else 0
+    if ConvLayer._prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib().hyres_ru_run(c1._h, c2._h, c3._h, C.byref(io), _stream()), "hyres_ru_run")
+        e1.record()
+        ConvLayer._prof.append((e0, e1))
+        ConvLayer._prof_info.append(dict(kind="ru", cin=Cc, cout=Cc, k=3, stride=1, dil=1, B=B, H=H, W=W, OH=H, OW=W,
+                                         epi=EPI_ADD, f32=False, sq=False))
+    else:
+        L.check(L.lib().hyres_ru_run(c1._h, c2._h, c3._h, C.byref(io), _stream()), "hyres_ru_run")
+    return out
+
+
 # --------------------------------------------------------------------------------------
 # memory-bound kernels
 # --------------------------------------------------------------------------------------

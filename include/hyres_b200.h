@@ -118,6 +118,25 @@ typedef struct {
 int hyres_conv_out_size(const hyres_conv* c, int H, int W, int* OH, int* OW);
 int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream);
 
+/* Fused bottleneck residual unit at C = 128 (one persistent kernel instead of three
+ * convolution launches; the two 64-channel intermediates never leave the SM):
+ *   out = [ReLU](x + c3(ReLU(c2(ReLU(c1(x))))))
+ * c1: 1x1 128->64, c2: 3x3 64->64 (stride 1, pad 1), c3: 1x1 64->128, created with
+ * hyres_conv_create. Replaces ResidualUnit.forward (models/layers/attention.py:16-33,
+ * final_relu = 1) and compressai ResidualBottleneckBlock.forward
+ * (models/checkerboard.py:38,42,51,55, final_relu = 0). */
+typedef struct {
+  const void* x; /* bf16 NHWC [B,H,W,128], channel stride ld_x */
+  int ld_x;
+  void* out;     /* bf16 NHWC [B,H,W,128], channel stride ld_out; must not alias x */
+  int ld_out;
+  int B, H, W;
+  int final_relu;
+} hyres_ru_io;
+int hyres_ru_supported(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c3);
+int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c3,
+                 const hyres_ru_io* io, void* stream);
+
 /* ------------------------------------------------------------------------- */
 /* Memory-bound kernels                                                       */
 /* ------------------------------------------------------------------------- */

@@ -42,3 +42,30 @@ def test_conv_argument_errors(build_lib):
     o, _, _ = layer(x)
     torch.cuda.synchronize()
     assert o.shape == (1, 8, 8, 64) and float(o.abs().max()) == 0.0
+
+
+import check_ru  # noqa: E402
+
+
+@pytest.mark.parametrize("idx", range(len(check_ru.CASES)), ids=[c["name"] for c in check_ru.CASES])
+def test_fused_residual_unit(build_lib, idx):
+    """csrc/ru_fused.cu (ResidualUnit / ResidualBottleneckBlock in one kernel) against the torch fp32
+    restatement with bf16 storage of the two intermediates, and against the three-launch conv path;
+    tolerance 1e-2 of the output range (one bf16 rounding of t1, t2 and the result)."""
+    r = check_ru.run_case(idx)
+    assert r["ok"], r
+
+
+def test_fused_residual_unit_argument_errors(build_lib):
+    import torch
+    from hyres_b200 import _lib, ops
+    c1 = ops.ConvLayer(torch.randn(64, 128, 1, 1), None)
+    c2 = ops.ConvLayer(torch.randn(64, 64, 3, 3), None, pad=1)
+    c3 = ops.ConvLayer(torch.randn(128, 64, 1, 1), None)
+    bad = ops.ConvLayer(torch.randn(64, 64, 3, 3), None, pad=2, dil=2)
+    assert ops.ru_supported(c1, c2, c3) and not ops.ru_supported(c1, bad, c3)
+    x = torch.zeros(1, 16, 8, 128, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(_lib.HyresError):
+        ops.ru_fused(x, c1, bad, c3, True)
+    with pytest.raises(_lib.HyresError):
+        ops.ru_fused(x, c1, c2, c3, True, out=x)  # in place
