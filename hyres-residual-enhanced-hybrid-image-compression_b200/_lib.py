@@ -30,7 +30,7 @@ class ConvIO(C.Structure):
         ("out_sq", C.c_void_p), ("ld_sq", C.c_int),
         ("out_f32", C.c_void_p),
         ("f32_sb", C.c_int64), ("f32_sh", C.c_int64), ("f32_sw", C.c_int64), ("f32_sc", C.c_int64),
-        ("mt_hint", C.c_int),
+        ("mt_hint", C.c_int), ("ld_x0", C.c_int), ("x0_square", C.c_int),
     ]
 
 

@@ -9,6 +9,8 @@
 #include <mutex>
 #include <vector>
 
+#include "hyres_b200.h"
+
 constexpr int kMaxTaps = 5;   // vertical taps per patch
 
 struct TapGroup {
@@ -61,3 +63,6 @@ inline EncodeTiledFn get_encode_fn() {
 // [cout_pad][ktot] K-major bf16 weights -> 2-D map, box = 64 k-elements x `rows` output channels, SWIZZLE_128B.
 int encode_w_map(CUtensorMap* m, const void* ptr, int ktot, int cout_pad, int rows);
 int num_sms();
+// conv_res.cu: persistent kernel with shared-memory-resident weights; *handled = 0 when the layer
+// does not qualify (the caller then uses the streaming kernel of conv_tc.cu).
+int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream, int* handled);

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -629,6 +630,16 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   if (io->out_bf16 && (io->ld_out % 8)) return hy_fail(HYRES_ERR_ARG, "conv_run: ld_out must be a multiple of 8");
   if (io->out_sq && (io->ld_sq % 8)) return hy_fail(HYRES_ERR_ARG, "conv_run: ld_sq must be a multiple of 8");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+
+  // layers whose weights fit in shared memory run on the persistent resident-weights kernel
+  static const bool no_res = getenv("HYRES_NO_RES") != nullptr;
+  if (!no_res) {
+    int handled = 0;
+    const int rc = conv_res_try_run(c, io, stream, &handled);
+    if (rc != HYRES_OK || handled) return rc;
+  }
+  if (io->x0_square) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: x0_square is only available on resident-weight 1x1 layers");
+  if (io->ld_x0 && io->ld_x0 != c->cin0) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: strided x0 is only available on resident-weight layers");
 
   ConvParams p;
   memset(&p, 0, sizeof p);

@@ -7,8 +7,8 @@ element-wise work folded into conv epilogues:
   * ReLU / PReLU / clamp, bias                      -> activation field of the epilogue
   * ResidualUnit / ResidualBottleneckBlock skips    -> HYRES_EPI_ADD (+ReLU)
   * AttentionBlock ``a*sigmoid(b)+x``               -> HYRES_EPI_GATE on conv_b.3
-  * GDN / IGDN                                      -> the producer also writes x^2 (out_sq); the
-                                                       gamma 1x1 GEMM ends in HYRES_EPI_(I)GDN
+  * GDN / IGDN                                      -> one 1x1 GEMM launch that squares its own input tile
+                                                       on chip (x0_square) and ends in HYRES_EPI_(I)GDN
   * SpatialAttention multiply                       -> HYRES_EPI_PIXSCALE on fusion.0
   * g_a.0 / refine.conv_in (3 input channels)       -> im2col + 1x1 GEMM
   * ``torch.cat([latent, ctx])``                    -> two-input conv (never materialised); the
@@ -192,12 +192,12 @@ class CodecEngine:
 
     # -- stages (NHWC bf16 in / out unless noted) --
     def g_a(self, a_im2col):
-        t, tsq, _ = self.ga0(a_im2col, out_sq=True)
-        t, _, _ = self.ga1(tsq, epi=EPI_GDN, aux0=t)
+        t, _, _ = self.ga0(a_im2col)
+        t, _, _ = self.ga1(t, epi=EPI_GDN, aux0=t, x0_square=True)
         t = self.ga2(t)
         t = self.ga3(t)
-        t, tsq, _ = self.ga4(t, out_sq=True)
-        t, _, _ = self.ga5(tsq, epi=EPI_GDN, aux0=t)
+        t, _, _ = self.ga4(t)
+        t, _, _ = self.ga5(t, epi=EPI_GDN, aux0=t, x0_square=True)
         t = self.ga6(t)
         t, _, _ = self.ga7(t)
         return self.ga8(t, out_f32="nhwc")  # (y bf16, y fp32)
@@ -230,12 +230,12 @@ class CodecEngine:
     def g_s(self, y_hat16, clamp=False):
         t = self.gs0(y_hat16)
         t, _, _ = self.gs1(t)
-        t, tsq = self.gs2(t, out_sq=True)
-        t, _, _ = self.gs3(tsq, epi=EPI_IGDN, aux0=t)
+        t = self.gs2(t)
+        t, _, _ = self.gs3(t, epi=EPI_IGDN, aux0=t, x0_square=True)
         t, _, _ = self.gs4(t)
         t = self.gs5(t)
-        t, tsq = self.gs6(t, out_sq=True)
-        t, _, _ = self.gs7(tsq, epi=EPI_IGDN, aux0=t)
+        t = self.gs6(t)
+        t, _, _ = self.gs7(t, epi=EPI_IGDN, aux0=t, x0_square=True)
         _, _, x = self.gs8(t, out_bf16=False, out_f32="nchw", act=ACT_CLAMP01 if clamp else ACT_NONE)
         return x  # fp32 NCHW [B,3,H,W]
 

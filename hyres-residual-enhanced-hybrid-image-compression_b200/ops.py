@@ -95,7 +95,7 @@ class ConvLayer:
         return oh.value, ow.value
 
     def __call__(self, x0, x1=None, epi=EPI_LINEAR, act=ACT_NONE, slope=0.0, aux0=None, aux1=None,
-                 pixscale=None, out_bf16=True, out_sq=False, out_f32=None, mt=0):
+                 pixscale=None, out_bf16=True, out_sq=False, out_f32=None, mt=0, x0_square=False):
         """Run the layer.
 
         out_bf16 / out_sq: True (allocate), False, or a preallocated NHWC tensor (its last
@@ -163,6 +163,7 @@ class ConvLayer:
             io.out_f32 = view.data_ptr()
             io.f32_sb, io.f32_sh, io.f32_sw, io.f32_sc = view.stride()
         io.mt_hint = mt
+        io.x0_square = 1 if x0_square else 0
         keep += [o16, osq, o32]
         if ConvLayer._prof is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -113,6 +113,9 @@ typedef struct {
   float* out_f32; /* fp32, arbitrary strides (elements), may be NULL */
   int64_t f32_sb, f32_sh, f32_sw, f32_sc;
   int mt_hint; /* 0 = auto; else force 1/2/4 sub-tiles per CTA */
+  int ld_x0;   /* channel stride of x0 in elements; 0 = dense (cin0) */
+  int x0_square; /* 1: the layer consumes x0*x0 (GDN: conv2d(x^2, gamma, beta)), squared on chip;
+                    1x1 layers only */
 } hyres_conv_io;
 
 int hyres_conv_out_size(const hyres_conv* c, int H, int W, int* OH, int* OW);

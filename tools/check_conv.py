@@ -37,12 +37,25 @@ CASES = [
     dict(name="epi_gdn", cin0=128, cout=128, k=1, B=1, H=32, W=16, epi="gdn"),
     dict(name="epi_igdn", cin0=128, cout=128, k=1, B=1, H=32, W=16, epi="igdn"),
     dict(name="epi_pixscale_prelu", cin0=192, cout=64, k=1, B=1, H=32, W=16, epi="pix", act="prelu"),
+    dict(name="gdn_x0_square", cin0=128, cout=128, k=1, B=2, H=40, W=20, epi="gdn", square=True),
+    dict(name="igdn_x0_square", cin0=128, cout=128, k=1, B=1, H=16, W=24, epi="igdn", square=True),
+    dict(name="epi_gate_ragged", cin0=128, cout=128, k=1, B=3, H=24, W=20, epi="gate"),
+    dict(name="epi_gate_192_f32", cin0=192, cout=192, k=1, B=2, H=16, W=24, epi="gate", f32="nhwc"),
+    dict(name="3x3_64_64_many_tiles", cin0=64, cout=64, k=3, B=3, H=80, W=72, act="prelu"),
+    dict(name="3x3_dil2_ragged", cin0=64, cout=64, k=3, dil=2, B=2, H=40, W=20, act="prelu"),
+    dict(name="1x1_192_96_relu", cin0=192, cout=96, k=1, B=2, H=16, W=24, act="relu"),
+    dict(name="1x1_96_192_add_relu", cin0=96, cout=192, k=1, B=2, H=16, W=24, epi="add", act="relu"),
+    dict(name="deconv_128_3_many_tiles", kind=1, cin0=128, cout=3, k=5, B=2, H=40, W=36, f32="nchw", bf16=False, act="clamp"),
     dict(name="out_sq", cin0=128, cout=128, k=1, B=1, H=16, W=16, sq=True),
     dict(name="3x3_64_3_clamp", cin0=64, cout=3, k=3, B=1, H=32, W=16, act="clamp", f32="nchw", bf16=False),
     dict(name="mt2_3x3", cin0=64, cout=64, k=3, B=1, H=64, W=32, mt=2),
     dict(name="mt4_3x3", cin0=64, cout=64, k=3, B=1, H=128, W=32, mt=4),
     dict(name="mt2_5x5s2", cin0=128, cout=128, k=5, stride=2, B=1, H=128, W=64, mt=2),
     dict(name="mt4_deconv", kind=1, cin0=128, cout=128, k=5, B=1, H=64, W=32, mt=4),
+    dict(name="auto_big_gate", cin0=128, cout=128, k=1, B=4, H=256, W=384, epi="gate", perf=True),
+    dict(name="auto_big_1x1_192_64_pix", cin0=192, cout=64, k=1, B=2, H=512, W=768, epi="pix", act="prelu", perf=True),
+    dict(name="auto_big_deconv_128_3", kind=1, cin0=128, cout=3, k=5, B=4, H=256, W=384, f32="nchw", bf16=False, perf=True),
+    dict(name="auto_big_gdn_sq", cin0=128, cout=128, k=1, B=4, H=256, W=384, epi="gdn", square=True, perf=True),
     dict(name="auto_big_3x3", cin0=64, cout=64, k=3, B=4, H=256, W=384, perf=True),
     dict(name="auto_big_1x1_128_64", cin0=128, cout=64, k=1, B=4, H=256, W=384, perf=True),
     dict(name="auto_big_5x5s2", cin0=128, cout=128, k=5, stride=2, B=4, H=256, W=384, perf=True),
@@ -89,6 +102,8 @@ def run_case(idx):
     aux0 = aux1 = pix = None
     if epi in ("add", "gate", "gdn", "igdn"):
         aux0 = torch.randn(B, OH, OW, cout, generator=g).to(dev).bfloat16()
+    if c.get("square"):
+        aux0 = x0
     if epi == "gate":
         aux1 = torch.randn(B, OH, OW, cout, generator=g).to(dev).bfloat16()
     if epi == "pix":
@@ -98,7 +113,7 @@ def run_case(idx):
     slope = 0.25
     o16, osq, o32 = layer(x0, x1, epi=epi_id, act=act_id, slope=slope, aux0=aux0, aux1=aux1,
                           pixscale=pix, out_bf16=c.get("bf16", True), out_sq=c.get("sq", False),
-                          out_f32=c.get("f32"), mt=c.get("mt", 0))
+                          out_f32=c.get("f32"), mt=c.get("mt", 0), x0_square=c.get("square", False))
     torch.cuda.synchronize()
 
     # reference: fp32 math on bf16-rounded operands
@@ -106,6 +121,8 @@ def run_case(idx):
     if mask is not None:
         wq = wq * mask.to(dev).float()
     xin = x0.float()
+    if c.get("square"):
+        xin = (xin * xin).bfloat16().float()
     if cin1:
         xin = torch.cat([xin, x1.float()], dim=-1)
     xin = xin.permute(0, 3, 1, 2)
@@ -162,15 +179,21 @@ def run_case(idx):
         ok &= d < 1e-2
     res["ok"] = bool(ok)
     if c.get("perf"):
+        kw = dict(epi=epi_id, act=act_id, slope=slope, aux0=aux0, aux1=aux1, pixscale=pix,
+                  x0_square=c.get("square", False))
+        if o16 is None:
+            kw.update(out_bf16=False, out_f32=o32 if c.get("f32") == "nhwc" else o32.permute(0, 2, 3, 1))
+        else:
+            kw.update(out_bf16=o16)
         for _ in range(3):
-            layer(x0, x1, out_bf16=o16)
+            layer(x0, x1, **kw)
         torch.cuda.synchronize()
-        for mt in (0, 1, 2, 4):
+        for mt in (0,):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             n = 20
             for _ in range(n):
-                layer(x0, x1, out_bf16=o16, mt=mt)
+                layer(x0, x1, mt=mt, **kw)
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / n
