@@ -237,9 +237,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
           const uint32_t r0 = sb + c * p.a_chunk_bytes + row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            uint4 v = lds128(r0 + j * 16);
+            // element-wise and in place, so any visiting order works: rotate the 16 B chunk by the row so
+            // that the 8 rows of a quarter-warp touch 8 different bank groups (rows are 128 B apart)
+            const uint32_t a = r0 + ((j ^ (row & 7)) << 4);
+            uint4 v = lds128(a);
             v.x = sq_bf16x2(v.x); v.y = sq_bf16x2(v.y); v.z = sq_bf16x2(v.z); v.w = sq_bf16x2(v.w);
-            sts128(r0 + j * 16, v);
+            sts128(a, v);
           }
         }
         hy::fence_async_smem();
@@ -298,13 +301,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
             float a[16];
             unpack16(lds128(sb + p.x1_off + coff + ((j0 ^ sw) << 4)), lds128(sb + p.x1_off + coff + (((j0 + 1) ^ sw) << 4)), a);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = a[i] * (1.f / (1.f + __expf(-v[i]))) + x[i];
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(a[i], hy::fast_sigmoid(v[i]), x[i]);
           } else if (p.epi == HYRES_EPI_GDN) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = x[i] * rsqrtf(v[i]);
+            for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_rsqrt(v[i]);
           } else if (p.epi == HYRES_EPI_IGDN) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = x[i] * sqrtf(v[i]);
+            for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_sqrt(v[i]);
           }
         }
 #pragma unroll

@@ -301,17 +301,17 @@ __global__ void __launch_bounds__(kThreads, 3) conv_tc_kernel(const __grid_const
           unpack(a1c, a);
           unpack(a0c, x);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = a[i] * (1.f / (1.f + __expf(-v[i]))) + x[i];
+          for (int i = 0; i < 16; ++i) v[i] = fmaf(a[i], hy::fast_sigmoid(v[i]), x[i]);
         } else if (p.epi == HYRES_EPI_GDN) {
           float x[16];
           unpack(a0c, x);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = x[i] * rsqrtf(v[i]);
+          for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_rsqrt(v[i]);
         } else if (p.epi == HYRES_EPI_IGDN) {
           float x[16];
           unpack(a0c, x);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = x[i] * sqrtf(v[i]);
+          for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_sqrt(v[i]);
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act, p.slope);

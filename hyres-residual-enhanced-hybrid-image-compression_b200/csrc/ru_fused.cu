@@ -22,6 +22,11 @@
 //
 // HBM traffic is the algorithmic minimum (read x once + halo, write out once); the next
 // tile's TMA load and the previous tile's TMA store overlap the three GEMMs.
+//
+// Eight epilogue warps: warp w reads TMEM lane quadrant (w & 3) and column half (w >> 2), so each
+// epilogue stage is half as long as with four warps.  The three GEMMs use disjoint TMEM column
+// ranges (G1 [0,128), G2 [128,192), G3 [256,384)), so G1 of the next tile is issued between G2 and
+// G3 of the current one and runs while the epilogue warps are busy with E2 / E3.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -36,7 +41,10 @@ namespace {
 constexpr int kTH = 16, kTW = 8;        // output tile
 constexpr int kPW = 10;                 // patch width (positions)
 constexpr int kNP = 180;                // patch positions (18 x 10)
-constexpr int kThreads = 224;           // warps 0-3 epilogue, 4 TMA load, 5 MMA, 6 TMA store
+constexpr int kEpiThreads = 256;        // warps 0-7 epilogue
+constexpr int kThreads = 352;           // warp 8 TMA load, 9 MMA, 10 TMA store
+constexpr int kWarpLoad = 8, kWarpMma = 9, kWarpStore = 10;
+constexpr uint32_t kColG1 = 0, kColG2 = 128, kColG3 = 256, kTmemCols = 512;
 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr uint32_t kW1 = 0;             // [2 k-chunks][64 n][128 B]
@@ -114,10 +122,10 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
     hy::mbar_init(bar(G1_DONE), 1);
     hy::mbar_init(bar(G2_DONE), 1);
     hy::mbar_init(bar(G3_DONE), 1);
-    hy::mbar_init(bar(T1_READY), 128);
-    hy::mbar_init(bar(T2_READY), 128);
-    hy::mbar_init(bar(ACC_FREE), 128);
-    hy::mbar_init(bar(STAGED), 128);
+    hy::mbar_init(bar(T1_READY), kEpiThreads);
+    hy::mbar_init(bar(T2_READY), kEpiThreads);
+    hy::mbar_init(bar(ACC_FREE), kEpiThreads);
+    hy::mbar_init(bar(STAGED), kEpiThreads);
     hy::mbar_fence_init();
   }
   {
@@ -126,15 +134,15 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
     for (int i = threadIdx.x; i < 256; i += kThreads)
       sb[i] = i < 64 ? __ldg(p.b1 + i) : (i < 128 ? __ldg(p.b2 + i - 64) : __ldg(p.b3 + i - 128));
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kWarpLoad && lane == 0) {
     hy::tma_prefetch_desc(&p.mapX);
     hy::tma_prefetch_desc(&p.mapW1);
     hy::tma_prefetch_desc(&p.mapW2);
     hy::tma_prefetch_desc(&p.mapW3);
   }
-  if (warp == 6 && lane == 0) hy::tma_prefetch_desc(&p.mapOut);
-  if (warp == 5) {
-    hy::tmem_alloc(tmem_slot, 256);
+  if (warp == kWarpStore && lane == 0) hy::tma_prefetch_desc(&p.mapOut);
+  if (warp == kWarpMma) {
+    hy::tmem_alloc(tmem_slot, kTmemCols);
     hy::tmem_relinquish();
   }
   hy::tc_fence_before();
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
     w0 = (rem - th * p.tiles_w) * kTW;
   };
 
-  if (warp == 4) {
+  if (warp == kWarpLoad) {
     // ============================ TMA load producer ============================
     if (lane == 0) {
       hy::mbar_arrive_expect_tx(bar(W_FULL), kWBytes);
@@ -172,30 +180,36 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
         hy::tma_load_4d(xb + kXChunk, &p.mapX, bar(X_FULL + b), 64, w0 - 1, h0 - 1, b_img);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kWarpMma) {
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc64 = hy::umma_idesc_bf16(128, 64);
       const uint32_t idesc128 = hy::umma_idesc_bf16(128, 128);
-      hy::mbar_wait(bar(W_FULL), 0);
-      int it = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-        const int b = it & 1;
-        const uint32_t ph = it & 1;
-        const uint32_t xb = base + kX0 + b * kXStride;
-        hy::mbar_wait(bar(X_FULL + b), (it >> 1) & 1);
-        if (it > 0) hy::mbar_wait(bar(ACC_FREE), (it - 1) & 1);  // E3 of the previous tile drained columns [0,128)
+      // G1: t1 = x . W1^T over the 180-position patch (2 blocks of 128 rows; rows >= 180 unused)
+      auto issue_g1 = [&](int jt) {
+        const uint32_t xb = base + kX0 + (jt & 1) * kXStride;
         hy::tc_fence_after();
-        // G1: t1 = x . W1^T over the 180-position patch (2 blocks of 128 rows; rows >= 180 unused)
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk)
 #pragma unroll
           for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              hy::umma_bf16(tmem_base + blk * 64, hy::umma_desc_sw128(xb + kc * kXChunk + blk * 16384 + k * 32),
+              hy::umma_bf16(tmem_base + kColG1 + blk * 64, hy::umma_desc_sw128(xb + kc * kXChunk + blk * 16384 + k * 32),
                             hy::umma_desc_sw128(base + kW1 + kc * 8192 + k * 32), idesc64, (kc | k) ? 1u : 0u);
         hy::umma_commit(bar(G1_DONE));
+      };
+      hy::mbar_wait(bar(W_FULL), 0);
+      int it = 0;
+      if (static_cast<int>(blockIdx.x) < p.ntiles) {
+        hy::mbar_wait(bar(X_FULL + 0), 0);
+        issue_g1(0);
+      }
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+        const uint32_t ph = it & 1;
+        const bool has_next = t + static_cast<int>(gridDim.x) < p.ntiles;
+        const int nb = (it + 1) & 1;
+        const uint32_t nph = ((it + 1) >> 1) & 1;
         // G2: 3x3 over the t1 patch in smem; tap (r,s) = start row r*10+s, row groups 1280 B apart
         hy::mbar_wait(bar(T1_READY), ph);
         hy::tc_fence_after();
@@ -205,22 +219,34 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
           for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              hy::umma_bf16(tmem_base + 128,
+              hy::umma_bf16(tmem_base + kColG2,
                             hy::umma_desc_sw128(base + kS + (r * kPW + s) * 128 + k * 32, kPW * 128),
                             hy::umma_desc_sw128(base + kW2 + (s * 3 + r) * 8192 + k * 32), idesc64,
                             (s | r | k) ? 1u : 0u);
         hy::umma_commit(bar(G2_DONE));
+        // G1 of the next tile rides behind G2 when its patch has landed (columns [0,128) were drained by E1
+        // of this tile); it then overlaps E2 / E3 of this tile.
+        bool g1_ahead = false;
+        if (has_next && hy::mbar_try_wait(bar(X_FULL + nb), nph)) {
+          issue_g1(it + 1);
+          g1_ahead = true;
+        }
         // G3: 1x1 expand
         hy::mbar_wait(bar(T2_READY), ph);
+        if (it > 0) hy::mbar_wait(bar(ACC_FREE), (it - 1) & 1);  // E3 of the previous tile drained [256,384)
         hy::tc_fence_after();
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          hy::umma_bf16(tmem_base, hy::umma_desc_sw128(base + kS + k * 32),
+          hy::umma_bf16(tmem_base + kColG3, hy::umma_desc_sw128(base + kS + k * 32),
                         hy::umma_desc_sw128(base + kW3 + k * 32), idesc128, k ? 1u : 0u);
         hy::umma_commit(bar(G3_DONE));
+        if (has_next && !g1_ahead) {
+          hy::mbar_wait(bar(X_FULL + nb), nph);
+          issue_g1(it + 1);
+        }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == kWarpStore) {
     // ============================ TMA store ============================
     if (lane == 0) {
       int it = 0;
@@ -239,9 +265,11 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       hy::tma_store_wait_all<0>();
     }
   } else {
-    // ============================ epilogue warps 0-3 ============================
-    const int tid = threadIdx.x;  // TMEM lane == GEMM row
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    // ============================ epilogue warps 0-7 ============================
+    const int q = warp & 3;        // TMEM lane quadrant
+    const int hsel = warp >> 2;    // column half handled by this warp
+    const int tid = q * 32 + lane; // TMEM lane == GEMM row
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sbias = base + kBias;
     const int ti = tid >> 3, tj = tid & 7;
     const int pc = (ti + 1) * kPW + tj + 1;  // this thread's output position inside the x patch
@@ -253,14 +281,16 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       tile_origin(t, b_img, h0, w0);
       const uint32_t xb = base + kX0 + b * kXStride;
       uint32_t ra[32], rb[32];
-      uint4 q[4];
+      uint4 qv[4];
 
-      // ---- E1: t1 patch ----
+      // ---- E1: t1 patch (this warp: 32 of the 64 channels) ----
       hy::mbar_wait(bar(G1_DONE), ph);
       hy::tc_fence_after();
+      hy::tmem_ld32(t_lane + kColG1 + hsel * 32, ra);
+      if (q < 2) hy::tmem_ld32(t_lane + kColG1 + 64 + hsel * 32, rb);  // rows 128.. exist in lanes 0..51 only
 #pragma unroll
       for (int blk = 0; blk < 2; ++blk) {
-        if (blk == 1 && warp >= 2) break;  // rows 192.. do not exist (warp-uniform)
+        if (blk == 1 && q >= 2) break;  // warp-uniform
         const int pp = blk * 128 + tid;
         const int pr = pp / kPW, pq = pp - pr * kPW;
         const int hh = h0 - 1 + pr, ww = w0 - 1 + pq;
@@ -268,19 +298,16 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
         const bool keep = live && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;  // conv2 zero-pads t1, not x
         const uint32_t row = base + kS + pp * 128;
         const uint32_t sw = pp & 7;
-        hy::tmem_ld32(t_lane + blk * 64, ra);
-        hy::tmem_ld_fence32(ra);
-        hy::tmem_ld32(t_lane + blk * 64 + 32, rb);
-        bias_relu_pack32(ra, sbias, keep, q);
-        if (live) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) sts128(row + ((g ^ sw) << 4), q[g]);
+        if (blk == 0) {
+          hy::tmem_ld_fence32(ra);
+          bias_relu_pack32(ra, sbias + hsel * 128, keep, qv);
+        } else {
+          hy::tmem_ld_fence32(rb);
+          bias_relu_pack32(rb, sbias + hsel * 128, keep, qv);
         }
-        hy::tmem_ld_fence32(rb);
-        bias_relu_pack32(rb, sbias + 128, keep, q);
         if (live) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) sts128(row + (((4 + g) ^ sw) << 4), q[g]);
+          for (int g = 0; g < 4; ++g) sts128(row + (((hsel * 4 + g) ^ sw) << 4), qv[g]);
         }
       }
       hy::fence_async_smem();
@@ -293,33 +320,28 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       {
         const uint32_t row = base + kS + tid * 128;
         const uint32_t sw = tid & 7;
-        hy::tmem_ld32(t_lane + 128, ra);
+        hy::tmem_ld32(t_lane + kColG2 + hsel * 32, ra);
         hy::tmem_ld_fence32(ra);
-        hy::tmem_ld32(t_lane + 128 + 32, rb);
-        bias_relu_pack32(ra, sbias + 256, true, q);
+        bias_relu_pack32(ra, sbias + 256 + hsel * 128, true, qv);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) sts128(row + ((g ^ sw) << 4), q[g]);
-        hy::tmem_ld_fence32(rb);
-        bias_relu_pack32(rb, sbias + 256 + 128, true, q);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) sts128(row + (((4 + g) ^ sw) << 4), q[g]);
+        for (int g = 0; g < 4; ++g) sts128(row + (((hsel * 4 + g) ^ sw) << 4), qv[g]);
       }
       hy::fence_async_smem();
       hy::tc_fence_before();
       hy::mbar_arrive(bar(T2_READY));
 
-      // ---- E3: + bias + skip, stage over the x buffer, hand to the store warp ----
+      // ---- E3: + bias + skip (this warp: 64-channel chunk `hsel`), stage over the x buffer ----
       hy::mbar_wait(bar(G3_DONE), ph);
       hy::mbar_wait(bar(X_FULL + b), (it >> 1) & 1);  // (already complete) acquire the TMA-written patch
       hy::tc_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      {
+        const int h = hsel;
         const uint32_t skip_row = xb + h * kXChunk + pc * 128;
         const uint32_t skip_sw = pc & 7;
         uint4 o[8];
-        hy::tmem_ld32(t_lane + h * 64, ra);
+        hy::tmem_ld32(t_lane + kColG3 + h * 64, ra);
+        hy::tmem_ld32(t_lane + kColG3 + h * 64 + 32, rb);
         hy::tmem_ld_fence32(ra);
-        hy::tmem_ld32(t_lane + h * 64 + 32, rb);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           if (half == 1) hy::tmem_ld_fence32(rb);
@@ -346,12 +368,10 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
             o[j].w = hy::pack_bf16(v[6], v[7]);
           }
         }
-        if (h == 1) {
-          hy::tc_fence_before();
-          hy::mbar_arrive(bar(ACC_FREE));  // TMEM columns [0,128) may be overwritten by the next G1
-        }
-        // the staging rows overlap other threads' skip rows of this chunk: all reads first
-        hy::named_bar_sync(1, 128);
+        hy::tc_fence_before();
+        hy::mbar_arrive(bar(ACC_FREE));  // TMEM columns [256,384) may be overwritten by the next G3
+        // the staging rows overlap other threads' skip rows of this chunk: all reads of the chunk first
+        hy::named_bar_sync(1 + h, 128);
         const uint32_t st_row = xb + h * kXChunk + tid * 128;
         const uint32_t st_sw = tid & 7;
 #pragma unroll
@@ -364,9 +384,9 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
 
   hy::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kWarpMma) {
     hy::tc_fence_after();
-    hy::tmem_dealloc(tmem_base, 256);
+    hy::tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 

@@ -150,17 +150,18 @@ class LightWeightCheckerboard(CompressionModel):
             raise ValueError("H and W must be multiples of 32 (the reference never pads)")
 
     # -- forward (models/checkerboard.py:90-147) --
-    def forward(self, x, noisequant=False, stats=None):
+    def forward(self, x, noisequant=False, stats=None, _im2col=None):
         """-> {"x_hat": [B,3,H,W], "likelihoods": {"y": [B,M,H/8,W/8], "z": [B,N,H/32,W/32]}}.
 
         ``stats``: optional 2-element CUDA double tensor accumulating sum(log2 lik_y), sum(log2 lik_z)
-        inside the likelihood kernels (used by the fused RD loss)."""
+        inside the likelihood kernels (used by the fused RD loss).  ``_im2col``: the g_a.0 operand when
+        the caller (the JPEG wrapper) already produced it together with the residual."""
         _require_cuda(x, "forward")
         self._check_input(x)
         eng = self.engine()
         x = x.contiguous().float()
         training = self.training
-        _, a = ops.residual_im2col5s2(x)
+        a = _im2col if _im2col is not None else ops.residual_im2col5s2(x)[1]
         y16, y32 = eng.g_a(a)
         z32 = eng.h_a(y16)
         ebp, med = eng.eb_params()
@@ -179,7 +180,7 @@ class LightWeightCheckerboard(CompressionModel):
         return {"x_hat": x_hat, "likelihoods": {"y": lik_y, "z": eb["lik"]}}
 
     # -- symbols of both passes (GPU part of compress) --
-    def encode_symbols(self, x):
+    def encode_symbols(self, x, _im2col=None):
         """GPU front-end of ``compress``: returns the integer streams the entropy coder consumes,
         all int32 CUDA tensors in (B,C,h,w) order, plus the shapes."""
         _require_cuda(x, "compress")
@@ -188,7 +189,7 @@ class LightWeightCheckerboard(CompressionModel):
         x = x.contiguous().float()
         table = self._scale_table(x.device)
         bound = float(self.gaussian_conditional.scale_bound.item())
-        _, a = ops.residual_im2col5s2(x)
+        a = _im2col if _im2col is not None else ops.residual_im2col5s2(x)[1]
         y16, y32 = eng.g_a(a)
         z32 = eng.h_a(y16)
         ebp, med = eng.eb_params()
@@ -203,9 +204,9 @@ class LightWeightCheckerboard(CompressionModel):
                 "y": y32, "z": z32, "params_a": pa, "params_na": pna}
 
     # -- compress (models/checkerboard.py:167-198) --
-    def compress(self, x):
+    def compress(self, x, _im2col=None):
         start_time = time.time()
-        s = self.encode_symbols(x)
+        s = self.encode_symbols(x, _im2col=_im2col)
         gc, ebm = self.gaussian_conditional, self.entropy_bottleneck
         z_strings = ebm.encode_symbols(s["sym_z"], ebm._build_indexes(s["sym_z"].size()))
         anchor_strings = gc.encode_symbols(s["sym_a"], s["idx_a"])
@@ -311,8 +312,8 @@ class ResidualJPEGCompression(CompressionModel):
         jpeg_decoded = jpeg_decoded_cpu.to(device, torch.float32).contiguous()
         xd = x.to(device, torch.float32).contiguous()
         self.residual_model._check_input(xd)
-        residual, _ = ops.residual_im2col5s2(xd, jpeg_decoded)
-        res = self.residual_model(residual, noisequant=noisequant, stats=stats)
+        residual, a = ops.residual_im2col5s2(xd, jpeg_decoded)
+        res = self.residual_model(residual, noisequant=noisequant, stats=stats, _im2col=a)
         residual_hat = res["x_hat"]
         x_hat = self._reconstruct(jpeg_decoded, residual_hat)
         return {"x_hat": x_hat, "likelihoods": res["likelihoods"],
@@ -326,8 +327,8 @@ class ResidualJPEGCompression(CompressionModel):
             jpeg_buffers = self.jpeg.compress(x)
         jpeg_decoded = self.jpeg.decompress(jpeg_buffers, device).float().contiguous()
         xd = x.to(device, torch.float32).contiguous()
-        residual, _ = ops.residual_im2col5s2(xd, jpeg_decoded)
-        out = self.residual_model.compress(residual)
+        residual, a = ops.residual_im2col5s2(xd, jpeg_decoded)
+        out = self.residual_model.compress(residual, _im2col=a)
         out["jpeg_buffers"] = jpeg_buffers
         return out
 

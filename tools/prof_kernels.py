@@ -1,0 +1,143 @@
+#!/usr/bin/env python
+"""Launch one hot layer at its bench shape a few times (target of `ncu --set full`, or a quick timer).
+
+    python tools/prof_kernels.py --case gate|gdn|c3x3|c1x1|ru|head0|head1|ctx|deconv|s2|gs8|fus0 [--n 3] [--time]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hyres_b200 import ops  # noqa: E402
+from hyres_b200.ops import (ACT_NONE, ACT_PRELU, ACT_RELU, EPI_ADD, EPI_GATE, EPI_GDN, EPI_LINEAR,  # noqa: E402
+                            EPI_PIXSCALE, HYRES_CONV, HYRES_DECONV_K5S2)
+
+B = 16
+
+
+def rnd(*shape):
+    return torch.randn(*shape, device="cuda").bfloat16()
+
+
+def make(case):
+    g = torch.Generator().manual_seed(5)
+
+    def w(co, ci, k):
+        return torch.randn(co, ci, k, k, generator=g) / (ci * k * k) ** 0.5
+
+    def bias(n):
+        return torch.randn(n, generator=g) * 0.1
+
+    if case == "gate":
+        L = ops.ConvLayer(w(128, 128, 1), bias(128))
+        x, a0, a1 = rnd(B, 256, 384, 128), rnd(B, 256, 384, 128), rnd(B, 256, 384, 128)
+        out = torch.empty_like(x)
+        return lambda: L(x, epi=EPI_GATE, aux0=a0, aux1=a1, out_bf16=out), 2.0 * B * 256 * 384 * 128 * 128, 4 * x.numel() * 2
+    if case == "gdn":
+        L = ops.ConvLayer(w(128, 128, 1).abs(), bias(128).abs() + 0.5)
+        x = rnd(B, 256, 384, 128)
+        out = torch.empty_like(x)
+        return lambda: L(x, epi=EPI_GDN, aux0=x, x0_square=True, out_bf16=out), 2.0 * B * 256 * 384 * 128 * 128, 2 * x.numel() * 2
+    if case == "c3x3":
+        L = ops.ConvLayer(w(64, 64, 3), bias(64), pad=1)
+        x = rnd(B, 512, 768, 64)
+        out = torch.empty_like(x)
+        return lambda: L(x, act=ACT_PRELU, slope=0.25, out_bf16=out), 2.0 * B * 512 * 768 * 64 * 576, 2 * x.numel() * 2
+    if case == "c1x1":
+        L = ops.ConvLayer(w(64, 128, 1), bias(64))
+        x = rnd(B, 256, 384, 128)
+        out = torch.empty(B, 256, 384, 64, device="cuda", dtype=torch.bfloat16)
+        return lambda: L(x, act=ACT_RELU, out_bf16=out), 2.0 * B * 256 * 384 * 64 * 128, (x.numel() + out.numel()) * 2
+    if case == "fus0":
+        L = ops.ConvLayer(w(64, 192, 1), bias(64))
+        x = rnd(B, 512, 768, 192)
+        ps = torch.rand(B, 512, 768, device="cuda")
+        out = torch.empty(B, 512, 768, 64, device="cuda", dtype=torch.bfloat16)
+        return (lambda: L(x, epi=EPI_PIXSCALE, pixscale=ps, act=ACT_PRELU, slope=0.2, out_bf16=out),
+                2.0 * B * 512 * 768 * 64 * 192, (x.numel() + out.numel()) * 2)
+    if case == "ru":
+        c1 = ops.ConvLayer(w(64, 128, 1), bias(64))
+        c2 = ops.ConvLayer(w(64, 64, 3), bias(64), pad=1)
+        c3 = ops.ConvLayer(w(128, 64, 1), bias(128))
+        x = rnd(B, 256, 384, 128)
+        out = torch.empty_like(x)
+        return (lambda: ops.ru_fused(x, c1, c2, c3, True, out=out),
+                2.0 * B * 256 * 384 * (128 * 64 + 576 * 64 + 64 * 128), 2 * x.numel() * 2)
+    if case == "ru192":
+        c1 = ops.ConvLayer(w(96, 192, 1), bias(96))
+        c2 = ops.ConvLayer(w(96, 96, 3), bias(96), pad=1)
+        c3 = ops.ConvLayer(w(192, 96, 1), bias(192))
+        x = rnd(B, 64, 96, 192)
+        out = torch.empty_like(x)
+
+        def run():
+            a, _, _ = c1(x, act=ACT_RELU)
+            b, _, _ = c2(a, act=ACT_RELU)
+            c3(b, epi=EPI_ADD, aux0=x, act=ACT_RELU, out_bf16=out)
+        return run, 2.0 * B * 64 * 96 * (192 * 96 + 864 * 96 + 96 * 192), 2 * x.numel() * 2
+    if case in ("head0", "head1", "head2"):
+        ci, co = dict(head0=(768, 640), head1=(640, 512), head2=(512, 384))[case]
+        L = ops.ConvLayer(w(co, ci, 1), bias(co), cin0=ci // 2 if case == "head0" else ci, cin1=ci // 2 if case == "head0" else 0)
+        x = rnd(B, 64, 96, ci // 2 if case == "head0" else ci)
+        x1 = rnd(B, 64, 96, ci // 2) if case == "head0" else None
+        if case == "head2":
+            o32 = torch.empty(B, 64, 96, co, device="cuda")
+            return lambda: L(x, out_bf16=False, out_f32=o32), 2.0 * B * 64 * 96 * ci * co, x.numel() * 2 + o32.numel() * 4
+        out = torch.empty(B, 64, 96, co, device="cuda", dtype=torch.bfloat16)
+        return lambda: L(x, x1, act=ACT_RELU, out_bf16=out), 2.0 * B * 64 * 96 * ci * co, (B * 64 * 96 * ci + out.numel()) * 2
+    if case == "ctx":
+        mask = torch.zeros(5, 5, dtype=torch.uint8)
+        mask[0::2, 1::2] = 1
+        mask[1::2, 0::2] = 1
+        L = ops.ConvLayer(w(384, 192, 5), bias(384), pad=2, tap_mask=mask)
+        x = rnd(B, 64, 96, 192)
+        out = torch.empty(B, 64, 96, 384, device="cuda", dtype=torch.bfloat16)
+        return lambda: L(x, out_bf16=out), 2.0 * B * 64 * 96 * 192 * 12 * 384, (x.numel() + out.numel()) * 2
+    if case == "deconv":
+        wt = torch.randn(128, 128, 5, 5, generator=g) / (128 * 25 / 4) ** 0.5
+        L = ops.ConvLayer(wt, bias(128), kind=HYRES_DECONV_K5S2)
+        x = rnd(B, 128, 192, 128)
+        out = torch.empty(B, 256, 384, 128, device="cuda", dtype=torch.bfloat16)
+        return lambda: L(x, out_bf16=out), 2.0 * B * 128 * 192 * 128 * 25 * 128, (x.numel() + out.numel()) * 2
+    if case == "s2":
+        L = ops.ConvLayer(w(128, 128, 5), bias(128), stride=2, pad=2)
+        x = rnd(B, 256, 384, 128)
+        out = torch.empty(B, 128, 192, 128, device="cuda", dtype=torch.bfloat16)
+        return lambda: L(x, out_bf16=out), 2.0 * B * 128 * 192 * 128 * 25 * 128, (x.numel() + out.numel()) * 2
+    if case == "gs8":
+        wt = torch.randn(128, 3, 5, 5, generator=g) / (128 * 25 / 4) ** 0.5
+        L = ops.ConvLayer(wt, bias(3), kind=HYRES_DECONV_K5S2)
+        x = rnd(B, 256, 384, 128)
+        o32 = torch.empty(B, 3, 512, 768, device="cuda")
+        return (lambda: L(x, out_bf16=False, out_f32=o32.permute(0, 2, 3, 1)), 2.0 * B * 256 * 384 * 128 * 25 * 3,
+                x.numel() * 2 + o32.numel() * 4)
+    raise SystemExit(f"unknown case {case}")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case", required=True)
+    ap.add_argument("--n", type=int, default=3)
+    ap.add_argument("--time", action="store_true")
+    a = ap.parse_args()
+    for case in a.case.split(","):
+        fn, flops, byts = make(case)
+        for _ in range(a.n):
+            fn()
+        torch.cuda.synchronize()
+        if a.time:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(20):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(json.dumps(dict(case=case, ms=round(ms, 4), tflops=round(flops / ms / 1e9, 1), gbs=round(byts / ms / 1e6, 0))))
+
+
+if __name__ == "__main__":
+    main()
