@@ -39,7 +39,10 @@ namespace {
 
 constexpr int kTileW = 8;     // output columns per tile
 constexpr int kSubH = 16;     // output rows per 128-row accumulator
-constexpr int kThreads = 192;
+constexpr int kThreads = 320; // warps 0-3 / 4-7: epilogue groups 0 / 1; warp 8: TMA producer; warp 9: MMA issuer
+constexpr int kWarpProd = 8, kWarpMma = 9;
+constexpr int kMaxNBlocks = 8;
+constexpr int kSmemLimit = 227 * 1024;
 
 struct alignas(64) ConvParams {
   CUtensorMap mapA0;
@@ -48,13 +51,16 @@ struct alignas(64) ConvParams {
   const TapGroup* groups;
   int32_t ph_begin[4];
   int32_t ph_count[4];
-  int32_t tiles_w, tiles_h;  // tiles per image
+  int32_t nb_n0[kMaxNBlocks];  // first output channel of each N block
+  int32_t nb_bn[kMaxNBlocks];  // its width (multiple of b_box_rows, <= 256)
+  int32_t n_blocks, b_box_rows, bn_max;
+  int32_t nphase, tiles_w, tiles_h, nitems;
   int32_t OHv, OWv;          // extent of the iterated output grid (per phase for deconv)
   int32_t OH, OW;            // true output extent
   int32_t out_mul;           // 1, or 2 for transposed conv
-  int32_t MT, BN, NA, NB;
+  int32_t MT, NA, NB;
   int32_t a_stage_bytes, b_stage_bytes, patch_rows;
-  int32_t tmem_cols;
+  int32_t tmem_cols, acc_cols, nbuf, acc_empty_count, fast_epi;
   int32_t cout;              // live output channels
   int32_t epi, act;
   float slope;
@@ -77,17 +83,6 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   return v;
 }
 
-__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* p, float (&f)[16]) {
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
-  const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-  const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    f[2 * i] = hy::bf16_lo(u[i]);
-    f[2 * i + 1] = hy::bf16_hi(u[i]);
-  }
-}
-
 __device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const float (&f)[16]) {
   uint4 a, b;
   a.x = hy::pack_bf16(f[0], f[1]);
@@ -102,35 +97,33 @@ __device__ __forceinline__ void store16_bf16(__nv_bfloat16* p, const float (&f)[
   reinterpret_cast<uint4*>(p)[1] = b;
 }
 
-__global__ void __launch_bounds__(kThreads, 3) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+struct Item {
+  int b_img, h0, w0, phase, n0, bn;
+};
+
+// Persistent streaming implicit GEMM: one CTA per SM walks work items
+// (output tile of MT x 128 positions) x (sub-pixel phase) x (block of <= 256 output channels),
+// N-block fastest so that the CTAs running side by side share the same activation patch in L2.
+// The A patches and the weight tiles stream through two deep TMA rings that keep filling across
+// item boundaries; the accumulators are double buffered in TMEM whenever 2 * MT * BN <= 512 columns,
+// and two epilogue warp groups drain them while the next item's MMAs are issued.
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
   const uint32_t b_base = a_base + p.NA * p.a_stage_bytes;
   const uint32_t bar_base = b_base + p.NB * p.b_stage_bytes;
-  // barrier slots (8 B each): a_full[NA] a_empty[NA] b_full[NB] b_empty[NB] acc_full ; tmem slot
+  // barrier slots (8 B each): a_full[NA] a_empty[NA] b_full[NB] b_empty[NB] acc_full[2] acc_empty[2] ; tmem slot
   const uint32_t a_full = bar_base;
   const uint32_t a_empty = a_full + 8 * p.NA;
   const uint32_t b_full = a_empty + 8 * p.NA;
   const uint32_t b_empty = b_full + 8 * p.NB;
   const uint32_t acc_full = b_empty + 8 * p.NB;
-  const uint32_t tmem_slot = acc_full + 8;
+  const uint32_t acc_empty = acc_full + 16;
+  const uint32_t tmem_slot = acc_empty + 16;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // tile coordinates
-  const int tiles_per_img = p.tiles_w * p.tiles_h;
-  const int b_img = blockIdx.x / tiles_per_img;
-  const int t_in = blockIdx.x - b_img * tiles_per_img;
-  const int th = t_in / p.tiles_w;
-  const int tw = t_in - th * p.tiles_w;
-  const int h0 = th * (kSubH * p.MT);
-  const int w0 = tw * kTileW;
-  const int n0 = blockIdx.y * p.BN;
-  const int phase = blockIdx.z;
-  const int g_begin = p.ph_begin[phase];
-  const int g_count = p.ph_count[phase];
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.NA; ++i) {
@@ -141,15 +134,18 @@ __global__ void __launch_bounds__(kThreads, 3) conv_tc_kernel(const __grid_const
       hy::mbar_init(b_full + 8 * i, 1);
       hy::mbar_init(b_empty + 8 * i, 1);
     }
-    hy::mbar_init(acc_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      hy::mbar_init(acc_full + 8 * i, 1);
+      hy::mbar_init(acc_empty + 8 * i, p.acc_empty_count);
+    }
     hy::mbar_fence_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == kWarpProd && lane == 0) {
     hy::tma_prefetch_desc(&p.mapA0);
     hy::tma_prefetch_desc(&p.mapA1);
     hy::tma_prefetch_desc(&p.mapB);
   }
-  if (warp == 5) {
+  if (warp == kWarpMma) {
     hy::tmem_alloc(tmem_slot, p.tmem_cols);
     hy::tmem_relinquish();
   }
@@ -159,210 +155,359 @@ __global__ void __launch_bounds__(kThreads, 3) conv_tc_kernel(const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 4) {
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  auto decode = [&](int item) {
+    Item it;
+    const int nb = item % p.n_blocks;
+    int rest = item / p.n_blocks;
+    it.phase = rest % p.nphase;
+    rest /= p.nphase;
+    it.b_img = rest / tiles_per_img;
+    const int t_in = rest - it.b_img * tiles_per_img;
+    const int th = t_in / p.tiles_w;
+    it.h0 = th * (kSubH * p.MT);
+    it.w0 = (t_in - th * p.tiles_w) * kTileW;
+    it.n0 = p.nb_n0[nb];
+    it.bn = p.nb_bn[nb];
+    return it;
+  };
+
+  if (warp == kWarpProd) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const uint32_t a_bytes = p.patch_rows * (kTileW * 128);
-      for (int g = 0; g < g_count; ++g) {
-        const TapGroup tg = p.groups[g_begin + g];
-        hy::mbar_wait(a_empty + 8 * sa, pa ^ 1u);
-        hy::mbar_arrive_expect_tx(a_full + 8 * sa, a_bytes);
-        hy::tma_load_5d(a_base + sa * p.a_stage_bytes, tg.src ? &p.mapA1 : &p.mapA0,
-                        a_full + 8 * sa, tg.c_off, w0 + tg.dw, tg.hpar, h0 + tg.dh, b_img);
-        for (int t = 0; t < tg.ntaps; ++t) {
-          hy::mbar_wait(b_empty + 8 * sb, pb ^ 1u);
-          hy::mbar_arrive_expect_tx(b_full + 8 * sb, p.b_stage_bytes);
-          hy::tma_load_2d(b_base + sb * p.b_stage_bytes, &p.mapB, b_full + 8 * sb,
-                          (tg.kslot0 + t) * 64, n0);
-          if (++sb == p.NB) { sb = 0; pb ^= 1u; }
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+        const Item it = decode(item);
+        const int g_begin = p.ph_begin[it.phase], g_count = p.ph_count[it.phase];
+        const uint32_t b_bytes = it.bn * 128;
+        for (int g = 0; g < g_count; ++g) {
+          const TapGroup tg = p.groups[g_begin + g];
+          hy::mbar_wait(a_empty + 8 * sa, pa ^ 1u);
+          hy::mbar_arrive_expect_tx(a_full + 8 * sa, a_bytes);
+          hy::tma_load_5d(a_base + sa * p.a_stage_bytes, tg.src ? &p.mapA1 : &p.mapA0,
+                          a_full + 8 * sa, tg.c_off, it.w0 + tg.dw, tg.hpar, it.h0 + tg.dh, it.b_img);
+          for (int t = 0; t < tg.ntaps; ++t) {
+            hy::mbar_wait(b_empty + 8 * sb, pb ^ 1u);
+            hy::mbar_arrive_expect_tx(b_full + 8 * sb, b_bytes);
+            const uint32_t dst = b_base + sb * p.b_stage_bytes;
+            for (int r = 0; r < it.bn; r += p.b_box_rows)
+              hy::tma_load_2d(dst + r * 128, &p.mapB, b_full + 8 * sb, (tg.kslot0 + t) * 64, it.n0 + r);
+            if (++sb == p.NB) { sb = 0; pb ^= 1u; }
+          }
+          if (++sa == p.NA) { sa = 0; pa ^= 1u; }
         }
-        if (++sa == p.NA) { sa = 0; pa ^= 1u; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = hy::umma_idesc_bf16(128, p.BN);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      uint32_t first = 0;  // becomes 1 after the first k-step (accumulate flag)
-      for (int g = 0; g < g_count; ++g) {
-        const TapGroup tg = p.groups[g_begin + g];
-        hy::mbar_wait(a_full + 8 * sa, pa);
+      int it_n = 0;
+      for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it_n) {
+        const Item it = decode(item);
+        const int g_begin = p.ph_begin[it.phase], g_count = p.ph_count[it.phase];
+        const uint32_t idesc = hy::umma_idesc_bf16(128, it.bn);
+        const int buf = p.nbuf == 2 ? (it_n & 1) : 0;
+        const uint32_t use = p.nbuf == 2 ? (it_n >> 1) : it_n;  // how often this buffer was used before
+        hy::mbar_wait(acc_empty + 8 * buf, (use & 1u) ^ 1u);
         hy::tc_fence_after();
-        const uint32_t a_stage = a_base + sa * p.a_stage_bytes;
-        for (int t = 0; t < tg.ntaps; ++t) {
-          hy::mbar_wait(b_full + 8 * sb, pb);
+        const uint32_t d_item = tmem_base + buf * p.acc_cols;
+        uint32_t first = 0;  // becomes 1 after the first k-step (accumulate flag)
+        for (int g = 0; g < g_count; ++g) {
+          const TapGroup tg = p.groups[g_begin + g];
+          hy::mbar_wait(a_full + 8 * sa, pa);
           hy::tc_fence_after();
-          const uint32_t b_stage = b_base + sb * p.b_stage_bytes;
-          const uint32_t a_tap = a_stage + tg.tap_row[t] * (kTileW * 128);
-          for (int sub = 0; sub < p.MT; ++sub) {
-            const uint32_t a_sub = a_tap + sub * (kSubH * kTileW * 128);
-            const uint32_t d_tmem = tmem_base + sub * p.BN;
+          const uint32_t a_stage = a_base + sa * p.a_stage_bytes;
+          for (int t = 0; t < tg.ntaps; ++t) {
+            hy::mbar_wait(b_full + 8 * sb, pb);
+            hy::tc_fence_after();
+            const uint32_t b_stage = b_base + sb * p.b_stage_bytes;
+            const uint32_t a_tap = a_stage + p.groups[g_begin + g].tap_row[t] * (kTileW * 128);
+            for (int sub = 0; sub < p.MT; ++sub) {
+              const uint32_t a_sub = a_tap + sub * (kSubH * kTileW * 128);
+              const uint32_t d_tmem = d_item + sub * p.bn_max;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              hy::umma_bf16(d_tmem, hy::umma_desc_sw128(a_sub + k * 32),
-                            hy::umma_desc_sw128(b_stage + k * 32), idesc, first | (uint32_t)k);
+              for (int k = 0; k < 4; ++k) {
+                hy::umma_bf16(d_tmem, hy::umma_desc_sw128(a_sub + k * 32),
+                              hy::umma_desc_sw128(b_stage + k * 32), idesc, first | (uint32_t)k);
+              }
             }
+            first = 1;
+            hy::umma_commit(b_empty + 8 * sb);
+            if (++sb == p.NB) { sb = 0; pb ^= 1u; }
           }
-          first = 1;
-          hy::umma_commit(b_empty + 8 * sb);
-          if (++sb == p.NB) { sb = 0; pb ^= 1u; }
+          hy::umma_commit(a_empty + 8 * sa);
+          if (++sa == p.NA) { sa = 0; pa ^= 1u; }
         }
-        hy::umma_commit(a_empty + 8 * sa);
-        if (++sa == p.NA) { sa = 0; pa ^= 1u; }
+        hy::umma_commit(acc_full + 8 * buf);
       }
-      hy::umma_commit(acc_full);
     }
   } else {
-    // ===================== epilogue (warps 0-3) =====================
+    // ===================== epilogue groups (warps 0-3, 4-7) =====================
+    // With two accumulator buffers the groups take alternate items; with one (MT * BN > 256) both
+    // groups drain the same item, sub-tile `sub` going to group (sub & 1).
     // Software-pipelined over 16-column chunks: the TMEM load and the global loads of the
     // epilogue operands (skip / gate / GDN inputs) of chunk c+1 are in flight while chunk c is
     // finished and stored, and the first chunk's operands are requested before the
-    // accumulator is complete, so one global-load latency is exposed per tile, not per chunk.
-    const int row = warp * 32 + lane;  // TMEM lane == tile row
+    // accumulator is complete, so one global-load latency is exposed per item, not per chunk.
+    const int grp = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row
     const int ti = row >> 3;
     const int tj = row & 7;
-    const int ph_p = phase >> 1, ph_q = phase & 1;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const bool need0 = p.epi == HYRES_EPI_ADD || p.epi == HYRES_EPI_GATE || p.epi == HYRES_EPI_GDN ||
                        p.epi == HYRES_EPI_IGDN;
     const bool need1 = p.epi == HYRES_EPI_GATE;
-    const int nchunk = p.BN >> 4;
-    const int total = p.MT * nchunk;
-    auto geom = [&](int it, long long& opix, int& oh, int& ow, bool& valid, int& n) {
-      const int sub = it / nchunk;
-      const int hv = h0 + sub * kSubH + ti;
-      const int wv = w0 + tj;
-      n = n0 + (it - sub * nchunk) * 16;
-      valid = (hv < p.OHv) && (wv < p.OWv) && (n < p.cout);
-      oh = hv * p.out_mul + ph_p;
-      ow = wv * p.out_mul + ph_q;
-      opix = (static_cast<long long>(b_img) * p.OH + oh) * p.OW + ow;
-    };
-    auto fetch_aux = [&](int it, uint4 (&x0)[2], uint4 (&x1)[2]) {
-      long long opix; int oh, ow, n; bool valid;
-      geom(it, opix, oh, ow, valid, n);
-      if (!valid) return;
-      if (need0) {
-        const uint4* q = reinterpret_cast<const uint4*>(p.aux0 + opix * p.ld_aux0 + n);
-        x0[0] = __ldg(q); x0[1] = __ldg(q + 1);
+    int it_n = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it_n) {
+      int buf, sub0, sub_step;
+      uint32_t use;
+      if (p.nbuf == 2) {
+        if ((it_n & 1) != grp) continue;
+        buf = it_n & 1; use = it_n >> 1; sub0 = 0; sub_step = 1;
+      } else {
+        if (grp >= p.MT) continue;
+        buf = 0; use = it_n; sub0 = grp; sub_step = 2;
       }
-      if (need1) {
-        const uint4* q = reinterpret_cast<const uint4*>(p.aux1 + opix * p.ld_aux1 + n);
-        x1[0] = __ldg(q); x1[1] = __ldg(q + 1);
-      }
-    };
-    auto unpack = [](const uint4 (&x)[2], float (&f)[16]) {
-      const uint32_t u[8] = {x[0].x, x[0].y, x[0].z, x[0].w, x[1].x, x[1].y, x[1].z, x[1].w};
+      const Item it = decode(item);
+      const int ph_p = it.phase >> 1, ph_q = it.phase & 1;
+      const int nchunk = it.bn >> 4;
+      const int nsub = (p.MT - sub0 + sub_step - 1) / sub_step;
+      const int total = nsub * nchunk;
+      const uint32_t t_item = t_lane + buf * p.acc_cols;
+      if (p.fast_epi) {
+        // bias (+ReLU) -> bf16 / fp32 rows: 32 accumulator columns per step, TMEM loads double buffered
+        const float lo = p.act == HYRES_ACT_RELU ? 0.f : -3.402823466e38f;
+        const int nch = it.bn >> 5;
+        const int steps = nsub * nch;
+        uint32_t r0[32], r1[32];
+        hy::mbar_wait(acc_full + 8 * buf, use & 1u);
+        hy::tc_fence_after();
+        hy::tmem_ld32(t_item + sub0 * p.bn_max, r0);
+        auto body = [&](int q, uint32_t (&r)[32]) {
+          const int si = q / nch;
+          const int sub = sub0 + si * sub_step;
+          const int n = it.n0 + ((q - si * nch) << 5);
+          const int hv = it.h0 + sub * kSubH + ti, wv = it.w0 + tj;
+          if (hv >= p.OHv || wv >= p.OWv || n >= p.cout) return;
+          const int oh = hv * p.out_mul + ph_p, ow = wv * p.out_mul + ph_q;
+          const long long opix = (static_cast<long long>(it.b_img) * p.OH + oh) * p.OW + ow;
+          float v[32];
+          const float4* bq = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { f[2 * i] = hy::bf16_lo(u[i]); f[2 * i + 1] = hy::bf16_hi(u[i]); }
-    };
-    uint4 a0c[2] = {}, a1c[2] = {}, a0n[2] = {}, a1n[2] = {};
-    uint32_t rc[16];
-    fetch_aux(0, a0c, a1c);
-    hy::mbar_wait(acc_full, 0);
-    hy::tc_fence_after();
-    hy::tmem_ld16(t_lane, rc);
-    hy::tmem_ld_fence(rc);
-    for (int it = 0; it < total; ++it) {
-      if (it + 1 < total) {
-        fetch_aux(it + 1, a0n, a1n);
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(bq + i);
+            v[4 * i] = fmaxf(__uint_as_float(r[4 * i]) + b4.x, lo);
+            v[4 * i + 1] = fmaxf(__uint_as_float(r[4 * i + 1]) + b4.y, lo);
+            v[4 * i + 2] = fmaxf(__uint_as_float(r[4 * i + 2]) + b4.z, lo);
+            v[4 * i + 3] = fmaxf(__uint_as_float(r[4 * i + 3]) + b4.w, lo);
+          }
+          const bool full = n + 32 <= p.cout;
+          if (p.out_bf16) {
+            __nv_bfloat16* o = p.out_bf16 + opix * p.ld_out + n;
+            if (full) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<uint4*>(o)[i] = make_uint4(hy::pack_bf16(v[8 * i], v[8 * i + 1]), hy::pack_bf16(v[8 * i + 2], v[8 * i + 3]),
+                                                            hy::pack_bf16(v[8 * i + 4], v[8 * i + 5]), hy::pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n + i < p.cout) o[i] = __float2bfloat16_rn(v[i]);
+            }
+          }
+          if (p.out_f32) {
+            float* o = p.out_f32 + it.b_img * p.f32_sb + oh * p.f32_sh + ow * p.f32_sw + n * p.f32_sc;
+            if (full && p.f32_sc == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n + i < p.cout) o[i * p.f32_sc] = v[i];
+            }
+          }
+        };
+        auto next_col = [&](int q) {
+          const int si = q / nch;
+          return static_cast<uint32_t>((sub0 + si * sub_step) * p.bn_max + ((q - si * nch) << 5));
+        };
+        for (int q = 0; q < steps; q += 2) {
+          hy::tmem_ld_fence32(r0);
+          if (q + 1 < steps) {
+            hy::tmem_ld32(t_item + next_col(q + 1), r1);
+          } else {
+            hy::tc_fence_before();
+            hy::mbar_arrive(acc_empty + 8 * buf);
+          }
+          body(q, r0);
+          if (q + 1 < steps) {
+            hy::tmem_ld_fence32(r1);
+            if (q + 2 < steps) {
+              hy::tmem_ld32(t_item + next_col(q + 2), r0);
+            } else {
+              hy::tc_fence_before();
+              hy::mbar_arrive(acc_empty + 8 * buf);
+            }
+            body(q + 1, r1);
+          }
+        }
+        continue;
       }
-      long long opix; int oh, ow, n; bool valid;
-      geom(it, opix, oh, ow, valid, n);
-      if (valid) {
+      auto geom = [&](int q, long long& opix, int& oh, int& ow, bool& valid, int& n, uint32_t& tcol) {
+        const int si = q / nchunk;
+        const int sub = sub0 + si * sub_step;
+        const int ch = q - si * nchunk;
+        const int hv = it.h0 + sub * kSubH + ti;
+        const int wv = it.w0 + tj;
+        n = it.n0 + ch * 16;
+        tcol = sub * p.bn_max + ch * 16;
+        valid = (hv < p.OHv) && (wv < p.OWv) && (n < p.cout);
+        oh = hv * p.out_mul + ph_p;
+        ow = wv * p.out_mul + ph_q;
+        opix = (static_cast<long long>(it.b_img) * p.OH + oh) * p.OW + ow;
+      };
+      auto fetch_aux = [&](int q, uint4 (&x0)[2], uint4 (&x1)[2]) {
+        long long opix; int oh, ow, n; bool valid; uint32_t tcol;
+        geom(q, opix, oh, ow, valid, n, tcol);
+        if (!valid) return;
+        if (need0) {
+          const uint4* g = reinterpret_cast<const uint4*>(p.aux0 + opix * p.ld_aux0 + n);
+          x0[0] = __ldg(g); x0[1] = __ldg(g + 1);
+        }
+        if (need1) {
+          const uint4* g = reinterpret_cast<const uint4*>(p.aux1 + opix * p.ld_aux1 + n);
+          x1[0] = __ldg(g); x1[1] = __ldg(g + 1);
+        }
+      };
+      auto unpack = [](const uint4 (&x)[2], float (&f)[16]) {
+        const uint32_t u[8] = {x[0].x, x[0].y, x[0].z, x[0].w, x[1].x, x[1].y, x[1].z, x[1].w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { f[2 * i] = hy::bf16_lo(u[i]); f[2 * i + 1] = hy::bf16_hi(u[i]); }
+      };
+      uint4 a0c[2] = {}, a1c[2] = {}, a0n[2] = {}, a1n[2] = {};
+      uint32_t rc[16];
+      fetch_aux(0, a0c, a1c);
+      hy::mbar_wait(acc_full + 8 * buf, use & 1u);
+      hy::tc_fence_after();
+      {
+        long long opix; int oh, ow, n; bool valid; uint32_t tcol;
+        geom(0, opix, oh, ow, valid, n, tcol);
+        hy::tmem_ld16(t_item + tcol, rc);
+        hy::tmem_ld_fence(rc);
+      }
+      for (int q = 0; q < total; ++q) {
+        if (q + 1 < total) fetch_aux(q + 1, a0n, a1n);
+        long long opix; int oh, ow, n; bool valid; uint32_t tcol;
+        geom(q, opix, oh, ow, valid, n, tcol);
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rc[i]);
-        const bool full16 = (n + 16 <= p.cout);
-        if (p.epi == HYRES_EPI_PIXSCALE) {
-          const float ps = __ldg(p.pixscale + opix);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= ps;
+        if (q + 1 < total) {
+          long long opix1; int oh1, ow1, n1; bool valid1; uint32_t tcol1;
+          geom(q + 1, opix1, oh1, ow1, valid1, n1, tcol1);
+          hy::tmem_ld16(t_item + tcol1, rc);
+        } else {
+          // every accumulator column of this thread's share now sits in registers: release the buffer
+          hy::tc_fence_before();
+          hy::mbar_arrive(acc_empty + 8 * buf);
         }
-        {
-          const float4* bq = reinterpret_cast<const float4*>(p.bias + n);  // bias padded to BN multiple
+        if (valid) {
+          const bool full16 = (n + 16 <= p.cout);
+          if (p.epi == HYRES_EPI_PIXSCALE) {
+            const float ps = __ldg(p.pixscale + opix);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 b4 = __ldg(bq + i);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            for (int i = 0; i < 16; ++i) v[i] *= ps;
           }
-        }
-        if (p.epi == HYRES_EPI_ADD) {
-          float a[16];
-          unpack(a0c, a);
+          {
+            const float4* bq = reinterpret_cast<const float4*>(p.bias + n);  // bias padded to cout_pad
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += a[i];
-        } else if (p.epi == HYRES_EPI_GATE) {
-          float a[16], x[16];
-          unpack(a1c, a);
-          unpack(a0c, x);
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = __ldg(bq + i);
+              v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            }
+          }
+          if (p.epi == HYRES_EPI_ADD) {
+            float a[16];
+            unpack(a0c, a);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = fmaf(a[i], hy::fast_sigmoid(v[i]), x[i]);
-        } else if (p.epi == HYRES_EPI_GDN) {
-          float x[16];
-          unpack(a0c, x);
+            for (int i = 0; i < 16; ++i) v[i] += a[i];
+          } else if (p.epi == HYRES_EPI_GATE) {
+            float a[16], x[16];
+            unpack(a1c, a);
+            unpack(a0c, x);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_rsqrt(v[i]);
-        } else if (p.epi == HYRES_EPI_IGDN) {
-          float x[16];
-          unpack(a0c, x);
+            for (int i = 0; i < 16; ++i) v[i] = fmaf(a[i], hy::fast_sigmoid(v[i]), x[i]);
+          } else if (p.epi == HYRES_EPI_GDN) {
+            float x[16];
+            unpack(a0c, x);
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_sqrt(v[i]);
-        }
+            for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_rsqrt(v[i]);
+          } else if (p.epi == HYRES_EPI_IGDN) {
+            float x[16];
+            unpack(a0c, x);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act, p.slope);
+            for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_sqrt(v[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = apply_act(v[i], p.act, p.slope);
 
-        if (p.out_bf16) {
-          __nv_bfloat16* o = p.out_bf16 + opix * p.ld_out + n;
-          if (full16) {
-            store16_bf16(o, v);
-          } else {
-            for (int i = 0; i < 16 && n + i < p.cout; ++i) o[i] = __float2bfloat16_rn(v[i]);
-          }
-        }
-        if (p.out_sq) {
-          __nv_bfloat16* o = p.out_sq + opix * p.ld_sq + n;
-          float s[16];
+          if (p.out_bf16) {
+            __nv_bfloat16* o = p.out_bf16 + opix * p.ld_out + n;
+            if (full16) {
+              store16_bf16(o, v);
+            } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            // square of the *stored* (bf16-rounded) activation: the GDN operand is x^2 of
-            // the tensor the next layer sees.
-            const float xb = __bfloat162float(__float2bfloat16_rn(v[i]));
-            s[i] = xb * xb;
+              for (int i = 0; i < 16; ++i)
+                if (n + i < p.cout) o[i] = __float2bfloat16_rn(v[i]);
+            }
           }
-          if (full16) {
-            store16_bf16(o, s);
-          } else {
-            for (int i = 0; i < 16 && n + i < p.cout; ++i) o[i] = __float2bfloat16_rn(s[i]);
-          }
-        }
-        if (p.out_f32) {
-          float* o = p.out_f32 + b_img * p.f32_sb + oh * p.f32_sh + ow * p.f32_sw + n * p.f32_sc;
-          if (full16 && p.f32_sc == 1) {
+          if (p.out_sq) {
+            __nv_bfloat16* o = p.out_sq + opix * p.ld_sq + n;
+            float sq[16];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          } else {
-            for (int i = 0; i < 16 && n + i < p.cout; ++i) o[i * p.f32_sc] = v[i];
+            for (int i = 0; i < 16; ++i) {
+              // square of the *stored* (bf16-rounded) activation: the GDN operand is x^2 of
+              // the tensor the next layer sees.
+              const float xb = __bfloat162float(__float2bfloat16_rn(v[i]));
+              sq[i] = xb * xb;
+            }
+            if (full16) {
+              store16_bf16(o, sq);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n + i < p.cout) o[i] = __float2bfloat16_rn(sq[i]);
+            }
+          }
+          if (p.out_f32) {
+            float* o = p.out_f32 + it.b_img * p.f32_sb + oh * p.f32_sh + ow * p.f32_sw + n * p.f32_sc;
+            if (full16 && p.f32_sc == 1) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (n + i < p.cout) o[i * p.f32_sc] = v[i];
+            }
           }
         }
-      }
-      if (it + 1 < total) {
-        const int sub1 = (it + 1) / nchunk;
-        hy::tmem_ld16(t_lane + sub1 * p.BN + (it + 1 - sub1 * nchunk) * 16, rc);
-        hy::tmem_ld_fence(rc);
-        a0c[0] = a0n[0]; a0c[1] = a0n[1]; a1c[0] = a1n[0]; a1c[1] = a1n[1];
+        if (q + 1 < total) {
+          hy::tmem_ld_fence(rc);
+          a0c[0] = a0n[0]; a0c[1] = a0n[1]; a1c[0] = a1n[0]; a1c[1] = a1n[1];
+        }
       }
     }
   }
 
   hy::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kWarpMma) {
     hy::tc_fence_after();
     hy::tmem_dealloc(tmem_base, p.tmem_cols);
   }
@@ -648,37 +793,83 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   p.OH = OH; p.OW = OW;
   p.out_mul = c->kind == HYRES_DECONV_K5S2 ? 2 : 1;
   p.OHv = OH / p.out_mul; p.OWv = OW / p.out_mul;
-  p.BN = c->BN;
-  // sub-tiles per CTA.  Measured on B200 (tools/check_conv.py, 4x256x384 maps): one 128-row
-  // accumulator per CTA with 2-3 co-resident CTAs per SM beats taller tiles, whose epilogue
-  // is not overlapped with another CTA's main loop.
+  p.nphase = c->nphase;
+
+  // N blocks: <= 256 output channels each, balanced, multiples of the weight TMA box
+  if (c->cout_pad <= 256) {
+    p.n_blocks = 1; p.nb_n0[0] = 0; p.nb_bn[0] = c->cout_pad;
+  } else {
+    if (c->cout_pad % 64) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: wide layers need a multiple of 64 output channels");
+    const int nblk = (c->cout_pad + 255) / 256;
+    const int bn = ((c->cout_pad + nblk - 1) / nblk + 63) / 64 * 64;
+    int n0 = 0, k = 0;
+    while (n0 < c->cout_pad) {
+      if (k >= kMaxNBlocks) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: too many output channels");
+      p.nb_n0[k] = n0; p.nb_bn[k] = std::min(bn, c->cout_pad - n0);
+      n0 += p.nb_bn[k]; ++k;
+    }
+    p.n_blocks = k;
+  }
+  p.bn_max = 0;
+  for (int k = 0; k < p.n_blocks; ++k) p.bn_max = std::max(p.bn_max, p.nb_bn[k]);
+  p.fast_epi = io->epi == HYRES_EPI_LINEAR && (io->act == HYRES_ACT_NONE || io->act == HYRES_ACT_RELU) && !io->out_sq;
+  for (int k = 0; k < p.n_blocks; ++k)
+    if (p.nb_bn[k] % 32) p.fast_epi = 0;
+  p.b_box_rows = 64;
+  for (int k = 0; k < p.n_blocks; ++k)
+    while (p.nb_bn[k] % p.b_box_rows) p.b_box_rows >>= 1;   // cout_pad is a multiple of 16
+
+  // Sub-tiles per item.  Taller items halve the weight traffic per MAC (the L2 -> SM path, about
+  // 42 B/clk/SM, bounds a 128 x 256 item at under half of the tensor peak); they are used when the
+  // layer still yields at least two waves of items.
+  const int tiles_w = (p.OWv + kTileW - 1) / kTileW;
+  auto items_for = [&](int mt) {
+    return static_cast<long long>(io->B) * tiles_w * ((p.OHv + kSubH * mt - 1) / (kSubH * mt)) * c->nphase * p.n_blocks;
+  };
   int mt = io->mt_hint;
-  if (mt != 1 && mt != 2 && mt != 4) mt = 1;
-  while (mt > 1 && mt * c->BN > 512) mt >>= 1;
+  if (mt != 1 && mt != 2 && mt != 4) mt = (p.bn_max * 2 <= 512 && items_for(2) >= 2LL * num_sms()) ? 2 : 1;
+  while (mt > 1 && mt * p.bn_max > 512) mt >>= 1;
   p.MT = mt;
+  p.acc_cols = mt * p.bn_max;
+  p.nbuf = 2 * p.acc_cols <= 512 ? 2 : 1;
+  p.acc_empty_count = p.nbuf == 2 ? 128 : 256;
+  int cols = 32;
+  while (cols < p.nbuf * p.acc_cols) cols <<= 1;
+  p.tmem_cols = cols;
   p.patch_rows = kSubH * mt + c->extra_rows;
   if (p.patch_rows > 256) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: patch too tall");
   p.a_stage_bytes = p.patch_rows * kTileW * 128;
-  p.b_stage_bytes = c->BN * 128;
-  // ring depths sized by what one tile actually consumes: small layers then fit several
-  // CTAs per SM, which is what hides the load -> MMA -> epilogue latency chain of a tile.
-  int max_groups = 0, max_btiles = 0;
+  p.b_stage_bytes = p.bn_max * 128;
+  // rings: fill shared memory; at least two patches and four weight tiles in flight
+  int total_groups = 0, total_btiles = 0;
   for (int ph = 0; ph < c->nphase; ++ph) {
-    max_groups = std::max(max_groups, c->ph_count[ph]);
-    int bt = 0;
-    for (int g = 0; g < c->ph_count[ph]; ++g) bt += c->groups[c->ph_begin[ph] + g].ntaps;
-    max_btiles = std::max(max_btiles, bt);
+    total_groups += c->ph_count[ph];
+    for (int g = 0; g < c->ph_count[ph]; ++g) total_btiles += c->groups[c->ph_begin[ph] + g].ntaps;
   }
-  p.NA = std::min(2, max_groups);
-  p.NB = std::min(4, max_btiles);
-  auto smem_need = [&]() { return p.NA * p.a_stage_bytes + p.NB * p.b_stage_bytes + 256 + 1024; };
-  while (smem_need() > 227 * 1024 && p.NB > 2) --p.NB;
-  if (smem_need() > 227 * 1024) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: tile does not fit shared memory");
-  int cols = 32;
-  while (cols < mt * c->BN) cols <<= 1;
-  p.tmem_cols = cols;
-  p.tiles_w = (p.OWv + kTileW - 1) / kTileW;
+  const int fixed = 512 /*barriers*/ + 1024 /*alignment*/;
+  const double taps_per_group = static_cast<double>(total_btiles) / total_groups;
+  p.NA = 2; p.NB = 2;
+  auto smem_need = [&]() { return p.NA * p.a_stage_bytes + p.NB * p.b_stage_bytes + fixed; };
+  if (smem_need() > kSmemLimit) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: tile does not fit shared memory");
+  for (;;) {
+    // grow the ring that is shallower in units of k-groups covered; fall back to the other one
+    const bool prefer_a = p.NA * taps_per_group <= p.NB;
+    bool grown = false;
+    for (int attempt = 0; attempt < 2 && !grown; ++attempt) {
+      const bool grow_a = (attempt == 0) == prefer_a;
+      int& n = grow_a ? p.NA : p.NB;
+      const int cap = grow_a ? 8 : 12;
+      if (n >= cap) continue;
+      ++n;
+      if (smem_need() > kSmemLimit) --n; else grown = true;
+    }
+    if (!grown) break;
+  }
+  p.tiles_w = tiles_w;
   p.tiles_h = (p.OHv + kSubH * mt - 1) / (kSubH * mt);
+  const long long nitems = items_for(mt);
+  if (nitems > 0x7fffffffLL) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: too many work items");
+  p.nitems = static_cast<int>(nitems);
   for (int i = 0; i < 4; ++i) { p.ph_begin[i] = c->ph_begin[i]; p.ph_count[i] = c->ph_count[i]; }
   p.groups = c->d_groups;
   p.cout = c->cout;
@@ -698,16 +889,16 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   if (c->cin1 > 0) rc = encode_act_map(&p.mapA1, io->x1, c->cin1, io->B, io->H, io->W, 0, p.patch_rows);
   else p.mapA1 = p.mapA0;
   if (rc != HYRES_OK) return rc;
-  rc = encode_w_map(&p.mapB, c->d_w, c->ktot, c->cout_pad, c->BN);
+  rc = encode_w_map(&p.mapB, c->d_w, c->ktot, c->cout_pad, p.b_box_rows);
   if (rc != HYRES_OK) return rc;
 
   const int smem = smem_need();
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    HY_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    smem_set = 227 * 1024;
+  static bool smem_set = false;
+  if (!smem_set) {
+    HY_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    smem_set = true;
   }
-  dim3 grid(static_cast<unsigned>(io->B * p.tiles_w * p.tiles_h), c->cout_pad / c->BN, c->nphase);
+  const int grid = std::min(p.nitems, num_sms());
   hy_count_launch();
   conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
   HY_CUDA(cudaGetLastError());
