@@ -158,6 +158,34 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-converged variants: every lane of the issuing warp executes the surrounding (warp-uniform)
+// address arithmetic, so the descriptors live in uniform registers, and one elected lane issues.
+// (A loop that runs inside `if (lane == 0)` makes the compiler rebuild every descriptor in vector
+// registers and move it to the uniform file per instruction: measured ~64 clk per MMA issued, twice the
+// tensor time of a 128x64x16 MMA.)  elect.sync picks the same lane every time, so tcgen05.commit issued
+// the same way tracks these MMAs.
+__device__ __forceinline__ void umma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}"
+      ::"r"(bar)
+      : "memory");
+}
 // Arrive on an mbarrier once all previously issued tcgen05 ops of this thread finished.
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -229,6 +257,65 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr, uint32_t sbo
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+// The same descriptor split into words: the start-address field is the only part that changes between
+// the MMAs of a tile, and since every shared-memory address is < 256 KB, advancing it by `bytes` is a
+// plain add of bytes >> 4 to the low word -- one integer add per operand per MMA in the issue loop.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3fffu) | (1u << 16); }
+__host__ __device__ constexpr uint32_t desc_hi_sw128(uint32_t sbo = 1024) { return (sbo >> 4) | (1u << 14) | (2u << 29); }
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// MMA issue in one of three styles (MODE): 0 = the calling code runs in a single lane; 1 = converged warp,
+// elect.sync per MMA; 2 = converged warp, `leader` (1 in exactly one lane) decided once by the caller.
+template <int MODE>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate, uint32_t leader) {
+  if (MODE == 0) {
+    umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else if (MODE == 1) {
+    umma_bf16_elect(tmem_d, adesc, bdesc, idesc, accumulate);
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+  }
+}
+template <int MODE>
+__device__ __forceinline__ void umma_commit_mode(uint32_t bar, uint32_t leader) {
+  if (MODE == 0) {
+    umma_commit(bar);
+  } else if (MODE == 1) {
+    umma_commit_elect(bar);
+  } else {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}"
+        ::"r"(bar), "r"(leader)
+        : "memory");
+  }
+}
+__device__ __forceinline__ uint32_t elect_leader() {
+  uint32_t is_leader;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, e;\n\t"
+      "}"
+      : "=r"(is_leader));
+  return is_leader;
 }
 // Instruction descriptor, kind::f16: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major,
 // N>>3 at [17,23), M>>4 at [24,29).

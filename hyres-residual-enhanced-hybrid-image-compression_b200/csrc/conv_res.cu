@@ -36,11 +36,14 @@ constexpr int kMaxSteps = 64;
 constexpr int kMaxStages = 4;
 constexpr int kSmemLimit = 227 * 1024;
 
+// One 64-deep k-step (four MMAs), with everything the issue loop needs precomputed on the host: the
+// loop is one 16-byte constant load and two adds per operand (measured: the issue thread, not the
+// tensor pipe, bounded the many-tap / narrow-N layers when it rebuilt descriptors per MMA).
 struct Step {
-  int16_t phase;
-  int16_t chunk;
-  int32_t a_row;  // start row of the tap inside the patch (ro * PW + co)
-  int32_t slot;   // 64-wide k-slot of the packed weights
+  int32_t a_off16;  // (chunk * a_chunk_bytes + tap start row * 128) >> 4, relative to the stage base
+  int32_t b_off16;  // (k-slot * BN * 128) >> 4, relative to the weight base
+  int32_t d_col;    // phase * BN: accumulator column offset
+  int32_t acc;      // 0 for the first step of a phase (overwrite), 1 afterwards
 };
 
 struct alignas(64) ResParams {
@@ -184,28 +187,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
     // ============================ MMA issuer ============================
     if (lane == 0) {
       const uint32_t idesc = hy::umma_idesc_bf16(128, p.BN);
-      const uint32_t sbo = p.PW * 128;
+      const uint32_t hi_a = hy::desc_hi_sw128(p.PW * 128), hi_b = hy::desc_hi_sw128();
+      const uint32_t w_lo = hy::desc_lo(w_base);
       hy::mbar_wait(W_FULL, 0);
       int stage = 0, it = 0;
       uint32_t par = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
         const int buf = it & 1;
-        const uint32_t sb = st_base + stage * p.stage_bytes;
+        const uint32_t a_lo0 = hy::desc_lo(st_base + stage * p.stage_bytes);
+        const uint32_t d0 = tmem_base + buf * acc_cols;
         hy::mbar_wait((p.a_square ? A_READY : A_FULL) + 8 * stage, par);
         hy::mbar_wait(ACC_EMPTY + 8 * buf, ((it >> 1) & 1) ^ 1u);
         hy::tc_fence_after();
-        uint32_t started = 0;
         for (int i = 0; i < p.nsteps; ++i) {
           const Step st = p.steps[i];
-          const uint32_t a0 = sb + st.chunk * p.a_chunk_bytes + st.a_row * 128;
-          const uint32_t b0 = w_base + st.slot * p.BN * 128;
-          const uint32_t d = tmem_base + buf * acc_cols + st.phase * p.BN;
-          const uint32_t acc = (started >> st.phase) & 1u;
+          const uint32_t a_lo = a_lo0 + st.a_off16, b_lo = w_lo + st.b_off16;
+          const uint32_t d = d0 + st.d_col;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            hy::umma_bf16(d, hy::umma_desc_sw128(a0 + k * 32, sbo), hy::umma_desc_sw128(b0 + k * 32), idesc,
-                          acc | static_cast<uint32_t>(k));
-          started |= 1u << st.phase;
+            hy::umma_bf16(d, hy::desc_pack(a_lo + 2 * k, hi_a), hy::desc_pack(b_lo + 2 * k, hi_b), idesc,
+                          static_cast<uint32_t>(st.acc | k));
         }
         hy::umma_commit(A_EMPTY + 8 * stage);
         hy::umma_commit(ACC_FULL + 8 * buf);
@@ -407,6 +408,7 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   }
   if (PW > 256 || PH > 256) return HYRES_OK;
   // tap list from the layer's plan
+  struct { int phase, chunk, a_row, slot; } steps_tmp[kMaxSteps];
   int ns = 0;
   for (int ph = 0; ph < c->nphase; ++ph)
     for (int g = c->ph_begin[ph]; g < c->ph_begin[ph] + c->ph_count[ph]; ++g) {
@@ -415,10 +417,10 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
         if (ns >= kMaxSteps) return HYRES_OK;
         const int ro = tg.dh + tg.tap_row[t] - org_h, co = tg.dw - org_w;
         if (ro < 0 || co < 0 || ro + kTH > PH || co + kTW > PW) return hy_fail(HYRES_ERR_STATE, "conv_res: tap outside patch");
-        p.steps[ns].phase = static_cast<int16_t>(ph);
-        p.steps[ns].chunk = static_cast<int16_t>(tg.c_off / 64);
-        p.steps[ns].a_row = ro * PW + co;
-        p.steps[ns].slot = tg.kslot0 + t;
+        steps_tmp[ns].phase = ph;
+        steps_tmp[ns].chunk = tg.c_off / 64;
+        steps_tmp[ns].a_row = ro * PW + co;
+        steps_tmp[ns].slot = tg.kslot0 + t;
         ++ns;
       }
     }
@@ -428,6 +430,16 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   p.nchunk_out = (c->cout + 63) / 64;
   p.PW = PW; p.PH = PH; p.org_h = org_h; p.org_w = org_w;
   p.a_chunk_bytes = (PH * PW * 128 + 1023) / 1024 * 1024;
+  {
+    uint32_t started = 0;
+    for (int i = 0; i < ns; ++i) {
+      p.steps[i].a_off16 = (steps_tmp[i].chunk * p.a_chunk_bytes + steps_tmp[i].a_row * 128) >> 4;
+      p.steps[i].b_off16 = (steps_tmp[i].slot * BN * 128) >> 4;
+      p.steps[i].d_col = steps_tmp[i].phase * BN;
+      p.steps[i].acc = (started >> steps_tmp[i].phase) & 1u;
+      started |= 1u << steps_tmp[i].phase;
+    }
+  }
   const bool need0 = io->epi == HYRES_EPI_ADD || io->epi == HYRES_EPI_GATE || io->epi == HYRES_EPI_GDN ||
                      io->epi == HYRES_EPI_IGDN;
   const bool need1 = io->epi == HYRES_EPI_GATE;

@@ -796,11 +796,12 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   p.nphase = c->nphase;
 
   // N blocks: <= 256 output channels each, balanced, multiples of the weight TMA box
-  if (c->cout_pad <= 256) {
+  static const int bn_cap = [] { const char* e = getenv("HYRES_TC_BNMAX"); const int v = e ? atoi(e) : 0; return (v >= 64 && v <= 256 && v % 64 == 0) ? v : 256; }();
+  if (c->cout_pad <= bn_cap || (c->cout_pad <= 256 && c->cout_pad % 64)) {
     p.n_blocks = 1; p.nb_n0[0] = 0; p.nb_bn[0] = c->cout_pad;
   } else {
     if (c->cout_pad % 64) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: wide layers need a multiple of 64 output channels");
-    const int nblk = (c->cout_pad + 255) / 256;
+    const int nblk = (c->cout_pad + bn_cap - 1) / bn_cap;
     const int bn = ((c->cout_pad + nblk - 1) / nblk + 63) / 64 * 64;
     int n0 = 0, k = 0;
     while (n0 < c->cout_pad) {

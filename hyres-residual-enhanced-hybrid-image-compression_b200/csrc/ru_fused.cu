@@ -29,12 +29,15 @@
 // G3 of the current one and runs while the epilogue warps are busy with E2 / E3.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 #include "conv_priv.h"
 #include "host_util.h"
 #include "hyres_b200.h"
+
+#define RU_STAMP(slot) do { if (p.trace && blockIdx.x == 0 && it < 64) p.trace[it * 16 + (slot)] = clock64(); } while (0)
 
 namespace {
 
@@ -69,6 +72,7 @@ struct alignas(64) RuParams {
   const float* b2;
   const float* b3;
   int32_t H, W, tiles_w, tiles_per_img, ntiles, final_relu;
+  long long* trace;  // optional: clock64 stamps of CTA 0 (tools/experiments), 16 slots per tile
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
@@ -105,6 +109,7 @@ __device__ __forceinline__ void bias_relu_pack32(const uint32_t (&r)[32], uint32
   }
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_constant__ RuParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -182,12 +187,16 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
     }
   } else if (warp == kWarpMma) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    if (MODE != 0 || lane == 0) {
+      const uint32_t leader = MODE == 2 ? hy::elect_leader() : 1u;
       const uint32_t idesc64 = hy::umma_idesc_bf16(128, 64);
       const uint32_t idesc128 = hy::umma_idesc_bf16(128, 128);
+      constexpr uint32_t hi = hy::desc_hi_sw128(), hi_t1 = hy::desc_hi_sw128(kPW * 128);
+      const uint32_t w1_lo = hy::desc_lo(base + kW1), w2_lo = hy::desc_lo(base + kW2), w3_lo = hy::desc_lo(base + kW3);
+      const uint32_t t_lo = hy::desc_lo(base + kS);
       // G1: t1 = x . W1^T over the 180-position patch (2 blocks of 128 rows; rows >= 180 unused)
       auto issue_g1 = [&](int jt) {
-        const uint32_t xb = base + kX0 + (jt & 1) * kXStride;
+        const uint32_t x_lo = hy::desc_lo(base + kX0 + (jt & 1) * kXStride);
         hy::tc_fence_after();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk)
@@ -195,9 +204,10 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
           for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              hy::umma_bf16(tmem_base + kColG1 + blk * 64, hy::umma_desc_sw128(xb + kc * kXChunk + blk * 16384 + k * 32),
-                            hy::umma_desc_sw128(base + kW1 + kc * 8192 + k * 32), idesc64, (kc | k) ? 1u : 0u);
-        hy::umma_commit(bar(G1_DONE));
+              hy::umma_issue<MODE>(tmem_base + kColG1 + blk * 64,
+                                   hy::desc_pack(x_lo + ((kc * kXChunk + blk * 16384 + k * 32) >> 4), hi),
+                                   hy::desc_pack(w1_lo + ((kc * 8192 + k * 32) >> 4), hi), idesc64, (kc | k) ? 1u : 0u, leader);
+        hy::umma_commit_mode<MODE>(bar(G1_DONE), leader);
       };
       hy::mbar_wait(bar(W_FULL), 0);
       int it = 0;
@@ -213,33 +223,40 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
         // G2: 3x3 over the t1 patch in smem; tap (r,s) = start row r*10+s, row groups 1280 B apart
         hy::mbar_wait(bar(T1_READY), ph);
         hy::tc_fence_after();
+        if (lane == 0) RU_STAMP(8);
 #pragma unroll
         for (int s = 0; s < 3; ++s)
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              hy::umma_bf16(tmem_base + kColG2,
-                            hy::umma_desc_sw128(base + kS + (r * kPW + s) * 128 + k * 32, kPW * 128),
-                            hy::umma_desc_sw128(base + kW2 + (s * 3 + r) * 8192 + k * 32), idesc64,
-                            (s | r | k) ? 1u : 0u);
-        hy::umma_commit(bar(G2_DONE));
+              hy::umma_issue<MODE>(tmem_base + kColG2, hy::desc_pack(t_lo + (((r * kPW + s) * 128 + k * 32) >> 4), hi_t1),
+                                   hy::desc_pack(w2_lo + (((s * 3 + r) * 8192 + k * 32) >> 4), hi), idesc64,
+                                   (s | r | k) ? 1u : 0u, leader);
+        hy::umma_commit_mode<MODE>(bar(G2_DONE), leader);
+        if (lane == 0) RU_STAMP(9);
         // G1 of the next tile rides behind G2 when its patch has landed (columns [0,128) were drained by E1
         // of this tile); it then overlaps E2 / E3 of this tile.
         bool g1_ahead = false;
-        if (has_next && hy::mbar_try_wait(bar(X_FULL + nb), nph)) {
-          issue_g1(it + 1);
-          g1_ahead = true;
+        if (has_next) {
+          bool landed = hy::mbar_try_wait(bar(X_FULL + nb), nph);
+          if (MODE != 0) landed = __all_sync(0xffffffffu, landed);
+          if (landed) {
+            issue_g1(it + 1);
+            g1_ahead = true;
+          }
         }
         // G3: 1x1 expand
         hy::mbar_wait(bar(T2_READY), ph);
         if (it > 0) hy::mbar_wait(bar(ACC_FREE), (it - 1) & 1);  // E3 of the previous tile drained [256,384)
         hy::tc_fence_after();
+        if (lane == 0) RU_STAMP(10);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          hy::umma_bf16(tmem_base + kColG3, hy::umma_desc_sw128(base + kS + k * 32),
-                        hy::umma_desc_sw128(base + kW3 + k * 32), idesc128, k ? 1u : 0u);
-        hy::umma_commit(bar(G3_DONE));
+          hy::umma_issue<MODE>(tmem_base + kColG3, hy::desc_pack(t_lo + ((k * 32) >> 4), hi),
+                               hy::desc_pack(w3_lo + ((k * 32) >> 4), hi), idesc128, k ? 1u : 0u, leader);
+        hy::umma_commit_mode<MODE>(bar(G3_DONE), leader);
+        if (lane == 0) RU_STAMP(11);
         if (has_next && !g1_ahead) {
           hy::mbar_wait(bar(X_FULL + nb), nph);
           issue_g1(it + 1);
@@ -284,8 +301,10 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       uint4 qv[4];
 
       // ---- E1: t1 patch (this warp: 32 of the 64 channels) ----
+      if (threadIdx.x == 0) RU_STAMP(0);
       hy::mbar_wait(bar(G1_DONE), ph);
       hy::tc_fence_after();
+      if (threadIdx.x == 0) RU_STAMP(1);
       hy::tmem_ld32(t_lane + kColG1 + hsel * 32, ra);
       if (q < 2) hy::tmem_ld32(t_lane + kColG1 + 64 + hsel * 32, rb);  // rows 128.. exist in lanes 0..51 only
 #pragma unroll
@@ -313,10 +332,12 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       hy::fence_async_smem();
       hy::tc_fence_before();
       hy::mbar_arrive(bar(T1_READY));
+      if (threadIdx.x == 0) RU_STAMP(2);
 
       // ---- E2: t2 ----
       hy::mbar_wait(bar(G2_DONE), ph);
       hy::tc_fence_after();
+      if (threadIdx.x == 0) RU_STAMP(3);
       {
         const uint32_t row = base + kS + tid * 128;
         const uint32_t sw = tid & 7;
@@ -329,11 +350,13 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       hy::fence_async_smem();
       hy::tc_fence_before();
       hy::mbar_arrive(bar(T2_READY));
+      if (threadIdx.x == 0) RU_STAMP(4);
 
       // ---- E3: + bias + skip (this warp: 64-channel chunk `hsel`), stage over the x buffer ----
       hy::mbar_wait(bar(G3_DONE), ph);
       hy::mbar_wait(bar(X_FULL + b), (it >> 1) & 1);  // (already complete) acquire the TMA-written patch
       hy::tc_fence_after();
+      if (threadIdx.x == 0) RU_STAMP(5);
       {
         const int h = hsel;
         const uint32_t skip_row = xb + h * kXChunk + pc * 128;
@@ -379,6 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       }
       hy::fence_async_smem();
       hy::mbar_arrive(bar(STAGED));
+      if (threadIdx.x == 0) RU_STAMP(6);
     }
   }
 
@@ -445,15 +469,24 @@ int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c
   p.tiles_per_img = p.tiles_w * ((io->H + kTH - 1) / kTH);
   p.ntiles = p.tiles_per_img * io->B;
   p.final_relu = io->final_relu ? 1 : 0;
+  {
+    // HYRES_RU_TRACE=<device pointer, hex>: 64 x 16 clock64 stamps of CTA 0 (tools/experiments/ru_trace.py)
+    static const char* e = getenv("HYRES_RU_TRACE");
+    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
+  }
   const int smem = kSmemUsed + 1024;
+  static const int mode = [] { const char* e = getenv("HYRES_RU_MODE"); return e ? atoi(e) : 0; }();
+  auto kern = mode == 1 ? ru_fused_kernel<1> : (mode == 2 ? ru_fused_kernel<2> : ru_fused_kernel<0>);
   static bool attr_set = false;
   if (!attr_set) {
-    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();
-  ru_fused_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
+  kern<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }

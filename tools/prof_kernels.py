@@ -16,6 +16,7 @@ from hyres_b200.ops import (ACT_NONE, ACT_PRELU, ACT_RELU, EPI_ADD, EPI_GATE, EP
                             EPI_PIXSCALE, HYRES_CONV, HYRES_DECONV_K5S2)
 
 B = 16
+MT = 0
 
 
 def rnd(*shape):
@@ -85,9 +86,9 @@ def make(case):
         x1 = rnd(B, 64, 96, ci // 2) if case == "head0" else None
         if case == "head2":
             o32 = torch.empty(B, 64, 96, co, device="cuda")
-            return lambda: L(x, out_bf16=False, out_f32=o32), 2.0 * B * 64 * 96 * ci * co, x.numel() * 2 + o32.numel() * 4
+            return lambda: L(x, out_bf16=False, out_f32=o32, mt=MT), 2.0 * B * 64 * 96 * ci * co, x.numel() * 2 + o32.numel() * 4
         out = torch.empty(B, 64, 96, co, device="cuda", dtype=torch.bfloat16)
-        return lambda: L(x, x1, act=ACT_RELU, out_bf16=out), 2.0 * B * 64 * 96 * ci * co, (B * 64 * 96 * ci + out.numel()) * 2
+        return lambda: L(x, x1, act=ACT_RELU, out_bf16=out, mt=MT), 2.0 * B * 64 * 96 * ci * co, (B * 64 * 96 * ci + out.numel()) * 2
     if case == "ctx":
         mask = torch.zeros(5, 5, dtype=torch.uint8)
         mask[0::2, 1::2] = 1
@@ -95,18 +96,24 @@ def make(case):
         L = ops.ConvLayer(w(384, 192, 5), bias(384), pad=2, tap_mask=mask)
         x = rnd(B, 64, 96, 192)
         out = torch.empty(B, 64, 96, 384, device="cuda", dtype=torch.bfloat16)
-        return lambda: L(x, out_bf16=out), 2.0 * B * 64 * 96 * 192 * 12 * 384, (x.numel() + out.numel()) * 2
+        return lambda: L(x, out_bf16=out, mt=MT), 2.0 * B * 64 * 96 * 192 * 12 * 384, (x.numel() + out.numel()) * 2
     if case == "deconv":
         wt = torch.randn(128, 128, 5, 5, generator=g) / (128 * 25 / 4) ** 0.5
         L = ops.ConvLayer(wt, bias(128), kind=HYRES_DECONV_K5S2)
         x = rnd(B, 128, 192, 128)
         out = torch.empty(B, 256, 384, 128, device="cuda", dtype=torch.bfloat16)
-        return lambda: L(x, out_bf16=out), 2.0 * B * 128 * 192 * 128 * 25 * 128, (x.numel() + out.numel()) * 2
+        return lambda: L(x, out_bf16=out, mt=MT), 2.0 * B * 128 * 192 * 128 * 25 * 128, (x.numel() + out.numel()) * 2
     if case == "s2":
         L = ops.ConvLayer(w(128, 128, 5), bias(128), stride=2, pad=2)
         x = rnd(B, 256, 384, 128)
         out = torch.empty(B, 128, 192, 128, device="cuda", dtype=torch.bfloat16)
-        return lambda: L(x, out_bf16=out), 2.0 * B * 128 * 192 * 128 * 25 * 128, (x.numel() + out.numel()) * 2
+        return lambda: L(x, out_bf16=out, mt=MT), 2.0 * B * 128 * 192 * 128 * 25 * 128, (x.numel() + out.numel()) * 2
+    if case == "fus2":
+        L = ops.ConvLayer(w(3, 64, 3), bias(3), pad=1)
+        x = rnd(B, 512, 768, 64)
+        o32 = torch.empty(B, 3, 512, 768, device="cuda")
+        return (lambda: L(x, out_bf16=False, out_f32=o32.permute(0, 2, 3, 1)), 2.0 * B * 512 * 768 * 64 * 9 * 3,
+                x.numel() * 2 + o32.numel() * 4)
     if case == "gs8":
         wt = torch.randn(128, 3, 5, 5, generator=g) / (128 * 25 / 4) ** 0.5
         L = ops.ConvLayer(wt, bias(3), kind=HYRES_DECONV_K5S2)
@@ -122,7 +129,10 @@ def main():
     ap.add_argument("--case", required=True)
     ap.add_argument("--n", type=int, default=3)
     ap.add_argument("--time", action="store_true")
+    ap.add_argument("--mt", type=int, default=0)
     a = ap.parse_args()
+    global MT
+    MT = a.mt
     for case in a.case.split(","):
         fn, flops, byts = make(case)
         for _ in range(a.n):
