@@ -63,6 +63,7 @@ SIGNATURES = {
     "hyres_ru_run": (_i, [_vp, _vp, _vp, C.POINTER(RuIO), _vp]),
     "hyres_residual_im2col5s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_addback_im2col3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hyres_conv3ch_run": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "hyres_final_clamp": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hyres_gc_quant_pass": (_i, [_vp, _vp, _i, _i, _u64, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_gc_merge_likelihood": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -191,8 +191,10 @@ class CodecEngine:
         return self._eb_cache
 
     # -- stages (NHWC bf16 in / out unless noted) --
-    def g_a(self, a_im2col):
-        t, _, _ = self.ga0(a_im2col)
+    def g_a(self, x, jpeg=None, want_residual=True):
+        """x (and optionally jpeg): fp32 NCHW [B,3,H,W]; g_a runs on residual = x - jpeg.
+        -> (y bf16 NHWC, y fp32 NHWC, residual fp32 NCHW or x)."""
+        residual, t = ops.conv3ch(self.ga0.layer, 5, 2, x, jpeg, sign=-1, want_sum=want_residual)
         t, _, _ = self.ga1(t, epi=EPI_GDN, aux0=t, x0_square=True)
         t = self.ga2(t)
         t = self.ga3(t)
@@ -200,7 +202,8 @@ class CodecEngine:
         t, _, _ = self.ga5(t, epi=EPI_GDN, aux0=t, x0_square=True)
         t = self.ga6(t)
         t, _, _ = self.ga7(t)
-        return self.ga8(t, out_f32="nhwc")  # (y bf16, y fp32)
+        y16, y32 = self.ga8(t, out_f32="nhwc")
+        return y16, y32, residual
 
     def h_a(self, y16):
         t, _, _ = self.ha[0](y16, act=ACT_RELU)
@@ -286,13 +289,16 @@ class RefineEngine:
             )
         return self._small
 
-    def __call__(self, a_im2col):
-        """a_im2col: bf16 [B,H,W,64] (3x3 im2col of x0) -> refined fp32 NCHW [B,3,H,W]."""
-        B, H, W, _ = a_im2col.shape
-        dev = a_im2col.device
+    def __call__(self, r_hat, jpeg=None):
+        """x0 = jpeg + r_hat (fp32 NCHW [B,3,H,W]; or r_hat alone) -> (x0, refined fp32 NCHW [B,3,H,W])."""
+        B, _, H, W = r_hat.shape
+        dev = r_hat.device
         sm = self.small(dev)
         sl = sm["slopes"]
-        feat0, _, _ = self.conv_in(a_im2col, act=ACT_PRELU, slope=sl[0])
+        if jpeg is None:
+            x0, feat0 = ops.conv3ch(self.conv_in.layer, 3, 1, r_hat, act=ACT_PRELU, slope=sl[0])
+        else:
+            x0, feat0 = ops.conv3ch(self.conv_in.layer, 3, 1, jpeg, r_hat, sign=1, act=ACT_PRELU, slope=sl[0])
         feat, feat_h, feat_q, _ = ops.refine_se_scale_down(feat0, sm["fc1"], sm["fc2"])
         multi = torch.empty((B, H, W, 192), dtype=torch.bfloat16, device=dev)
         t, _, _ = self.scales[0][0](feat, act=ACT_PRELU, slope=sl[1])
@@ -305,4 +311,4 @@ class RefineEngine:
         att = ops.refine_spatial_att(stats, sm["w7"])
         h, _, _ = self.fusion0(multi, epi=EPI_PIXSCALE, pixscale=att, act=ACT_PRELU, slope=sl[7])
         _, _, refined = self.fusion2(h, out_bf16=False, out_f32="nchw")
-        return refined
+        return x0, refined

@@ -150,19 +150,18 @@ class LightWeightCheckerboard(CompressionModel):
             raise ValueError("H and W must be multiples of 32 (the reference never pads)")
 
     # -- forward (models/checkerboard.py:90-147) --
-    def forward(self, x, noisequant=False, stats=None, _im2col=None):
+    def forward(self, x, noisequant=False, stats=None, _jpeg=None):
         """-> {"x_hat": [B,3,H,W], "likelihoods": {"y": [B,M,H/8,W/8], "z": [B,N,H/32,W/32]}}.
 
         ``stats``: optional 2-element CUDA double tensor accumulating sum(log2 lik_y), sum(log2 lik_z)
-        inside the likelihood kernels (used by the fused RD loss).  ``_im2col``: the g_a.0 operand when
-        the caller (the JPEG wrapper) already produced it together with the residual."""
+        inside the likelihood kernels (used by the fused RD loss).  ``_jpeg``: set by the JPEG wrapper; the
+        codec then runs on ``x - _jpeg`` (subtraction fused into g_a.0) and returns it as ``"_residual"``."""
         _require_cuda(x, "forward")
         self._check_input(x)
         eng = self.engine()
         x = x.contiguous().float()
         training = self.training
-        a = _im2col if _im2col is not None else ops.residual_im2col5s2(x)[1]
-        y16, y32 = eng.g_a(a)
+        y16, y32, residual = eng.g_a(x, _jpeg)
         z32 = eng.h_a(y16)
         ebp, med = eng.eb_params()
         eb = ops.eb_forward(z32, ebp, med, lik_noise=training, out_noise=training and noisequant, seed=self._seed(),
@@ -177,10 +176,13 @@ class LightWeightCheckerboard(CompressionModel):
         y_hat16, lik_y = ops.gc_merge_likelihood(y32, pa, pna, yqa32, yqna32, noise=training, seed=self._seed(),
                                                  sum_log2=None if stats is None else stats[0:1])
         x_hat = eng.g_s(y_hat16)
-        return {"x_hat": x_hat, "likelihoods": {"y": lik_y, "z": eb["lik"]}}
+        out = {"x_hat": x_hat, "likelihoods": {"y": lik_y, "z": eb["lik"]}}
+        if _jpeg is not None:
+            out["_residual"] = residual
+        return out
 
     # -- symbols of both passes (GPU part of compress) --
-    def encode_symbols(self, x, _im2col=None):
+    def encode_symbols(self, x, _jpeg=None):
         """GPU front-end of ``compress``: returns the integer streams the entropy coder consumes,
         all int32 CUDA tensors in (B,C,h,w) order, plus the shapes."""
         _require_cuda(x, "compress")
@@ -189,8 +191,7 @@ class LightWeightCheckerboard(CompressionModel):
         x = x.contiguous().float()
         table = self._scale_table(x.device)
         bound = float(self.gaussian_conditional.scale_bound.item())
-        a = _im2col if _im2col is not None else ops.residual_im2col5s2(x)[1]
-        y16, y32 = eng.g_a(a)
+        y16, y32, _ = eng.g_a(x, _jpeg, want_residual=False)
         z32 = eng.h_a(y16)
         ebp, med = eng.eb_params()
         eb = ops.eb_forward(z32, ebp, med, want_lik=False, want_symbols=True)
@@ -204,9 +205,9 @@ class LightWeightCheckerboard(CompressionModel):
                 "y": y32, "z": z32, "params_a": pa, "params_na": pna}
 
     # -- compress (models/checkerboard.py:167-198) --
-    def compress(self, x, _im2col=None):
+    def compress(self, x, _jpeg=None):
         start_time = time.time()
-        s = self.encode_symbols(x, _im2col=_im2col)
+        s = self.encode_symbols(x, _jpeg=_jpeg)
         gc, ebm = self.gaussian_conditional, self.entropy_bottleneck
         z_strings = ebm.encode_symbols(s["sym_z"], ebm._build_indexes(s["sym_z"].size()))
         anchor_strings = gc.encode_symbols(s["sym_a"], s["idx_a"])
@@ -294,8 +295,7 @@ class ResidualJPEGCompression(CompressionModel):
         return out
 
     def _reconstruct(self, jpeg_decoded, residual_hat):
-        x0, a = ops.addback_im2col3(residual_hat, jpeg_decoded)
-        refined = self.refine_engine()(a)
+        x0, refined = self.refine_engine()(residual_hat, jpeg_decoded)
         return ops.final_clamp(x0, refined)
 
     # -- forward (models/hyres.py:23-77) --
@@ -312,9 +312,8 @@ class ResidualJPEGCompression(CompressionModel):
         jpeg_decoded = jpeg_decoded_cpu.to(device, torch.float32).contiguous()
         xd = x.to(device, torch.float32).contiguous()
         self.residual_model._check_input(xd)
-        residual, a = ops.residual_im2col5s2(xd, jpeg_decoded)
-        res = self.residual_model(residual, noisequant=noisequant, stats=stats, _im2col=a)
-        residual_hat = res["x_hat"]
+        res = self.residual_model(xd, noisequant=noisequant, stats=stats, _jpeg=jpeg_decoded)
+        residual, residual_hat = res["_residual"], res["x_hat"]
         x_hat = self._reconstruct(jpeg_decoded, residual_hat)
         return {"x_hat": x_hat, "likelihoods": res["likelihoods"],
                 "jpeg_bpp_loss": torch.tensor(jpeg_bpp, device=device), "jpeg_decoded": jpeg_decoded,
@@ -327,8 +326,7 @@ class ResidualJPEGCompression(CompressionModel):
             jpeg_buffers = self.jpeg.compress(x)
         jpeg_decoded = self.jpeg.decompress(jpeg_buffers, device).float().contiguous()
         xd = x.to(device, torch.float32).contiguous()
-        residual, a = ops.residual_im2col5s2(xd, jpeg_decoded)
-        out = self.residual_model.compress(residual, _im2col=a)
+        out = self.residual_model.compress(xd, _jpeg=jpeg_decoded)
         out["jpeg_buffers"] = jpeg_buffers
         return out
 

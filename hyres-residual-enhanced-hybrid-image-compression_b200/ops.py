@@ -254,6 +254,42 @@ def addback_im2col3(r_hat, jpeg=None):
     return (x0 if x0 is not None else r_hat), a
 
 
+def conv3ch(layer, ksize, stride, a, b=None, sign=1, want_sum=True, act=ACT_NONE, slope=0.0, out=None):
+    """First-layer convolution of a 3-channel fp32 NCHW image, fused with ``src = a + sign*b``
+    (csrc/conv_c3.cu).  ``layer``: the 1x1 ConvLayer over the im2col ordering.  Returns
+    (src fp32 NCHW -- ``a`` itself when b is None --, activation bf16 NHWC [B,OH,OW,cout])."""
+    _f32c(a, "a")
+    B, Cc, H, W = a.shape
+    if Cc != 3:
+        raise ValueError("expected 3 channels")
+    src = a
+    if b is not None:
+        _f32c(b, "b")
+        if b.shape != a.shape:
+            raise ValueError("a / b shape mismatch")
+        src = torch.empty_like(a) if want_sum else None
+    OH, OW = (H // 2, W // 2) if stride == 2 else (H, W)
+    if out is None:
+        out = torch.empty((B, OH, OW, layer.cout), dtype=torch.bfloat16, device=a.device)
+    ConvLayer._chk_aux(out, B, OH, OW, "out")
+
+    def run():
+        L.check(L.lib().hyres_conv3ch_run(layer._h, ksize, stride, _ptr(a), _ptr(b), sign,
+                                          _ptr(src if b is not None else None), _ptr(out), out.stride(2), B, H, W,
+                                          act, float(slope), _stream()), "hyres_conv3ch_run")
+    if ConvLayer._prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        ConvLayer._prof.append((e0, e1))
+        ConvLayer._prof_info.append(dict(kind="c3", cin=3, cout=layer.cout, k=ksize, stride=stride, dil=1, B=B, H=H, W=W,
+                                         OH=OH, OW=OW, epi=EPI_LINEAR, f32=False, sq=False))
+    else:
+        run()
+    return src, out
+
+
 def final_clamp(x0, refined):
     _f32c(x0, "x0"), _f32c(refined, "refined")
     out = torch.empty_like(x0)

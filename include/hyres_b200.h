@@ -155,6 +155,19 @@ int hyres_residual_im2col5s2(const float* x, const float* jpeg, float* residual,
  * models/hyres.py:62,127 + models/layers/enhancement.py:60 */
 int hyres_addback_im2col3(const float* jpeg, const float* r_hat, float* x0, void* a_out, int B,
                           int H, int W, void* stream);
+/* The two 3-channel first-layer convolutions fused with the residual arithmetic around them
+ * (no im2col tensor in HBM; the im2col row is built on chip):
+ *   src = a + sign * b        (fp32 NCHW [B,3,H,W]; b may be NULL)
+ *   sum_out = src             (optional fp32 NCHW; requires b)
+ *   out = act(conv(src) + bias)   bf16 NHWC [B,OH,OW,cout], channel stride ld_out
+ * ksize 5 / stride 2 (g_a.0 on residual = x - jpeg: models/hyres.py:48,96 +
+ * models/checkerboard.py:36, cout 128) or ksize 3 / stride 1 (refine.conv_in + PReLU on
+ * x0 = jpeg + r_hat: models/hyres.py:62,127 + models/layers/enhancement.py:60,89, cout 64).
+ * `c` is the layer created as the 1x1 GEMM over the im2col ordering k = (r*ksize+s)*3 + c
+ * (cin 128 / 64, zero beyond 75 / 27), exactly what the im2col entry points above feed. */
+int hyres_conv3ch_run(hyres_conv* c, int ksize, int stride, const float* a, const float* b, int sign,
+                      float* sum_out, void* out_bf16, int ld_out, int B, int H, int W, int act,
+                      float slope, void* stream);
 /* x_hat = clamp(x0 + refined, 0, 1), all fp32 NCHW. models/hyres.py:66-67,131-132 */
 int hyres_final_clamp(const float* x0, const float* refined, float* x_hat, int64_t n, void* stream);
 

@@ -121,6 +121,22 @@ def make(case):
         o32 = torch.empty(B, 3, 512, 768, device="cuda")
         return (lambda: L(x, out_bf16=False, out_f32=o32.permute(0, 2, 3, 1)), 2.0 * B * 256 * 384 * 128 * 25 * 3,
                 x.numel() * 2 + o32.numel() * 4)
+    if case in ("c3in", "c3ga"):
+        a = torch.rand(B, 3, 512, 768, device="cuda")
+        b2 = torch.rand(B, 3, 512, 768, device="cuda")
+        if case == "c3in":
+            w2 = torch.zeros(64, 64, 1, 1)
+            w2[:, :27] = torch.randn(64, 27, 1, 1, generator=g) / 27 ** 0.5
+            L = ops.ConvLayer(w2, bias(64))
+            out = torch.empty(B, 512, 768, 64, device="cuda", dtype=torch.bfloat16)
+            return (lambda: ops.conv3ch(L, 3, 1, a, b2, sign=1, act=ACT_PRELU, slope=0.2, out=out),
+                    2.0 * B * 512 * 768 * 64 * 27, a.numel() * 12 + out.numel() * 2)
+        w2 = torch.zeros(128, 128, 1, 1)
+        w2[:, :75] = torch.randn(128, 75, 1, 1, generator=g) / 75 ** 0.5
+        L = ops.ConvLayer(w2, bias(128))
+        out = torch.empty(B, 256, 384, 128, device="cuda", dtype=torch.bfloat16)
+        return (lambda: ops.conv3ch(L, 5, 2, a, b2, sign=-1, out=out),
+                2.0 * B * 256 * 384 * 128 * 75, a.numel() * 12 + out.numel() * 2)
     raise SystemExit(f"unknown case {case}")
 
 
