@@ -316,7 +316,8 @@ class ResidualJPEGCompression(CompressionModel):
         residual, residual_hat = res["_residual"], res["x_hat"]
         x_hat = self._reconstruct(jpeg_decoded, residual_hat)
         return {"x_hat": x_hat, "likelihoods": res["likelihoods"],
-                "jpeg_bpp_loss": torch.tensor(jpeg_bpp, device=device), "jpeg_decoded": jpeg_decoded,
+                "jpeg_bpp_loss": torch.full((), float(jpeg_bpp), dtype=torch.float32, device=device),  # fill kernel: no host sync
+                "jpeg_decoded": jpeg_decoded,
                 "residual": residual, "residual_hat": residual_hat}
 
     # -- compress / decompress (models/hyres.py:79-134) --
