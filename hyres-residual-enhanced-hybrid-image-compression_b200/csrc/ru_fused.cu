@@ -54,20 +54,21 @@ constexpr uint32_t kW1 = 0;             // [2 k-chunks][64 n][128 B]
 constexpr uint32_t kW2 = 16384;         // [9 taps][64 n][128 B]
 constexpr uint32_t kW3 = 90112;         // [128 n][128 B]
 constexpr uint32_t kWBytes = 106496;
-constexpr uint32_t kX0 = 106496;        // 2 buffers x 2 chunks
 constexpr uint32_t kXChunk = 23552;     // 180 rows x 128 B, padded to a multiple of 1024
-constexpr uint32_t kXStride = 2 * kXChunk;
 constexpr uint32_t kXBytes = kNP * 128; // bytes one TMA chunk load delivers
-constexpr uint32_t kS = kX0 + 2 * kXStride;  // t1 patch, then t2
-constexpr uint32_t kBars = kS + kXChunk;
+constexpr uint32_t kX = kWBytes;                 // x halo patch: 2 chunks (one buffer: it only feeds G1)
+constexpr uint32_t kT1 = kX + 2 * kXChunk;       // t1 patch [180][64]
+constexpr uint32_t kT2 = kT1 + kXChunk;          // t2 [128][64]
+constexpr uint32_t kStg = kT2 + 16384;           // skip tile in, result out: 2 chunks [128][64]
+constexpr uint32_t kBars = kStg + 32768;
 constexpr uint32_t kBias = kBars + 256;
 constexpr uint32_t kSmemUsed = kBias + 1024;
 
-enum { W_FULL = 0, X_FULL = 1, X_EMPTY = 3, G1_DONE = 5, T1_READY = 6, G2_DONE = 7, T2_READY = 8, G3_DONE = 9,
-       ACC_FREE = 10, STAGED = 11, NUM_BARS = 12 };
+enum { W_FULL = 0, X_FULL, X_FREE, G1_DONE, T1_READY, G2_DONE, T2_READY, G3_DONE, ACC3_FREE, SKIP_FULL, STAGED, STG_FREE,
+       NUM_BARS };
 
 struct alignas(64) RuParams {
-  CUtensorMap mapX, mapOut, mapW1, mapW2, mapW3;
+  CUtensorMap mapX, mapSkip, mapOut, mapW1, mapW2, mapW3;
   const float* b1;
   const float* b2;
   const float* b3;
@@ -109,7 +110,11 @@ __device__ __forceinline__ void bias_relu_pack32(const uint32_t (&r)[32], uint32
   }
 }
 
-template <int MODE>
+// Software pipeline across tiles (i = this CTA's i-th tile):
+//   epilogue warps :  E1(i)  E3(i-1)  E2(i)   E1(i+1)  E3(i)  E2(i+1) ...
+//   tensor pipe    :         G2(i)  G1(i+1)   G3(i)           G2(i+1) ...
+// The 3x3 GEMM of tile i and the first GEMM of tile i+1 run under the (long) output epilogue of tile i-1, and
+// G3(i) under E1(i+1); every buffer has one producer and one consumer phase per tile, tracked by an mbarrier.
 __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_constant__ RuParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -120,16 +125,16 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     hy::mbar_init(bar(W_FULL), 1);
-    for (int i = 0; i < 2; ++i) {
-      hy::mbar_init(bar(X_FULL + i), 1);
-      hy::mbar_init(bar(X_EMPTY + i), 1);
-    }
+    hy::mbar_init(bar(X_FULL), 1);
+    hy::mbar_init(bar(X_FREE), 1);
     hy::mbar_init(bar(G1_DONE), 1);
     hy::mbar_init(bar(G2_DONE), 1);
     hy::mbar_init(bar(G3_DONE), 1);
+    hy::mbar_init(bar(SKIP_FULL), 1);
+    hy::mbar_init(bar(STG_FREE), 1);
     hy::mbar_init(bar(T1_READY), kEpiThreads);
     hy::mbar_init(bar(T2_READY), kEpiThreads);
-    hy::mbar_init(bar(ACC_FREE), kEpiThreads);
+    hy::mbar_init(bar(ACC3_FREE), kEpiThreads);
     hy::mbar_init(bar(STAGED), kEpiThreads);
     hy::mbar_fence_init();
   }
@@ -141,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
   }
   if (warp == kWarpLoad && lane == 0) {
     hy::tma_prefetch_desc(&p.mapX);
+    hy::tma_prefetch_desc(&p.mapSkip);
     hy::tma_prefetch_desc(&p.mapW1);
     hy::tma_prefetch_desc(&p.mapW2);
     hy::tma_prefetch_desc(&p.mapW3);
@@ -163,40 +169,51 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
     h0 = th * kTH;
     w0 = (rem - th * p.tiles_w) * kTW;
   };
+  const int stride = static_cast<int>(gridDim.x);
+  const int first = static_cast<int>(blockIdx.x);
 
   if (warp == kWarpLoad) {
     // ============================ TMA load producer ============================
     if (lane == 0) {
+      auto load_x = [&](int t) {
+        int b_img, h0, w0;
+        tile_origin(t, b_img, h0, w0);
+        hy::mbar_arrive_expect_tx(bar(X_FULL), 2 * kXBytes);
+        hy::tma_load_4d(base + kX, &p.mapX, bar(X_FULL), 0, w0 - 1, h0 - 1, b_img);
+        hy::tma_load_4d(base + kX + kXChunk, &p.mapX, bar(X_FULL), 64, w0 - 1, h0 - 1, b_img);
+      };
       hy::mbar_arrive_expect_tx(bar(W_FULL), kWBytes);
       hy::tma_load_2d(base + kW1, &p.mapW1, bar(W_FULL), 0, 0);
       hy::tma_load_2d(base + kW1 + 8192, &p.mapW1, bar(W_FULL), 64, 0);
       for (int s = 0; s < 9; ++s) hy::tma_load_2d(base + kW2 + s * 8192, &p.mapW2, bar(W_FULL), s * 64, 0);
       hy::tma_load_2d(base + kW3, &p.mapW3, bar(W_FULL), 0, 0);
+      if (first < p.ntiles) load_x(first);
       int it = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-        const int b = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
+      for (int t = first; t < p.ntiles; t += stride, ++it) {
+        // x(i+1): the patch buffer only feeds G1, so it is free as soon as G1(i) has been executed
+        if (t + stride < p.ntiles) {
+          hy::mbar_wait(bar(X_FREE), it & 1);
+          load_x(t + stride);
+        }
+        // skip(i): the centre of x(i) again (an L2 hit), into the staging tile the result will leave from
         int b_img, h0, w0;
         tile_origin(t, b_img, h0, w0);
-        hy::mbar_wait(bar(X_EMPTY + b), ph ^ 1u);
-        hy::mbar_arrive_expect_tx(bar(X_FULL + b), 2 * kXBytes);
-        const uint32_t xb = base + kX0 + b * kXStride;
-        hy::tma_load_4d(xb, &p.mapX, bar(X_FULL + b), 0, w0 - 1, h0 - 1, b_img);
-        hy::tma_load_4d(xb + kXChunk, &p.mapX, bar(X_FULL + b), 64, w0 - 1, h0 - 1, b_img);
+        if (it > 0) hy::mbar_wait(bar(STG_FREE), (it - 1) & 1);
+        hy::mbar_arrive_expect_tx(bar(SKIP_FULL), 32768);
+        hy::tma_load_4d(base + kStg, &p.mapSkip, bar(SKIP_FULL), 0, w0, h0, b_img);
+        hy::tma_load_4d(base + kStg + 16384, &p.mapSkip, bar(SKIP_FULL), 64, w0, h0, b_img);
       }
     }
   } else if (warp == kWarpMma) {
     // ============================ MMA issuer ============================
-    if (MODE != 0 || lane == 0) {
-      const uint32_t leader = MODE == 2 ? hy::elect_leader() : 1u;
+    if (lane == 0) {
       const uint32_t idesc64 = hy::umma_idesc_bf16(128, 64);
       const uint32_t idesc128 = hy::umma_idesc_bf16(128, 128);
       constexpr uint32_t hi = hy::desc_hi_sw128(), hi_t1 = hy::desc_hi_sw128(kPW * 128);
       const uint32_t w1_lo = hy::desc_lo(base + kW1), w2_lo = hy::desc_lo(base + kW2), w3_lo = hy::desc_lo(base + kW3);
-      const uint32_t t_lo = hy::desc_lo(base + kS);
+      const uint32_t x_lo = hy::desc_lo(base + kX), t1_lo = hy::desc_lo(base + kT1), t2_lo = hy::desc_lo(base + kT2);
       // G1: t1 = x . W1^T over the 180-position patch (2 blocks of 128 rows; rows >= 180 unused)
-      auto issue_g1 = [&](int jt) {
-        const uint32_t x_lo = hy::desc_lo(base + kX0 + (jt & 1) * kXStride);
+      auto issue_g1 = [&]() {
         hy::tc_fence_after();
 #pragma unroll
         for (int blk = 0; blk < 2; ++blk)
@@ -204,62 +221,55 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
           for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              hy::umma_issue<MODE>(tmem_base + kColG1 + blk * 64,
-                                   hy::desc_pack(x_lo + ((kc * kXChunk + blk * 16384 + k * 32) >> 4), hi),
-                                   hy::desc_pack(w1_lo + ((kc * 8192 + k * 32) >> 4), hi), idesc64, (kc | k) ? 1u : 0u, leader);
-        hy::umma_commit_mode<MODE>(bar(G1_DONE), leader);
+              hy::umma_bf16(tmem_base + kColG1 + blk * 64,
+                            hy::desc_pack(x_lo + ((kc * kXChunk + blk * 16384 + k * 32) >> 4), hi),
+                            hy::desc_pack(w1_lo + ((kc * 8192 + k * 32) >> 4), hi), idesc64, (kc | k) ? 1u : 0u);
+        hy::umma_commit(bar(G1_DONE));
+        hy::umma_commit(bar(X_FREE));
       };
       hy::mbar_wait(bar(W_FULL), 0);
       int it = 0;
-      if (static_cast<int>(blockIdx.x) < p.ntiles) {
-        hy::mbar_wait(bar(X_FULL + 0), 0);
-        issue_g1(0);
+      if (first < p.ntiles) {
+        hy::mbar_wait(bar(X_FULL), 0);
+        issue_g1();
       }
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
+      for (int t = first; t < p.ntiles; t += stride, ++it) {
         const uint32_t ph = it & 1;
-        const bool has_next = t + static_cast<int>(gridDim.x) < p.ntiles;
-        const int nb = (it + 1) & 1;
-        const uint32_t nph = ((it + 1) >> 1) & 1;
+        const bool has_next = t + stride < p.ntiles;
         // G2: 3x3 over the t1 patch in smem; tap (r,s) = start row r*10+s, row groups 1280 B apart
         hy::mbar_wait(bar(T1_READY), ph);
         hy::tc_fence_after();
-        if (lane == 0) RU_STAMP(8);
+        RU_STAMP(8);
 #pragma unroll
         for (int s = 0; s < 3; ++s)
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              hy::umma_issue<MODE>(tmem_base + kColG2, hy::desc_pack(t_lo + (((r * kPW + s) * 128 + k * 32) >> 4), hi_t1),
-                                   hy::desc_pack(w2_lo + (((s * 3 + r) * 8192 + k * 32) >> 4), hi), idesc64,
-                                   (s | r | k) ? 1u : 0u, leader);
-        hy::umma_commit_mode<MODE>(bar(G2_DONE), leader);
-        if (lane == 0) RU_STAMP(9);
-        // G1 of the next tile rides behind G2 when its patch has landed (columns [0,128) were drained by E1
-        // of this tile); it then overlaps E2 / E3 of this tile.
+              hy::umma_bf16(tmem_base + kColG2, hy::desc_pack(t1_lo + (((r * kPW + s) * 128 + k * 32) >> 4), hi_t1),
+                            hy::desc_pack(w2_lo + (((s * 3 + r) * 8192 + k * 32) >> 4), hi), idesc64, (s | r | k) ? 1u : 0u);
+        hy::umma_commit(bar(G2_DONE));
+        RU_STAMP(9);
+        // G1 of the next tile rides behind G2 (its columns were drained by E1 of this tile) and runs under E3 / E2
         bool g1_ahead = false;
-        if (has_next) {
-          bool landed = hy::mbar_try_wait(bar(X_FULL + nb), nph);
-          if (MODE != 0) landed = __all_sync(0xffffffffu, landed);
-          if (landed) {
-            issue_g1(it + 1);
-            g1_ahead = true;
-          }
+        if (has_next && hy::mbar_try_wait(bar(X_FULL), (it + 1) & 1)) {
+          issue_g1();
+          g1_ahead = true;
         }
-        // G3: 1x1 expand
+        // G3: 1x1 expand of t2
         hy::mbar_wait(bar(T2_READY), ph);
-        if (it > 0) hy::mbar_wait(bar(ACC_FREE), (it - 1) & 1);  // E3 of the previous tile drained [256,384)
+        if (it > 0) hy::mbar_wait(bar(ACC3_FREE), (it - 1) & 1);  // E3 of the previous tile drained [256,384)
         hy::tc_fence_after();
-        if (lane == 0) RU_STAMP(10);
+        RU_STAMP(10);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          hy::umma_issue<MODE>(tmem_base + kColG3, hy::desc_pack(t_lo + ((k * 32) >> 4), hi),
-                               hy::desc_pack(w3_lo + ((k * 32) >> 4), hi), idesc128, k ? 1u : 0u, leader);
-        hy::umma_commit_mode<MODE>(bar(G3_DONE), leader);
-        if (lane == 0) RU_STAMP(11);
+          hy::umma_bf16(tmem_base + kColG3, hy::desc_pack(t2_lo + ((k * 32) >> 4), hi),
+                        hy::desc_pack(w3_lo + ((k * 32) >> 4), hi), idesc128, k ? 1u : 0u);
+        hy::umma_commit(bar(G3_DONE));
+        RU_STAMP(11);
         if (has_next && !g1_ahead) {
-          hy::mbar_wait(bar(X_FULL + nb), nph);
-          issue_g1(it + 1);
+          hy::mbar_wait(bar(X_FULL), (it + 1) & 1);
+          issue_g1();
         }
       }
     }
@@ -267,17 +277,15 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
     // ============================ TMA store ============================
     if (lane == 0) {
       int it = 0;
-      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-        const int b = it & 1;
+      for (int t = first; t < p.ntiles; t += stride, ++it) {
         int b_img, h0, w0;
         tile_origin(t, b_img, h0, w0);
-        const uint32_t xb = base + kX0 + b * kXStride;
         hy::mbar_wait(bar(STAGED), it & 1);
-        hy::tma_store_4d(&p.mapOut, xb, 0, w0, h0, b_img);
-        hy::tma_store_4d(&p.mapOut, xb + kXChunk, 64, w0, h0, b_img);
+        hy::tma_store_4d(&p.mapOut, base + kStg, 0, w0, h0, b_img);
+        hy::tma_store_4d(&p.mapOut, base + kStg + 16384, 64, w0, h0, b_img);
         hy::tma_store_commit();
-        hy::tma_store_wait_read<0>();           // smem of this x buffer may be refilled
-        hy::mbar_arrive(bar(X_EMPTY + b));
+        hy::tma_store_wait_read<0>();           // the staging tile may be refilled with the next skip
+        hy::mbar_arrive(bar(STG_FREE));
       }
       hy::tma_store_wait_all<0>();
     }
@@ -288,19 +296,68 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
     const int tid = q * 32 + lane; // TMEM lane == GEMM row
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sbias = base + kBias;
-    const int ti = tid >> 3, tj = tid & 7;
-    const int pc = (ti + 1) * kPW + tj + 1;  // this thread's output position inside the x patch
+
+    // E3: + bias + skip (this warp: 64-channel chunk `hsel`), in place in the staging tile
+    auto epilogue3 = [&](int it) {
+      const uint32_t ph = it & 1;
+      uint32_t ra[32], rb[32];
+      hy::mbar_wait(bar(G3_DONE), ph);
+      hy::tc_fence_after();
+      if (threadIdx.x == 0) RU_STAMP(5);
+      hy::tmem_ld32(t_lane + kColG3 + hsel * 64, ra);
+      hy::tmem_ld32(t_lane + kColG3 + hsel * 64 + 32, rb);
+      hy::mbar_wait(bar(SKIP_FULL), ph);
+      const uint32_t row = base + kStg + hsel * 16384 + tid * 128;
+      const uint32_t sw = tid & 7;
+      uint4 sk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sk[j] = lds128(row + ((j ^ sw) << 4));
+      hy::tmem_ld_fence32(ra);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half == 1) {
+          hy::tmem_ld_fence32(rb);
+          hy::tc_fence_before();
+          hy::mbar_arrive(bar(ACC3_FREE));  // TMEM columns [256,384) may be overwritten by the next G3
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int j = half * 4 + g;  // 16-byte chunk (8 channels) of the 64-channel row
+          const uint32_t bias_addr = sbias + 512 + (hsel * 64 + j * 8) * 4;
+          const float4 ba = lds_f4(bias_addr), bb = lds_f4(bias_addr + 16);
+          float v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(half ? rb[g * 8 + i] : ra[g * 8 + i]);
+          v[0] += ba.x + hy::bf16_lo(sk[j].x); v[1] += ba.y + hy::bf16_hi(sk[j].x);
+          v[2] += ba.z + hy::bf16_lo(sk[j].y); v[3] += ba.w + hy::bf16_hi(sk[j].y);
+          v[4] += bb.x + hy::bf16_lo(sk[j].z); v[5] += bb.y + hy::bf16_hi(sk[j].z);
+          v[6] += bb.z + hy::bf16_lo(sk[j].w); v[7] += bb.w + hy::bf16_hi(sk[j].w);
+          if (p.final_relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+          uint4 o;
+          o.x = hy::pack_bf16(v[0], v[1]);
+          o.y = hy::pack_bf16(v[2], v[3]);
+          o.z = hy::pack_bf16(v[4], v[5]);
+          o.w = hy::pack_bf16(v[6], v[7]);
+          sts128(row + ((j ^ sw) << 4), o);
+        }
+      }
+      hy::fence_async_smem();
+      hy::mbar_arrive(bar(STAGED));
+      if (threadIdx.x == 0) RU_STAMP(6);
+    };
+
     int it = 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
-      const int b = it & 1;
+    for (int t = first; t < p.ntiles; t += stride, ++it) {
       const uint32_t ph = it & 1;
       int b_img, h0, w0;
       tile_origin(t, b_img, h0, w0);
-      const uint32_t xb = base + kX0 + b * kXStride;
       uint32_t ra[32], rb[32];
       uint4 qv[4];
 
-      // ---- E1: t1 patch (this warp: 32 of the 64 channels) ----
+      // ---- E1: t1 patch (this warp: 32 of the 64 channels); the t1 buffer was released by G2_DONE(i-1) ----
       if (threadIdx.x == 0) RU_STAMP(0);
       hy::mbar_wait(bar(G1_DONE), ph);
       hy::tc_fence_after();
@@ -315,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
         const int hh = h0 - 1 + pr, ww = w0 - 1 + pq;
         const bool live = pp < kNP;
         const bool keep = live && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;  // conv2 zero-pads t1, not x
-        const uint32_t row = base + kS + pp * 128;
+        const uint32_t row = base + kT1 + pp * 128;
         const uint32_t sw = pp & 7;
         if (blk == 0) {
           hy::tmem_ld_fence32(ra);
@@ -334,12 +391,15 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       hy::mbar_arrive(bar(T1_READY));
       if (threadIdx.x == 0) RU_STAMP(2);
 
-      // ---- E2: t2 ----
+      // ---- E3 of the previous tile, under G2(i) / G1(i+1) ----
+      if (it > 0) epilogue3(it - 1);
+
+      // ---- E2: t2 (the t2 buffer was released by G3_DONE(i-1), observed in E3 above) ----
       hy::mbar_wait(bar(G2_DONE), ph);
       hy::tc_fence_after();
       if (threadIdx.x == 0) RU_STAMP(3);
       {
-        const uint32_t row = base + kS + tid * 128;
+        const uint32_t row = base + kT2 + tid * 128;
         const uint32_t sw = tid & 7;
         hy::tmem_ld32(t_lane + kColG2 + hsel * 32, ra);
         hy::tmem_ld_fence32(ra);
@@ -351,59 +411,8 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       hy::tc_fence_before();
       hy::mbar_arrive(bar(T2_READY));
       if (threadIdx.x == 0) RU_STAMP(4);
-
-      // ---- E3: + bias + skip (this warp: 64-channel chunk `hsel`), stage over the x buffer ----
-      hy::mbar_wait(bar(G3_DONE), ph);
-      hy::mbar_wait(bar(X_FULL + b), (it >> 1) & 1);  // (already complete) acquire the TMA-written patch
-      hy::tc_fence_after();
-      if (threadIdx.x == 0) RU_STAMP(5);
-      {
-        const int h = hsel;
-        const uint32_t skip_row = xb + h * kXChunk + pc * 128;
-        const uint32_t skip_sw = pc & 7;
-        uint4 o[8];
-        hy::tmem_ld32(t_lane + kColG3 + h * 64, ra);
-        hy::tmem_ld32(t_lane + kColG3 + h * 64 + 32, rb);
-        hy::tmem_ld_fence32(ra);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (half == 1) hy::tmem_ld_fence32(rb);
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int j = half * 4 + g;  // 16-byte chunk (8 channels) of the 64-channel row
-            const uint4 sk = lds128(skip_row + ((j ^ skip_sw) << 4));
-            const uint32_t bias_addr = sbias + 512 + (h * 64 + j * 8) * 4;
-            const float4 ba = lds_f4(bias_addr), bb = lds_f4(bias_addr + 16);
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(half ? rb[g * 8 + i] : ra[g * 8 + i]);
-            v[0] += ba.x + hy::bf16_lo(sk.x); v[1] += ba.y + hy::bf16_hi(sk.x);
-            v[2] += ba.z + hy::bf16_lo(sk.y); v[3] += ba.w + hy::bf16_hi(sk.y);
-            v[4] += bb.x + hy::bf16_lo(sk.z); v[5] += bb.y + hy::bf16_hi(sk.z);
-            v[6] += bb.z + hy::bf16_lo(sk.w); v[7] += bb.w + hy::bf16_hi(sk.w);
-            if (p.final_relu) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-            }
-            o[j].x = hy::pack_bf16(v[0], v[1]);
-            o[j].y = hy::pack_bf16(v[2], v[3]);
-            o[j].z = hy::pack_bf16(v[4], v[5]);
-            o[j].w = hy::pack_bf16(v[6], v[7]);
-          }
-        }
-        hy::tc_fence_before();
-        hy::mbar_arrive(bar(ACC_FREE));  // TMEM columns [256,384) may be overwritten by the next G3
-        // the staging rows overlap other threads' skip rows of this chunk: all reads of the chunk first
-        hy::named_bar_sync(1 + h, 128);
-        const uint32_t st_row = xb + h * kXChunk + tid * 128;
-        const uint32_t st_sw = tid & 7;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sts128(st_row + ((j ^ st_sw) << 4), o[j]);
-      }
-      hy::fence_async_smem();
-      hy::mbar_arrive(bar(STAGED));
-      if (threadIdx.x == 0) RU_STAMP(6);
     }
+    if (it > 0) epilogue3(it - 1);
   }
 
   hy::tc_fence_before();
@@ -458,6 +467,8 @@ int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c
   memset(&p, 0, sizeof p);
   int rc = encode_act4d(&p.mapX, io->x, 128, io->ld_x, io->B, io->H, io->W, kPW, kTH + 2);
   if (rc != HYRES_OK) return rc;
+  rc = encode_act4d(&p.mapSkip, io->x, 128, io->ld_x, io->B, io->H, io->W, kTW, kTH);
+  if (rc != HYRES_OK) return rc;
   rc = encode_act4d(&p.mapOut, io->out, 128, io->ld_out, io->B, io->H, io->W, kTW, kTH);
   if (rc != HYRES_OK) return rc;
   if ((rc = encode_w_map(&p.mapW1, c1->d_w, c1->ktot, c1->cout_pad, 64)) != HYRES_OK) return rc;
@@ -475,18 +486,14 @@ int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c
     p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
   }
   const int smem = kSmemUsed + 1024;
-  static const int mode = [] { const char* e = getenv("HYRES_RU_MODE"); return e ? atoi(e) : 0; }();
-  auto kern = mode == 1 ? ru_fused_kernel<1> : (mode == 2 ? ru_fused_kernel<2> : ru_fused_kernel<0>);
   static bool attr_set = false;
   if (!attr_set) {
-    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();
-  kern<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
+  ru_fused_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }
