@@ -268,6 +268,31 @@ __device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
+// Descriptor as plain integer arithmetic (no inline asm): in a converged warp whose role was picked through a
+// warp-uniform value (warp index broadcast by __shfl_sync), ptxas keeps such descriptors and their per-MMA
+// offsets in uniform registers (UIADD3.64), so an MMA costs one UTCHMMA plus one or two uniform adds.
+__device__ __forceinline__ uint64_t desc_u64(uint32_t saddr, uint32_t sbo = 1024) {
+  return (static_cast<uint64_t>(desc_hi_sw128(sbo)) << 32) | desc_lo(saddr);
+}
+// Packed fp32 pair add (FADD2): (a, b) += (c, d).
+__device__ __forceinline__ void add2(float& a, float& b, float c, float d) {
+  asm("{\n\t"
+      ".reg .b64 x, y;\n\t"
+      "mov.b64 x, {%0, %1};\n\t"
+      "mov.b64 y, {%2, %3};\n\t"
+      "add.rn.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t"
+      "}"
+      : "+f"(a), "+f"(b)
+      : "f"(c), "f"(d));
+}
+// max(x, 0) on a packed bf16 pair (HMNMX2): ReLU commutes with the bf16 rounding, so relu(pack(a, b)) ==
+// pack(relu(a), relu(b)).
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t u) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(u), "r"(0u));
+  return r;
+}
 // MMA issue in one of three styles (MODE): 0 = the calling code runs in a single lane; 1 = converged warp,
 // elect.sync per MMA; 2 = converged warp, `leader` (1 in exactly one lane) decided once by the caller.
 template <int MODE>

@@ -44,9 +44,6 @@ namespace {
 constexpr int kTH = 16, kTW = 8;        // output tile
 constexpr int kPW = 10;                 // patch width (positions)
 constexpr int kNP = 180;                // patch positions (18 x 10)
-constexpr int kEpiThreads = 256;        // warps 0-7 epilogue
-constexpr int kThreads = 352;           // warp 8 TMA load, 9 MMA, 10 TMA store
-constexpr int kWarpLoad = 8, kWarpMma = 9, kWarpStore = 10;
 constexpr uint32_t kColG1 = 0, kColG2 = 128, kColG3 = 256, kTmemCols = 512;
 
 // shared-memory map (bytes from the 1024-aligned base)
@@ -90,23 +87,24 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
   return v;
 }
 
-// 32 accumulator columns -> (+bias) ReLU -> 32 bf16 in q[0..3]; `keep` = 0 zeroes the row.
-__device__ __forceinline__ void bias_relu_pack32(const uint32_t (&r)[32], uint32_t bias_addr, bool keep, uint4 (&q)[4]) {
+// 16 accumulator columns -> (+bias) ReLU -> 16 bf16 in q[0..1]; `keep` = false zeroes the row.
+__device__ __forceinline__ void bias_relu_pack16(uint32_t (&r)[16], uint32_t bias_addr, bool keep, uint4 (&q)[2]) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < 2; ++g) {
     const float4 ba = lds_f4(bias_addr + g * 32);
     const float4 bb = lds_f4(bias_addr + g * 32 + 16);
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-    v[0] += ba.x; v[1] += ba.y; v[2] += ba.z; v[3] += ba.w;
-    v[4] += bb.x; v[5] += bb.y; v[6] += bb.z; v[7] += bb.w;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = keep ? fmaxf(v[i], 0.f) : 0.f;
-    q[g].x = hy::pack_bf16(v[0], v[1]);
-    q[g].y = hy::pack_bf16(v[2], v[3]);
-    q[g].z = hy::pack_bf16(v[4], v[5]);
-    q[g].w = hy::pack_bf16(v[6], v[7]);
+    hy::add2(v[0], v[1], ba.x, ba.y);
+    hy::add2(v[2], v[3], ba.z, ba.w);
+    hy::add2(v[4], v[5], bb.x, bb.y);
+    hy::add2(v[6], v[7], bb.z, bb.w);
+    q[g].x = hy::relu_bf16x2(hy::pack_bf16(v[0], v[1]));
+    q[g].y = hy::relu_bf16x2(hy::pack_bf16(v[2], v[3]));
+    q[g].z = hy::relu_bf16x2(hy::pack_bf16(v[4], v[5]));
+    q[g].w = hy::relu_bf16x2(hy::pack_bf16(v[6], v[7]));
+    if (!keep) q[g] = make_uint4(0u, 0u, 0u, 0u);
   }
 }
 
@@ -115,12 +113,17 @@ __device__ __forceinline__ void bias_relu_pack32(const uint32_t (&r)[32], uint32
 //   tensor pipe    :         G2(i)  G1(i+1)   G3(i)           G2(i+1) ...
 // The 3x3 GEMM of tile i and the first GEMM of tile i+1 run under the (long) output epilogue of tile i-1, and
 // G3(i) under E1(i+1); every buffer has one producer and one consumer phase per tile, tracked by an mbarrier.
-__global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_constant__ RuParams p) {
+// CS: column splits = epilogue warps per TMEM lane quadrant (2 -> 8 epilogue warps, 4 -> 16).
+template <int CS>
+__global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid_constant__ RuParams p) {
+  constexpr int kEpiThreads = 128 * CS;
+  constexpr int kThreads = kEpiThreads + 96;
+  constexpr int kWarpLoad = 4 * CS, kWarpMma = 4 * CS + 1, kWarpStore = 4 * CS + 2;  // one warp each
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   auto bar = [&](int i) { return base + kBars + 8u * i; };
   const uint32_t tmem_slot = base + kBars + 128;
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction: uniform role branches
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -159,8 +162,9 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
   hy::tc_fence_before();
   __syncthreads();
   hy::tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  uint32_t tmem_base_v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
 
   auto tile_origin = [&](int t, int& b_img, int& h0, int& w0) {
     b_img = t / p.tiles_per_img;
@@ -206,12 +210,13 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
     }
   } else if (warp == kWarpMma) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // The whole warp runs the loop converged (descriptors stay in uniform registers); one elected lane issues.
+    {
+      const uint32_t leader = hy::elect_leader();
       const uint32_t idesc64 = hy::umma_idesc_bf16(128, 64);
       const uint32_t idesc128 = hy::umma_idesc_bf16(128, 128);
-      constexpr uint32_t hi = hy::desc_hi_sw128(), hi_t1 = hy::desc_hi_sw128(kPW * 128);
-      const uint32_t w1_lo = hy::desc_lo(base + kW1), w2_lo = hy::desc_lo(base + kW2), w3_lo = hy::desc_lo(base + kW3);
-      const uint32_t x_lo = hy::desc_lo(base + kX), t1_lo = hy::desc_lo(base + kT1), t2_lo = hy::desc_lo(base + kT2);
+      const uint64_t w1_d = hy::desc_u64(base + kW1), w2_d = hy::desc_u64(base + kW2), w3_d = hy::desc_u64(base + kW3);
+      const uint64_t x_d = hy::desc_u64(base + kX), t1_d = hy::desc_u64(base + kT1, kPW * 128), t2_d = hy::desc_u64(base + kT2);
       // G1: t1 = x . W1^T over the 180-position patch (2 blocks of 128 rows; rows >= 180 unused)
       auto issue_g1 = [&]() {
         hy::tc_fence_after();
@@ -221,11 +226,10 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
           for (int kc = 0; kc < 2; ++kc)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              hy::umma_bf16(tmem_base + kColG1 + blk * 64,
-                            hy::desc_pack(x_lo + ((kc * kXChunk + blk * 16384 + k * 32) >> 4), hi),
-                            hy::desc_pack(w1_lo + ((kc * 8192 + k * 32) >> 4), hi), idesc64, (kc | k) ? 1u : 0u);
-        hy::umma_commit(bar(G1_DONE));
-        hy::umma_commit(bar(X_FREE));
+              hy::umma_issue<2>(tmem_base + kColG1 + blk * 64, x_d + ((kc * kXChunk + blk * 16384 + k * 32) >> 4),
+                                w1_d + ((kc * 8192 + k * 32) >> 4), idesc64, (kc | k) ? 1u : 0u, leader);
+        hy::umma_commit_mode<2>(bar(G1_DONE), leader);
+        hy::umma_commit_mode<2>(bar(X_FREE), leader);
       };
       hy::mbar_wait(bar(W_FULL), 0);
       int it = 0;
@@ -239,20 +243,20 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
         // G2: 3x3 over the t1 patch in smem; tap (r,s) = start row r*10+s, row groups 1280 B apart
         hy::mbar_wait(bar(T1_READY), ph);
         hy::tc_fence_after();
-        RU_STAMP(8);
+        if (lane == 0) RU_STAMP(8);
 #pragma unroll
         for (int s = 0; s < 3; ++s)
 #pragma unroll
           for (int r = 0; r < 3; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              hy::umma_bf16(tmem_base + kColG2, hy::desc_pack(t1_lo + (((r * kPW + s) * 128 + k * 32) >> 4), hi_t1),
-                            hy::desc_pack(w2_lo + (((s * 3 + r) * 8192 + k * 32) >> 4), hi), idesc64, (s | r | k) ? 1u : 0u);
-        hy::umma_commit(bar(G2_DONE));
-        RU_STAMP(9);
+              hy::umma_issue<2>(tmem_base + kColG2, t1_d + (((r * kPW + s) * 128 + k * 32) >> 4),
+                                w2_d + (((s * 3 + r) * 8192 + k * 32) >> 4), idesc64, (s | r | k) ? 1u : 0u, leader);
+        hy::umma_commit_mode<2>(bar(G2_DONE), leader);
+        if (lane == 0) RU_STAMP(9);
         // G1 of the next tile rides behind G2 (its columns were drained by E1 of this tile) and runs under E3 / E2
         bool g1_ahead = false;
-        if (has_next && hy::mbar_try_wait(bar(X_FULL), (it + 1) & 1)) {
+        if (has_next && __all_sync(0xffffffffu, hy::mbar_try_wait(bar(X_FULL), (it + 1) & 1))) {
           issue_g1();
           g1_ahead = true;
         }
@@ -260,13 +264,12 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
         hy::mbar_wait(bar(T2_READY), ph);
         if (it > 0) hy::mbar_wait(bar(ACC3_FREE), (it - 1) & 1);  // E3 of the previous tile drained [256,384)
         hy::tc_fence_after();
-        RU_STAMP(10);
+        if (lane == 0) RU_STAMP(10);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          hy::umma_bf16(tmem_base + kColG3, hy::desc_pack(t2_lo + ((k * 32) >> 4), hi),
-                        hy::desc_pack(w3_lo + ((k * 32) >> 4), hi), idesc128, k ? 1u : 0u);
-        hy::umma_commit(bar(G3_DONE));
-        RU_STAMP(11);
+          hy::umma_issue<2>(tmem_base + kColG3, t2_d + ((k * 32) >> 4), w3_d + ((k * 32) >> 4), idesc128, k ? 1u : 0u, leader);
+        hy::umma_commit_mode<2>(bar(G3_DONE), leader);
+        if (lane == 0) RU_STAMP(11);
         if (has_next && !g1_ahead) {
           hy::mbar_wait(bar(X_FULL), (it + 1) & 1);
           issue_g1();
@@ -290,60 +293,66 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       hy::tma_store_wait_all<0>();
     }
   } else {
-    // ============================ epilogue warps 0-7 ============================
-    const int q = warp & 3;        // TMEM lane quadrant
-    const int hsel = warp >> 2;    // column half handled by this warp
+    // ============================ epilogue warps ============================
+    // warp w: TMEM lane quadrant (w & 3), column split csel = w >> 2 of CS
+    constexpr int U12 = 64 / CS / 16;   // 16-column units of the 64-wide t1 / t2 rows per warp: 2 (CS=2), 1 (CS=4)
+    constexpr int U3 = 128 / CS / 16;   // 16-column units of the 128-wide output row per warp: 4, 2
+    const int q = warp & 3;
+    const int csel = warp >> 2;
     const int tid = q * 32 + lane; // TMEM lane == GEMM row
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t sbias = base + kBias;
 
-    // E3: + bias + skip (this warp: 64-channel chunk `hsel`), in place in the staging tile
+    // E3: + bias + skip, in place in the staging tile; this warp: columns [csel*128/CS, +128/CS)
     auto epilogue3 = [&](int it) {
       const uint32_t ph = it & 1;
-      uint32_t ra[32], rb[32];
+      uint32_t r[U3][16];
       hy::mbar_wait(bar(G3_DONE), ph);
       hy::tc_fence_after();
       if (threadIdx.x == 0) RU_STAMP(5);
-      hy::tmem_ld32(t_lane + kColG3 + hsel * 64, ra);
-      hy::tmem_ld32(t_lane + kColG3 + hsel * 64 + 32, rb);
+      const int c0 = csel * (128 / CS);  // first output channel of this warp
+#pragma unroll
+      for (int u = 0; u < U3; ++u) hy::tmem_ld16(t_lane + kColG3 + c0 + u * 16, r[u]);
       hy::mbar_wait(bar(SKIP_FULL), ph);
-      const uint32_t row = base + kStg + hsel * 16384 + tid * 128;
+      const uint32_t row = base + kStg + (c0 >> 6) * 16384 + tid * 128;
       const uint32_t sw = tid & 7;
-      uint4 sk[8];
+      const int j0 = (c0 & 63) >> 3;   // first 16-byte chunk of this warp inside the 64-channel row
+      uint4 sk[2 * U3];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) sk[j] = lds128(row + ((j ^ sw) << 4));
-      hy::tmem_ld_fence32(ra);
+      for (int j = 0; j < 2 * U3; ++j) sk[j] = lds128(row + (((j0 + j) ^ sw) << 4));
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        if (half == 1) {
-          hy::tmem_ld_fence32(rb);
-          hy::tc_fence_before();
-          hy::mbar_arrive(bar(ACC3_FREE));  // TMEM columns [256,384) may be overwritten by the next G3
-        }
+      for (int u = 0; u < U3; ++u) hy::tmem_ld_fence(r[u]);  // the first waits; all tie the registers to the wait
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int j = half * 4 + g;  // 16-byte chunk (8 channels) of the 64-channel row
-          const uint32_t bias_addr = sbias + 512 + (hsel * 64 + j * 8) * 4;
+      for (int u = 0; u < U3; ++u) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int j = 2 * u + g;
+          const uint32_t bias_addr = sbias + 512 + (c0 + j * 8) * 4;
           const float4 ba = lds_f4(bias_addr), bb = lds_f4(bias_addr + 16);
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(half ? rb[g * 8 + i] : ra[g * 8 + i]);
-          v[0] += ba.x + hy::bf16_lo(sk[j].x); v[1] += ba.y + hy::bf16_hi(sk[j].x);
-          v[2] += ba.z + hy::bf16_lo(sk[j].y); v[3] += ba.w + hy::bf16_hi(sk[j].y);
-          v[4] += bb.x + hy::bf16_lo(sk[j].z); v[5] += bb.y + hy::bf16_hi(sk[j].z);
-          v[6] += bb.z + hy::bf16_lo(sk[j].w); v[7] += bb.w + hy::bf16_hi(sk[j].w);
-          if (p.final_relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-          }
+          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[u][g * 8 + i]);
+          hy::add2(v[0], v[1], ba.x, ba.y);
+          hy::add2(v[2], v[3], ba.z, ba.w);
+          hy::add2(v[4], v[5], bb.x, bb.y);
+          hy::add2(v[6], v[7], bb.z, bb.w);
+          hy::add2(v[0], v[1], hy::bf16_lo(sk[j].x), hy::bf16_hi(sk[j].x));
+          hy::add2(v[2], v[3], hy::bf16_lo(sk[j].y), hy::bf16_hi(sk[j].y));
+          hy::add2(v[4], v[5], hy::bf16_lo(sk[j].z), hy::bf16_hi(sk[j].z));
+          hy::add2(v[6], v[7], hy::bf16_lo(sk[j].w), hy::bf16_hi(sk[j].w));
           uint4 o;
           o.x = hy::pack_bf16(v[0], v[1]);
           o.y = hy::pack_bf16(v[2], v[3]);
           o.z = hy::pack_bf16(v[4], v[5]);
           o.w = hy::pack_bf16(v[6], v[7]);
-          sts128(row + ((j ^ sw) << 4), o);
+          if (p.final_relu) {
+            o.x = hy::relu_bf16x2(o.x); o.y = hy::relu_bf16x2(o.y); o.z = hy::relu_bf16x2(o.z); o.w = hy::relu_bf16x2(o.w);
+          }
+          sts128(row + (((j0 + j) ^ sw) << 4), o);
         }
       }
+      hy::tc_fence_before();
+      hy::mbar_arrive(bar(ACC3_FREE));  // TMEM columns [256,384) may be overwritten by the next G3
       hy::fence_async_smem();
       hy::mbar_arrive(bar(STAGED));
       if (threadIdx.x == 0) RU_STAMP(6);
@@ -354,36 +363,45 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       const uint32_t ph = it & 1;
       int b_img, h0, w0;
       tile_origin(t, b_img, h0, w0);
-      uint32_t ra[32], rb[32];
-      uint4 qv[4];
+      uint4 qv[2];
 
-      // ---- E1: t1 patch (this warp: 32 of the 64 channels); the t1 buffer was released by G2_DONE(i-1) ----
+      // ---- E1: t1 patch (this warp: 64/CS of the 64 channels); the t1 buffer was released by G2_DONE(i-1) ----
       if (threadIdx.x == 0) RU_STAMP(0);
       hy::mbar_wait(bar(G1_DONE), ph);
       hy::tc_fence_after();
       if (threadIdx.x == 0) RU_STAMP(1);
-      hy::tmem_ld32(t_lane + kColG1 + hsel * 32, ra);
-      if (q < 2) hy::tmem_ld32(t_lane + kColG1 + 64 + hsel * 32, rb);  // rows 128.. exist in lanes 0..51 only
+      {
+        uint32_t ra[U12][16], rb[U12][16];
 #pragma unroll
-      for (int blk = 0; blk < 2; ++blk) {
-        if (blk == 1 && q >= 2) break;  // warp-uniform
-        const int pp = blk * 128 + tid;
-        const int pr = pp / kPW, pq = pp - pr * kPW;
-        const int hh = h0 - 1 + pr, ww = w0 - 1 + pq;
-        const bool live = pp < kNP;
-        const bool keep = live && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;  // conv2 zero-pads t1, not x
-        const uint32_t row = base + kT1 + pp * 128;
-        const uint32_t sw = pp & 7;
-        if (blk == 0) {
-          hy::tmem_ld_fence32(ra);
-          bias_relu_pack32(ra, sbias + hsel * 128, keep, qv);
-        } else {
-          hy::tmem_ld_fence32(rb);
-          bias_relu_pack32(rb, sbias + hsel * 128, keep, qv);
+        for (int u = 0; u < U12; ++u) hy::tmem_ld16(t_lane + kColG1 + csel * (64 / CS) + u * 16, ra[u]);
+        if (q < 2) {  // rows 128.. exist in lanes 0..51 only
+#pragma unroll
+          for (int u = 0; u < U12; ++u) hy::tmem_ld16(t_lane + kColG1 + 64 + csel * (64 / CS) + u * 16, rb[u]);
         }
-        if (live) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) sts128(row + (((hsel * 4 + g) ^ sw) << 4), qv[g]);
+        for (int u = 0; u < U12; ++u) {
+          hy::tmem_ld_fence(ra[u]);
+          if (q < 2) hy::tmem_ld_fence(rb[u]);
+        }
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          if (blk == 1 && q >= 2) break;  // warp-uniform
+          const int pp = blk * 128 + tid;
+          const int pr = pp / kPW, pq = pp - pr * kPW;
+          const int hh = h0 - 1 + pr, ww = w0 - 1 + pq;
+          const bool live = pp < kNP;
+          const bool keep = live && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;  // conv2 zero-pads t1, not x
+          const uint32_t row = base + kT1 + pp * 128;
+          const uint32_t sw = pp & 7;
+#pragma unroll
+          for (int u = 0; u < U12; ++u) {
+            const int c0 = csel * (64 / CS) + u * 16;
+            bias_relu_pack16(blk ? rb[u] : ra[u], sbias + c0 * 4, keep, qv);
+            if (live) {
+              sts128(row + ((((c0 >> 3)) ^ sw) << 4), qv[0]);
+              sts128(row + ((((c0 >> 3) + 1) ^ sw) << 4), qv[1]);
+            }
+          }
         }
       }
       hy::fence_async_smem();
@@ -401,11 +419,18 @@ __global__ void __launch_bounds__(kThreads, 1) ru_fused_kernel(const __grid_cons
       {
         const uint32_t row = base + kT2 + tid * 128;
         const uint32_t sw = tid & 7;
-        hy::tmem_ld32(t_lane + kColG2 + hsel * 32, ra);
-        hy::tmem_ld_fence32(ra);
-        bias_relu_pack32(ra, sbias + 256 + hsel * 128, true, qv);
+        uint32_t ra[U12][16];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) sts128(row + (((hsel * 4 + g) ^ sw) << 4), qv[g]);
+        for (int u = 0; u < U12; ++u) hy::tmem_ld16(t_lane + kColG2 + csel * (64 / CS) + u * 16, ra[u]);
+#pragma unroll
+        for (int u = 0; u < U12; ++u) hy::tmem_ld_fence(ra[u]);
+#pragma unroll
+        for (int u = 0; u < U12; ++u) {
+          const int c0 = csel * (64 / CS) + u * 16;
+          bias_relu_pack16(ra[u], sbias + 256 + c0 * 4, true, qv);
+          sts128(row + (((c0 >> 3) ^ sw) << 4), qv[0]);
+          sts128(row + ((((c0 >> 3) + 1) ^ sw) << 4), qv[1]);
+        }
       }
       hy::fence_async_smem();
       hy::tc_fence_before();
@@ -486,14 +511,17 @@ int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c
     p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
   }
   const int smem = kSmemUsed + 1024;
+  static const int cs = [] { const char* e = getenv("HYRES_RU_CS"); const int v = e ? atoi(e) : 0; return v == 4 ? 4 : 2; }();
   static bool attr_set = false;
   if (!attr_set) {
-    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();
-  ru_fused_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
+  if (cs == 2) ru_fused_kernel<2><<<grid, 128 * 2 + 96, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
+  else ru_fused_kernel<4><<<grid, 128 * 4 + 96, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }
