@@ -9,6 +9,7 @@
 //     in the epilogue of fusion.0 (HYRES_EPI_PIXSCALE): W*(multi*att) == att*(W*multi).
 // NHWC bf16 activations, 16-byte (8-channel) vectors per thread.
 #include <cstdint>
+#include <cstring>
 
 #include "common.cuh"
 #include "host_util.h"
@@ -170,11 +171,58 @@ __device__ __forceinline__ void bilinear8(const __nv_bfloat16* __restrict__ src,
 }
 
 // multi[..., 64:128] = up2(f2), multi[..., 128:192] = up4(f3); stats = (mean, max) over 192 channels.
-// 8 threads per position (one per 8-channel group of each 64-channel branch).
-__global__ void up_concat_stats_kernel(const __nv_bfloat16* __restrict__ f2, const __nv_bfloat16* __restrict__ f3,
-                                       __nv_bfloat16* __restrict__ multi, float* __restrict__ stats, int H, int W,
-                                       int64_t npix_total) {
-  const int64_t total = npix_total * 8;
+// One thread: a 2x2 block of output positions x one 8-channel group; 8 lanes cover the 64 channels of a block.
+// The block shares its sources (3x3 of f2, 2x2 of f3 instead of 4 + 4 per position) and, with
+// align_corners=False, its interpolation weights are constants: x2 -> (.25,.75) / (.75,.25),
+// x4 -> (.375,.625) (.125,.875) / (.875,.125) (.625,.375).  Clamping the neighbour index at the image border
+// reproduces PyTorch's clamp of the source coordinate (both taps then read the same row / column).
+// acc += w * unpack(u), as packed fp32 pairs; NP bf16 pairs per vector
+template <int NP>
+__device__ __forceinline__ void fma_pairs(float (&acc)[2 * NP], const uint32_t (&q)[NP], float w) {
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    asm("{\n\t"
+        ".reg .b64 a, x, ww;\n\t"
+        "mov.b64 a, {%0, %1};\n\t"
+        "mov.b64 x, {%2, %3};\n\t"
+        "mov.b64 ww, {%4, %4};\n\t"
+        "fma.rn.f32x2 a, x, ww, a;\n\t"
+        "mov.b64 {%0, %1}, a;\n\t"
+        "}"
+        : "+f"(acc[2 * i]), "+f"(acc[2 * i + 1])
+        : "f"(hy::bf16_lo(q[i])), "f"(hy::bf16_hi(q[i])), "f"(w));
+  }
+}
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+template <int NP> struct VecOf;
+template <> struct VecOf<4> { using type = uint4; };
+template <> struct VecOf<2> { using type = uint2; };
+template <int NP>
+__device__ __forceinline__ void ldv(const __nv_bfloat16* p, uint32_t (&q)[NP]) {
+  const typename VecOf<NP>::type v = __ldg(reinterpret_cast<const typename VecOf<NP>::type*>(p));
+  memcpy(q, &v, sizeof v);
+}
+template <int NP>
+__device__ __forceinline__ void stv(__nv_bfloat16* p, const uint32_t (&q)[NP]) {
+  typename VecOf<NP>::type v;
+  memcpy(&v, q, sizeof v);
+  *reinterpret_cast<typename VecOf<NP>::type*>(p) = v;
+}
+
+// NP: bf16 pairs per thread (4 -> 8 channels, 8 lanes per block; 2 -> 4 channels, 16 lanes per block)
+template <int NP>
+__global__ void __launch_bounds__(kThreads, 3) up_concat_stats_kernel(const __nv_bfloat16* __restrict__ f2,
+                                                                      const __nv_bfloat16* __restrict__ f3,
+                                                                      __nv_bfloat16* __restrict__ multi,
+                                                                      float* __restrict__ stats, int H, int W,
+                                                                      int64_t nblk_total) {
+  constexpr int LPB = 32 / NP;   // lanes per 2x2 block
+  constexpr int CH = 2 * NP;     // channels per thread
+  const int64_t total = nblk_total * LPB;
   const int Wh = W / 2, Hh = H / 2, Wq = W / 4, Hq = H / 4;
   const int lane = threadIdx.x & 31;
   // warp-uniform loop bound: every lane of a warp stays in the loop for the shuffles
@@ -183,40 +231,107 @@ __global__ void up_concat_stats_kernel(const __nv_bfloat16* __restrict__ f2, con
     const int64_t t = base + lane;
     const bool live = t < total;
     const int64_t tt = live ? t : total - 1;
-    const int g = static_cast<int>(tt & 7);
-    const int64_t pix = tt >> 3;
-    const int x = static_cast<int>(pix % W);
-    const int y = static_cast<int>((pix / W) % H);
-    const int b = static_cast<int>(pix / (static_cast<int64_t>(W) * H));
-    float v1[8], v2[8], v3[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(multi + pix * 192) + g), v1);
-    int y0, y1, x0, x1;
-    float ly, lx;
-    bilinear_coord(y, 0.5f, Hh, y0, y1, ly);
-    bilinear_coord(x, 0.5f, Wh, x0, x1, lx);
-    bilinear8(f2, static_cast<int64_t>(b) * Hh * Wh, Wh, y0, y1, x0, x1, ly, lx, g, v2);
-    bilinear_coord(y, 0.25f, Hq, y0, y1, ly);
-    bilinear_coord(x, 0.25f, Wq, x0, x1, lx);
-    bilinear8(f3, static_cast<int64_t>(b) * Hq * Wq, Wq, y0, y1, x0, x1, ly, lx, g, v3);
-    float s = 0.f, m = -3.4e38f;
+    const int g = static_cast<int>(tt % LPB);
+    const int64_t blk = tt / LPB;
+    const int n = static_cast<int>(blk % Wh);           // block column == f2 column
+    const int m = static_cast<int>((blk / Wh) % Hh);    // block row == f2 row
+    const int b = static_cast<int>(blk / (static_cast<int64_t>(Wh) * Hh));
+    // ---- sources ----
+    const int r2[3] = {max(m - 1, 0), m, min(m + 1, Hh - 1)};
+    const int c2[3] = {max(n - 1, 0), n, min(n + 1, Wh - 1)};
+    const int64_t img2 = static_cast<int64_t>(b) * Hh * Wh;
+    uint32_t S[3][3][NP];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      v2[k] = round_bf16(v2[k]);
-      v3[k] = round_bf16(v3[k]);
-      s += v1[k] + v2[k] + v3[k];
-      m = fmaxf(m, fmaxf(v1[k], fmaxf(v2[k], v3[k])));
-    }
-    if (live) {
-      reinterpret_cast<uint4*>(multi + pix * 192 + 64)[g] = pack8(v2);
-      reinterpret_cast<uint4*>(multi + pix * 192 + 128)[g] = pack8(v3);
-    }
-    // reduce across the 8 lanes of this position (groups of 8 lanes are aligned: base % 32 == 0)
+    for (int a = 0; a < 3; ++a)
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      for (int c = 0; c < 3; ++c) ldv<NP>(f2 + (img2 + static_cast<int64_t>(r2[a]) * Wh + c2[c]) * 64 + g * CH, S[a][c]);
+    const int iq = m >> 1, jq = n >> 1, mo = m & 1, no = n & 1;
+    const int r3[2] = {mo ? iq : max(iq - 1, 0), mo ? min(iq + 1, Hq - 1) : iq};
+    const int c3[2] = {no ? jq : max(jq - 1, 0), no ? min(jq + 1, Wq - 1) : jq};
+    const int64_t img3 = static_cast<int64_t>(b) * Hq * Wq;
+    uint32_t Q[2][2][NP];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) ldv<NP>(f3 + (img3 + static_cast<int64_t>(r3[a]) * Wq + c3[c]) * 64 + g * CH, Q[a][c]);
+    const int64_t img = static_cast<int64_t>(b) * H * W;
+    uint32_t F1[2][2][NP];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx)
+        ldv<NP>(multi + (img + static_cast<int64_t>(2 * m + dy) * W + 2 * n + dx) * 192 + g * CH, F1[dy][dx]);
+    // weight of the second (lower / right) tap: x2 -> .75 (even output) / .25 (odd); x4 by (block parity, offset)
+    const float l3y[2] = {mo ? 0.125f : 0.625f, mo ? 0.375f : 0.875f};
+    const float l3x[2] = {no ? 0.125f : 0.625f, no ? 0.375f : 0.875f};
+    float ps[4];      // per-position partial channel sum
+    uint32_t pm[4];   // per-position partial channel max, packed bf16 pair
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const float ly = dy ? 0.25f : 0.75f, lx = dx ? 0.25f : 0.75f;
+        float v2[CH], v3[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) v2[k] = v3[k] = 0.f;
+        fma_pairs<NP>(v2, S[dy][dx], (1.f - ly) * (1.f - lx));
+        fma_pairs<NP>(v2, S[dy][dx + 1], (1.f - ly) * lx);
+        fma_pairs<NP>(v2, S[dy + 1][dx], ly * (1.f - lx));
+        fma_pairs<NP>(v2, S[dy + 1][dx + 1], ly * lx);
+        const float my = l3y[dy], mx = l3x[dx];
+        fma_pairs<NP>(v3, Q[0][0], (1.f - my) * (1.f - mx));
+        fma_pairs<NP>(v3, Q[0][1], (1.f - my) * mx);
+        fma_pairs<NP>(v3, Q[1][0], my * (1.f - mx));
+        fma_pairs<NP>(v3, Q[1][1], my * mx);
+        uint32_t u2[NP], u3[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) {
+          u2[k] = hy::pack_bf16(v2[2 * k], v2[2 * k + 1]);
+          u3[k] = hy::pack_bf16(v3[2 * k], v3[2 * k + 1]);
+        }
+        if (live) {
+          __nv_bfloat16* o = multi + (img + static_cast<int64_t>(2 * m + dy) * W + 2 * n + dx) * 192 + g * CH;
+          stv<NP>(o + 64, u2);
+          stv<NP>(o + 128, u3);
+        }
+        // statistics of the stored (bf16) values: max exactly on the packed pairs, sum in fp32
+        uint32_t mx2 = F1[dy][dx][0];
+        float acc[CH];
+#pragma unroll
+        for (int k = 0; k < CH; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < NP; ++k) mx2 = max_bf16x2(mx2, max_bf16x2(F1[dy][dx][k], max_bf16x2(u2[k], u3[k])));
+        fma_pairs<NP>(acc, F1[dy][dx], 1.f);
+        fma_pairs<NP>(acc, u2, 1.f);
+        fma_pairs<NP>(acc, u3, 1.f);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < CH; ++k) sum += acc[k];
+        ps[dy * 2 + dx] = sum;
+        pm[dy * 2 + dx] = mx2;
+      }
     }
-    if (live && g == 0) reinterpret_cast<float2*>(stats)[pix] = make_float2(s * (1.f / 192.f), m);
+    // ---- reduce over the LPB lanes of the block (aligned groups), halving the positions in the first two rounds ----
+    const bool hiA = (lane & (LPB / 2)) != 0;  // keeps positions 2,3 (else 0,1)
+    float s0, s1;
+    uint32_t m0, m1;
+    s0 = (hiA ? ps[2] : ps[0]) + __shfl_xor_sync(0xffffffffu, hiA ? ps[0] : ps[2], LPB / 2);
+    s1 = (hiA ? ps[3] : ps[1]) + __shfl_xor_sync(0xffffffffu, hiA ? ps[1] : ps[3], LPB / 2);
+    m0 = max_bf16x2(hiA ? pm[2] : pm[0], __shfl_xor_sync(0xffffffffu, hiA ? pm[0] : pm[2], LPB / 2));
+    m1 = max_bf16x2(hiA ? pm[3] : pm[1], __shfl_xor_sync(0xffffffffu, hiA ? pm[1] : pm[3], LPB / 2));
+    const bool hiB = (lane & (LPB / 4)) != 0;  // keeps the second of the pair
+    float sum = (hiB ? s1 : s0) + __shfl_xor_sync(0xffffffffu, hiB ? s0 : s1, LPB / 4);
+    uint32_t mm = max_bf16x2(hiB ? m1 : m0, __shfl_xor_sync(0xffffffffu, hiB ? m0 : m1, LPB / 4));
+#pragma unroll
+    for (int o = LPB / 8; o > 0; o >>= 1) {
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      mm = max_bf16x2(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+    }
+    if (live && (lane & (LPB / 4 - 1)) == 0) {
+      const int pos = (hiA ? 2 : 0) + (hiB ? 1 : 0);  // dy * 2 + dx
+      const int64_t pix = img + static_cast<int64_t>(2 * m + (pos >> 1)) * W + 2 * n + (pos & 1);
+      reinterpret_cast<float2*>(stats)[pix] = make_float2(sum * (1.f / 192.f), fmaxf(hy::bf16_lo(mm), hy::bf16_hi(mm)));
+    }
   }
 }
 
@@ -290,12 +405,12 @@ int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi, fl
   if (!f2 || !f3 || !multi || !stats || B <= 0) return hy_fail(HYRES_ERR_ARG, "up_concat_stats: bad argument");
   if (C != 64) return hy_fail(HYRES_ERR_UNSUPPORTED, "up_concat_stats: C must be 64");
   if ((H & 3) || (W & 3)) return hy_fail(HYRES_ERR_ARG, "up_concat_stats: H and W must be multiples of 4");
-  const int64_t npix = static_cast<int64_t>(B) * H * W;
-  int gx = static_cast<int>(std::min<int64_t>((npix * 8 + kThreads - 1) / kThreads, 148 * 16));
+  const int64_t nblk = static_cast<int64_t>(B) * (H / 2) * (W / 2);
+  int gx = static_cast<int>(std::min<int64_t>((nblk * 16 + kThreads - 1) / kThreads, 148 * 24));
   hy_count_launch();
-  up_concat_stats_kernel<<<gx, kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
+  up_concat_stats_kernel<2><<<gx, kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
       static_cast<const __nv_bfloat16*>(f2), static_cast<const __nv_bfloat16*>(f3), static_cast<__nv_bfloat16*>(multi),
-      stats, H, W, npix);
+      stats, H, W, nblk);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }
