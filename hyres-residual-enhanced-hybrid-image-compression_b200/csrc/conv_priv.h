@@ -35,6 +35,7 @@ struct hyres_conv {
   std::vector<Slot> slots;
   TapGroup* d_groups = nullptr;
   __nv_bfloat16* d_w = nullptr;
+  __nv_bfloat16* d_w_tap = nullptr;  // tap-major packing for the three-output-channel layers (conv_sc.cu)
   float* d_bias = nullptr;
   int64_t macs_per_pos = 0;
 };
@@ -66,3 +67,7 @@ int num_sms();
 // conv_res.cu: persistent kernel with shared-memory-resident weights; *handled = 0 when the layer
 // does not qualify (the caller then uses the streaming kernel of conv_tc.cu).
 int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream, int* handled);
+// conv_sc.cu: layers with three output channels as one tap-major GEMM per tile plus a gather epilogue.
+bool conv_sc_applicable(const hyres_conv* c);
+void conv_sc_pack(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16>& out);
+int conv_sc_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream, int* handled);

@@ -633,6 +633,11 @@ int upload_weights(hyres_conv* c, const float* weight, const float* bias) {
   std::vector<float> b(c->cout_pad, 0.f);
   if (bias) std::copy(bias, bias + c->cout, b.begin());
   HY_CUDA(cudaMemcpy(c->d_bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  if (conv_sc_applicable(c)) {
+    conv_sc_pack(c, weight, packed);
+    if (!c->d_w_tap) HY_CUDA(cudaMalloc(&c->d_w_tap, packed.size() * sizeof(__nv_bfloat16)));
+    HY_CUDA(cudaMemcpy(c->d_w_tap, packed.data(), packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  }
   return HYRES_OK;
 }
 
@@ -746,6 +751,7 @@ void hyres_conv_destroy(hyres_conv* c) {
   if (!c) return;
   if (c->d_groups) cudaFree(c->d_groups);
   if (c->d_w) cudaFree(c->d_w);
+  if (c->d_w_tap) cudaFree(c->d_w_tap);
   if (c->d_bias) cudaFree(c->d_bias);
   delete c;
 }
@@ -777,6 +783,12 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
 
   // layers whose weights fit in shared memory run on the persistent resident-weights kernel
+  static const bool no_sc = getenv("HYRES_NO_SC") != nullptr;
+  if (!no_sc) {
+    int handled = 0;
+    const int rc = conv_sc_try_run(c, io, stream, &handled);
+    if (rc != HYRES_OK || handled) return rc;
+  }
   static const bool no_res = getenv("HYRES_NO_RES") != nullptr;
   if (!no_res) {
     int handled = 0;
