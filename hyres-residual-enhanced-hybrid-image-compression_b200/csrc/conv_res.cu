@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
   const uint32_t ACC_FULL = A_READY + 8 * kMaxStages;
   const uint32_t ACC_EMPTY = ACC_FULL + 16;
   const uint32_t tmem_slot = ACC_EMPTY + 16;
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -147,8 +147,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
   hy::tc_fence_before();
   __syncthreads();
   hy::tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  uint32_t tmem_base_v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
 
   auto tile_origin = [&](int t, int& b_img, int& h0, int& w0) {
     b_img = t / p.tiles_per_img;
@@ -185,31 +186,32 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
     }
   } else if (warp == 9) {
     // ============================ MMA issuer ============================
-    if (lane == 0) {
+    // The whole warp runs the loop converged (descriptor arithmetic in uniform registers); one elected lane issues.
+    {
+      const uint32_t leader = hy::elect_leader();
       const uint32_t idesc = hy::umma_idesc_bf16(128, p.BN);
-      const uint32_t hi_a = hy::desc_hi_sw128(p.PW * 128), hi_b = hy::desc_hi_sw128();
-      const uint32_t w_lo = hy::desc_lo(w_base);
+      const uint64_t w_d = hy::desc_u64(w_base);
+      const uint32_t sbo_a = p.PW * 128;
       hy::mbar_wait(W_FULL, 0);
       int stage = 0, it = 0;
       uint32_t par = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
         const int buf = it & 1;
-        const uint32_t a_lo0 = hy::desc_lo(st_base + stage * p.stage_bytes);
+        const uint64_t a_d0 = hy::desc_u64(st_base + stage * p.stage_bytes, sbo_a);
         const uint32_t d0 = tmem_base + buf * acc_cols;
         hy::mbar_wait((p.a_square ? A_READY : A_FULL) + 8 * stage, par);
         hy::mbar_wait(ACC_EMPTY + 8 * buf, ((it >> 1) & 1) ^ 1u);
         hy::tc_fence_after();
         for (int i = 0; i < p.nsteps; ++i) {
           const Step st = p.steps[i];
-          const uint32_t a_lo = a_lo0 + st.a_off16, b_lo = w_lo + st.b_off16;
+          const uint64_t a_d = a_d0 + static_cast<uint32_t>(st.a_off16), b_d = w_d + static_cast<uint32_t>(st.b_off16);
           const uint32_t d = d0 + st.d_col;
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            hy::umma_bf16(d, hy::desc_pack(a_lo + 2 * k, hi_a), hy::desc_pack(b_lo + 2 * k, hi_b), idesc,
-                          static_cast<uint32_t>(st.acc | k));
+            hy::umma_issue<2>(d, a_d + 2 * k, b_d + 2 * k, idesc, static_cast<uint32_t>(st.acc | k), leader);
         }
-        hy::umma_commit(A_EMPTY + 8 * stage);
-        hy::umma_commit(ACC_FULL + 8 * buf);
+        hy::umma_commit_mode<2>(A_EMPTY + 8 * stage, leader);
+        hy::umma_commit_mode<2>(ACC_FULL + 8 * buf, leader);
         if (++stage == p.NA) { stage = 0; par ^= 1u; }
       }
     }

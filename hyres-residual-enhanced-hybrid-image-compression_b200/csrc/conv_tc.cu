@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const uint32_t acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -152,8 +152,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   hy::tc_fence_before();
   __syncthreads();
   hy::tc_fence_after();
-  uint32_t tmem_base;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  uint32_t tmem_base_v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   auto decode = [&](int item) {
@@ -202,7 +203,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     }
   } else if (warp == kWarpMma) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop converged (descriptor arithmetic in uniform registers); one elected lane issues.
+    {
+      const uint32_t leader = hy::elect_leader();
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       int it_n = 0;
@@ -224,25 +227,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int t = 0; t < tg.ntaps; ++t) {
             hy::mbar_wait(b_full + 8 * sb, pb);
             hy::tc_fence_after();
-            const uint32_t b_stage = b_base + sb * p.b_stage_bytes;
-            const uint32_t a_tap = a_stage + p.groups[g_begin + g].tap_row[t] * (kTileW * 128);
+            const uint64_t b_d = hy::desc_u64(b_base + sb * p.b_stage_bytes);
+            const uint64_t a_d = hy::desc_u64(a_stage + p.groups[g_begin + g].tap_row[t] * (kTileW * 128));
             for (int sub = 0; sub < p.MT; ++sub) {
-              const uint32_t a_sub = a_tap + sub * (kSubH * kTileW * 128);
+              const uint64_t a_sub = a_d + ((sub * (kSubH * kTileW * 128)) >> 4);
               const uint32_t d_tmem = d_item + sub * p.bn_max;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                hy::umma_bf16(d_tmem, hy::umma_desc_sw128(a_sub + k * 32),
-                              hy::umma_desc_sw128(b_stage + k * 32), idesc, first | (uint32_t)k);
-              }
+              for (int k = 0; k < 4; ++k)
+                hy::umma_issue<2>(d_tmem, a_sub + 2 * k, b_d + 2 * k, idesc, first | static_cast<uint32_t>(k), leader);
             }
             first = 1;
-            hy::umma_commit(b_empty + 8 * sb);
+            hy::umma_commit_mode<2>(b_empty + 8 * sb, leader);
             if (++sb == p.NB) { sb = 0; pb ^= 1u; }
           }
-          hy::umma_commit(a_empty + 8 * sa);
+          hy::umma_commit_mode<2>(a_empty + 8 * sa, leader);
           if (++sa == p.NA) { sa = 0; pa ^= 1u; }
         }
-        hy::umma_commit(acc_full + 8 * buf);
+        hy::umma_commit_mode<2>(acc_full + 8 * buf, leader);
       }
     }
   } else {
