@@ -67,6 +67,17 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 }
 
 // ----------------------------------------------------------------------------
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor in the stream is still draining.  Every kernel of the convolution path lets its
+// successor in right away (pdl_launch_dependents, first instruction) and runs its own prologue -- barrier
+// init, TMEM allocation, the TMA load of its weights: nothing the predecessor can write -- before pdl_wait,
+// after which the predecessor has completed and its memory is visible.  All threads wait: even the epilogue
+// stores must not land before the predecessor finished reading (the allocator may have recycled its inputs).
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {

@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kThreads, KS == 3 ? 3 : 2) conv_c3_kernel(cons
   constexpr uint32_t kPatchBytes = (3 * RH * RW * 2 + 127) / 128 * 128;  // bf16
   static_assert(KLIVE + 2 <= NK16 * 16, "two spare K columns carry the bias");
 
+  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(kThreads, KS == 3 ? 3 : 2) conv_c3_kernel(cons
   hy::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  hy::pdl_wait();  // (the weight / bias loads below are cheap; everything dependent comes after this)
 
   // tile k of this CTA is global tile blockIdx.x + k * gridDim.x; group (k & 1) owns it
   if (warp == 8) {
@@ -342,8 +344,7 @@ int launch(const C3Params& p, cudaStream_t stream) {
   }
   const int grid = std::max(1, std::min((p.ntiles + 1) / 2, num_sms() * per_sm));
   hy_count_launch();
-  conv_c3_kernel<KS, STRIDE, NOUT><<<grid, kThreads, smem, stream>>>(p);
-  HY_CUDA(cudaGetLastError());
+  HY_CUDA(hy_launch_pdl(conv_c3_kernel<KS, STRIDE, NOUT>, grid, kThreads, smem, stream, p));
   return HYRES_OK;
 }
 

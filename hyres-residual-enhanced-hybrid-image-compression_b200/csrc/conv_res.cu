@@ -100,6 +100,7 @@ __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (
 }
 
 __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_constant__ ResParams p) {
+  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
@@ -129,6 +130,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
       hy::mbar_init(ACC_EMPTY + 8 * i, 128);
     }
     hy::mbar_fence_init();
+    // the weights do not depend on the predecessor kernel: their load starts before the dependency wait
+    hy::tma_prefetch_desc(&p.mapW);
+    hy::mbar_arrive_expect_tx(W_FULL, p.w_bytes);
+    for (int s = 0; s < p.nslots; ++s) hy::tma_load_2d(w_base + s * p.BN * 128, &p.mapW, W_FULL, s * 64, 0);
   }
   {
     float* sb = reinterpret_cast<float*>(smem_raw + (bias_base - hy::smem_u32(smem_raw)));
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
   uint32_t tmem_base_v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
+  hy::pdl_wait();  // everything above is independent of the predecessor kernel
 
   auto tile_origin = [&](int t, int& b_img, int& h0, int& w0) {
     b_img = t / p.tiles_per_img;
@@ -163,8 +169,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
   if (warp == 8) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      hy::mbar_arrive_expect_tx(W_FULL, p.w_bytes);
-      for (int s = 0; s < p.nslots; ++s) hy::tma_load_2d(w_base + s * p.BN * 128, &p.mapW, W_FULL, s * 64, 0);
       int stage = 0;
       uint32_t par = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -500,8 +504,7 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();
-  conv_res_kernel<<<grid, kThreads, smem, stream>>>(p);
-  HY_CUDA(cudaGetLastError());
+  HY_CUDA(hy_launch_pdl(conv_res_kernel, grid, kThreads, smem, stream, p));
   *handled = 1;
   return HYRES_OK;
 }

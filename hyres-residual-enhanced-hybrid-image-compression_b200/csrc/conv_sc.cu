@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sc_kernel(const __grid_const
   constexpr int ACCW = 2 * C::N;                       // two 128-row blocks cover the 180-position patch
   constexpr int TMEM_COLS = 2 * ACCW <= 128 ? 128 : (2 * ACCW <= 256 ? 256 : 512);
 
+  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
@@ -81,11 +82,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sc_kernel(const __grid_const
       hy::mbar_init(ACC_EMPTY + 8 * i, 128);
     }
     hy::mbar_fence_init();
+    // the weights do not depend on the predecessor kernel: their load starts before the dependency wait
+    hy::mbar_arrive_expect_tx(W_FULL, kWBytes);
+    for (int c = 0; c < C::KCH; ++c) hy::tma_load_2d(w_base + c * C::N * 128, &p.mapW, W_FULL, c * 64, 0);
   }
-  if (warp == 8 && lane == 0) {
-    hy::tma_prefetch_desc(&p.mapA);
-    hy::tma_prefetch_desc(&p.mapW);
-  }
+  if (warp == 8 && lane == 0) hy::tma_prefetch_desc(&p.mapA);
   if (warp == 9) {
     hy::tmem_alloc(tmem_slot, TMEM_COLS);
     hy::tmem_relinquish();
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sc_kernel(const __grid_const
   hy::tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  hy::pdl_wait();  // everything above is independent of the predecessor kernel
 
   auto tile_origin = [&](int t, int& b_img, int& h0, int& w0) {
     b_img = t / p.tiles_per_img;
@@ -107,8 +109,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sc_kernel(const __grid_const
   if (warp == 8) {
     // ============================ TMA producer ============================
     if (lane == 0) {
-      hy::mbar_arrive_expect_tx(W_FULL, kWBytes);
-      for (int c = 0; c < C::KCH; ++c) hy::tma_load_2d(w_base + c * C::N * 128, &p.mapW, W_FULL, c * 64, 0);
       int it = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++it) {
         const int stage = it % C::NA;
@@ -292,8 +292,7 @@ int launch(const ScParams& p, cudaStream_t stream) {
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();
-  conv_sc_kernel<MODE><<<grid, kThreads, smem, stream>>>(p);
-  HY_CUDA(cudaGetLastError());
+  HY_CUDA(hy_launch_pdl(conv_sc_kernel<MODE>, grid, kThreads, smem, stream, p));
   return HYRES_OK;
 }
 

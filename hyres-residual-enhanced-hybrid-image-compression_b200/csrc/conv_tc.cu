@@ -108,6 +108,7 @@ struct Item {
 // item boundaries; the accumulators are double buffered in TMEM whenever 2 * MT * BN <= 512 columns,
 // and two epilogue warp groups drain them while the next item's MMAs are issued.
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint32_t tmem_base_v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
+  hy::pdl_wait();  // everything above is independent of the predecessor kernel
 
   const int tiles_per_img = p.tiles_w * p.tiles_h;
   auto decode = [&](int item) {
@@ -914,8 +916,7 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   }
   const int grid = std::min(p.nitems, num_sms());
   hy_count_launch();
-  conv_tc_kernel<<<grid, kThreads, smem, stream>>>(p);
-  HY_CUDA(cudaGetLastError());
+  HY_CUDA(hy_launch_pdl(conv_tc_kernel, grid, kThreads, smem, stream, p));
   return HYRES_OK;
 }
 

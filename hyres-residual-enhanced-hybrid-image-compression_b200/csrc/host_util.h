@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 int hy_fail(int code, const char* msg);
 // Every kernel launch of the library is counted (hyres_launch_count): bench.py reports it.
 void hy_count_launch();
@@ -13,3 +15,21 @@ void hy_count_launch();
     cudaError_t _e = (expr);                                            \
     if (_e != cudaSuccess) return hy_fail(-2, cudaGetErrorString(_e));  \
   } while (0)
+
+// Launch with the programmatic-stream-serialization attribute (see pdl_wait in common.cuh); HYRES_NO_PDL=1
+// falls back to plain stream order.
+template <typename P>
+inline cudaError_t hy_launch_pdl(void (*kernel)(P), int grid, int block, int smem, cudaStream_t stream, const P& params) {
+  static const bool no_pdl = getenv("HYRES_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, params);
+}

@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
   constexpr int kEpiThreads = 128 * CS;
   constexpr int kThreads = kEpiThreads + 96;
   constexpr int kWarpLoad = 4 * CS, kWarpMma = 4 * CS + 1, kWarpStore = 4 * CS + 2;  // one warp each
+  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   auto bar = [&](int i) { return base + kBars + 8u * i; };
@@ -140,6 +141,12 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
     hy::mbar_init(bar(ACC3_FREE), kEpiThreads);
     hy::mbar_init(bar(STAGED), kEpiThreads);
     hy::mbar_fence_init();
+    // the weights do not depend on the predecessor kernel: their load starts before the dependency wait
+    hy::mbar_arrive_expect_tx(bar(W_FULL), kWBytes);
+    hy::tma_load_2d(base + kW1, &p.mapW1, bar(W_FULL), 0, 0);
+    hy::tma_load_2d(base + kW1 + 8192, &p.mapW1, bar(W_FULL), 64, 0);
+    for (int s = 0; s < 9; ++s) hy::tma_load_2d(base + kW2 + s * 8192, &p.mapW2, bar(W_FULL), s * 64, 0);
+    hy::tma_load_2d(base + kW3, &p.mapW3, bar(W_FULL), 0, 0);
   }
   {
     // biases -> smem: b1 [64] | b2 [64] | b3 [128]
@@ -165,6 +172,7 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
   uint32_t tmem_base_v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
+  hy::pdl_wait();  // everything above is independent of the predecessor kernel
 
   auto tile_origin = [&](int t, int& b_img, int& h0, int& w0) {
     b_img = t / p.tiles_per_img;
@@ -186,11 +194,6 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
         hy::tma_load_4d(base + kX, &p.mapX, bar(X_FULL), 0, w0 - 1, h0 - 1, b_img);
         hy::tma_load_4d(base + kX + kXChunk, &p.mapX, bar(X_FULL), 64, w0 - 1, h0 - 1, b_img);
       };
-      hy::mbar_arrive_expect_tx(bar(W_FULL), kWBytes);
-      hy::tma_load_2d(base + kW1, &p.mapW1, bar(W_FULL), 0, 0);
-      hy::tma_load_2d(base + kW1 + 8192, &p.mapW1, bar(W_FULL), 64, 0);
-      for (int s = 0; s < 9; ++s) hy::tma_load_2d(base + kW2 + s * 8192, &p.mapW2, bar(W_FULL), s * 64, 0);
-      hy::tma_load_2d(base + kW3, &p.mapW3, bar(W_FULL), 0, 0);
       if (first < p.ntiles) load_x(first);
       int it = 0;
       for (int t = first; t < p.ntiles; t += stride, ++it) {
@@ -520,9 +523,8 @@ int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();
-  if (cs == 2) ru_fused_kernel<2><<<grid, 128 * 2 + 96, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
-  else ru_fused_kernel<4><<<grid, 128 * 4 + 96, smem, static_cast<cudaStream_t>(stream_v)>>>(p);
-  HY_CUDA(cudaGetLastError());
+  if (cs == 2) HY_CUDA(hy_launch_pdl(ru_fused_kernel<2>, grid, 128 * 2 + 96, smem, static_cast<cudaStream_t>(stream_v), p));
+  else HY_CUDA(hy_launch_pdl(ru_fused_kernel<4>, grid, 128 * 4 + 96, smem, static_cast<cudaStream_t>(stream_v), p));
   return HYRES_OK;
 }
 
