@@ -14,8 +14,9 @@ boundary (libjpeg-turbo) on both arms: it runs once at set-up and its output (`j
   value : Mpixel/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
   e2e   : Mpixel/s through the public API with pinned HOST inputs, H2D copies and the D2H read of
           the loss inside the timed region
-  roofline     : the tcgen05 implicit-GEMM convolution kernel (tensor bound), canonical
-                 algorithmic FLOPs of the step / summed CUDA-event time of its launches
+  roofline     : the dominant kernel, ru_fused_kernel (tensor bound): its algorithmic FLOPs per launch / its
+                 average CUDA-event launch time; `all_tensor_kernels` = canonical FLOPs of the step / summed
+                 time of every tcgen05 launch
   cpu_baseline : the CPU oracle (the reference's PyTorch semantics, fp32) on a bounded sample
 
 `--impl reference` times that CPU path alone, on every host core, for the driver's ratio.
@@ -37,6 +38,8 @@ LMBDA = 0.008
 # canonical algorithmic work, BASELINE.md section 3 (1 MAC = 2 FLOP; masked conv = 12 taps;
 # anchor pass of the parameter head K = 384)
 MAC_PER_PX_CONV = 483_234  # codec forward 370 624 + MultiScaleRefine 112 610
+RU_MAC_PER_POS = 128 * 64 + 9 * 64 * 64 + 64 * 128  # one fused ResidualUnit, per position
+RU_DRAM_BYTES_PER_LAUNCH = 763_905_792  # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_full.md
 
 
 def load_peaks():
@@ -255,7 +258,14 @@ def main():
     peaks = load_peaks()
     value = world * px_step / (ms * 1e-3) / 1e6
     flops_step = 2.0 * MAC_PER_PX_CONV * px_step
-    achieved = flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms else None
+    all_tc = flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms else None
+    # dominant kernel: ru_fused_kernel (the 14 C=128 ResidualUnit / ResidualBottleneckBlock instances at H/2).
+    # algorithmic MACs per position = 128*64 + 576*64 + 64*128; traffic per launch from the
+    # ncu --set full capture of the same shape (profiles/r01_ncu_full.md): dram read + write.
+    ru = [r for r in ops.ConvLayer.last_profile if r["kind"] == "ru" and r["H"] == H // 2]
+    ru_flops = 2.0 * RU_MAC_PER_POS * BATCH * (H // 2) * (W // 2)
+    ru_ms = sum(r["ms"] for r in ru) / len(ru) if ru else None
+    achieved = ru_flops / (ru_ms * 1e-3) / 1e12 if ru_ms else None
     line = {
         "metric": "hyres_forward_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -265,13 +275,18 @@ def main():
         "gpu_launches": int(launches) * args.steps,
         "gpu_launches_per_step": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM kernels (conv_tc / conv_res / ru_fused / conv_c3): all %d launches "
-                                                       "of one step" % conv_n,
-                     "ru_fused_ms_per_step": sum(r["ms"] for r in ops.ConvLayer.last_profile if r["kind"] == "ru"),
+        "roofline": {"bound": "tensor", "kernel": "ru_fused_kernel (fused 1x1 -> 3x3 -> 1x1 + skip at 16x256x384x128, "
+                                                  "%d launches per step)" % len(ru),
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops"] if achieved else None, "traffic": None,
-                     "peak_source": peaks["source"], "conv_ms_per_step": conv_ms,
-                     "conv_share_of_step": conv_ms / ms_local if conv_ms else None,
+                     "frac": achieved / peaks["tflops"] if achieved else None,
+                     "traffic": RU_DRAM_BYTES_PER_LAUNCH, "algorithmic_bytes": 2 * BATCH * (H // 2) * (W // 2) * 128 * 2,
+                     "ms_per_launch": ru_ms, "peak_source": peaks["source"],
+                     "note": "N = 64 tcgen05.mma is bound by shared-memory operand fetch at 2/3 of the dense peak "
+                             "(profiles/r01_microbench.md); the kernel is shared-memory-bandwidth bound",
+                     "share_of_step": (ru_ms * len(ru)) / ms_local if ru_ms else None,
+                     "all_tensor_kernels": {"launches": conv_n, "ms_per_step": conv_ms, "achieved": all_tc,
+                                            "frac": all_tc / peaks["tflops"] if all_tc else None,
+                                            "share_of_step": conv_ms / ms_local if conv_ms else None},
                      "step_tflops": flops_step / (ms * 1e-3) / 1e12,
                      "step_frac": flops_step / (ms * 1e-3) / 1e12 / peaks["tflops"]},
         "loss": loss_val, "e2e_loss": e2e_loss,
