@@ -22,6 +22,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kPix = 32;  // positions per block
+constexpr int kPixEb = 8; // positions per block of the (small, math-heavy) EntropyBottleneck kernels: 4x the blocks
 
 // counter-based uniform noise in (-0.5, 0.5): splitmix64 of (seed, element index)
 __device__ __forceinline__ float uniform_noise(uint64_t seed, uint64_t idx) {
@@ -261,14 +262,14 @@ __global__ void eb_forward_kernel(const float* __restrict__ z, const EbChan* __r
                                   __nv_bfloat16* __restrict__ zhat_bf16, float* __restrict__ zhat_nchw,
                                   float* __restrict__ lik_nchw, int32_t* __restrict__ symbols,
                                   double* __restrict__ sum_log2, int hw, int C) {
-  extern __shared__ float tile[];  // [3][kPix][C+1]: lik, zhat, symbol(bits)
+  extern __shared__ float tile[];  // [3][kPixEb][C+1]: lik, zhat, symbol(bits)
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * kPix;
-  const int np = min(kPix, hw - p0);
+  const int p0 = blockIdx.x * kPixEb;
+  const int np = min(kPixEb, hw - p0);
   const int ld = C + 1;
   float* t_lik = tile;
-  float* t_zh = tile + kPix * ld;
-  int32_t* t_sym = reinterpret_cast<int32_t*>(tile + 2 * kPix * ld);
+  float* t_zh = tile + kPixEb * ld;
+  int32_t* t_sym = reinterpret_cast<int32_t*>(tile + 2 * kPixEb * ld);
   float acc = 0.f;
   for (int t = threadIdx.x; t < np * C; t += kThreads) {
     const int px = t / C, c = t - px * C;
@@ -315,8 +316,8 @@ __global__ void eb_dequant_kernel(const int32_t* __restrict__ symbols, const flo
                                   __nv_bfloat16* __restrict__ zhat, int hw, int C) {
   extern __shared__ int32_t itile[];
   const int b = blockIdx.y;
-  const int p0 = blockIdx.x * kPix;
-  const int np = min(kPix, hw - p0);
+  const int p0 = blockIdx.x * kPixEb;
+  const int np = min(kPixEb, hw - p0);
   const int ld = C + 1;
   for (int t = threadIdx.x; t < np * C; t += kThreads) {
     const int c = t / np, px = t - c * np;
@@ -427,10 +428,10 @@ int hyres_eb_forward(const float* z, const float* eb_params, const float* median
                      double* sum_log2, int B, int h, int w, int C, void* stream_v) {
   if (!z || !eb_params || !medians || B <= 0 || h <= 0 || w <= 0 || C <= 0)
     return hy_fail(HYRES_ERR_ARG, "eb_forward: bad argument");
-  const int smem = 3 * kPix * (C + 1) * 4;
+  const int smem = 3 * kPixEb * (C + 1) * 4;
   int rc = set_smem(reinterpret_cast<const void*>(eb_forward_kernel), smem);
   if (rc) return rc;
-  dim3 grid((h * w + kPix - 1) / kPix, B);
+  dim3 grid((h * w + kPixEb - 1) / kPixEb, B);
   hy_count_launch();
   eb_forward_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       z, reinterpret_cast<const EbChan*>(eb_params), medians, mode, seed, lik_bound,
@@ -443,10 +444,10 @@ int hyres_eb_dequant(const int32_t* symbols, const float* medians, void* zhat_bf
                      void* stream_v) {
   if (!symbols || !medians || !zhat_bf16 || B <= 0 || h <= 0 || w <= 0 || C <= 0)
     return hy_fail(HYRES_ERR_ARG, "eb_dequant: bad argument");
-  const int smem = kPix * (C + 1) * 4;
+  const int smem = kPixEb * (C + 1) * 4;
   int rc = set_smem(reinterpret_cast<const void*>(eb_dequant_kernel), smem);
   if (rc) return rc;
-  dim3 grid((h * w + kPix - 1) / kPix, B);
+  dim3 grid((h * w + kPixEb - 1) / kPixEb, B);
   hy_count_launch();
   eb_dequant_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       symbols, medians, static_cast<__nv_bfloat16*>(zhat_bf16), h * w, C);
