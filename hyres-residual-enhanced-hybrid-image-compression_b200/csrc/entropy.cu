@@ -116,20 +116,35 @@ __global__ void gc_merge_likelihood_kernel(const float* __restrict__ y, const fl
   const int np = min(kPix, hw - p0);
   const int ld = M + 1;
   float acc = 0.f;
-  for (int t = threadIdx.x; t < np * M; t += kThreads) {
-    const int px = t / M, c = t - px * M;
+  const int M4 = M >> 2;  // M % 4 == 0 (checked by the entry point): four channels per thread, 16-byte loads
+  for (int t = threadIdx.x; t < np * M4; t += kThreads) {
+    const int px = t / M4, c = (t - px * M4) * 4;
     const int64_t pix = static_cast<int64_t>(b) * hw + p0 + px;
     const int64_t e = pix * M + c;
-    const float yv = __ldg(y + e);
-    const float s = __ldg(pa + pix * 2 * M + c) + __ldg(pna + pix * 2 * M + c);
-    const float m = __ldg(pa + pix * 2 * M + M + c) + __ldg(pna + pix * 2 * M + M + c);
-    if (y_hat) y_hat[e] = __float2bfloat16_rn(__ldg(yq_a + e) + __ldg(yq_na + e));
-    float outv;
-    if (mode == 0) outv = rintf(yv - m) + m;
-    else outv = yv + uniform_noise(seed ^ 0xA5A5A5A5DEADBEEFull, static_cast<uint64_t>(e));
-    const float lik = gauss_likelihood(fabsf(outv - m), s, scale_bound, lik_bound);
-    tile[px * ld + c] = lik;
-    acc += log2f(lik);
+    const float4 yv = __ldg(reinterpret_cast<const float4*>(y + e));
+    const float4 sa = __ldg(reinterpret_cast<const float4*>(pa + pix * 2 * M + c));
+    const float4 sn = __ldg(reinterpret_cast<const float4*>(pna + pix * 2 * M + c));
+    const float4 ma = __ldg(reinterpret_cast<const float4*>(pa + pix * 2 * M + M + c));
+    const float4 mn = __ldg(reinterpret_cast<const float4*>(pna + pix * 2 * M + M + c));
+    if (y_hat) {
+      const float4 qa = __ldg(reinterpret_cast<const float4*>(yq_a + e)), qn = __ldg(reinterpret_cast<const float4*>(yq_na + e));
+      uint2 o;
+      o.x = hy::pack_bf16(qa.x + qn.x, qa.y + qn.y);
+      o.y = hy::pack_bf16(qa.z + qn.z, qa.w + qn.w);
+      *reinterpret_cast<uint2*>(y_hat + e) = o;
+    }
+    const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
+    const float ss[4] = {sa.x + sn.x, sa.y + sn.y, sa.z + sn.z, sa.w + sn.w};
+    const float mm[4] = {ma.x + mn.x, ma.y + mn.y, ma.z + mn.z, ma.w + mn.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float outv;
+      if (mode == 0) outv = rintf(yy[k] - mm[k]) + mm[k];
+      else outv = yy[k] + uniform_noise(seed ^ 0xA5A5A5A5DEADBEEFull, static_cast<uint64_t>(e + k));
+      const float lik = gauss_likelihood(fabsf(outv - mm[k]), ss[k], scale_bound, lik_bound);
+      tile[px * ld + c + k] = lik;
+      acc += log2f(lik);
+    }
   }
   __syncthreads();
   if (lik_nchw) {
@@ -360,8 +375,8 @@ int hyres_gc_quant_pass(const float* y, const float* params, int pass, int mode,
 int hyres_gc_merge_likelihood(const float* y, const float* params_a, const float* params_na, const float* yq_a,
                               const float* yq_na, int mode, uint64_t seed, void* y_hat_bf16, float* lik_nchw,
                               double* sum_log2, int B, int h, int w, int M, void* stream_v) {
-  if (!y || !params_a || !params_na || B <= 0 || h <= 0 || w <= 0 || M <= 0)
-    return hy_fail(HYRES_ERR_ARG, "gc_merge_likelihood: bad argument");
+  if (!y || !params_a || !params_na || B <= 0 || h <= 0 || w <= 0 || M <= 0 || (M & 3))
+    return hy_fail(HYRES_ERR_ARG, "gc_merge_likelihood: bad argument (M must be a positive multiple of 4)");
   if (y_hat_bf16 && (!yq_a || !yq_na)) return hy_fail(HYRES_ERR_ARG, "gc_merge_likelihood: yq_a/yq_na required");
   const int hw = h * w;
   const int smem = kPix * (M + 1) * 4;

@@ -217,3 +217,31 @@ def test_full_size_properties_cfg2(nets, oracle):
     assert torch.equal(one["x_hat"][0], a["x_hat"][5])  # images are independent: sharding by image is exact
     lo = hyres_b200.RateDistortionLoss(lmbda=0.008)(a, x.cuda())
     assert torch.isfinite(lo["loss"])
+
+
+def test_host_pipeline_matches_direct_calls(nets, oracle):
+    """hyres_b200.HostPipeline (pinned host batches, H2D on a copy stream under the previous batch's kernels, results
+    read one batch late) returns, in order, exactly the scalars of direct forward + RateDistortionLoss calls."""
+    import hyres_b200
+    onet, pnet = nets
+    crit = hyres_b200.RateDistortionLoss(lmbda=0.008)
+    batches = []
+    for k in range(5):
+        x = oracle.synthetic_image(2, 64, 96, seed=40 + k).pin_memory()
+        jd, bpp = onet.jpeg(x)
+        batches.append((x, jd.contiguous().pin_memory(), bpp))
+    want = []
+    with torch.no_grad():
+        for x, jd, bpp in batches:
+            stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+            out = pnet(x.cuda(), jpeg=(jd.cuda(), bpp), stats=stats)
+            lo = crit(out, x.cuda(), stats=stats)
+            want.append({k: float(lo[k]) for k in ("loss", "bpp_loss", "mse_loss")})
+    pipe = hyres_b200.HostPipeline(pnet, crit)
+    got = list(pipe.run(iter(batches)))
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for k in w:
+            assert g[k] == pytest.approx(w[k], rel=1e-6), (k, g, w)
+    assert pipe.h2d_bytes == 5 * 2 * 2 * 3 * 64 * 96 * 4 and pipe.d2h_bytes == 5 * 24
+    assert list(pipe.run(iter([]))) == []
