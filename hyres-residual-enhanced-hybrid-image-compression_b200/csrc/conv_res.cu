@@ -21,6 +21,7 @@
 //     write x^2 to HBM.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -32,6 +33,7 @@ namespace {
 
 constexpr int kTH = 16, kTW = 8;
 constexpr int kThreads = 320;  // warps 0-3 / 4-7: epilogue groups 0 / 1; warp 8: TMA loads; warp 9: MMA
+constexpr int kThreadsSq = 448;  // + warps 10-13: x0_square transform (GDN layers only)
 constexpr int kMaxSteps = 64;
 constexpr int kMaxStages = 4;
 constexpr int kSmemLimit = 227 * 1024;
@@ -60,6 +62,7 @@ struct alignas(64) ResParams {
   int32_t cout, epi, act;
   float slope;
   int32_t a_square, has_aux0, has_aux1, store_bf16;
+  int32_t pf_extra;  // L2 prefetch distance beyond the ring, in tiles; < 0: no prefetch
   const float* bias;
   const float* pixscale;
   float* out_f32;
@@ -99,7 +102,7 @@ __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_constant__ ResParams p) {
+__global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_constant__ ResParams p) {
   hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
   }
   {
     float* sb = reinterpret_cast<float*>(smem_raw + (bias_base - hy::smem_u32(smem_raw)));
-    for (int i = threadIdx.x; i < p.BN; i += kThreads) sb[i] = __ldg(p.bias + i);  // bias padded to BN
+    for (int i = threadIdx.x; i < p.BN; i += blockDim.x) sb[i] = __ldg(p.bias + i);  // bias padded to BN
   }
   if (warp == 8 && lane == 0) {
     hy::tma_prefetch_desc(&p.mapA);
@@ -171,6 +174,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t par = 0;
+      auto prefetch = [&](int t) {
+        int b_img, h0, w0;
+        tile_origin(t, b_img, h0, w0);
+        for (int c = 0; c < p.nchunk_in; ++c) hy::tma_prefetch_4d(&p.mapA, c * 64, w0 + p.org_w, h0 + p.org_h, b_img);
+        if (p.has_aux0)
+          for (int c = 0; c < p.nchunk_out; ++c) hy::tma_prefetch_4d(&p.mapAux0, c * 64, w0, h0, b_img);
+        if (p.has_aux1)
+          for (int c = 0; c < p.nchunk_out; ++c) hy::tma_prefetch_4d(&p.mapAux1, c * 64, w0, h0, b_img);
+      };
+      // the ring is shallow when a stage also holds the epilogue operands (gate: two stages): tiles beyond the ring
+      // are prefetched into L2, so a freed stage refills at L2 latency
+      const int ahead = (p.NA + p.pf_extra) * static_cast<int>(gridDim.x);
+      for (int k = 0; k < p.pf_extra; ++k) {
+        const int t = blockIdx.x + (p.NA + k) * static_cast<int>(gridDim.x);
+        if (p.pf_extra >= 0 && t < p.ntiles) prefetch(t);
+      }
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
         int b_img, h0, w0;
         tile_origin(t, b_img, h0, w0);
@@ -185,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
         if (p.has_aux1)
           for (int c = 0; c < p.nchunk_out; ++c)
             hy::tma_load_4d(sb + p.x1_off + c * 16384, &p.mapAux1, A_FULL + 8 * stage, c * 64, w0, h0, b_img);
+        if (p.pf_extra >= 0 && t + ahead < p.ntiles) prefetch(t + ahead);
         if (++stage == p.NA) { stage = 0; par ^= 1u; }
       }
     }
@@ -219,6 +239,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
         if (++stage == p.NA) { stage = 0; par ^= 1u; }
       }
     }
+  } else if (warp >= 10) {
+    // ============================ x0_square transform (GDN) ============================
+    // GDN operand: square the activation tile in place (bf16 RN of the exact product, the same value a
+    // producer-side x*x store would have held), then release it to the MMA warp.  Its own four warps, so the
+    // transform of tile t+1 runs under the MMAs of tile t and the epilogues of tiles t-1, t-2.
+    if (p.a_square) {
+      const int row = threadIdx.x - 320;
+      int stage = 0;
+      uint32_t par = 0;
+      for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        const uint32_t sb = st_base + stage * p.stage_bytes;
+        hy::mbar_wait(A_FULL + 8 * stage, par);
+        for (int c = 0; c < p.nchunk_in; ++c) {
+          const uint32_t r0 = sb + c * p.a_chunk_bytes + row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            // element-wise and in place, so any visiting order works: rotate the 16 B chunk by the row so
+            // that the 8 rows of a quarter-warp touch 8 different bank groups (rows are 128 B apart)
+            const uint32_t a = r0 + ((j ^ (row & 7)) << 4);
+            uint4 v = lds128(a);
+            v.x = sq_bf16x2(v.x); v.y = sq_bf16x2(v.y); v.z = sq_bf16x2(v.z); v.w = sq_bf16x2(v.w);
+            sts128(a, v);
+          }
+        }
+        hy::fence_async_smem();
+        hy::mbar_arrive(A_READY + 8 * stage);
+        if (++stage == p.NA) { stage = 0; par ^= 1u; }
+      }
+    }
   } else {
     // ============================ epilogue groups ============================
     const int grp = warp >> 2;
@@ -236,27 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_res_kernel(const __grid_cons
       const uint32_t sb = st_base + stage * p.stage_bytes;
       int b_img, h0, w0;
       tile_origin(t, b_img, h0, w0);
-      if (p.a_square) {
-        // GDN operand: square the activation tile in place (bf16 RN of the exact product, the
-        // same value a producer-side x*x store would have held), then release it to the MMA warp
-        hy::mbar_wait(A_FULL + 8 * stage, par);
-        for (int c = 0; c < p.nchunk_in; ++c) {
-          const uint32_t r0 = sb + c * p.a_chunk_bytes + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            // element-wise and in place, so any visiting order works: rotate the 16 B chunk by the row so
-            // that the 8 rows of a quarter-warp touch 8 different bank groups (rows are 128 B apart)
-            const uint32_t a = r0 + ((j ^ (row & 7)) << 4);
-            uint4 v = lds128(a);
-            v.x = sq_bf16x2(v.x); v.y = sq_bf16x2(v.y); v.z = sq_bf16x2(v.z); v.w = sq_bf16x2(v.w);
-            sts128(a, v);
-          }
-        }
-        hy::fence_async_smem();
-        hy::mbar_arrive(A_READY + 8 * stage);
-      } else if (need0) {
-        hy::mbar_wait(A_FULL + 8 * stage, par);  // acquire the TMA-written epilogue operands
-      }
+      if (need0) hy::mbar_wait(A_FULL + 8 * stage, par);  // acquire the TMA-written epilogue operands
       hy::mbar_wait(ACC_FULL + 8 * grp, (it >> 1) & 1);
       hy::tc_fence_after();
 
@@ -452,6 +481,10 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   p.has_aux0 = need0; p.has_aux1 = need1;
   p.store_bf16 = io->out_bf16 ? 1 : 0;
   p.a_square = io->x0_square ? 1 : 0;
+  {
+    static const int pf = [] { const char* e = getenv("HYRES_RES_PF"); return e ? atoi(e) : 0; }();
+    p.pf_extra = pf;
+  }
   if (p.a_square && (PH != kTH || PW != kTW)) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: x0_square needs a 1x1 layer");
   if (deconv && (need0 || need1)) return HYRES_OK;
   int stage = p.nchunk_in * p.a_chunk_bytes;
@@ -504,7 +537,7 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();
-  HY_CUDA(hy_launch_pdl(conv_res_kernel, grid, kThreads, smem, stream, p));
+  HY_CUDA(hy_launch_pdl(conv_res_kernel, grid, p.a_square ? kThreadsSq : kThreads, smem, stream, p));
   *handled = 1;
   return HYRES_OK;
 }
