@@ -78,32 +78,41 @@ def _threads(n):
 
 
 def encode_batch(symbols, indexes, tables, threads=None):
-    """symbols / indexes: int32 arrays [count, n] (rows = independent strings) -> list of bytes."""
-    s, ix = _i32(symbols), _i32(indexes)
-    if s.shape != ix.shape or s.ndim != 2:
-        raise ValueError("`symbols` and `indexes` should be [count, n] arrays of the same size.")
-    count, n = s.shape
+    """symbols / indexes: int32 arrays [count, n] (rows = independent strings), or equally long lists of such
+    arrays (their rows are coded as one batch, without concatenating them) -> list of bytes."""
+    if isinstance(symbols, (list, tuple)):
+        s_list, ix_list = [_i32(a) for a in symbols], [_i32(a) for a in indexes]
+    else:
+        s_list, ix_list = [_i32(symbols)], [_i32(indexes)]
+    if len(s_list) != len(ix_list):
+        raise ValueError("`symbols` and `indexes` should have the same size.")
+    rows_s, rows_i = [], []
+    for s, ix in zip(s_list, ix_list):
+        if s.shape != ix.shape or s.ndim != 2:
+            raise ValueError("`symbols` and `indexes` should be [count, n] arrays of the same size.")
+        rows_s += [s[i] for i in range(s.shape[0])]
+        rows_i += [ix[i] for i in range(s.shape[0])]
+    count = len(rows_s)
     if count == 0:
         return []
     lib = L.lib()
-    cap = int(lib.hyres_rans_encode_bound(n))
+    ns = np.array([r.size for r in rows_s], dtype=np.int64)
+    caps = np.array([int(lib.hyres_rans_encode_bound(int(n))) for n in ns], dtype=np.int64)
     t = tables
     while True:
-        out = np.empty((count, cap), dtype=np.uint8)
-        sp = (C.c_void_p * count)(*[s[i].ctypes.data for i in range(count)])
-        ip = (C.c_void_p * count)(*[ix[i].ctypes.data for i in range(count)])
-        op = (C.c_void_p * count)(*[out[i].ctypes.data for i in range(count)])
-        ns = np.full(count, n, dtype=np.int64)
-        caps = np.full(count, cap, dtype=np.int64)
+        outs = [np.empty(int(c), dtype=np.uint8) for c in caps]
+        sp = (C.c_void_p * count)(*[r.ctypes.data for r in rows_s])
+        ip = (C.c_void_p * count)(*[r.ctypes.data for r in rows_i])
+        op = (C.c_void_p * count)(*[o.ctypes.data for o in outs])
         lens = np.zeros(count, dtype=np.int64)
         rc = lib.hyres_rans_encode_batch(count, sp, ip, ns.ctypes.data, t.cdf.ctypes.data, t.cdf.shape[0],
                                          t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data, op,
                                          caps.ctypes.data, lens.ctypes.data, _threads(threads or count))
-        if rc != 0 and lens.max() > cap:
-            cap = int(lens.max())
+        if rc != 0 and (lens > caps).any():
+            caps = np.maximum(caps, lens)
             continue
         L.check(rc, "hyres_rans_encode_batch")
-        return [out[i, : lens[i]].tobytes() for i in range(count)]
+        return [outs[i][: lens[i]].tobytes() for i in range(count)]
 
 
 def decode_batch(strings, indexes, tables, threads=None):

@@ -88,29 +88,64 @@ class EntropyModel(nn.Module):
         return self._tables_cache[1]
 
     # -- coding of already-quantised symbols --
+    _pinned = {}
+
+    @classmethod
+    def _host_i32(cls, t, slot):
+        """int32 [B, n] numpy view of a tensor; CUDA tensors come back through a cached pinned buffer (a pageable
+        ``.cpu()`` of the 35 MB symbol tensors of a 2048x1408 image runs at a fraction of the PCIe rate)."""
+        B = t.size(0)
+        t = t.reshape(B, -1)
+        if t.dtype != torch.int32:
+            t = t.to(torch.int32)
+        if not t.is_cuda:
+            return t.contiguous().numpy()
+        key = (slot, t.numel())
+        buf = cls._pinned.get(key)
+        if buf is None:
+            if len(cls._pinned) > 16:
+                cls._pinned.clear()
+            buf = cls._pinned[key] = torch.empty(t.numel(), dtype=torch.int32).pin_memory()
+        view = buf.view(B, -1)
+        view.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return view.numpy()
+
     def encode_symbols(self, symbols, indexes):
         """symbols / indexes: int32 tensors [B, ...] (any device) -> list of B byte strings."""
-        if symbols.dim() < 2:
-            raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
-        if symbols.size() != indexes.size():
-            raise ValueError("`inputs` and `indexes` should have the same size.")
-        B = symbols.size(0)
-        s = symbols.reshape(B, -1).to("cpu", torch.int32).numpy()
-        ix = indexes.reshape(B, -1).to("cpu", torch.int32).numpy()
-        return coder.encode_batch(s, ix, self.tables())
+        return self.encode_symbol_groups([(symbols, indexes)])[0]
+
+    def encode_symbol_groups(self, groups):
+        """groups: list of (symbols, indexes) pairs of equal shape -> list (per group) of lists of B byte strings.
+        All strings of all groups are coded in ONE batch, so e.g. the anchor and non-anchor passes of a batch of
+        8 tiles keep 16 host threads busy instead of 8 twice."""
+        syms, idxs = [], []
+        for g, (symbols, indexes) in enumerate(groups):
+            if symbols.dim() < 2:
+                raise ValueError("Invalid `inputs` size. Expected a tensor with at least 2 dimensions.")
+            if symbols.size() != indexes.size():
+                raise ValueError("`inputs` and `indexes` should have the same size.")
+            syms.append(self._host_i32(symbols, ("s", g)))
+            idxs.append(self._host_i32(indexes, ("i", g)))
+        out = coder.encode_batch(syms, idxs, self.tables())
+        res, k = [], 0
+        for a in syms:
+            res.append(out[k:k + a.shape[0]])
+            k += a.shape[0]
+        return res
 
     def decode_symbols(self, strings, indexes):
-        """-> int32 CPU tensor shaped like ``indexes``."""
+        """-> int32 CPU tensor shaped like ``indexes`` (pinned when the indexes came from the GPU)."""
         if not isinstance(strings, (tuple, list)):
             raise ValueError("Invalid `strings` parameter type.")
         if len(strings) != indexes.size(0):
             raise ValueError("Invalid strings or indexes parameters")
         if indexes.dim() < 2:
             raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
-        B = indexes.size(0)
-        ix = indexes.reshape(B, -1).to("cpu", torch.int32).numpy()
+        ix = self._host_i32(indexes, ("d", 0))
         out = coder.decode_batch(list(strings), ix, self.tables())
-        return torch.from_numpy(out).reshape(indexes.shape)
+        res = torch.from_numpy(out).reshape(indexes.shape)
+        return res.pin_memory() if indexes.is_cuda else res
 
 
 class EntropyBottleneck(EntropyModel):

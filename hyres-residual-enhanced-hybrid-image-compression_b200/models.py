@@ -210,8 +210,8 @@ class LightWeightCheckerboard(CompressionModel):
         s = self.encode_symbols(x, _jpeg=_jpeg)
         gc, ebm = self.gaussian_conditional, self.entropy_bottleneck
         z_strings = ebm.encode_symbols(s["sym_z"], ebm._build_indexes(s["sym_z"].size()))
-        anchor_strings = gc.encode_symbols(s["sym_a"], s["idx_a"])
-        non_anchor_strings = gc.encode_symbols(s["sym_na"], s["idx_na"])
+        anchor_strings, non_anchor_strings = gc.encode_symbol_groups([(s["sym_a"], s["idx_a"]),
+                                                                      (s["sym_na"], s["idx_na"])])
         return {"strings": [[anchor_strings, non_anchor_strings], z_strings],
                 "shape": torch.Size(s["sym_z"].shape[-2:]), "time": time.time() - start_time}
 
@@ -230,12 +230,12 @@ class LightWeightCheckerboard(CompressionModel):
         latent = eng.h_s(ops.eb_dequant(sym_z.contiguous(), med))
         pa = eng.head(latent)
         idx_a = ops.gc_indexes(pa, table, self.M, bound)
-        sym_a = gc.decode_symbols(strings[0][0], idx_a).to(dev)
+        sym_a = gc.decode_symbols(strings[0][0], idx_a).to(dev, non_blocking=True)
         yqa32, yqa16 = ops.gc_dequant(sym_a.contiguous(), pa)
         ctx = eng.context(yqa16)
         pna = eng.head(latent, ctx)
         idx_na = ops.gc_indexes(pna, table, self.M, bound)
-        sym_na = gc.decode_symbols(strings[0][1], idx_na).to(dev)
+        sym_na = gc.decode_symbols(strings[0][1], idx_na).to(dev, non_blocking=True)
         yqna32, _ = ops.gc_dequant(sym_na.contiguous(), pna, want_bf16=False)
         y_hat16 = ops.add_to_bf16(yqa32, yqna32)
         x_hat = eng.g_s(y_hat16, clamp=True)  # Q3
