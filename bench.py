@@ -154,6 +154,36 @@ def workload_config(n):
             "weights": "random init, seed 1926"}
 
 
+def codec_cfg3(net, dev, reps=3):
+    """BASELINE.json configs[2] on one GPU: compress + decompress (strings out and back, host rANS included) of one
+    2048x1408 image as eight 704x512 tiles (tier T-A of SURVEY section 8e).  Extra evidence next to the headline."""
+    import torch
+    from hyres_b200 import synthetic
+    tiles, h, w = 8, 704, 512
+    x = synthetic.synthetic_image(tiles, h, w, seed=7)
+    bufs = net.jpeg.compress(x)
+    xd = x.to(dev)
+    with torch.no_grad():
+        for _ in range(2):
+            d = net.decompress(net.compress(xd, jpeg_buffers=bufs))
+        t_enc = t_dec = 0.0
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            c = net.compress(xd, jpeg_buffers=bufs)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            d = net.decompress(c)
+            torch.cuda.synchronize()
+            t_enc += t1 - t0
+            t_dec += time.perf_counter() - t1
+    px = tiles * h * w
+    nbytes = sum(len(s) for grp in (c["strings"][0][0], c["strings"][0][1], c["strings"][1]) for s in grp)
+    return {"workload": "compress + decompress, 8 tiles of 704x512 (one 2048x1408 image), host rANS included",
+            "enc_ms": t_enc / reps * 1e3, "dec_ms": t_dec / reps * 1e3, "encdec_mpixel_per_s": px * reps / (t_enc + t_dec) / 1e6,
+            "residual_bpp": 8.0 * nbytes / px, "host_cores": os.cpu_count(), "x_hat_shape": list(d["x_hat"].shape)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -291,6 +321,8 @@ def main():
                      "step_frac": flops_step / (ms * 1e-3) / 1e12 / peaks["tflops"]},
         "loss": loss_val, "e2e_loss": e2e_loss,
     }
+    if world == 1:
+        line["codec_cfg3"] = codec_cfg3(net, dev)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         step, px = oracle_step_factory(1, cores)
