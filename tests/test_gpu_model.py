@@ -245,3 +245,31 @@ def test_host_pipeline_matches_direct_calls(nets, oracle):
             assert g[k] == pytest.approx(w[k], rel=1e-6), (k, g, w)
     assert pipe.h2d_bytes == 5 * 2 * 2 * 3 * 64 * 96 * 4 and pipe.d2h_bytes == 5 * 24
     assert list(pipe.run(iter([]))) == []
+
+
+def test_full_size_properties_cfg4_refine(nets, oracle):
+    """BASELINE.json configs[3] shape (MultiScaleRefine on frozen-codec output, batch 32 of 512x512): the refine
+    engine alone, fed x0 = jpeg + r_hat.  Size-independent properties: x0 is the exact fp32 sum; images are
+    independent (any slice of the batch reproduces its rows bit for bit); the wrapper's reconstruction is the clamp
+    of their sum.  Oracle parity is checked on one whole small image of the same generator (the three-scale
+    network with its global SE pool has no crop-local receptive field), at the bf16 trunk's tolerance."""
+    onet, pnet = nets
+    eng = pnet.refine_engine()
+    g = torch.Generator().manual_seed(44)
+    jpeg = torch.rand(32, 3, 512, 512, generator=g).cuda()
+    r_hat = (torch.randn(32, 3, 512, 512, generator=g) * 0.05).cuda()
+    with torch.no_grad():
+        x0, refined = eng(r_hat, jpeg)
+        x0_b, refined_b = eng(r_hat[7:9].contiguous(), jpeg[7:9].contiguous())
+        out = pnet._reconstruct(jpeg, r_hat)
+    assert torch.equal(x0, jpeg + r_hat)
+    assert refined.shape == (32, 3, 512, 512) and torch.isfinite(refined).all()
+    assert torch.equal(refined[7:9], refined_b) and torch.equal(x0[7:9], x0_b)
+    assert torch.equal(out, torch.clamp(x0 + refined, 0, 1))
+    # oracle parity on one small image (bf16-storage restatement)
+    js, rs = jpeg[:1, :, :96, :128].contiguous(), r_hat[:1, :, :96, :128].contiguous()
+    with torch.no_grad():
+        _, got = eng(rs, js)
+        with oracle.precision("bf16"):
+            want = onet.refine((js + rs).cpu())
+    assert _rel(got.cpu(), want) < 3e-2
