@@ -139,6 +139,18 @@ def test_wrapper_compress_decompress(nets, oracle):
     assert abs(psnr(d["x_hat"].cpu()) - psnr(od["x_hat"])) < 0.05
 
 
+def test_container_survives_decompress(nets, oracle):
+    """decompress(unpack(pack(compress(x)))) == decompress(compress(x)) bit for bit."""
+    from hyres_b200 import container
+    onet, pnet = nets
+    x = oracle.synthetic_image(2, 64, 96, seed=12)
+    with torch.no_grad():
+        c = pnet.compress(x.cuda())
+        a = pnet.decompress(c)["x_hat"]
+        b = pnet.decompress(container.unpack(container.pack(c)))["x_hat"]
+    assert torch.equal(a, b)
+
+
 def test_oracle_decodes_product_strings_when_symbols_agree(nets, oracle):
     """Cross-implementation decode: the oracle's decoder reads the product's hyper-latent string
     (z symbols depend only on the analysis trunk) whenever the z symbols agree."""

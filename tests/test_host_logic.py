@@ -127,3 +127,25 @@ def test_jpeg_stage_contract(build_lib):
     bufs = j.compress(x)
     assert bpp == pytest.approx(len(bufs[0].getvalue()) * 8 / (32 * 32))
     assert torch.equal(j.decompress(bufs, "cpu"), dec)
+
+
+def test_container_roundtrip_and_errors(build_lib):
+    """hyres_b200.container: pack / unpack of the compress() dict are exact inverses; malformed input raises."""
+    import io
+    import torch
+    from hyres_b200 import container
+    c = {"strings": [[[b"\x01\x02\x03\x04" * 3, b""], [b"abcdabcd", b"\x00" * 8]], [b"zzzzzzzz", b"yyyyyyyy"]],
+         "shape": torch.Size([22, 16]), "time": 0.1, "jpeg_buffers": [io.BytesIO(b"\xff\xd8jpeg0"), io.BytesIO(b"\xff\xd8jpeg1")]}
+    blob = container.pack(c)
+    d = container.unpack(blob)
+    assert d["strings"] == c["strings"] and d["shape"] == c["shape"]
+    assert [b.getvalue() for b in d["jpeg_buffers"]] == [b.getvalue() for b in c["jpeg_buffers"]]
+    assert container.pack(d) == blob
+    no_jpeg = {k: v for k, v in c.items() if k != "jpeg_buffers"}
+    d2 = container.unpack(container.pack(no_jpeg))
+    assert "jpeg_buffers" not in d2 and d2["strings"] == c["strings"]
+    for bad in (b"", b"XXXX" + blob[4:], blob[:-1], blob + b"\x00"):
+        with pytest.raises(ValueError):
+            container.unpack(bad)
+    with pytest.raises(ValueError):
+        container.pack({"strings": [[[b"a"], [b"b", b"c"]], [b"z"]], "shape": (1, 1)})
