@@ -7,9 +7,9 @@
 
 Workload (BASELINE.json configs[1]): full ResidualJPEGCompression forward + rate-distortion loss on
 a batch of 16 synthetic 768x512 images per GPU (N=128, M=192, random-init weights, seed 1926).
-One step = one pass of the hot path over one batch.  The JPEG round trip is a third-party CPU
-boundary (libjpeg-turbo) on both arms: it runs once at set-up and its output (`jpeg_decoded`,
-`jpeg_bpp`) is an input of every step.
+One step = one pass of the hot path over one batch, JPEG stage included on both arms: on the B200 arm
+it runs on the device (csrc/jpeg.cu, bit-exact with libjpeg-turbo), on the reference arm it is the
+per-image libjpeg-turbo loop the reference runs on the CPU (models/utils/turbo_jpeg_compression.py).
 
   value : Mpixel/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
   e2e   : Mpixel/s through the public API with pinned HOST inputs, H2D copies and the D2H read of
@@ -110,11 +110,10 @@ def oracle_step_factory(sample_images, threads):
     net = O.make_model(seed=1926, wrapper=True)
     crit = O.RateDistortionLoss(lmbda=LMBDA)
     x = O.synthetic_image(sample_images, H, W)
-    jpeg = net.jpeg(x)
 
     def step():
         with torch.no_grad(), O.precision("fp32"):
-            out = net(x, jpeg=jpeg)
+            out = net(x)  # JPEG round trip (libjpeg-turbo, CPU) + residual codec + refine, as the reference runs it
             return float(crit(out, x)["loss"])
     return step, sample_images * H * W
 
@@ -134,7 +133,7 @@ def run_reference(args, rank):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = px / dt / 1e6
-    sample = f"{sample_images} synthetic {W}x{H} image per step (of the {BATCH}-image batch), full forward + RD loss, fp32"
+    sample = f"{sample_images} synthetic {W}x{H} image per step (of the {BATCH}-image batch), full forward (CPU JPEG stage included) + RD loss, fp32"
     print(json.dumps({
         "impl": "reference", "metric": "hyres_forward_mpixel_per_s", "value": v, "unit": "Mpixel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -146,7 +145,7 @@ def run_reference(args, rank):
 
 
 def workload_config(n):
-    return {"workload": "BASELINE.json configs[1]: ResidualJPEGCompression (JPEG q=1 stage injected + residual codec "
+    return {"workload": "BASELINE.json configs[1]: ResidualJPEGCompression (JPEG q=1 stage + residual codec "
                         "N=128 M=192 + MultiScaleRefine) forward + RD loss, batch 16 of 768x512 synthetic images per GPU",
             "batch_per_gpu": BATCH, "height": H, "width": W, "global_batch": BATCH * n, "lambda": LMBDA,
             "sharding": "by image, no data-path collective; 4-double statistics all-reduce",
@@ -218,15 +217,13 @@ def main():
     crit = hyres_b200.RateDistortionLoss(lmbda=LMBDA)
 
     x_host = synthetic.synthetic_image(BATCH, H, W, seed=1926 + rank).pin_memory()
-    jd, jpeg_bpp = net.jpeg(x_host)  # third-party CPU boundary, outside the timed region
-    jd_host = jd.contiguous().pin_memory()
-    x_dev, jd_dev = x_host.to(dev), jd_host.to(dev)
+    x_dev = x_host.to(dev)
     px_step = BATCH * H * W
     stats = torch.zeros(2, dtype=torch.float64, device=dev)
 
     def step_resident():
         stats.zero_()
-        out = net(x_dev, jpeg=(jd_dev, jpeg_bpp), stats=stats)
+        out = net(x_dev, stats=stats)  # JPEG stage (device) + residual codec + refine
         return crit(out, x_dev, stats=stats)
 
     def barrier():
@@ -254,13 +251,14 @@ def main():
         loss_val = float(lo["loss"])
 
         # ---- end to end through the public API with host buffers ----
-        # hyres_b200.HostPipeline: every step's x and jpeg_decoded leave pinned host memory inside the timed
-        # region (on a copy stream, under the previous step's kernels) and every step's loss is read back.
+        # hyres_b200.HostPipeline: every step's x leaves pinned host memory inside the timed region (on a copy
+        # stream, under the previous step's kernels), the JPEG stage runs on the device, and every step's loss
+        # is read back.
         pipe = hyres_b200.HostPipeline(net, crit)
 
         def host_batches(n):
             for _ in range(n):
-                yield x_host, jd_host, jpeg_bpp
+                yield x_host
 
         for _ in pipe.run(host_batches(3)):
             pass
@@ -333,8 +331,8 @@ def main():
             step()
         dt = (time.perf_counter() - t0) / n
         line["cpu_baseline"] = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-                                "sample": f"1 synthetic {W}x{H} image (1/16 of the batch), full forward + RD loss, "
-                                          f"fp32 oracle, mean of {n} after 1 warm-up"}
+                                "sample": f"1 synthetic {W}x{H} image (1/16 of the batch), full forward (CPU JPEG stage "
+                                          f"included) + RD loss, fp32 oracle, mean of {n} after 1 warm-up"}
     print(json.dumps(line))
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -77,6 +77,11 @@ SIGNATURES = {
     "hyres_refine_se_scale_down": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_refine_up_concat_stats": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_spatial_att": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    "hyres_jpeg_workspace_bytes": (_i64, [_i, _i, _i]),
+    "hyres_jpeg_scan_words": (_i64, [_i, _i]),
+    "hyres_jpeg_header_bytes": (_i, []),
+    "hyres_jpeg_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hyres_jpeg_assemble": (_i, [_vp, _i64, _i, _i, _i, _vp, _i64, C.POINTER(_i64)]),
     "hyres_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_nhwc_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_nhwc_bf16_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -1,9 +1,12 @@
-"""JPEG stage at the boundary of the hot path (models/utils/turbo_jpeg_compression.py:17-77).
+"""JPEG stage of the hot path (models/utils/turbo_jpeg_compression.py:17-77).
 
-The JPEG round trip itself is third-party CPU code on both sides (libturbojpeg); only the
-residual subtraction / add-back it feeds is in the kernel scope.
-PyTurboJPEG is used when importable; otherwise OpenCV's libjpeg-turbo build stands in with
-the parameters PyTurboJPEG's defaults imply (RGB array handed over as BGR, 4:2:2).
+The reference round-trips every image through libjpeg-turbo on the CPU, one image at a time.  For CUDA inputs the
+encode side runs on the device instead (``csrc/jpeg.cu``: colour conversion, 4:2:2 down-sampling, ISLOW DCT,
+quantisation, Huffman coding, and the decoder's reconstruction), bit-exact with libjpeg-turbo: ``forward`` never
+leaves the GPU, and ``compress`` only copies the entropy-coded scans to the host to wrap them into JPEG files that
+are byte-identical to the library's (``tests/test_gpu_jpeg.py``).  Decoding JPEG *files* (``decompress``) and CPU
+inputs stay on libjpeg-turbo itself: PyTurboJPEG when importable, otherwise OpenCV's build of the same library
+with the parameters PyTurboJPEG's defaults imply (RGB array handed over as BGR, 4:2:2).
 """
 import io
 import os
@@ -70,7 +73,42 @@ class TurboJPEGCompression(nn.Module):
         import cv2
         return cv2.imdecode(np.frombuffer(raw, dtype=np.uint8), cv2.IMREAD_COLOR)
 
+    # ---- device stage (CUDA inputs) ----
+    @staticmethod
+    def _device_ok(x):
+        return x.is_cuda and x.dim() == 4 and x.size(1) in (1, 3) and x.size(2) % 8 == 0 and x.size(3) % 16 == 0
+
+    @staticmethod
+    def _rgb(x):
+        x = x.float()
+        if x.size(1) == 1:
+            x = x.repeat(1, 3, 1, 1)
+        return x.contiguous()
+
+    def forward_device(self, x):
+        """CUDA ``[B,3,H,W]`` -> (decoded fp32 ``[B,3,H,W]``, bpp as a 0-d fp32 CUDA tensor); no host sync."""
+        from . import ops
+        r = ops.jpeg_forward(self._rgb(x), self.quality)
+        N, _, H, W = x.shape
+        bpp = (r["sizes"].sum().double() * 8.0 / (N * H * W)).float()
+        return r["decoded"], bpp
+
+    def compress_device(self, x):
+        """CUDA ``[B,3,H,W]`` -> (list of ``io.BytesIO`` JPEG files, decoded fp32 ``[B,3,H,W]`` on the device):
+        the files are what libjpeg-turbo writes for these images, the pixels what it decodes from them."""
+        from . import ops
+        xr = self._rgb(x)
+        r = ops.jpeg_forward(xr, self.quality, want_sizes=False, want_scan=True)
+        nbits = r["nbits"].cpu()
+        nwords = int((int(nbits.max()) + 31) // 32)
+        words = r["words"][:, :max(nwords, 1)].cpu().numpy()
+        H, W = xr.shape[2:]
+        return [io.BytesIO(ops.jpeg_assemble(words[i], int(nbits[i]), H, W, self.quality))
+                for i in range(xr.size(0))], r["decoded"]
+
     def compress(self, x):
+        if self._device_ok(x):
+            return self.compress_device(x)[0]
         x_cpu = x.cpu() if x.device.type != "cpu" else x
         x_cpu = torch.clamp(x_cpu, 0, 1)
         if x_cpu.size(1) == 1:
@@ -88,12 +126,18 @@ class TurboJPEGCompression(nn.Module):
         u8 = torch.from_numpy(np.stack(decs, axis=0))  # [N, H, W, 3] uint8
         dev = torch.device(device)
         if dev.type == "cuda":
-            # 1 byte per sample over PCIe from pinned memory; the float conversion (u8 / 255.0, the same fp32
-            # division as on the host) and the NHWC -> NCHW permute run on the device
+            # 1 byte per sample over PCIe from pinned memory; the NHWC -> NCHW permute runs on the device and the
+            # division (torch's CUDA division by a Python scalar multiplies by the reciprocal, which is 1 ulp off
+            # for some bytes) goes through a 256-entry table computed with the host's IEEE division
             u8 = u8.pin_memory().to(dev, non_blocking=True)
+            lut = (torch.arange(256, dtype=torch.float32) / 255.0).to(dev)
+            return lut[u8.permute(0, 3, 1, 2).long()].contiguous()
         return (u8.permute(0, 3, 1, 2).float() / 255.0).contiguous()
 
     def forward(self, x):
+        if self._device_ok(x):
+            dec, bpp = self.forward_device(x)
+            return dec, float(bpp)  # the reference returns a Python float (one host sync)
         device = x.device
         bufs = self.compress(x)
         N, _, H, W = x.size()

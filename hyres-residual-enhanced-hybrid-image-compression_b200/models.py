@@ -300,33 +300,34 @@ class ResidualJPEGCompression(CompressionModel):
 
     # -- forward (models/hyres.py:23-77) --
     def forward(self, x, noisequant=False, jpeg=None, stats=None):
-        """``jpeg=(jpeg_decoded, jpeg_bpp)`` injects the JPEG stage's result (tensor on any device);
-        by default the CPU JPEG round trip of the reference runs here."""
+        """The JPEG stage runs on the device (``csrc/jpeg.cu``, bit-exact with libjpeg-turbo's round trip and file
+        size).  ``jpeg=(jpeg_decoded, jpeg_bpp)`` injects a precomputed result instead (tensor on any device)."""
         device = next(self.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("move the model to a CUDA sm_100 device first; the B200 hot path has no CPU fallback")
-        if jpeg is None:
-            jpeg_decoded_cpu, jpeg_bpp = self.jpeg(x.cpu() if x.is_cuda else x)
-        else:
-            jpeg_decoded_cpu, jpeg_bpp = jpeg
-        jpeg_decoded = jpeg_decoded_cpu.to(device, torch.float32).contiguous()
         xd = x.to(device, torch.float32).contiguous()
         self.residual_model._check_input(xd)
+        if jpeg is None:
+            jpeg_decoded, jpeg_bpp = self.jpeg.forward_device(xd)  # 0-d device tensor: no host sync
+        else:
+            jpeg_decoded, jpeg_bpp = jpeg
+            jpeg_decoded = jpeg_decoded.to(device, torch.float32).contiguous()
+            jpeg_bpp = torch.full((), float(jpeg_bpp), dtype=torch.float32, device=device)  # fill kernel: no host sync
         res = self.residual_model(xd, noisequant=noisequant, stats=stats, _jpeg=jpeg_decoded)
         residual, residual_hat = res["_residual"], res["x_hat"]
         x_hat = self._reconstruct(jpeg_decoded, residual_hat)
-        return {"x_hat": x_hat, "likelihoods": res["likelihoods"],
-                "jpeg_bpp_loss": torch.full((), float(jpeg_bpp), dtype=torch.float32, device=device),  # fill kernel: no host sync
-                "jpeg_decoded": jpeg_decoded,
-                "residual": residual, "residual_hat": residual_hat}
+        return {"x_hat": x_hat, "likelihoods": res["likelihoods"], "jpeg_bpp_loss": jpeg_bpp,
+                "jpeg_decoded": jpeg_decoded, "residual": residual, "residual_hat": residual_hat}
 
     # -- compress / decompress (models/hyres.py:79-134) --
     def compress(self, x, jpeg_buffers=None):
         device = next(self.parameters()).device
-        if jpeg_buffers is None:
-            jpeg_buffers = self.jpeg.compress(x)
-        jpeg_decoded = self.jpeg.decompress(jpeg_buffers, device).float().contiguous()
         xd = x.to(device, torch.float32).contiguous()
+        if jpeg_buffers is None:
+            # device JPEG encoder: the files libjpeg-turbo would write + the pixels it would decode from them
+            jpeg_buffers, jpeg_decoded = self.jpeg.compress_device(xd)
+        else:
+            jpeg_decoded = self.jpeg.decompress(jpeg_buffers, device).float().contiguous()
         out = self.residual_model.compress(xd, _jpeg=jpeg_decoded)
         out["jpeg_buffers"] = jpeg_buffers
         return out

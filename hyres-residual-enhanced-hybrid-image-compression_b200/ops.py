@@ -451,3 +451,62 @@ def reduce_sqdiff(a, b, out):
 
 def reduce_log2(x, out):
     L.check(L.lib().hyres_reduce_log2(_ptr(x), x.numel(), _ptr(out), _stream()), "hyres_reduce_log2")
+
+
+# ---------------------------------------------------------------------------------------------
+# JPEG stage on the device (models/utils/turbo_jpeg_compression.py:17-40,62-77)
+# ---------------------------------------------------------------------------------------------
+_jpeg_ws = {}
+
+
+def _jpeg_buffers(dev, B, H, W, want_scan):
+    key = (dev.index, B, H, W)
+    ws = _jpeg_ws.get(key)
+    if ws is None:
+        n = L.lib().hyres_jpeg_workspace_bytes(B, H, W)
+        if n <= 0:
+            raise ValueError(f"jpeg_forward: unsupported size {H}x{W} (H must be a multiple of 8, W of 16)")
+        if len(_jpeg_ws) > 8:
+            _jpeg_ws.clear()
+        ws = {"ws": torch.empty(n, dtype=torch.uint8, device=dev)}
+        _jpeg_ws[key] = ws
+    if want_scan and "words" not in ws:
+        wpi = L.lib().hyres_jpeg_scan_words(H, W)
+        ws["wpi"] = wpi
+        ws["words"] = torch.empty(B * wpi, dtype=torch.int32, device=dev)
+    return ws
+
+
+def jpeg_forward(x, quality, want_decoded=True, want_sizes=True, want_scan=False):
+    """x fp32 NCHW [B,3,H,W] in [0,1] on the device -> dict(decoded fp32 NCHW, sizes int64 [B] (file bytes),
+    words int32 [B, words_per_image] + nbits int64 [B] (the entropy-coded scans, big-endian bit strings)).
+    Bit-exact with libjpeg-turbo's 4:2:2 baseline round trip (tests/test_gpu_jpeg.py).  The scan buffer is a cached
+    scratch tensor: consume ``words`` before the next call with the same shape."""
+    _f32c(x, "x")
+    B, C3, H, W = x.shape
+    if C3 != 3:
+        raise ValueError("jpeg_forward: expected [B,3,H,W]")
+    need_scan = want_sizes or want_scan
+    ws = _jpeg_buffers(x.device, B, H, W, need_scan)
+    dec = torch.empty_like(x) if want_decoded else None
+    sizes = torch.empty(B, dtype=torch.int64, device=x.device) if want_sizes else None
+    nbits = torch.empty(B, dtype=torch.int64, device=x.device) if need_scan else None
+    L.check(L.lib().hyres_jpeg_forward(_ptr(x), B, H, W, int(quality), _ptr(ws["ws"]), _ptr(dec), _ptr(sizes),
+                                       _ptr(ws["words"]) if need_scan else C.c_void_p(0), _ptr(nbits), _stream()),
+            "hyres_jpeg_forward")
+    out = {"decoded": dec, "sizes": sizes, "nbits": nbits}
+    if want_scan:
+        out["words"] = ws["words"].view(B, ws["wpi"])
+    return out
+
+
+def jpeg_assemble(words_host, nbits, H, W, quality):
+    """Host: one image's scan words (int32 numpy / CPU tensor, as produced by jpeg_forward) -> JPEG file bytes."""
+    import numpy as np
+    w = np.ascontiguousarray(words_host, dtype=np.int32)
+    cap = int(L.lib().hyres_jpeg_header_bytes()) + 2 * ((int(nbits) + 7) // 8) + 16
+    out = np.empty(cap, dtype=np.uint8)
+    n = C.c_int64(0)
+    L.check(L.lib().hyres_jpeg_assemble(C.c_void_p(w.ctypes.data), int(nbits), H, W, int(quality),
+                                        C.c_void_p(out.ctypes.data), cap, C.byref(n)), "hyres_jpeg_assemble")
+    return out[:n.value].tobytes()

@@ -4,8 +4,8 @@ The reference moves every batch with a blocking ``d.to(device)`` and reads the l
 (src/utils/engine.py:36,92-104), so PCIe time and kernel time add up.  Here the copy of batch k+1 runs on
 a copy stream under the kernels of batch k, and the scalars of batch k-1 are read while batch k runs, so a
 step costs max(copy, compute) instead of their sum.  Nothing else changes: the model is called through its
-public ``forward`` with the JPEG stage's result injected exactly as ``ResidualJPEGCompression.forward``
-accepts it.
+public ``forward``; the JPEG stage runs on the device inside it (``csrc/jpeg.cu``) unless a batch carries a
+precomputed JPEG result, which is then injected exactly as ``ResidualJPEGCompression.forward`` accepts it.
 """
 import torch
 
@@ -23,9 +23,10 @@ class _Slot:
 
 
 class HostPipeline:
-    """``run(batches)``: batches is an iterable of ``(x_host, jpeg_decoded_host, jpeg_bpp)`` with the two
-    tensors fp32 ``[B,3,H,W]`` in pinned host memory.  Yields, in order, one dict per batch with the host
-    floats ``loss``, ``bpp_loss``, ``mse_loss`` (``src/losses/rd_loss.py:18-44``)."""
+    """``run(batches)``: batches is an iterable of ``x_host`` (the JPEG stage then runs on the device) or of
+    ``(x_host, jpeg_decoded_host, jpeg_bpp)`` (injected JPEG result), tensors fp32 ``[B,3,H,W]`` in pinned host
+    memory.  Yields, in order, one dict per batch with the host floats ``loss``, ``bpp_loss``, ``mse_loss``
+    (``src/losses/rd_loss.py:18-44``)."""
 
     def __init__(self, model, criterion, depth=2):
         self.model, self.criterion = model, criterion
@@ -37,23 +38,33 @@ class HostPipeline:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
+    @staticmethod
+    def _unpack(batch):
+        if torch.is_tensor(batch):
+            return batch, None, None
+        x, jd, bpp = batch
+        return x, jd, bpp
+
     def _stage(self, slot, x_host, jd_host):
         if slot.x is None or slot.x.shape != x_host.shape:
             slot.x = torch.empty(x_host.shape, dtype=torch.float32, device=self.dev)
+        if jd_host is not None and (slot.jd is None or slot.jd.shape != jd_host.shape):
             slot.jd = torch.empty(jd_host.shape, dtype=torch.float32, device=self.dev)
         if slot.used:
             self.copy_stream.wait_event(slot.free)  # the kernels of the batch that used this slot are done
         with torch.cuda.stream(self.copy_stream):
             slot.x.copy_(x_host, non_blocking=True)
-            slot.jd.copy_(jd_host, non_blocking=True)
+            if jd_host is not None:
+                slot.jd.copy_(jd_host, non_blocking=True)
             slot.ready.record(self.copy_stream)
-        self.h2d_bytes += x_host.numel() * 4 + jd_host.numel() * 4
+        self.h2d_bytes += x_host.numel() * 4 + (jd_host.numel() * 4 if jd_host is not None else 0)
 
-    def _launch(self, slot, jpeg_bpp):
+    def _launch(self, slot, jd_host, jpeg_bpp):
         cur = torch.cuda.current_stream(self.dev)
         cur.wait_event(slot.ready)
         slot.stats.zero_()
-        out = self.model(slot.x, jpeg=(slot.jd, jpeg_bpp), stats=slot.stats)
+        jpeg = None if jd_host is None else (slot.jd, jpeg_bpp)
+        out = self.model(slot.x, jpeg=jpeg, stats=slot.stats)
         lo = self.criterion(out, slot.x, stats=slot.stats)
         slot.result_dev.copy_(torch.stack([lo["loss"].double(), lo["bpp_loss"].double(), lo["mse_loss"].double()]))
         slot.free.record(cur)
@@ -74,13 +85,17 @@ class HostPipeline:
         n = len(self.slots)
         pending = []  # slots launched, results not yet read
         k = 0
-        nxt = next(it, None)
+        def pull():
+            b = next(it, None)
+            return None if b is None else self._unpack(b)
+
+        nxt = pull()
         if nxt is not None:
             self._stage(self.slots[0], nxt[0], nxt[1])
         while nxt is not None:
             cur_batch, slot = nxt, self.slots[k % n]
-            nxt = next(it, None)
-            self._launch(slot, cur_batch[2])
+            nxt = pull()
+            self._launch(slot, cur_batch[1], cur_batch[2])
             if nxt is not None:
                 # the slot about to be restaged must have had its results read (its pinned buffer is reused)
                 tgt = self.slots[(k + 1) % n]

@@ -24,6 +24,9 @@
  *                           decompress} via models/checkerboard.py:96-101,172-173,206
  *   hyres_refine_*          models/layers/enhancement.py:15-21,36-40,87-112
  *   hyres_reduce_*          src/losses/rd_loss.py:23-26,39
+ *   hyres_jpeg_*            models/utils/turbo_jpeg_compression.py:17-40,62-77
+ *                           (TurboJPEG.encode / .decode of PyTurboJPEG 1.7.7 over
+ *                           libjpeg-turbo; decoded pixels + file size)
  *   hyres_rans_*, hyres_pmf_to_quantized_cdf
  *                           compressai.ans.{RansEncoder.encode_with_indexes,
  *                           RansDecoder.decode_with_indexes} and
@@ -225,6 +228,32 @@ int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi /*[
                                  void* stream);
 int hyres_refine_spatial_att(const float* stats, const float* w7x7, float* att /*[B,H,W]*/,
                              int B, int H, int W, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* JPEG stage on the device. Replaces TurboJPEGCompression.forward / .compress  */
+/* (models/utils/turbo_jpeg_compression.py:17-40,62-77: TurboJPEG.encode with  */
+/* PyTurboJPEG's defaults -- RGB array read as BGR, 4:2:2, baseline Huffman --  */
+/* then TurboJPEG.decode) with libjpeg-turbo's integer algorithm reproduced bit */
+/* for bit: decoded pixels and file sizes are identical to the library's.       */
+/* ------------------------------------------------------------------------- */
+
+/* Scratch bytes hyres_jpeg_forward needs (0 if the size is unsupported: H % 8, W % 16). */
+int64_t hyres_jpeg_workspace_bytes(int B, int H, int W);
+/* 32-bit words per image of the scan buffer (worst case of baseline Huffman). */
+int64_t hyres_jpeg_scan_words(int H, int W);
+/* Bytes of everything before the scan (SOI, APP0, 2 DQT, SOF0, 4 DHT, SOS): 623. */
+int hyres_jpeg_header_bytes(void);
+/* x: fp32 NCHW [B,3,H,W] in [0,1] (clamped, then `.byte()`-truncated like the reference).
+ * decoded (optional): fp32 NCHW [B,3,H,W] = decoded u8 / 255.
+ * scan_words (optional, device, [B][hyres_jpeg_scan_words]): the entropy-coded scan of every image
+ * as big-endian bit strings, without byte stuffing; scan_bits (device, [B]): their lengths in bits;
+ * sizes (optional, device, [B]): the size in bytes of the JPEG file of every image. */
+int hyres_jpeg_forward(const float* x, int B, int H, int W, int quality, void* workspace,
+                       float* decoded, int64_t* sizes, uint32_t* scan_words, int64_t* scan_bits,
+                       void* stream);
+/* Host: the complete JPEG file of one image (markers + stuffed scan + EOI) from its scan bits. */
+int hyres_jpeg_assemble(const uint32_t* scan_words_host, int64_t nbits, int H, int W, int quality,
+                        uint8_t* out, int64_t cap, int64_t* len);
 
 /* layout helpers */
 int hyres_nchw_f32_to_nhwc_bf16(const float* in, void* out, int B, int C, int H, int W,
