@@ -31,6 +31,7 @@ class ConvIO(C.Structure):
         ("out_f32", C.c_void_p),
         ("f32_sb", C.c_int64), ("f32_sh", C.c_int64), ("f32_sw", C.c_int64), ("f32_sc", C.c_int64),
         ("mt_hint", C.c_int), ("ld_x0", C.c_int), ("x0_square", C.c_int),
+        ("out_pad", C.c_int), ("up_t2", C.c_void_p), ("up_t3", C.c_void_p),
     ]
 
 
@@ -76,6 +77,8 @@ SIGNATURES = {
     "hyres_refine_se_pool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_se_scale_down": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_refine_up_concat_stats": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_refine_stats3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_replicate_border": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_spatial_att": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_jpeg_workspace_bytes": (_i64, [_i, _i, _i]),
     "hyres_jpeg_scan_words": (_i64, [_i, _i]),

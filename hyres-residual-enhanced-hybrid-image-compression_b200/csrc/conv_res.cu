@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "conv_priv.h"
@@ -32,10 +33,11 @@
 namespace {
 
 constexpr int kTH = 16, kTW = 8;
-constexpr int kThreads = 320;  // warps 0-3 / 4-7: epilogue groups 0 / 1; warp 8: TMA loads; warp 9: MMA
-constexpr int kThreadsSq = 448;  // + warps 10-13: x0_square transform (GDN layers only)
+constexpr int kThreads = 384;  // warps 0-3 / 4-7: epilogue groups 0 / 1; warp 8: TMA loads; warp 9: MMA;
+                               // warps 10 / 11: TMA stores + stage release of group 0 / 1
+constexpr int kThreadsSq = 512;  // + warps 12-15: x0_square transform (GDN layers only)
 constexpr int kMaxSteps = 64;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 constexpr int kSmemLimit = 227 * 1024;
 
 // One 64-deep k-step (four MMAs), with everything the issue loop needs precomputed on the host: the
@@ -48,8 +50,11 @@ struct Step {
   int32_t acc;      // 0 for the first step of a phase (overwrite), 1 afterwards
 };
 
+#define RES_STAMP(itv, slot) do { if (p.trace && blockIdx.x == 0 && (itv) < 64) p.trace[(itv) * 16 + (slot)] = clock64(); } while (0)
+
 struct alignas(64) ResParams {
   CUtensorMap mapA, mapW, mapOut, mapAux0, mapAux1;
+  CUtensorMap mapT2, mapT3, mapU;  // up-add mode: half / quarter resolution addends and the interpolation matrices
   Step steps[kMaxSteps];
   int32_t nsteps, nphase, nchunk_in, nchunk_out;
   int32_t PW, PH, org_h, org_w;
@@ -63,6 +68,9 @@ struct alignas(64) ResParams {
   float slope;
   int32_t a_square, has_aux0, has_aux1, store_bf16;
   int32_t pf_extra;  // L2 prefetch distance beyond the ring, in tiles; < 0: no prefetch
+  int32_t up, u_bytes, t2_off, t3_off;  // up-add mode (see conv_res_try_run)
+  int32_t decoupled, stg_base_off;  // result staging outside the TMA ring (one buffer per epilogue group)
+  long long* trace;  // optional: clock64 stamps of CTA 0 (tools/experiments/res_trace.py), 16 slots per tile
   const float* bias;
   const float* pixscale;
   float* out_f32;
@@ -87,6 +95,30 @@ __device__ __forceinline__ uint32_t sq_bf16x2(uint32_t u) {
   t = __hmul2(t, t);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+// (a, b) = (a, b) * s + (c, d) and (a, b) *= s as packed fp32 pairs (FFMA2 / FMUL2)
+__device__ __forceinline__ void fma2(float& a, float& b, float s, float c, float d) {
+  asm("{\n\t"
+      ".reg .b64 x, y, z;\n\t"
+      "mov.b64 x, {%0, %1};\n\t"
+      "mov.b64 y, {%2, %2};\n\t"
+      "mov.b64 z, {%3, %4};\n\t"
+      "fma.rn.f32x2 x, x, y, z;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t"
+      "}"
+      : "+f"(a), "+f"(b)
+      : "f"(s), "f"(c), "f"(d));
+}
+__device__ __forceinline__ void mul2(float& a, float& b, float s) {
+  asm("{\n\t"
+      ".reg .b64 x, y;\n\t"
+      "mov.b64 x, {%0, %1};\n\t"
+      "mov.b64 y, {%2, %2};\n\t"
+      "mul.rn.f32x2 x, x, y;\n\t"
+      "mov.b64 {%0, %1}, x;\n\t"
+      "}"
+      : "+f"(a), "+f"(b)
+      : "f"(s));
+}
 __device__ __forceinline__ float act_fn(float v, int act, float slope) {
   if (act == HYRES_ACT_RELU) return fmaxf(v, 0.f);
   if (act == HYRES_ACT_PRELU) return v >= 0.f ? v : v * slope;
@@ -102,13 +134,21 @@ __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (
   }
 }
 
+// EPI / ACT >= 0: the epilogue mode / activation are compile-time constants (straight-line chunk code: measured,
+// the generic epilogue spends a third of a chunk's ~500 clk in uniform branches and instruction fetch); -1: taken
+// from the parameters at run time.
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_constant__ ResParams p) {
+  const int epi = EPI >= 0 ? EPI : p.epi;
+  const int act = ACT >= 0 ? ACT : p.act;
   hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
-  const uint32_t st_base = base + p.w_bytes;
-  const uint32_t bias_base = st_base + p.NA * p.stage_bytes;
+  const uint32_t u_base = base + p.w_bytes;  // interpolation matrices (up-add mode), resident like the weights
+  const uint32_t st_base = u_base + p.u_bytes;
+  const uint32_t stg_base = st_base + p.stg_base_off;
+  const uint32_t bias_base = stg_base + (p.decoupled ? 2 * p.nchunk_out * 16384 : 0);
   const uint32_t bar_base = bias_base + 1024;
   // barriers: W_FULL | A_FULL[4] | A_EMPTY[4] | A_READY[4] | ACC_FULL[2] | ACC_EMPTY[2] ; tmem slot
   const uint32_t W_FULL = bar_base;
@@ -117,7 +157,9 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
   const uint32_t A_READY = A_EMPTY + 8 * kMaxStages;
   const uint32_t ACC_FULL = A_READY + 8 * kMaxStages;
   const uint32_t ACC_EMPTY = ACC_FULL + 16;
-  const uint32_t tmem_slot = ACC_EMPTY + 16;
+  const uint32_t STAGED = ACC_EMPTY + 16;  // [2]: a group's result tile is staged (and its operands consumed)
+  const uint32_t STG_FREE = STAGED + 16;   // [2]: decoupled mode: the group's staging buffer has been read by its store
+  const uint32_t tmem_slot = STG_FREE + 16;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
 
@@ -125,18 +167,27 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
     hy::mbar_init(W_FULL, 1);
     for (int i = 0; i < p.NA; ++i) {
       hy::mbar_init(A_FULL + 8 * i, 1);
-      hy::mbar_init(A_EMPTY + 8 * i, 2);    // MMA commit + the epilogue group's release
+      // coupled: MMA commit + the store warp's release (the stage also holds the epilogue operands / the result);
+      // decoupled: the MMA commit alone frees the activation patch
+      hy::mbar_init(A_EMPTY + 8 * i, p.decoupled ? 1 : 2);
       hy::mbar_init(A_READY + 8 * i, 128);  // x0_square transform
     }
     for (int i = 0; i < 2; ++i) {
       hy::mbar_init(ACC_FULL + 8 * i, 1);
       hy::mbar_init(ACC_EMPTY + 8 * i, 128);
+      hy::mbar_init(STAGED + 8 * i, 128);
+      hy::mbar_init(STG_FREE + 8 * i, 1);
     }
     hy::mbar_fence_init();
     // the weights do not depend on the predecessor kernel: their load starts before the dependency wait
     hy::tma_prefetch_desc(&p.mapW);
-    hy::mbar_arrive_expect_tx(W_FULL, p.w_bytes);
+    hy::mbar_arrive_expect_tx(W_FULL, p.w_bytes + p.u_bytes);
     for (int s = 0; s < p.nslots; ++s) hy::tma_load_2d(w_base + s * p.BN * 128, &p.mapW, W_FULL, s * 64, 0);
+    if (p.up) {
+      hy::tma_prefetch_desc(&p.mapU);
+      hy::tma_load_2d(u_base, &p.mapU, W_FULL, 0, 0);
+      hy::tma_load_2d(u_base + 16384, &p.mapU, W_FULL, 0, 128);
+    }
   }
   {
     float* sb = reinterpret_cast<float*>(smem_raw + (bias_base - hy::smem_u32(smem_raw)));
@@ -147,6 +198,10 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
     hy::tma_prefetch_desc(&p.mapW);
     if (p.has_aux0) hy::tma_prefetch_desc(&p.mapAux0);
     if (p.has_aux1) hy::tma_prefetch_desc(&p.mapAux1);
+    if (p.up) {
+      hy::tma_prefetch_desc(&p.mapT2);
+      hy::tma_prefetch_desc(&p.mapT3);
+    }
   }
   if (warp == 9) {
     hy::tmem_alloc(tmem_slot, p.tmem_cols);
@@ -195,6 +250,7 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
         tile_origin(t, b_img, h0, w0);
         const uint32_t sb = st_base + stage * p.stage_bytes;
         hy::mbar_wait(A_EMPTY + 8 * stage, par ^ 1u);
+        RES_STAMP((t - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x), 0);  // load issued
         hy::mbar_arrive_expect_tx(A_FULL + 8 * stage, p.stage_tx_bytes);
         for (int c = 0; c < p.nchunk_in; ++c)
           hy::tma_load_4d(sb + c * p.a_chunk_bytes, &p.mapA, A_FULL + 8 * stage, c * 64, w0 + p.org_w, h0 + p.org_h, b_img);
@@ -204,6 +260,12 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
         if (p.has_aux1)
           for (int c = 0; c < p.nchunk_out; ++c)
             hy::tma_load_4d(sb + p.x1_off + c * 16384, &p.mapAux1, A_FULL + 8 * stage, c * 64, w0, h0, b_img);
+        if (p.up) {
+          // addend patches of the tile, read from tensors padded by one replicated pixel: tile rows h0 .. h0+15
+          // interpolate half-resolution rows h0/2-1 .. h0/2+8 (padded coordinate h0/2), quarter rows h0/4-1 .. h0/4+4
+          hy::tma_load_4d(sb + p.t2_off, &p.mapT2, A_FULL + 8 * stage, 0, w0 >> 1, h0 >> 1, b_img);
+          hy::tma_load_4d(sb + p.t3_off, &p.mapT3, A_FULL + 8 * stage, 0, w0 >> 2, h0 >> 2, b_img);
+        }
         if (p.pf_extra >= 0 && t + ahead < p.ntiles) prefetch(t + ahead);
         if (++stage == p.NA) { stage = 0; par ^= 1u; }
       }
@@ -224,7 +286,9 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
         const uint64_t a_d0 = hy::desc_u64(st_base + stage * p.stage_bytes, sbo_a);
         const uint32_t d0 = tmem_base + buf * acc_cols;
         hy::mbar_wait((p.a_square ? A_READY : A_FULL) + 8 * stage, par);
+        if (lane == 0) RES_STAMP(it, 1);  // operands landed
         hy::mbar_wait(ACC_EMPTY + 8 * buf, ((it >> 1) & 1) ^ 1u);
+        if (lane == 0) RES_STAMP(it, 2);  // accumulator free
         hy::tc_fence_after();
         for (int i = 0; i < p.nsteps; ++i) {
           const Step st = p.steps[i];
@@ -234,18 +298,59 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
           for (int k = 0; k < 4; ++k)
             hy::umma_issue<2>(d, a_d + 2 * k, b_d + 2 * k, idesc, static_cast<uint32_t>(st.acc | k), leader);
         }
+        if (p.up) {
+          // acc += U2 . T2patch + U4 . T3patch: bilinear x2 / x4 up-sampling as two small GEMMs.  A = the constant
+          // interpolation matrix [128 tile positions][64 patch pixels] (K-major); B = the patch as TMA wrote it,
+          // [patch pixel][64 channels], i.e. N-contiguous: an MN-major operand (idesc bit 16; 16 pixels = 2048 B
+          // per K step; measured in tools/experiments/umma_mn.cu).
+          const uint32_t idesc_mn = idesc | (1u << 16);
+          const uint64_t u2_d = hy::desc_u64(u_base), u4_d = hy::desc_u64(u_base + 16384);
+          const uint64_t t2_d = hy::desc_u64(st_base + stage * p.stage_bytes + p.t2_off);
+          const uint64_t t3_d = hy::desc_u64(st_base + stage * p.stage_bytes + p.t3_off);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) hy::umma_issue<2>(d0, u2_d + 2 * k, t2_d + 128 * k, idesc_mn, 1u, leader);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) hy::umma_issue<2>(d0, u4_d + 2 * k, t3_d + 128 * k, idesc_mn, 1u, leader);
+        }
         hy::umma_commit_mode<2>(A_EMPTY + 8 * stage, leader);
         hy::umma_commit_mode<2>(ACC_FULL + 8 * buf, leader);
+        if (lane == 0) RES_STAMP(it, 3);  // MMAs issued
         if (++stage == p.NA) { stage = 0; par ^= 1u; }
       }
     }
-  } else if (warp >= 10) {
+  } else if (warp == 10 || warp == 11) {
+    // ============================ store warps ============================
+    // One per epilogue group: waits until the group has staged a tile, sends it with a TMA store and releases the
+    // stage once the store has read it.  (Measured with the clock64 trace: when a thread of the group did this,
+    // its warp -- and through the group barrier the whole group -- lost ~880 clk per tile waiting for the store.)
+    if (lane == 0) {
+      const int grp = warp - 10;
+      for (int it = grp;; it += 2) {
+        const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
+        if (t >= p.ntiles) break;
+        const int stage = it % p.NA;
+        const uint32_t sb = st_base + stage * p.stage_bytes;
+        int b_img, h0, w0;
+        tile_origin(t, b_img, h0, w0);
+        const uint32_t src = p.decoupled ? stg_base + grp * p.nchunk_out * 16384 : sb + p.o_off;
+        hy::mbar_wait(STAGED + 8 * grp, (it >> 1) & 1);
+        if (p.store_bf16) {
+          for (int c = 0; c < p.nchunk_out; ++c) hy::tma_store_4d(&p.mapOut, src + c * 16384, c * 64, w0, h0, b_img);
+          hy::tma_store_commit();
+          hy::tma_store_wait_read<0>();
+        }
+        hy::mbar_arrive(p.decoupled ? STG_FREE + 8 * grp : A_EMPTY + 8 * stage);
+        RES_STAMP(it, 8);  // store read done, stage released
+      }
+      if (p.store_bf16) hy::tma_store_wait_all<0>();
+    }
+  } else if (warp >= 12) {
     // ============================ x0_square transform (GDN) ============================
     // GDN operand: square the activation tile in place (bf16 RN of the exact product, the same value a
     // producer-side x*x store would have held), then release it to the MMA warp.  Its own four warps, so the
     // transform of tile t+1 runs under the MMAs of tile t and the epilogues of tiles t-1, t-2.
     if (p.a_square) {
-      const int row = threadIdx.x - 320;
+      const int row = threadIdx.x - 384;
       int stage = 0;
       uint32_t par = 0;
       for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
@@ -276,7 +381,8 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     const uint32_t sw = row & 7;
     const int nchunk16 = p.BN >> 4;
-    const bool need0 = p.has_aux0 != 0, need1 = p.has_aux1 != 0;
+    const bool need0 = p.has_aux0 != 0;
+    const bool pixscale1 = epi == HYRES_EPI_PIXSCALE && p.nphase == 1;  // one scale per tile position
     for (int it = grp;; it += 2) {
       const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
       if (t >= p.ntiles) break;
@@ -285,79 +391,112 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
       const uint32_t sb = st_base + stage * p.stage_bytes;
       int b_img, h0, w0;
       tile_origin(t, b_img, h0, w0);
-      if (need0) hy::mbar_wait(A_FULL + 8 * stage, par);  // acquire the TMA-written epilogue operands
-      hy::mbar_wait(ACC_FULL + 8 * grp, (it >> 1) & 1);
-      hy::tc_fence_after();
-
       const int hv = h0 + ti, wv = w0 + tj;
       const bool valid = hv < p.Hv && wv < p.Wv;
+      // the per-pixel scale is issued before the waits so that its latency hides under them
+      float ps = 0.f;
+      if (pixscale1 && valid) ps = __ldg(p.pixscale + (static_cast<long long>(b_img) * p.OH + hv) * p.OW + wv);
+      if (need0) hy::mbar_wait(A_FULL + 8 * stage, par);  // acquire the TMA-written epilogue operands
+      if (row == 0) RES_STAMP(it, 4);  // epilogue group at the loop top
+      hy::mbar_wait(ACC_FULL + 8 * grp, (it >> 1) & 1);
+      hy::tc_fence_after();
+      if (row == 0) RES_STAMP(it, 5);  // accumulator seen
+
       const uint32_t acc0 = t_lane + grp * acc_cols;
       const int total = p.nphase * nchunk16;
-      uint32_t rc[16];
-      hy::tmem_ld16(acc0, rc);
-      hy::tmem_ld_fence(rc);
-      for (int q = 0; q < total; ++q) {
-        const int ph = q / nchunk16;
-        const int n = (q - ph * nchunk16) << 4;
+      const uint32_t so_row = (p.decoupled ? stg_base + grp * p.nchunk_out * 16384 : sb + p.o_off) + row * 128;
+      const uint32_t sx_row = sb + p.x1_off + row * 128;
+      // decoupled: the previous tile of this group must have left the staging buffer (first use passes at once)
+      if (p.decoupled && p.store_bf16) hy::mbar_wait(STG_FREE + 8 * grp, ((it >> 1) & 1) ^ 1u);
+      int ph = 0, n = 0;  // phase / first channel of the chunk, advanced incrementally (no division per chunk)
+      auto chunk = [&](const uint32_t (&r)[16]) {
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(rc[i]);
-        if (q + 1 < total) {
-          hy::tmem_ld16(acc0 + (q + 1) * 16, rc);  // columns of successive phases are contiguous
-        } else {
-          // nothing left to read from TMEM once the last chunk sits in registers
-        }
-        const int oh = hv * p.out_mul + (ph >> 1), ow = wv * p.out_mul + (ph & 1);
-        const long long opix = (static_cast<long long>(b_img) * p.OH + oh) * p.OW + ow;
-        if (p.epi == HYRES_EPI_PIXSCALE) {
-          const float ps = valid ? __ldg(p.pixscale + opix) : 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= ps;
-        }
-        {
-          const uint32_t ba = bias_base + n * 4;
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        const uint32_t ba = bias_base + n * 4;
+        if (epi == HYRES_EPI_PIXSCALE) {
+          if (!pixscale1) {
+            const long long opix = (static_cast<long long>(b_img) * p.OH + hv * p.out_mul + (ph >> 1)) * p.OW + wv * p.out_mul + (ph & 1);
+            ps = valid ? __ldg(p.pixscale + opix) : 0.f;
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 b4 = lds_f4(ba + i * 16);
-            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+            fma2(v[4 * i], v[4 * i + 1], ps, b4.x, b4.y);
+            fma2(v[4 * i + 2], v[4 * i + 3], ps, b4.z, b4.w);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 b4 = lds_f4(ba + i * 16);
+            hy::add2(v[4 * i], v[4 * i + 1], b4.x, b4.y);
+            hy::add2(v[4 * i + 2], v[4 * i + 3], b4.z, b4.w);
           }
         }
         // smem address of this thread's 16 channels inside a [128 rows][64 ch] swizzled chunk
-        const uint32_t coff = (n >> 6) * 16384 + row * 128;
+        const uint32_t coff = (n >> 6) * 16384;
         const uint32_t j0 = (n & 63) >> 3;
-        const uint32_t oa0 = sb + p.o_off + coff + ((j0 ^ sw) << 4);
-        const uint32_t oa1 = sb + p.o_off + coff + (((j0 + 1) ^ sw) << 4);
+        const uint32_t c0 = coff + ((j0 ^ sw) << 4), c1 = coff + (((j0 + 1) ^ sw) << 4);
+        const uint32_t oa0 = so_row + c0, oa1 = so_row + c1;
         if (need0) {
           float x[16];
           unpack16(lds128(oa0), lds128(oa1), x);
-          if (p.epi == HYRES_EPI_ADD) {
+          if (epi == HYRES_EPI_ADD) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += x[i];
-          } else if (p.epi == HYRES_EPI_GATE) {
+            for (int i = 0; i < 8; ++i) hy::add2(v[2 * i], v[2 * i + 1], x[2 * i], x[2 * i + 1]);
+          } else if (epi == HYRES_EPI_GATE) {
             float a[16];
-            unpack16(lds128(sb + p.x1_off + coff + ((j0 ^ sw) << 4)), lds128(sb + p.x1_off + coff + (((j0 + 1) ^ sw) << 4)), a);
+            unpack16(lds128(sx_row + c0), lds128(sx_row + c1), a);
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaf(a[i], hy::fast_sigmoid(v[i]), x[i]);
-          } else if (p.epi == HYRES_EPI_GDN) {
+          } else if (epi == HYRES_EPI_GDN) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_rsqrt(v[i]);
-          } else if (p.epi == HYRES_EPI_IGDN) {
+          } else if (epi == HYRES_EPI_IGDN) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = x[i] * hy::fast_sqrt(v[i]);
           }
         }
+        bool relu_packed = false;
+        if (act == HYRES_ACT_PRELU) {
+          if (p.slope >= 0.f && p.slope <= 1.f) {
+            // 0 <= slope <= 1: prelu(v) = max(v, slope * v)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = act_fn(v[i], p.act, p.slope);
+            for (int i = 0; i < 8; ++i) {
+              float t0 = v[2 * i], t1 = v[2 * i + 1];
+              mul2(t0, t1, p.slope);
+              v[2 * i] = fmaxf(v[2 * i], t0);
+              v[2 * i + 1] = fmaxf(v[2 * i + 1], t1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = v[i] >= 0.f ? v[i] : v[i] * p.slope;
+          }
+        } else if (act == HYRES_ACT_RELU) {
+          // ReLU commutes with the bf16 rounding: applied on the packed pairs when only bf16 leaves the kernel
+          if (p.store_bf16 && !p.out_f32) {
+            relu_packed = true;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+          }
+        } else if (act == HYRES_ACT_CLAMP01) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fminf(fmaxf(v[i], 0.f), 1.f);
+        }
         if (p.store_bf16) {
-          uint4 a, b;
-          a.x = hy::pack_bf16(v[0], v[1]); a.y = hy::pack_bf16(v[2], v[3]);
-          a.z = hy::pack_bf16(v[4], v[5]); a.w = hy::pack_bf16(v[6], v[7]);
-          b.x = hy::pack_bf16(v[8], v[9]); b.y = hy::pack_bf16(v[10], v[11]);
-          b.z = hy::pack_bf16(v[12], v[13]); b.w = hy::pack_bf16(v[14], v[15]);
-          sts128(oa0, a);
-          sts128(oa1, b);
+          uint32_t u[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) u[i] = hy::pack_bf16(v[2 * i], v[2 * i + 1]);
+          if (relu_packed) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) u[i] = hy::relu_bf16x2(u[i]);
+          }
+          sts128(oa0, make_uint4(u[0], u[1], u[2], u[3]));
+          sts128(oa1, make_uint4(u[4], u[5], u[6], u[7]));
         }
         if (p.out_f32 && valid && n < p.cout) {
+          const int oh = hv * p.out_mul + (ph >> 1), ow = wv * p.out_mul + (ph & 1);
           float* o = p.out_f32 + b_img * p.f32_sb + oh * p.f32_sh + ow * p.f32_sw + n * p.f32_sc;
           if (n + 16 <= p.cout && p.f32_sc == 1) {
 #pragma unroll
@@ -369,23 +508,30 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
               if (n + i < p.cout) o[i * p.f32_sc] = v[i];
           }
         }
-        if (q + 1 < total) hy::tmem_ld_fence(rc);
+        n += 16;
+        if (n == p.BN) { n = 0; ++ph; }
+      };
+      // two register buffers: chunk q + 1 is in flight from TMEM while chunk q is processed (columns of successive
+      // phases are contiguous)
+      uint32_t ra[16], rb[16];
+      hy::tmem_ld16(acc0, ra);
+      hy::tmem_ld_fence(ra);
+      for (int q = 0; q < total; q += 2) {
+        if (q + 1 < total) hy::tmem_ld16(acc0 + (q + 1) * 16, rb);
+        chunk(ra);
+        if (q + 1 < total) {
+          hy::tmem_ld_fence(rb);
+          if (q + 2 < total) hy::tmem_ld16(acc0 + (q + 2) * 16, ra);
+          chunk(rb);
+          if (q + 2 < total) hy::tmem_ld_fence(ra);
+        }
       }
       hy::tc_fence_before();
       hy::mbar_arrive(ACC_EMPTY + 8 * grp);
+      if (row == 0) RES_STAMP(it, 6);  // chunks done
       if (p.store_bf16) hy::fence_async_smem();
-      hy::named_bar_sync(1 + grp, 128);  // staging complete / every thread done with the stage's operands
-      if (row == 0) {
-        if (p.store_bf16) {
-          for (int c = 0; c < p.nchunk_out; ++c)
-            hy::tma_store_4d(&p.mapOut, sb + p.o_off + c * 16384, c * 64, w0, h0, b_img);
-          hy::tma_store_commit();
-          hy::tma_store_wait_read<0>();
-        }
-        hy::mbar_arrive(A_EMPTY + 8 * stage);
-      }
+      hy::mbar_arrive(STAGED + 8 * grp);  // this thread's part is staged and its operands are consumed
     }
-    if (row == 0 && p.store_bf16) hy::tma_store_wait_all<0>();
   }
 
   hy::tc_fence_before();
@@ -396,11 +542,16 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
   }
 }
 
-int encode_map4(CUtensorMap* m, const void* ptr, int C, int ld, int B, int H, int W, int box_w, int box_h) {
+// pitch_w / pitch_h: pixels per row / rows per image of the allocation when it is larger than the W x H view
+// (a view into the interior of a padded tensor); 0 = dense.
+int encode_map4(CUtensorMap* m, const void* ptr, int C, int ld, int B, int H, int W, int box_w, int box_h,
+                int pitch_w = 0, int pitch_h = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return hy_fail(HYRES_ERR_DRIVER, "cuTensorMapEncodeTiled entry point unavailable");
+  if (!pitch_w) pitch_w = W;
+  if (!pitch_h) pitch_h = H;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)pitch_w * ld * 2, (cuuint64_t)pitch_h * pitch_w * ld * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
@@ -413,6 +564,53 @@ int encode_map4(CUtensorMap* m, const void* ptr, int C, int ld, int B, int H, in
     return hy_fail(HYRES_ERR_DRIVER, msg);
   }
   return HYRES_OK;
+}
+
+template <int EPI, int ACT>
+cudaError_t launch_res(int grid, int threads, int smem, cudaStream_t stream, const ResParams& p) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(conv_res_kernel<EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return hy_launch_pdl(conv_res_kernel<EPI, ACT>, grid, threads, smem, stream, p);
+}
+
+// Interpolation matrices of the up-add mode, [256][64] bf16 on the device: rows 0..127 = U2, rows 128..255 = U4.
+// Row = tile position ti * 8 + tj of a 16 x 8 tile.  U2 column = pixel pr * 6 + pc of the 10 x 6 (+ padding) patch of
+// the half-resolution tensor whose origin is one pixel up-left of the tile's first source pixel; U4 column = pixel
+// pr * 4 + pc of the 8 x 4 quarter-resolution patch.  Entries are the bilinear weights of
+// F.interpolate(scale_factor = 2 / 4, mode = "bilinear", align_corners = False)
+// (models/layers/enhancement.py:101-104): source coordinate (o + 0.5) / s - 0.5; the clamp at the image border is
+// realised by the replicated one-pixel border of the padded source tensors.  All weights are j / 64: exact in bf16.
+const void* up_table() {
+  static void* tab[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return nullptr;
+  if (tab[dev]) return tab[dev];
+  std::vector<__nv_bfloat16> h(256 * 64, __float2bfloat16(0.f));
+  for (int ti = 0; ti < kTH; ++ti)
+    for (int tj = 0; tj < kTW; ++tj) {
+      const int row = ti * kTW + tj;
+      for (int s = 0; s < 2; ++s) {
+        const float sc = s ? 4.f : 2.f;
+        const int pw = s ? 4 : 6;
+        const float py = (ti + 0.5f) / sc - 0.5f + 1.f, px = (tj + 0.5f) / sc - 0.5f + 1.f;  // patch origin = source - 1
+        const int y0 = static_cast<int>(py), x0 = static_cast<int>(px);
+        const float ly = py - y0, lx = px - x0;
+        __nv_bfloat16* u = h.data() + (s * 128 + row) * 64;
+        u[y0 * pw + x0] = __float2bfloat16((1.f - ly) * (1.f - lx));
+        u[y0 * pw + x0 + 1] = __float2bfloat16((1.f - ly) * lx);
+        u[(y0 + 1) * pw + x0] = __float2bfloat16(ly * (1.f - lx));
+        u[(y0 + 1) * pw + x0 + 1] = __float2bfloat16(ly * lx);
+      }
+    }
+  void* d = nullptr;
+  if (cudaMalloc(&d, h.size() * 2) != cudaSuccess) return nullptr;
+  if (cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+  tab[dev] = d;
+  return d;
 }
 
 }  // namespace
@@ -484,21 +682,46 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   {
     static const int pf = [] { const char* e = getenv("HYRES_RES_PF"); return e ? atoi(e) : 0; }();
     p.pf_extra = pf;
+    // HYRES_RES_TRACE=<device pointer, hex>: 64 x 16 clock64 stamps of CTA 0 (tools/experiments/res_trace.py)
+    const char* e = getenv("HYRES_RES_TRACE");
+    p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
   }
   if (p.a_square && (PH != kTH || PW != kTW)) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: x0_square needs a 1x1 layer");
+  const bool up = io->up_t2 != nullptr || io->up_t3 != nullptr;
+  if (up) {
+    if (!io->up_t2 || !io->up_t3) return hy_fail(HYRES_ERR_ARG, "conv_run: up-add needs both up_t2 and up_t3");
+    if (deconv || BN != 64 || c->nphase != 1 || (io->H % 32) || (io->W % 32))
+      return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: up-add needs a stride-1 layer with 64 output channels and H, W multiples of 32");
+  }
+  if (io->out_pad < 0 || io->out_pad > 8 || (io->out_pad && (!io->out_bf16 || deconv)))
+    return hy_fail(HYRES_ERR_ARG, "conv_run: out_pad needs a bf16 output of a stride-1 layer");
   if (deconv && (need0 || need1)) return HYRES_OK;
+  // Without epilogue operands the result staging lives outside the ring (one buffer per epilogue group): the MMA
+  // commit alone frees a patch, so the ring runs several tiles ahead of the epilogues instead of waiting for the
+  // TMA store of the tile that last used the stage (measured: the store's read adds ~1000 clk to a stage's life).
+  p.decoupled = (!need0 && !need1 && p.store_bf16) ? 1 : 0;
   int stage = p.nchunk_in * p.a_chunk_bytes;
   p.o_off = stage;
-  if (need0 || p.store_bf16) stage += p.nchunk_out * 16384;
+  if ((need0 || p.store_bf16) && !p.decoupled) stage += p.nchunk_out * 16384;
   p.x1_off = stage;
   if (need1) stage += p.nchunk_out * 16384;
+  constexpr int kT2Rows = 6 * 11, kT3Rows = 4 * 8;  // 10 x 6 live pixels + 4 padding rows of the K = 64 GEMM; 6 x 4 live
+  p.up = up;
+  p.u_bytes = up ? 32768 : 0;
+  p.t2_off = stage;
+  if (up) stage += (kT2Rows * 128 + 1023) / 1024 * 1024;
+  p.t3_off = stage;
+  if (up) stage += kT3Rows * 128;
   p.stage_bytes = stage;
-  p.stage_tx_bytes = p.nchunk_in * PH * PW * 128 + (need0 ? p.nchunk_out * 16384 : 0) + (need1 ? p.nchunk_out * 16384 : 0);
-  const int fixed = static_cast<int>(w_bytes) + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+  p.stage_tx_bytes = p.nchunk_in * PH * PW * 128 + (need0 ? p.nchunk_out * 16384 : 0) + (need1 ? p.nchunk_out * 16384 : 0) +
+                     (up ? (kT2Rows + kT3Rows) * 128 : 0);
+  const int stg_bytes = p.decoupled ? 2 * p.nchunk_out * 16384 : 0;
+  const int fixed = static_cast<int>(w_bytes) + p.u_bytes + stg_bytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
   int NA = (kSmemLimit - fixed) / stage;
   if (NA < 2) return HYRES_OK;
   NA = std::min(NA, kMaxStages);
   p.NA = NA;
+  p.stg_base_off = NA * stage;
   p.w_bytes = static_cast<int>(w_bytes);
   p.nslots = nslots;
   p.BN = BN;
@@ -525,19 +748,44 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   int rc = encode_map4(&p.mapA, io->x0, c->cin0, ld_x0, io->B, io->H, io->W, PW, PH);
   if (rc != HYRES_OK) return rc;
   if ((rc = encode_w_map(&p.mapW, c->d_w, c->ktot, c->cout_pad, BN)) != HYRES_OK) return rc;
-  if (p.store_bf16 && (rc = encode_map4(&p.mapOut, io->out_bf16, c->cout, io->ld_out, io->B, OH, OW, kTW, kTH)) != HYRES_OK) return rc;
+  if (p.store_bf16) {
+    // out_pad: the output view is the interior of a tensor padded by out_pad pixels on every side
+    const int op = io->out_pad;
+    const uint8_t* optr = static_cast<const uint8_t*>(io->out_bf16) + (static_cast<int64_t>(op) * (OW + 2 * op) + op) * io->ld_out * 2;
+    if ((rc = encode_map4(&p.mapOut, optr, c->cout, io->ld_out, io->B, OH, OW, kTW, kTH, OW + 2 * op, OH + 2 * op)) != HYRES_OK) return rc;
+  }
+  if (up) {
+    const void* tab = up_table();
+    if (!tab) return hy_fail(HYRES_ERR_CUDA, "conv_run: cannot allocate the interpolation table");
+    if ((rc = encode_map4(&p.mapT2, io->up_t2, 64, 64, io->B, OH / 2 + 2, OW / 2 + 2, 6, 11)) != HYRES_OK) return rc;
+    if ((rc = encode_map4(&p.mapT3, io->up_t3, 64, 64, io->B, OH / 4 + 2, OW / 4 + 2, 4, 8)) != HYRES_OK) return rc;
+    if ((rc = encode_w_map(&p.mapU, tab, 64, 256, 128)) != HYRES_OK) return rc;
+  }
   if (need0 && (rc = encode_map4(&p.mapAux0, io->aux0, c->cout, io->ld_aux0, io->B, OH, OW, kTW, kTH)) != HYRES_OK) return rc;
   if (need1 && (rc = encode_map4(&p.mapAux1, io->aux1, c->cout, io->ld_aux1, io->B, OH, OW, kTW, kTH)) != HYRES_OK) return rc;
 
   const int smem = fixed + NA * stage;
-  static int smem_set = 0;
-  if (!smem_set) {
-    HY_CUDA(cudaFuncSetAttribute(conv_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    smem_set = 1;
-  }
   const int grid = std::min(p.ntiles, num_sms());
+  const int threads = p.a_square ? kThreadsSq : kThreads;
   hy_count_launch();
-  HY_CUDA(hy_launch_pdl(conv_res_kernel, grid, p.a_square ? kThreadsSq : kThreads, smem, stream, p));
+  // the combinations the codec uses are compiled straight-line; anything else runs the generic instance
+#define RES_CASE(E, A)                                                \
+  if (p.epi == (E) && p.act == (A)) {                                 \
+    HY_CUDA((launch_res<E, A>(grid, threads, smem, stream, p)));      \
+    *handled = 1;                                                     \
+    return HYRES_OK;                                                  \
+  }
+  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_RELU)
+  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_PRELU)
+  RES_CASE(HYRES_EPI_ADD, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_ADD, HYRES_ACT_RELU)
+  RES_CASE(HYRES_EPI_GATE, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_GDN, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_IGDN, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_PIXSCALE, HYRES_ACT_PRELU)
+#undef RES_CASE
+  HY_CUDA((launch_res<-1, -1>(grid, threads, smem, stream, p)));
   *handled = 1;
   return HYRES_OK;
 }

@@ -786,8 +786,9 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
 
   // layers whose weights fit in shared memory run on the persistent resident-weights kernel
+  const bool res_only = io->out_pad != 0 || io->up_t2 != nullptr || io->up_t3 != nullptr;
   static const bool no_sc = getenv("HYRES_NO_SC") != nullptr;
-  if (!no_sc) {
+  if (!no_sc && !res_only) {
     int handled = 0;
     const int rc = conv_sc_try_run(c, io, stream, &handled);
     if (rc != HYRES_OK || handled) return rc;
@@ -799,6 +800,7 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
     if (rc != HYRES_OK || handled) return rc;
   }
   if (io->x0_square) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: x0_square is only available on resident-weight 1x1 layers");
+  if (res_only) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: out_pad / up-add are only available on resident-weight layers");
   if (io->ld_x0 && io->ld_x0 != c->cin0) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: strided x0 is only available on resident-weight layers");
 
   ConvParams p;

@@ -217,9 +217,12 @@ __device__ __forceinline__ void stv(__nv_bfloat16* p, const uint32_t (&q)[NP]) {
 template <int NP>
 __global__ void __launch_bounds__(kThreads, 3) up_concat_stats_kernel(const __nv_bfloat16* __restrict__ f2,
                                                                       const __nv_bfloat16* __restrict__ f3,
-                                                                      __nv_bfloat16* __restrict__ multi,
+                                                                      const __nv_bfloat16* f1, int ld1,
+                                                                      __nv_bfloat16* multi,
                                                                       float* __restrict__ stats, int H, int W,
                                                                       int64_t nblk_total) {
+  // f1: the full-resolution 64 channels, pixel stride ld1 (the concat variant passes multi / 192);
+  // multi == nullptr: statistics only, the up-sampled channels are not materialised
   constexpr int LPB = 32 / NP;   // lanes per 2x2 block
   constexpr int CH = 2 * NP;     // channels per thread
   const int64_t total = nblk_total * LPB;
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 3) up_concat_stats_kernel(const __nv
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx)
-        ldv<NP>(multi + (img + static_cast<int64_t>(2 * m + dy) * W + 2 * n + dx) * 192 + g * CH, F1[dy][dx]);
+        ldv<NP>(f1 + (img + static_cast<int64_t>(2 * m + dy) * W + 2 * n + dx) * ld1 + g * CH, F1[dy][dx]);
     // weight of the second (lower / right) tap: x2 -> .75 (even output) / .25 (odd); x4 by (block parity, offset)
     const float l3y[2] = {mo ? 0.125f : 0.625f, mo ? 0.375f : 0.875f};
     const float l3x[2] = {no ? 0.125f : 0.625f, no ? 0.375f : 0.875f};
@@ -289,7 +292,7 @@ __global__ void __launch_bounds__(kThreads, 3) up_concat_stats_kernel(const __nv
           u2[k] = hy::pack_bf16(v2[2 * k], v2[2 * k + 1]);
           u3[k] = hy::pack_bf16(v3[2 * k], v3[2 * k + 1]);
         }
-        if (live) {
+        if (live && multi) {
           __nv_bfloat16* o = multi + (img + static_cast<int64_t>(2 * m + dy) * W + 2 * n + dx) * 192 + g * CH;
           stv<NP>(o + 64, u2);
           stv<NP>(o + 128, u3);
@@ -333,6 +336,25 @@ __global__ void __launch_bounds__(kThreads, 3) up_concat_stats_kernel(const __nv
       reinterpret_cast<float2*>(stats)[pix] = make_float2(sum * (1.f / 192.f), fmaxf(hy::bf16_lo(mm), hy::bf16_hi(mm)));
     }
   }
+}
+
+// Fills the one-pixel border of a padded NHWC tensor [B,Hp,Wp,C] with the nearest interior pixel (corners included),
+// so that a bilinear read that steps outside the image sees the clamped source PyTorch would use.
+__global__ void replicate_border_kernel(uint4* __restrict__ t, int B, int Hp, int Wp, int c8) {
+  const int per_img = 2 * Wp + 2 * (Hp - 2);
+  const int64_t total = static_cast<int64_t>(B) * per_img * c8;
+  const int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % c8);
+  const int64_t r = i / c8;
+  const int k = static_cast<int>(r % per_img);
+  const int64_t b = r / per_img;
+  int y, x;
+  if (k < Wp) { y = 0; x = k; }
+  else if (k < 2 * Wp) { y = Hp - 1; x = k - Wp; }
+  else { const int q = k - 2 * Wp; y = 1 + (q >> 1); x = (q & 1) ? Wp - 1 : 0; }
+  const int sy = min(max(y, 1), Hp - 2), sx = min(max(x, 1), Wp - 2);
+  t[((b * Hp + y) * Wp + x) * c8 + c] = t[((b * Hp + sy) * Wp + sx) * c8 + c];
 }
 
 // att = sigmoid(conv7x7(stats; zero pad 3, no bias)); stats [B,H,W,2], weights [1][2][7][7]
@@ -409,8 +431,34 @@ int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi, fl
   int gx = static_cast<int>(std::min<int64_t>((nblk * 16 + kThreads - 1) / kThreads, 148 * 24));
   hy_count_launch();
   up_concat_stats_kernel<2><<<gx, kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
-      static_cast<const __nv_bfloat16*>(f2), static_cast<const __nv_bfloat16*>(f3), static_cast<__nv_bfloat16*>(multi),
-      stats, H, W, nblk);
+      static_cast<const __nv_bfloat16*>(f2), static_cast<const __nv_bfloat16*>(f3),
+      static_cast<const __nv_bfloat16*>(multi), 192, static_cast<__nv_bfloat16*>(multi), stats, H, W, nblk);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_refine_stats3(const void* f1, const void* f2, const void* f3, float* stats, int B, int H, int W, int C,
+                        void* stream_v) {
+  if (!f1 || !f2 || !f3 || !stats || B <= 0) return hy_fail(HYRES_ERR_ARG, "stats3: bad argument");
+  if (C != 64) return hy_fail(HYRES_ERR_UNSUPPORTED, "stats3: C must be 64");
+  if ((H & 3) || (W & 3)) return hy_fail(HYRES_ERR_ARG, "stats3: H and W must be multiples of 4");
+  const int64_t nblk = static_cast<int64_t>(B) * (H / 2) * (W / 2);
+  int gx = static_cast<int>(std::min<int64_t>((nblk * 16 + kThreads - 1) / kThreads, 148 * 24));
+  hy_count_launch();
+  up_concat_stats_kernel<2><<<gx, kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      static_cast<const __nv_bfloat16*>(f2), static_cast<const __nv_bfloat16*>(f3),
+      static_cast<const __nv_bfloat16*>(f1), 64, nullptr, stats, H, W, nblk);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_replicate_border(void* t, int B, int Hp, int Wp, int C, void* stream_v) {
+  if (!t || B <= 0 || Hp < 3 || Wp < 3) return hy_fail(HYRES_ERR_ARG, "replicate_border: bad argument");
+  if (C % 8) return hy_fail(HYRES_ERR_ARG, "replicate_border: C must be a multiple of 8");
+  const int64_t total = static_cast<int64_t>(B) * (2 * Wp + 2 * (Hp - 2)) * (C / 8);
+  hy_count_launch();
+  replicate_border_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream_v)>>>(
+      static_cast<uint4*>(t), B, Hp, Wp, C / 8);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }

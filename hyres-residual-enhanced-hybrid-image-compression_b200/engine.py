@@ -258,13 +258,24 @@ class RefineEngine:
 
         self.conv_in = _Bound(conv_in, kind=HYRES_CONV)
         self.scales = [[_conv(s[0]), _conv(s[2])] for s in (r.scale1, r.scale2, r.scale3)]
-        self.fusion0 = _conv(r.fusion[0])
+        # fusion[0] (1x1, 192 -> 64) over cat([s1, up2(s2), up4(s3)]) * att is linear and per pixel, and bilinear
+        # up-sampling commutes with a 1x1 convolution, so the 192-channel concat is never materialised:
+        #   att * (W[:, :64] s1 + up2(W[:, 64:128] s2) + up4(W[:, 128:] s3)) + b
+        # the two low-resolution products are small 1x1 layers; their up-sampling runs on the tensor cores inside
+        # the full-resolution layer (ops.ConvLayer up_t2 / up_t3)
+        def f0_slice(lo, with_bias):
+            def get():
+                w = r.fusion[0].weight[:, lo:lo + 64]
+                return w, (r.fusion[0].bias if with_bias else None)
+            return get
+        self.fusion0 = [_Bound(f0_slice(0, True), kind=HYRES_CONV), _Bound(f0_slice(64, False), kind=HYRES_CONV),
+                        _Bound(f0_slice(128, False), kind=HYRES_CONV)]
         self.fusion2 = _conv(r.fusion[2])
         self._versions = None
         self._small = None
 
     def _all_bound(self):
-        return [self.conv_in, self.fusion0, self.fusion2] + [c for s in self.scales for c in s]
+        return [self.conv_in, self.fusion2] + self.fusion0 + [c for s in self.scales for c in s]
 
     def sync(self, force=False):
         key = tuple((p.data_ptr(), p._version) for p in self.m.parameters())
@@ -300,15 +311,18 @@ class RefineEngine:
         else:
             x0, feat0 = ops.conv3ch(self.conv_in.layer, 3, 1, jpeg, r_hat, sign=1, act=ACT_PRELU, slope=sl[0])
         feat, feat_h, feat_q, _ = ops.refine_se_scale_down(feat0, sm["fc1"], sm["fc2"])
-        multi = torch.empty((B, H, W, 192), dtype=torch.bfloat16, device=dev)
         t, _, _ = self.scales[0][0](feat, act=ACT_PRELU, slope=sl[1])
-        self.scales[0][1](t, act=ACT_PRELU, slope=sl[2], out_bf16=multi[..., 0:64])
+        f1, _, _ = self.scales[0][1](t, act=ACT_PRELU, slope=sl[2])
         t, _, _ = self.scales[1][0](feat_h, act=ACT_PRELU, slope=sl[3])
         f2, _, _ = self.scales[1][1](t, act=ACT_PRELU, slope=sl[4])
         t, _, _ = self.scales[2][0](feat_q, act=ACT_PRELU, slope=sl[5])
         f3, _, _ = self.scales[2][1](t, act=ACT_PRELU, slope=sl[6])
-        stats = ops.refine_up_concat_stats(f2, f3, multi)
+        stats = ops.refine_stats3(f1, f2, f3)
         att = ops.refine_spatial_att(stats, sm["w7"])
-        h, _, _ = self.fusion0(multi, epi=EPI_PIXSCALE, pixscale=att, act=ACT_PRELU, slope=sl[7])
+        t2, _, _ = self.fusion0[1](f2, out_pad=1)
+        t3, _, _ = self.fusion0[2](f3, out_pad=1)
+        ops.replicate_border(t2)
+        ops.replicate_border(t3)
+        h, _, _ = self.fusion0[0](f1, epi=EPI_PIXSCALE, pixscale=att, act=ACT_PRELU, slope=sl[7], up_t2=t2, up_t3=t3)
         _, _, refined = self.fusion2(h, out_bf16=False, out_f32="nchw")
         return x0, refined

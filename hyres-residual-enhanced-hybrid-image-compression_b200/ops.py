@@ -95,7 +95,8 @@ class ConvLayer:
         return oh.value, ow.value
 
     def __call__(self, x0, x1=None, epi=EPI_LINEAR, act=ACT_NONE, slope=0.0, aux0=None, aux1=None,
-                 pixscale=None, out_bf16=True, out_sq=False, out_f32=None, mt=0, x0_square=False):
+                 pixscale=None, out_bf16=True, out_sq=False, out_f32=None, mt=0, x0_square=False, out_pad=0,
+                 up_t2=None, up_t3=None):
         """Run the layer.
 
         out_bf16 / out_sq: True (allocate), False, or a preallocated NHWC tensor (its last
@@ -103,6 +104,9 @@ class ConvLayer:
         out_f32: None, "nhwc", "nchw", or a preallocated fp32 tensor in NHWC or (if
         ``out_f32_nchw`` attribute semantics are needed) pass a permuted view -- strides are
         taken from the tensor, dims interpreted as [B, OH, OW, C].
+        out_pad: > 0 allocates (or expects) the bf16 output as [B, OH+2p, OW+2p, C] and stores into its interior.
+        up_t2 / up_t3: padded bf16 [B, OH/2+2, OW/2+2, 64] / [B, OH/4+2, OW/4+2, 64]; their bilinear x2 / x4
+        up-samplings are added to the accumulator before the epilogue (MultiScaleRefine fusion).
         Returns (bf16, sq, f32) with None for absent outputs.
         """
         _chk_nhwc(x0, "x0")
@@ -132,12 +136,22 @@ class ConvLayer:
             io.pixscale = pixscale.data_ptr()
         o16 = osq = o32 = None
         if out_bf16 is True:
-            o16 = torch.empty((B, OH, OW, self.cout), dtype=torch.bfloat16, device=dev)
+            o16 = torch.empty((B, OH + 2 * out_pad, OW + 2 * out_pad, self.cout), dtype=torch.bfloat16, device=dev)
         elif out_bf16 is not False and out_bf16 is not None:
             o16 = out_bf16
         if o16 is not None:
-            self._chk_aux(o16, B, OH, OW, "out_bf16")
+            self._chk_aux(o16, B, OH + 2 * out_pad, OW + 2 * out_pad, "out_bf16")
             io.out_bf16, io.ld_out = o16.data_ptr(), o16.stride(2)
+            io.out_pad = int(out_pad)
+        if (up_t2 is None) != (up_t3 is None):
+            raise ValueError("up_t2 and up_t3 go together")
+        if up_t2 is not None:
+            for t, d, nm in ((up_t2, 2, "up_t2"), (up_t3, 4, "up_t3")):
+                if (t.dtype != torch.bfloat16 or not t.is_cuda or not t.is_contiguous()
+                        or tuple(t.shape) != (B, OH // d + 2, OW // d + 2, 64)):
+                    raise ValueError(f"{nm}: expected contiguous CUDA bf16 [B,{OH // d + 2},{OW // d + 2},64]")
+            io.up_t2, io.up_t3 = up_t2.data_ptr(), up_t3.data_ptr()
+            keep += [up_t2, up_t3]
         if out_sq is True:
             osq = torch.empty((B, OH, OW, self.cout), dtype=torch.bfloat16, device=dev)
         elif out_sq is not False and out_sq is not None:
@@ -411,6 +425,27 @@ def refine_up_concat_stats(f2, f3, multi):
     L.check(L.lib().hyres_refine_up_concat_stats(_ptr(f2), _ptr(f3), _ptr(multi), _ptr(stats), B, H, W, C3 // 3,
                                                  _stream()), "hyres_refine_up_concat_stats")
     return stats
+
+
+def refine_stats3(f1, f2, f3):
+    """Channel mean / max over the virtual concat [f1 | up2(f2) | up4(f3)] (bf16 NHWC, 64 channels each) -> fp32
+    [B,H,W,2], without materialising the up-sampled channels."""
+    _chk_nhwc(f1, "f1"), _chk_nhwc(f2, "f2"), _chk_nhwc(f3, "f3")
+    B, H, W, Cc = f1.shape
+    if tuple(f2.shape) != (B, H // 2, W // 2, Cc) or tuple(f3.shape) != (B, H // 4, W // 4, Cc):
+        raise ValueError("refine_stats3: f2 / f3 must be the half / quarter resolution tensors")
+    stats = torch.empty((B, H, W, 2), dtype=torch.float32, device=f1.device)
+    L.check(L.lib().hyres_refine_stats3(_ptr(f1), _ptr(f2), _ptr(f3), _ptr(stats), B, H, W, Cc, _stream()),
+            "hyres_refine_stats3")
+    return stats
+
+
+def replicate_border(t):
+    """In place: the one-pixel border of a padded bf16 NHWC tensor [B,Hp,Wp,C] <- nearest interior pixel."""
+    _chk_nhwc(t, "t")
+    B, Hp, Wp, Cc = t.shape
+    L.check(L.lib().hyres_replicate_border(_ptr(t), B, Hp, Wp, Cc, _stream()), "hyres_replicate_border")
+    return t
 
 
 def refine_spatial_att(stats, w7):

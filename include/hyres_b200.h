@@ -119,6 +119,14 @@ typedef struct {
   int ld_x0;   /* channel stride of x0 in elements; 0 = dense (cin0) */
   int x0_square; /* 1: the layer consumes x0*x0 (GDN: conv2d(x^2, gamma, beta)), squared on chip;
                     1x1 layers only */
+  int out_pad;   /* > 0: out_bf16 points at a tensor [B,OH+2p,OW+2p,ld_out] and the result is stored
+                    into its interior (the caller fills the border, hyres_replicate_border) */
+  /* up-add (MultiScaleRefine fusion, models/layers/enhancement.py:101-110): acc += bilinear x2
+   * up-sampling of up_t2 + bilinear x4 up-sampling of up_t3 before the epilogue. Both are bf16 NHWC,
+   * 64 channels, padded by one replicated pixel: [B,OH/2+2,OW/2+2,64] and [B,OH/4+2,OW/4+2,64].
+   * The interpolation runs on the tensor cores (two small GEMMs per tile). NULL = off. */
+  const void* up_t2;
+  const void* up_t3;
 } hyres_conv_io;
 
 int hyres_conv_out_size(const hyres_conv* c, int H, int W, int* OH, int* OW);
@@ -226,6 +234,12 @@ int hyres_refine_se_scale_down(const void* feat, const float* pooled, const floa
 int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi /*[B,H,W,3C]*/,
                                  float* stats /*[B,H,W,2]*/, int B, int H, int W, int C,
                                  void* stream);
+/* The same channel mean / max over the virtual concat [f1 | up2(f2) | up4(f3)] without materialising it
+ * (the fusion conv then up-samples on the tensor cores: hyres_conv_io.up_t2 / up_t3). f1: [B,H,W,C]. */
+int hyres_refine_stats3(const void* f1, const void* f2, const void* f3, float* stats /*[B,H,W,2]*/,
+                        int B, int H, int W, int C, void* stream);
+/* Fill the one-pixel border of a padded bf16 NHWC tensor [B,Hp,Wp,C] with the nearest interior pixel. */
+int hyres_replicate_border(void* t, int B, int Hp, int Wp, int C, void* stream);
 int hyres_refine_spatial_att(const float* stats, const float* w7x7, float* att /*[B,H,W]*/,
                              int B, int H, int W, void* stream);
 

@@ -59,6 +59,21 @@ def make(case):
         out = torch.empty(B, 512, 768, 64, device="cuda", dtype=torch.bfloat16)
         return (lambda: L(x, epi=EPI_PIXSCALE, pixscale=ps, act=ACT_PRELU, slope=0.2, out_bf16=out),
                 2.0 * B * 512 * 768 * 64 * 192, (x.numel() + out.numel()) * 2)
+    if case in ("fus0up", "fus0ps", "fus0lin"):
+        # MultiScaleRefine fusion[0] without the concat: 64 -> 64 1x1 + tensor-core up-add + pixel scale
+        L = ops.ConvLayer(w(64, 64, 1), bias(64))
+        x = rnd(B, 512, 768, 64)
+        t2, t3 = rnd(B, 258, 386, 64), rnd(B, 130, 194, 64)
+        ps = torch.rand(B, 512, 768, device="cuda")
+        out = torch.empty(B, 512, 768, 64, device="cuda", dtype=torch.bfloat16)
+        nbytes = (x.numel() + out.numel()) * 2
+        if case == "fus0up":
+            return (lambda: L(x, epi=EPI_PIXSCALE, pixscale=ps, act=ACT_PRELU, slope=0.2, out_bf16=out, up_t2=t2, up_t3=t3),
+                    2.0 * B * 512 * 768 * 64 * 160, nbytes + (t2.numel() + t3.numel()) * 2 + ps.numel() * 4)
+        if case == "fus0ps":
+            return (lambda: L(x, epi=EPI_PIXSCALE, pixscale=ps, act=ACT_PRELU, slope=0.2, out_bf16=out),
+                    2.0 * B * 512 * 768 * 64 * 64, nbytes + ps.numel() * 4)
+        return lambda: L(x, act=ACT_PRELU, slope=0.2, out_bf16=out), 2.0 * B * 512 * 768 * 64 * 64, nbytes
     if case == "ru":
         c1 = ops.ConvLayer(w(64, 128, 1), bias(64))
         c2 = ops.ConvLayer(w(64, 64, 3), bias(64), pad=1)
