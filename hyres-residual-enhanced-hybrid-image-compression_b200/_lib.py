@@ -78,6 +78,7 @@ SIGNATURES = {
     "hyres_refine_se_scale_down": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_refine_up_concat_stats": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_stats3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_refine_stats3_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_replicate_border": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_spatial_att": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_jpeg_workspace_bytes": (_i64, [_i, _i, _i]),

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
     }
     hy::mbar_fence_init();
     // the weights do not depend on the predecessor kernel: their load starts before the dependency wait
-    hy::tma_prefetch_desc(&p.mapW);
+    if (p.nslots) hy::tma_prefetch_desc(&p.mapW);
     hy::mbar_arrive_expect_tx(W_FULL, p.w_bytes + p.u_bytes);
     for (int s = 0; s < p.nslots; ++s) hy::tma_load_2d(w_base + s * p.BN * 128, &p.mapW, W_FULL, s * 64, 0);
     if (p.up) {
@@ -191,11 +191,12 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
   }
   {
     float* sb = reinterpret_cast<float*>(smem_raw + (bias_base - hy::smem_u32(smem_raw)));
-    for (int i = threadIdx.x; i < p.BN; i += blockDim.x) sb[i] = __ldg(p.bias + i);  // bias padded to BN
+    if (p.bias)
+      for (int i = threadIdx.x; i < p.BN; i += blockDim.x) sb[i] = __ldg(p.bias + i);  // bias padded to BN
   }
   if (warp == 8 && lane == 0) {
     hy::tma_prefetch_desc(&p.mapA);
-    hy::tma_prefetch_desc(&p.mapW);
+    if (p.nslots) hy::tma_prefetch_desc(&p.mapW);
     if (p.has_aux0) hy::tma_prefetch_desc(&p.mapAux0);
     if (p.has_aux1) hy::tma_prefetch_desc(&p.mapAux1);
     if (p.up) {
@@ -303,14 +304,18 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
           // interpolation matrix [128 tile positions][64 patch pixels] (K-major); B = the patch as TMA wrote it,
           // [patch pixel][64 channels], i.e. N-contiguous: an MN-major operand (idesc bit 16; 16 pixels = 2048 B
           // per K step; measured in tools/experiments/umma_mn.cu).
-          const uint32_t idesc_mn = idesc | (1u << 16);
+          const uint32_t idesc_mn = hy::umma_idesc_bf16(128, 64) | (1u << 16);
+          // up == 2 (statistics mode): no weight GEMM; the two up-sampled tensors go to columns [0, 64) and [64, 128)
+          const uint32_t d1 = p.up == 2 ? d0 + 64 : d0;
           const uint64_t u2_d = hy::desc_u64(u_base), u4_d = hy::desc_u64(u_base + 16384);
           const uint64_t t2_d = hy::desc_u64(st_base + stage * p.stage_bytes + p.t2_off);
           const uint64_t t3_d = hy::desc_u64(st_base + stage * p.stage_bytes + p.t3_off);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) hy::umma_issue<2>(d0, u2_d + 2 * k, t2_d + 128 * k, idesc_mn, 1u, leader);
+          for (int k = 0; k < 4; ++k)
+            hy::umma_issue<2>(d0, u2_d + 2 * k, t2_d + 128 * k, idesc_mn, (p.up == 2 && k == 0) ? 0u : 1u, leader);
 #pragma unroll
-          for (int k = 0; k < 2; ++k) hy::umma_issue<2>(d0, u4_d + 2 * k, t3_d + 128 * k, idesc_mn, 1u, leader);
+          for (int k = 0; k < 2; ++k)
+            hy::umma_issue<2>(d1, u4_d + 2 * k, t3_d + 128 * k, idesc_mn, (p.up == 2 && k == 0) ? 0u : 1u, leader);
         }
         hy::umma_commit_mode<2>(A_EMPTY + 8 * stage, leader);
         hy::umma_commit_mode<2>(ACC_FULL + 8 * buf, leader);
@@ -408,6 +413,46 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
       const uint32_t sx_row = sb + p.x1_off + row * 128;
       // decoupled: the previous tile of this group must have left the staging buffer (first use passes at once)
       if (p.decoupled && p.store_bf16) hy::mbar_wait(STG_FREE + 8 * grp, ((it >> 1) & 1) ^ 1u);
+      if (epi == HYRES_EPI_STATS) {
+        // channel mean / max over [s1 | up2(s2) | up4(s3)] of this thread's position: the 128 up-sampled channels sit
+        // in the accumulator (rounded to bf16 like the concat the reference materialises), s1 in the activation tile
+        float sum = 0.f, mx = -3.0e38f;
+        uint32_t ra[16], rb[16];
+        auto fold = [&](const uint32_t (&r)[16]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t u = hy::pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            const float a = hy::bf16_lo(u), b = hy::bf16_hi(u);
+            sum += a + b;
+            mx = fmaxf(mx, fmaxf(a, b));
+          }
+        };
+        hy::tmem_ld16(acc0, ra);
+        hy::tmem_ld_fence(ra);
+#pragma unroll
+        for (int q = 0; q < 8; q += 2) {
+          hy::tmem_ld16(acc0 + (q + 1) * 16, rb);
+          fold(ra);
+          hy::tmem_ld_fence(rb);
+          if (q + 2 < 8) hy::tmem_ld16(acc0 + (q + 2) * 16, ra);
+          fold(rb);
+          if (q + 2 < 8) hy::tmem_ld_fence(ra);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 w = lds128(sb + row * 128 + ((j ^ sw) << 4));
+          const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = hy::bf16_lo(u[i]), b = hy::bf16_hi(u[i]);
+            sum += a + b;
+            mx = fmaxf(mx, fmaxf(a, b));
+          }
+        }
+        if (valid)
+          reinterpret_cast<float2*>(p.out_f32)[(static_cast<long long>(b_img) * p.OH + hv) * p.OW + wv] =
+              make_float2(sum * (1.f / 192.f), mx);
+      }
       int ph = 0, n = 0;  // phase / first channel of the chunk, advanced incrementally (no division per chunk)
       auto chunk = [&](const uint32_t (&r)[16]) {
         float v[16];
@@ -514,9 +559,11 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
       // two register buffers: chunk q + 1 is in flight from TMEM while chunk q is processed (columns of successive
       // phases are contiguous)
       uint32_t ra[16], rb[16];
+      if (epi != HYRES_EPI_STATS) {
       hy::tmem_ld16(acc0, ra);
       hy::tmem_ld_fence(ra);
-      for (int q = 0; q < total; q += 2) {
+      }
+      for (int q = 0; q < (epi == HYRES_EPI_STATS ? 0 : total); q += 2) {
         if (q + 1 < total) hy::tmem_ld16(acc0 + (q + 1) * 16, rb);
         chunk(ra);
         if (q + 1 < total) {
@@ -611,6 +658,32 @@ const void* up_table() {
   if (cudaMemcpy(d, h.data(), h.size() * 2, cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
   tab[dev] = d;
   return d;
+}
+
+// Launch with the epilogue variant of p.epi / p.act.
+int res_dispatch(const ResParams& p, int smem, cudaStream_t stream) {
+  const int grid = std::min(p.ntiles, num_sms());
+  const int threads = p.a_square ? kThreadsSq : kThreads;
+  hy_count_launch();
+  // the combinations the codec uses are compiled straight-line; anything else runs the generic instance
+#define RES_CASE(E, A)                                                \
+  if (p.epi == (E) && p.act == (A)) {                                 \
+    HY_CUDA((launch_res<E, A>(grid, threads, smem, stream, p)));      \
+    return HYRES_OK;                                                  \
+  }
+  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_RELU)
+  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_PRELU)
+  RES_CASE(HYRES_EPI_ADD, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_ADD, HYRES_ACT_RELU)
+  RES_CASE(HYRES_EPI_GATE, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_GDN, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_IGDN, HYRES_ACT_NONE)
+  RES_CASE(HYRES_EPI_PIXSCALE, HYRES_ACT_PRELU)
+  RES_CASE(HYRES_EPI_STATS, HYRES_ACT_NONE)
+#undef RES_CASE
+  HY_CUDA((launch_res<-1, -1>(grid, threads, smem, stream, p)));
+  return HYRES_OK;
 }
 
 }  // namespace
@@ -764,28 +837,49 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   if (need0 && (rc = encode_map4(&p.mapAux0, io->aux0, c->cout, io->ld_aux0, io->B, OH, OW, kTW, kTH)) != HYRES_OK) return rc;
   if (need1 && (rc = encode_map4(&p.mapAux1, io->aux1, c->cout, io->ld_aux1, io->B, OH, OW, kTW, kTH)) != HYRES_OK) return rc;
 
-  const int smem = fixed + NA * stage;
-  const int grid = std::min(p.ntiles, num_sms());
-  const int threads = p.a_square ? kThreadsSq : kThreads;
-  hy_count_launch();
-  // the combinations the codec uses are compiled straight-line; anything else runs the generic instance
-#define RES_CASE(E, A)                                                \
-  if (p.epi == (E) && p.act == (A)) {                                 \
-    HY_CUDA((launch_res<E, A>(grid, threads, smem, stream, p)));      \
-    *handled = 1;                                                     \
-    return HYRES_OK;                                                  \
-  }
-  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_NONE)
-  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_RELU)
-  RES_CASE(HYRES_EPI_LINEAR, HYRES_ACT_PRELU)
-  RES_CASE(HYRES_EPI_ADD, HYRES_ACT_NONE)
-  RES_CASE(HYRES_EPI_ADD, HYRES_ACT_RELU)
-  RES_CASE(HYRES_EPI_GATE, HYRES_ACT_NONE)
-  RES_CASE(HYRES_EPI_GDN, HYRES_ACT_NONE)
-  RES_CASE(HYRES_EPI_IGDN, HYRES_ACT_NONE)
-  RES_CASE(HYRES_EPI_PIXSCALE, HYRES_ACT_PRELU)
-#undef RES_CASE
-  HY_CUDA((launch_res<-1, -1>(grid, threads, smem, stream, p)));
+  const int rc2 = res_dispatch(p, fixed + NA * stage, stream);
+  if (rc2 != HYRES_OK) return rc2;
   *handled = 1;
   return HYRES_OK;
+}
+
+// Channel mean / max over the virtual concat [f1 | up2(s2) | up4(s3)] on the resident-weights kernel in its
+// statistics mode: the two bilinear up-samplings are tensor-core GEMMs (interpolation matrix x TMA patch), the
+// epilogue folds the 128 accumulator columns and the 64 channels of the f1 tile of its position.
+extern "C" int hyres_refine_stats3_tc(const void* f1, const void* s2_padded, const void* s3_padded, float* stats, int B,
+                                      int H, int W, void* stream_v) {
+  if (!f1 || !s2_padded || !s3_padded || !stats || B <= 0) return hy_fail(HYRES_ERR_ARG, "stats3_tc: bad argument");
+  if ((H % 32) || (W % 32)) return hy_fail(HYRES_ERR_UNSUPPORTED, "stats3_tc: H and W must be multiples of 32");
+  const void* tab = up_table();
+  if (!tab) return hy_fail(HYRES_ERR_CUDA, "stats3_tc: cannot allocate the interpolation table");
+  ResParams p;
+  memset(&p, 0, sizeof p);
+  constexpr int kT2Rows = 6 * 11, kT3Rows = 4 * 8;
+  p.nsteps = 0; p.nphase = 1; p.nchunk_in = 1; p.nchunk_out = 0;
+  p.PW = kTW; p.PH = kTH; p.org_h = p.org_w = 0;
+  p.a_chunk_bytes = kTH * kTW * 128;
+  p.up = 2; p.u_bytes = 32768;
+  p.o_off = p.x1_off = p.a_chunk_bytes;
+  p.t2_off = p.a_chunk_bytes;
+  p.t3_off = p.t2_off + (kT2Rows * 128 + 1023) / 1024 * 1024;
+  p.stage_bytes = p.t3_off + kT3Rows * 128;
+  p.stage_tx_bytes = p.a_chunk_bytes + (kT2Rows + kT3Rows) * 128;
+  const int fixed = p.u_bytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+  p.NA = std::min((kSmemLimit - fixed) / p.stage_bytes, kMaxStages);
+  p.stg_base_off = p.NA * p.stage_bytes;
+  p.BN = 128; p.tmem_cols = 256;
+  p.Hv = p.OH = H; p.Wv = p.OW = W; p.out_mul = 1;
+  p.tiles_w = W / kTW; p.tiles_per_img = p.tiles_w * (H / kTH); p.ntiles = p.tiles_per_img * B;
+  p.epi = HYRES_EPI_STATS; p.act = HYRES_ACT_NONE;
+  p.out_f32 = stats;
+  {
+    static const int pf = [] { const char* e = getenv("HYRES_RES_PF"); return e ? atoi(e) : 0; }();
+    p.pf_extra = pf;
+  }
+  int rc = encode_map4(&p.mapA, f1, 64, 64, B, H, W, kTW, kTH);
+  if (rc != HYRES_OK) return rc;
+  if ((rc = encode_map4(&p.mapT2, s2_padded, 64, 64, B, H / 2 + 2, W / 2 + 2, 6, 11)) != HYRES_OK) return rc;
+  if ((rc = encode_map4(&p.mapT3, s3_padded, 64, 64, B, H / 4 + 2, W / 4 + 2, 4, 8)) != HYRES_OK) return rc;
+  if ((rc = encode_w_map(&p.mapU, tab, 64, 256, 128)) != HYRES_OK) return rc;
+  return res_dispatch(p, fixed + p.NA * p.stage_bytes, static_cast<cudaStream_t>(stream_v));
 }

@@ -313,16 +313,19 @@ class RefineEngine:
         feat, feat_h, feat_q, _ = ops.refine_se_scale_down(feat0, sm["fc1"], sm["fc2"])
         t, _, _ = self.scales[0][0](feat, act=ACT_PRELU, slope=sl[1])
         f1, _, _ = self.scales[0][1](t, act=ACT_PRELU, slope=sl[2])
+        # the half / quarter resolution branches are kept with a one-pixel replicated border: the bilinear
+        # up-samplings (tensor-core GEMMs in the statistics and fusion kernels) then need no clamping, and the 1x1
+        # products of the fusion layer are computed on the padded grid (pointwise, so the border stays a replica)
         t, _, _ = self.scales[1][0](feat_h, act=ACT_PRELU, slope=sl[3])
-        f2, _, _ = self.scales[1][1](t, act=ACT_PRELU, slope=sl[4])
+        f2p, _, _ = self.scales[1][1](t, act=ACT_PRELU, slope=sl[4], out_pad=1)
         t, _, _ = self.scales[2][0](feat_q, act=ACT_PRELU, slope=sl[5])
-        f3, _, _ = self.scales[2][1](t, act=ACT_PRELU, slope=sl[6])
-        stats = ops.refine_stats3(f1, f2, f3)
+        f3p, _, _ = self.scales[2][1](t, act=ACT_PRELU, slope=sl[6], out_pad=1)
+        ops.replicate_border(f2p)
+        ops.replicate_border(f3p)
+        stats = ops.refine_stats3_tc(f1, f2p, f3p)
         att = ops.refine_spatial_att(stats, sm["w7"])
-        t2, _, _ = self.fusion0[1](f2, out_pad=1)
-        t3, _, _ = self.fusion0[2](f3, out_pad=1)
-        ops.replicate_border(t2)
-        ops.replicate_border(t3)
+        t2, _, _ = self.fusion0[1](f2p)
+        t3, _, _ = self.fusion0[2](f3p)
         h, _, _ = self.fusion0[0](f1, epi=EPI_PIXSCALE, pixscale=att, act=ACT_PRELU, slope=sl[7], up_t2=t2, up_t3=t3)
         _, _, refined = self.fusion2(h, out_bf16=False, out_f32="nchw")
         return x0, refined

@@ -440,6 +440,19 @@ def refine_stats3(f1, f2, f3):
     return stats
 
 
+def refine_stats3_tc(f1, s2p, s3p):
+    """As refine_stats3, on the tensor cores: s2p / s3p are the half / quarter resolution tensors padded by one
+    replicated pixel ([B,H/2+2,W/2+2,64] / [B,H/4+2,W/4+2,64])."""
+    _chk_nhwc(f1, "f1"), _chk_nhwc(s2p, "s2p"), _chk_nhwc(s3p, "s3p")
+    B, H, W, Cc = f1.shape
+    if Cc != 64 or tuple(s2p.shape) != (B, H // 2 + 2, W // 2 + 2, 64) or tuple(s3p.shape) != (B, H // 4 + 2, W // 4 + 2, 64):
+        raise ValueError("refine_stats3_tc: expected 64-channel f1 and padded half / quarter resolution tensors")
+    stats = torch.empty((B, H, W, 2), dtype=torch.float32, device=f1.device)
+    L.check(L.lib().hyres_refine_stats3_tc(_ptr(f1), _ptr(s2p), _ptr(s3p), _ptr(stats), B, H, W, _stream()),
+            "hyres_refine_stats3_tc")
+    return stats
+
+
 def replicate_border(t):
     """In place: the one-pixel border of a padded bf16 NHWC tensor [B,Hp,Wp,C] <- nearest interior pixel."""
     _chk_nhwc(t, "t")

@@ -76,6 +76,7 @@ typedef struct hyres_conv hyres_conv;
 #define HYRES_EPI_GDN 3      /* v = aux0 * rsqrt(acc + bias)    (GDN; input is x^2)        */
 #define HYRES_EPI_IGDN 4     /* v = aux0 * sqrt(acc + bias)     (inverse GDN)              */
 #define HYRES_EPI_PIXSCALE 5 /* v = acc * pixscale[pixel] + bias (spatial attention)       */
+#define HYRES_EPI_STATS 6    /* internal: hyres_refine_stats3_tc                           */
 
 /* activation applied after the epilogue mode */
 #define HYRES_ACT_NONE 0
@@ -238,6 +239,11 @@ int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi /*[
  * (the fusion conv then up-samples on the tensor cores: hyres_conv_io.up_t2 / up_t3). f1: [B,H,W,C]. */
 int hyres_refine_stats3(const void* f1, const void* f2, const void* f3, float* stats /*[B,H,W,2]*/,
                         int B, int H, int W, int C, void* stream);
+/* The tensor-core version (the product path): s2 / s3 are bf16 NHWC tensors padded by one replicated
+ * pixel, [B,H/2+2,W/2+2,64] / [B,H/4+2,W/4+2,64]; the bilinear up-samplings are GEMMs with a constant
+ * interpolation matrix, the epilogue reduces over the channels. H, W multiples of 32. */
+int hyres_refine_stats3_tc(const void* f1, const void* s2_padded, const void* s3_padded, float* stats,
+                           int B, int H, int W, void* stream);
 /* Fill the one-pixel border of a padded bf16 NHWC tensor [B,Hp,Wp,C] with the nearest interior pixel. */
 int hyres_replicate_border(void* t, int B, int Hp, int Wp, int C, void* stream);
 int hyres_refine_spatial_att(const float* stats, const float* w7x7, float* att /*[B,H,W]*/,
