@@ -74,6 +74,13 @@ def make(case):
             return (lambda: L(x, epi=EPI_PIXSCALE, pixscale=ps, act=ACT_PRELU, slope=0.2, out_bf16=out),
                     2.0 * B * 512 * 768 * 64 * 64, nbytes + ps.numel() * 4)
         return lambda: L(x, act=ACT_PRELU, slope=0.2, out_bf16=out), 2.0 * B * 512 * 768 * 64 * 64, nbytes
+    if case == "stats3":
+        f1, s2p, s3p = rnd(B, 512, 768, 64), rnd(B, 258, 386, 64), rnd(B, 130, 194, 64)
+        return (lambda: ops.refine_stats3_tc(f1, s2p, s3p), 2.0 * B * 512 * 768 * 64 * 96,
+                (f1.numel() + s2p.numel() + s3p.numel()) * 2 + B * 512 * 768 * 8)
+    if case == "jpeg":
+        x = torch.rand(B, 3, 512, 768, device="cuda")
+        return lambda: ops.jpeg_forward(x, 1), 0.0, x.numel() * 8 + B * 512 * 768 * 10
     if case == "ru":
         c1 = ops.ConvLayer(w(64, 128, 1), bias(64))
         c2 = ops.ConvLayer(w(64, 64, 3), bias(64), pad=1)
