@@ -69,7 +69,7 @@ struct alignas(64) ResParams {
   int32_t a_square, has_aux0, has_aux1, store_bf16;
   int32_t pf_extra;  // L2 prefetch distance beyond the ring, in tiles; < 0: no prefetch
   int32_t up, u_bytes, t2_off, t3_off;  // up-add mode (see conv_res_try_run)
-  int32_t decoupled, stg_base_off;  // result staging outside the TMA ring (one buffer per epilogue group)
+  int32_t decoupled, stg_base_off, stg_per_grp;  // result staging outside the TMA ring (1 or 2 buffers per epilogue group)
   long long* trace;  // optional: clock64 stamps of CTA 0 (tools/experiments/res_trace.py), 16 slots per tile
   const float* bias;
   const float* pixscale;
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
   const uint32_t u_base = base + p.w_bytes;  // interpolation matrices (up-add mode), resident like the weights
   const uint32_t st_base = u_base + p.u_bytes;
   const uint32_t stg_base = st_base + p.stg_base_off;
-  const uint32_t bias_base = stg_base + (p.decoupled ? 2 * p.nchunk_out * 16384 : 0);
+  const uint32_t bias_base = stg_base + (p.decoupled ? 2 * p.stg_per_grp * p.nchunk_out * 16384 : 0);
   const uint32_t bar_base = bias_base + 1024;
   // barriers: W_FULL | A_FULL[4] | A_EMPTY[4] | A_READY[4] | ACC_FULL[2] | ACC_EMPTY[2] ; tmem slot
   const uint32_t W_FULL = bar_base;
@@ -158,8 +158,8 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
   const uint32_t ACC_FULL = A_READY + 8 * kMaxStages;
   const uint32_t ACC_EMPTY = ACC_FULL + 16;
   const uint32_t STAGED = ACC_EMPTY + 16;  // [2]: a group's result tile is staged (and its operands consumed)
-  const uint32_t STG_FREE = STAGED + 16;   // [2]: decoupled mode: the group's staging buffer has been read by its store
-  const uint32_t tmem_slot = STG_FREE + 16;
+  const uint32_t STG_FREE = STAGED + 16;   // [2][2]: decoupled mode: a staging buffer of the group has been read by its store
+  const uint32_t tmem_slot = STG_FREE + 32;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
 
@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
       hy::mbar_init(ACC_FULL + 8 * i, 1);
       hy::mbar_init(ACC_EMPTY + 8 * i, 128);
       hy::mbar_init(STAGED + 8 * i, 128);
-      hy::mbar_init(STG_FREE + 8 * i, 1);
+      hy::mbar_init(STG_FREE + 16 * i, 1);
+      hy::mbar_init(STG_FREE + 16 * i + 8, 1);
     }
     hy::mbar_fence_init();
     // the weights do not depend on the predecessor kernel: their load starts before the dependency wait
@@ -337,14 +338,15 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
         const uint32_t sb = st_base + stage * p.stage_bytes;
         int b_img, h0, w0;
         tile_origin(t, b_img, h0, w0);
-        const uint32_t src = p.decoupled ? stg_base + grp * p.nchunk_out * 16384 : sb + p.o_off;
+        const int sk = p.stg_per_grp == 2 ? ((it >> 1) & 1) : 0;  // staging buffer of this tile (decoupled mode)
+        const uint32_t src = p.decoupled ? stg_base + (grp * p.stg_per_grp + sk) * p.nchunk_out * 16384 : sb + p.o_off;
         hy::mbar_wait(STAGED + 8 * grp, (it >> 1) & 1);
         if (p.store_bf16) {
           for (int c = 0; c < p.nchunk_out; ++c) hy::tma_store_4d(&p.mapOut, src + c * 16384, c * 64, w0, h0, b_img);
           hy::tma_store_commit();
           hy::tma_store_wait_read<0>();
         }
-        hy::mbar_arrive(p.decoupled ? STG_FREE + 8 * grp : A_EMPTY + 8 * stage);
+        hy::mbar_arrive(p.decoupled ? STG_FREE + 16 * grp + 8 * sk : A_EMPTY + 8 * stage);
         RES_STAMP(it, 8);  // store read done, stage released
       }
       if (p.store_bf16) hy::tma_store_wait_all<0>();
@@ -409,21 +411,23 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
 
       const uint32_t acc0 = t_lane + grp * acc_cols;
       const int total = p.nphase * nchunk16;
-      const uint32_t so_row = (p.decoupled ? stg_base + grp * p.nchunk_out * 16384 : sb + p.o_off) + row * 128;
+      const int sk = p.stg_per_grp == 2 ? ((it >> 1) & 1) : 0;
+      const uint32_t so_row = (p.decoupled ? stg_base + (grp * p.stg_per_grp + sk) * p.nchunk_out * 16384 : sb + p.o_off) + row * 128;
       const uint32_t sx_row = sb + p.x1_off + row * 128;
-      // decoupled: the previous tile of this group must have left the staging buffer (first use passes at once)
-      if (p.decoupled && p.store_bf16) hy::mbar_wait(STG_FREE + 8 * grp, ((it >> 1) & 1) ^ 1u);
+      // decoupled: the tile that last used this staging buffer must have left it (first use passes at once); with two
+      // buffers per group that store was issued two tiles of the group ago
+      if (p.decoupled && p.store_bf16)
+        hy::mbar_wait(STG_FREE + 16 * grp + 8 * sk, (((it >> 1) / p.stg_per_grp) & 1) ^ 1u);
       if (epi == HYRES_EPI_STATS) {
         // channel mean / max over [s1 | up2(s2) | up4(s3)] of this thread's position: the 128 up-sampled channels sit
-        // in the accumulator (rounded to bf16 like the concat the reference materialises), s1 in the activation tile
-        float sum = 0.f, mx = -3.0e38f;
+        // in the accumulator (fp32, as the reference interpolates), s1 in the activation tile
+        float sum = 0.f, sum1 = 0.f, mx = -3.0e38f;
         uint32_t ra[16], rb[16];
         auto fold = [&](const uint32_t (&r)[16]) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const uint32_t u = hy::pack_bf16(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
-            const float a = hy::bf16_lo(u), b = hy::bf16_hi(u);
-            sum += a + b;
+            const float a = __uint_as_float(r[2 * i]), b = __uint_as_float(r[2 * i + 1]);
+            hy::add2(sum, sum1, a, b);
             mx = fmaxf(mx, fmaxf(a, b));
           }
         };
@@ -445,13 +449,13 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float a = hy::bf16_lo(u[i]), b = hy::bf16_hi(u[i]);
-            sum += a + b;
+            hy::add2(sum, sum1, a, b);
             mx = fmaxf(mx, fmaxf(a, b));
           }
         }
         if (valid)
           reinterpret_cast<float2*>(p.out_f32)[(static_cast<long long>(b_img) * p.OH + hv) * p.OW + wv] =
-              make_float2(sum * (1.f / 192.f), mx);
+              make_float2((sum + sum1) * (1.f / 192.f), mx);
       }
       int ph = 0, n = 0;  // phase / first channel of the chunk, advanced incrementally (no division per chunk)
       auto chunk = [&](const uint32_t (&r)[16]) {
@@ -788,8 +792,13 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   p.stage_bytes = stage;
   p.stage_tx_bytes = p.nchunk_in * PH * PW * 128 + (need0 ? p.nchunk_out * 16384 : 0) + (need1 ? p.nchunk_out * 16384 : 0) +
                      (up ? (kT2Rows + kT3Rows) * 128 : 0);
-  const int stg_bytes = p.decoupled ? 2 * p.nchunk_out * 16384 : 0;
-  const int fixed = static_cast<int>(w_bytes) + p.u_bytes + stg_bytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+  const int fixed0 = static_cast<int>(w_bytes) + p.u_bytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+  // two staging buffers per group when the ring keeps >= 3 stages next to them: the group then never waits for the
+  // read of its previous store (~1000 clk)
+  p.stg_per_grp = 1;
+  if (p.decoupled && (kSmemLimit - fixed0 - 4 * p.nchunk_out * 16384) / stage >= 3) p.stg_per_grp = 2;
+  const int stg_bytes = p.decoupled ? 2 * p.stg_per_grp * p.nchunk_out * 16384 : 0;
+  const int fixed = fixed0 + stg_bytes;
   int NA = (kSmemLimit - fixed) / stage;
   if (NA < 2) return HYRES_OK;
   NA = std::min(NA, kMaxStages);
@@ -867,6 +876,7 @@ extern "C" int hyres_refine_stats3_tc(const void* f1, const void* s2_padded, con
   const int fixed = p.u_bytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
   p.NA = std::min((kSmemLimit - fixed) / p.stage_bytes, kMaxStages);
   p.stg_base_off = p.NA * p.stage_bytes;
+  p.stg_per_grp = 1;
   p.BN = 128; p.tmem_cols = 256;
   p.Hv = p.OH = H; p.Wv = p.OW = W; p.out_mul = 1;
   p.tiles_w = W / kTW; p.tiles_per_img = p.tiles_w * (H / kTH); p.ntiles = p.tiles_per_img * B;
