@@ -160,16 +160,15 @@ def codec_cfg3(net, dev, reps=3):
     from hyres_b200 import synthetic
     tiles, h, w = 8, 704, 512
     x = synthetic.synthetic_image(tiles, h, w, seed=7)
-    bufs = net.jpeg.compress(x)
     xd = x.to(dev)
     with torch.no_grad():
         for _ in range(2):
-            d = net.decompress(net.compress(xd, jpeg_buffers=bufs))
+            d = net.decompress(net.compress(xd))
         t_enc = t_dec = 0.0
         for _ in range(reps):
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            c = net.compress(xd, jpeg_buffers=bufs)
+            c = net.compress(xd)  # device JPEG encoder + residual codec; decompress decodes the JPEG files on the CPU
             torch.cuda.synchronize()
             t1 = time.perf_counter()
             d = net.decompress(c)
@@ -178,7 +177,7 @@ def codec_cfg3(net, dev, reps=3):
             t_dec += time.perf_counter() - t1
     px = tiles * h * w
     nbytes = sum(len(s) for grp in (c["strings"][0][0], c["strings"][0][1], c["strings"][1]) for s in grp)
-    return {"workload": "compress + decompress, 8 tiles of 704x512 (one 2048x1408 image), host rANS included",
+    return {"workload": "compress + decompress, 8 tiles of 704x512 (one 2048x1408 image), JPEG stage and host rANS included",
             "enc_ms": t_enc / reps * 1e3, "dec_ms": t_dec / reps * 1e3, "encdec_mpixel_per_s": px * reps / (t_enc + t_dec) / 1e6,
             "residual_bpp": 8.0 * nbytes / px, "host_cores": os.cpu_count(), "x_hat_shape": list(d["x_hat"].shape)}
 

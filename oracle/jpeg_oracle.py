@@ -226,18 +226,21 @@ def roundtrip(img, quality):
 
 # ---- entropy coder + markers (jchuff.c, jcmarker.c) ----
 class _BitWriter:
-    def __init__(self):
+    def __init__(self, stuff=True):
         self.out = bytearray()
         self.acc = 0
         self.n = 0
+        self.stuff = stuff
+        self.nbits = 0
 
     def put(self, code, length):
         self.acc = (self.acc << length) | code
         self.n += length
+        self.nbits += length
         while self.n >= 8:
             byte = (self.acc >> (self.n - 8)) & 0xFF
             self.out.append(byte)
-            if byte == 0xFF:
+            if byte == 0xFF and self.stuff:
                 self.out.append(0)
             self.n -= 8
         self.acc &= (1 << self.n) - 1
@@ -291,12 +294,29 @@ def header(H, W, quality):
     return bytes(o)
 
 
+def scan_bits(coefs):
+    """The scan as the device kernels leave it (hyres_jpeg_forward's scan_words / scan_bits): the raw bit string,
+    no byte stuffing, no padding -> (big-endian uint32 words, number of bits)."""
+    bw = _scan(coefs, stuff=False)
+    nbits = bw.nbits
+    if bw.n:
+        bw.out.append((bw.acc << (8 - bw.n)) & 0xFF)
+    raw = bytes(bw.out) + b"\x00" * (-len(bw.out) % 4)
+    return np.frombuffer(raw, dtype=">u4").astype(np.uint32), nbits
+
+
 def entropy_segment(coefs):
     """The interleaved 4:2:2 scan (MCU = Y Y Cb Cr), byte-stuffed, final byte padded with one bits."""
+    bw = _scan(coefs, stuff=True)
+    bw.flush()
+    return bytes(bw.out)
+
+
+def _scan(coefs, stuff):
     cy, ccb, ccr = coefs
     dcl, acl = huff_codes(DC_LUM_BITS, DC_VALS), huff_codes(AC_LUM_BITS, AC_LUM_VALS)
     dcc, acc = huff_codes(DC_CHR_BITS, DC_VALS), huff_codes(AC_CHR_BITS, AC_CHR_VALS)
-    bw = _BitWriter()
+    bw = _BitWriter(stuff)
     last = [0, 0, 0]
     for my in range(cy.shape[0]):
         for mx in range(ccb.shape[1]):
@@ -304,8 +324,7 @@ def entropy_segment(coefs):
             last[0] = _encode_block(bw, cy[my, 2 * mx + 1], last[0], dcl, acl)
             last[1] = _encode_block(bw, ccb[my, mx], last[1], dcc, acc)
             last[2] = _encode_block(bw, ccr[my, mx], last[2], dcc, acc)
-    bw.flush()
-    return bytes(bw.out)
+    return bw
 
 
 def encode(img, quality):

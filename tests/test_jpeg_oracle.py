@@ -62,3 +62,23 @@ def test_live_against_cv2_on_random_cases():
                                             cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422])
         assert ok and J.encode(img, q) == enc.tobytes(), (H, W, q)
         assert np.array_equal(J.roundtrip(img, q), cv2.imdecode(enc, cv2.IMREAD_COLOR)), (H, W, q)
+
+
+@pytest.mark.parametrize("i", range(N))
+def test_host_assembly_of_the_c_abi_writes_libjpeg_turbos_file(build_lib, i):
+    """hyres_jpeg_assemble (host half of the device JPEG stage: markers, byte stuffing, padding, EOI) fed the oracle's
+    raw scan bits reproduces the library's file; needs no GPU."""
+    from hyres_b200 import ops
+    img, q = G[f"img{i}"], int(G[f"q{i}"])
+    coefs, _ = J.coefficients(img, q)
+    words, nbits = J.scan_bits(coefs)
+    mine = ops.jpeg_assemble(words.view(np.int32), nbits, img.shape[0], img.shape[1], q)
+    assert mine == G[f"file{i}"].tobytes()
+    assert mine == J.encode(img, q)
+
+
+def test_host_assembly_rejects_bad_arguments(build_lib):
+    from hyres_b200 import ops
+    from hyres_b200._lib import HyresError
+    with pytest.raises(HyresError):
+        ops.jpeg_assemble(np.zeros(4, np.int32), 64, 70000, 32, 1)
