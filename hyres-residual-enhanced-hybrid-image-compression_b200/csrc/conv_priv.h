@@ -37,6 +37,7 @@ struct hyres_conv {
   __nv_bfloat16* d_w = nullptr;
   __nv_bfloat16* d_w_tap = nullptr;  // tap-major packing for the three-output-channel layers (conv_sc.cu)
   float* d_bias = nullptr;
+  std::vector<float> h_bias;  // host copy (cout_pad entries): kernels that take the bias as launch parameters
   int64_t macs_per_pos = 0;
 };
 

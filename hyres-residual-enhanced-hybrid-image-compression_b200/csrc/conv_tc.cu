@@ -636,6 +636,7 @@ int upload_weights(hyres_conv* c, const float* weight, const float* bias) {
   std::vector<float> b(c->cout_pad, 0.f);
   if (bias) std::copy(bias, bias + c->cout, b.begin());
   HY_CUDA(cudaMemcpy(c->d_bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
+  c->h_bias = b;
   if (conv_sc_applicable(c)) {
     conv_sc_pack(c, weight, packed);
     if (!c->d_w_tap) HY_CUDA(cudaMalloc(&c->d_w_tap, packed.size() * sizeof(__nv_bfloat16)));

@@ -66,9 +66,10 @@ enum { W_FULL = 0, X_FULL, X_FREE, G1_DONE, T1_READY, G2_DONE, T2_READY, G3_DONE
 
 struct alignas(64) RuParams {
   CUtensorMap mapX, mapSkip, mapOut, mapW1, mapW2, mapW3;
-  const float* b1;
-  const float* b2;
-  const float* b3;
+  // b1 [64] | b2 [64] | b3 [128] as launch parameters: the epilogues read them through the constant cache with
+  // warp-uniform indices, not through shared memory (whose 128 B/clk port bounds this kernel: the broadcast bias
+  // loads were ~290 wavefronts of a tile's ~4600)
+  float bias[256];
   int32_t H, W, tiles_w, tiles_per_img, ntiles, final_relu;
   long long* trace;  // optional: clock64 stamps of CTA 0 (tools/experiments), 16 slots per tile
 };
@@ -88,18 +89,14 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 }
 
 // 16 accumulator columns -> (+bias) ReLU -> 16 bf16 in q[0..1]; `keep` = false zeroes the row.
-__device__ __forceinline__ void bias_relu_pack16(uint32_t (&r)[16], uint32_t bias_addr, bool keep, uint4 (&q)[2]) {
+__device__ __forceinline__ void bias_relu_pack16(uint32_t (&r)[16], const float (&b)[16], bool keep, uint4 (&q)[2]) {
 #pragma unroll
   for (int g = 0; g < 2; ++g) {
-    const float4 ba = lds_f4(bias_addr + g * 32);
-    const float4 bb = lds_f4(bias_addr + g * 32 + 16);
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-    hy::add2(v[0], v[1], ba.x, ba.y);
-    hy::add2(v[2], v[3], ba.z, ba.w);
-    hy::add2(v[4], v[5], bb.x, bb.y);
-    hy::add2(v[6], v[7], bb.z, bb.w);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) hy::add2(v[2 * i], v[2 * i + 1], b[g * 8 + 2 * i], b[g * 8 + 2 * i + 1]);
     q[g].x = hy::relu_bf16x2(hy::pack_bf16(v[0], v[1]));
     q[g].y = hy::relu_bf16x2(hy::pack_bf16(v[2], v[3]));
     q[g].z = hy::relu_bf16x2(hy::pack_bf16(v[4], v[5]));
@@ -147,12 +144,6 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
     hy::tma_load_2d(base + kW1 + 8192, &p.mapW1, bar(W_FULL), 64, 0);
     for (int s = 0; s < 9; ++s) hy::tma_load_2d(base + kW2 + s * 8192, &p.mapW2, bar(W_FULL), s * 64, 0);
     hy::tma_load_2d(base + kW3, &p.mapW3, bar(W_FULL), 0, 0);
-  }
-  {
-    // biases -> smem: b1 [64] | b2 [64] | b3 [128]
-    float* sb = reinterpret_cast<float*>(smem_raw + (base - hy::smem_u32(smem_raw)) + kBias);
-    for (int i = threadIdx.x; i < 256; i += kThreads)
-      sb[i] = i < 64 ? __ldg(p.b1 + i) : (i < 128 ? __ldg(p.b2 + i - 64) : __ldg(p.b3 + i - 128));
   }
   if (warp == kWarpLoad && lane == 0) {
     hy::tma_prefetch_desc(&p.mapX);
@@ -304,7 +295,10 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
     const int csel = warp >> 2;
     const int tid = q * 32 + lane; // TMEM lane == GEMM row
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const uint32_t sbias = base + kBias;
+    auto load_bias16 = [&](int off, float (&b)[16]) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) b[i] = p.bias[off + i];
+    };
 
     // E3: + bias + skip, in place in the staging tile; this warp: columns [csel*128/CS, +128/CS)
     auto epilogue3 = [&](int it) {
@@ -330,15 +324,12 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int j = 2 * u + g;
-          const uint32_t bias_addr = sbias + 512 + (c0 + j * 8) * 4;
-          const float4 ba = lds_f4(bias_addr), bb = lds_f4(bias_addr + 16);
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[u][g * 8 + i]);
-          hy::add2(v[0], v[1], ba.x, ba.y);
-          hy::add2(v[2], v[3], ba.z, ba.w);
-          hy::add2(v[4], v[5], bb.x, bb.y);
-          hy::add2(v[6], v[7], bb.z, bb.w);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            hy::add2(v[2 * i], v[2 * i + 1], p.bias[128 + c0 + j * 8 + 2 * i], p.bias[128 + c0 + j * 8 + 2 * i + 1]);
           hy::add2(v[0], v[1], hy::bf16_lo(sk[j].x), hy::bf16_hi(sk[j].x));
           hy::add2(v[2], v[3], hy::bf16_lo(sk[j].y), hy::bf16_hi(sk[j].y));
           hy::add2(v[4], v[5], hy::bf16_lo(sk[j].z), hy::bf16_hi(sk[j].z));
@@ -399,7 +390,9 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
 #pragma unroll
           for (int u = 0; u < U12; ++u) {
             const int c0 = csel * (64 / CS) + u * 16;
-            bias_relu_pack16(blk ? rb[u] : ra[u], sbias + c0 * 4, keep, qv);
+            float bb[16];
+            load_bias16(c0, bb);
+            bias_relu_pack16(blk ? rb[u] : ra[u], bb, keep, qv);
             if (live) {
               sts128(row + ((((c0 >> 3)) ^ sw) << 4), qv[0]);
               sts128(row + ((((c0 >> 3) + 1) ^ sw) << 4), qv[1]);
@@ -430,7 +423,9 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
 #pragma unroll
         for (int u = 0; u < U12; ++u) {
           const int c0 = csel * (64 / CS) + u * 16;
-          bias_relu_pack16(ra[u], sbias + 256 + c0 * 4, true, qv);
+          float bb[16];
+          load_bias16(64 + c0, bb);
+          bias_relu_pack16(ra[u], bb, true, qv);
           sts128(row + (((c0 >> 3) ^ sw) << 4), qv[0]);
           sts128(row + ((((c0 >> 3) + 1) ^ sw) << 4), qv[1]);
         }
@@ -502,7 +497,11 @@ int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c
   if ((rc = encode_w_map(&p.mapW1, c1->d_w, c1->ktot, c1->cout_pad, 64)) != HYRES_OK) return rc;
   if ((rc = encode_w_map(&p.mapW2, c2->d_w, c2->ktot, c2->cout_pad, 64)) != HYRES_OK) return rc;
   if ((rc = encode_w_map(&p.mapW3, c3->d_w, c3->ktot, c3->cout_pad, 128)) != HYRES_OK) return rc;
-  p.b1 = c1->d_bias; p.b2 = c2->d_bias; p.b3 = c3->d_bias;
+  if (c1->h_bias.size() < 64 || c2->h_bias.size() < 64 || c3->h_bias.size() < 128)
+    return hy_fail(HYRES_ERR_STATE, "ru_run: layer without a host bias copy");
+  std::copy(c1->h_bias.begin(), c1->h_bias.begin() + 64, p.bias);
+  std::copy(c2->h_bias.begin(), c2->h_bias.begin() + 64, p.bias + 64);
+  std::copy(c3->h_bias.begin(), c3->h_bias.begin() + 128, p.bias + 128);
   p.H = io->H; p.W = io->W;
   p.tiles_w = (io->W + kTW - 1) / kTW;
   p.tiles_per_img = p.tiles_w * ((io->H + kTH - 1) / kTH);
