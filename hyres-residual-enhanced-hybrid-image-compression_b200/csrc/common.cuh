@@ -349,6 +349,28 @@ __device__ __forceinline__ void umma_commit_mode(uint32_t bar, uint32_t leader) 
         : "memory");
   }
 }
+// tensor-memory stores (epilogue -> TMEM): 8 columns per call, lane = this thread's lane of its warp's quadrant
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand is read from tensor memory (bf16, two K elements per 32-bit column,
+// element 2j in the low half of column j, lane = row; 8 columns per K = 16 instruction) -- measured in
+// tools/experiments/umma_ts.cu.  Converged-warp form: `leader` is 1 in exactly one lane.
+__device__ __forceinline__ void umma_ts_issue(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t leader) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ uint32_t elect_leader() {
   uint32_t is_leader;
   asm volatile(

@@ -44,7 +44,7 @@ namespace {
 constexpr int kTH = 16, kTW = 8;        // output tile
 constexpr int kPW = 10;                 // patch width (positions)
 constexpr int kNP = 180;                // patch positions (18 x 10)
-constexpr uint32_t kColG1 = 0, kColG2 = 128, kColG3 = 256, kTmemCols = 512;
+constexpr uint32_t kColG1 = 0, kColG2 = 128, kColT2 = 192, kColG3 = 256, kTmemCols = 512;
 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr uint32_t kW1 = 0;             // [2 k-chunks][64 n][128 B]
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
         if (lane == 0) RU_STAMP(10);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          hy::umma_issue<2>(tmem_base + kColG3, t2_d + ((k * 32) >> 4), w3_d + ((k * 32) >> 4), idesc128, k ? 1u : 0u, leader);
+          hy::umma_ts_issue(tmem_base + kColG3, tmem_base + kColT2 + k * 8, w3_d + ((k * 32) >> 4), idesc128, k ? 1u : 0u, leader);
         hy::umma_commit_mode<2>(bar(G3_DONE), leader);
         if (lane == 0) RU_STAMP(11);
         if (has_next && !g1_ahead) {
@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
       hy::tc_fence_after();
       if (threadIdx.x == 0) RU_STAMP(3);
       {
-        const uint32_t row = base + kT2 + tid * 128;
-        const uint32_t sw = tid & 7;
+        // t2 goes to tensor memory (columns [192, 224): two channels per column) and G3 reads it from there as its A
+        // operand: 16 KB of shared-memory writes and 16 KB of MMA operand reads per tile leave the shared-memory port
         uint32_t ra[U12][16];
 #pragma unroll
         for (int u = 0; u < U12; ++u) hy::tmem_ld16(t_lane + kColG2 + csel * (64 / CS) + u * 16, ra[u]);
@@ -426,11 +426,11 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
           float bb[16];
           load_bias16(64 + c0, bb);
           bias_relu_pack16(ra[u], bb, true, qv);
-          sts128(row + (((c0 >> 3) ^ sw) << 4), qv[0]);
-          sts128(row + ((((c0 >> 3) + 1) ^ sw) << 4), qv[1]);
+          const uint32_t w8[8] = {qv[0].x, qv[0].y, qv[0].z, qv[0].w, qv[1].x, qv[1].y, qv[1].z, qv[1].w};
+          hy::tmem_st8(t_lane + kColT2 + (c0 >> 1), w8);
         }
       }
-      hy::fence_async_smem();
+      hy::tmem_st_wait();
       hy::tc_fence_before();
       hy::mbar_arrive(bar(T2_READY));
       if (threadIdx.x == 0) RU_STAMP(4);
