@@ -85,12 +85,14 @@ SIGNATURES = {
     "hyres_jpeg_scan_words": (_i64, [_i, _i]),
     "hyres_jpeg_header_bytes": (_i, []),
     "hyres_jpeg_forward": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hyres_jpeg_bpp": (_i, [_vp, _i, _i64, _vp, _vp]),
     "hyres_jpeg_assemble": (_i, [_vp, _i64, _i, _i, _i, _vp, _i64, C.POINTER(_i64)]),
     "hyres_nchw_f32_to_nhwc_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_nhwc_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_nhwc_bf16_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_reduce_sqdiff": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "hyres_reduce_log2": (_i, [_vp, _i64, _vp, _vp]),
+    "hyres_rd_loss_finalize": (_i, [_vp, _vp, _vp, _vp, C.c_double, C.c_double, _f, _vp, _vp]),
     "hyres_pmf_to_quantized_cdf": (_i, [_vp, _i, _i, _vp]),
     "hyres_rans_encode_bound": (_i64, [_i64]),
     "hyres_rans_encode": (_i, [_vp, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),

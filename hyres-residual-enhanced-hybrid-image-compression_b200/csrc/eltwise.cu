@@ -144,6 +144,21 @@ __device__ __forceinline__ void block_accumulate(double v, double* out) {
   }
 }
 
+// src/losses/rd_loss.py:23-44 from the three device sums (one thread; the float operations in the reference's order):
+// out = [y_bpp, z_bpp, residual_bpp, bpp, mse * 255^2, lambda * mse + bpp]
+__global__ void rd_loss_finalize_kernel(const double* __restrict__ sy, const double* __restrict__ sz,
+                                        const double* __restrict__ se, const float* __restrict__ jpeg_bpp,
+                                        double num_pixels, double num_elems, float lmbda, float* __restrict__ out) {
+  if (threadIdx.x != 0) return;
+  const float y = static_cast<float>(-sy[0] / num_pixels);
+  const float z = static_cast<float>(-sz[0] / num_pixels);
+  const float res = y + z;
+  const float bpp = res + (jpeg_bpp ? jpeg_bpp[0] : 0.f);
+  const float mse = static_cast<float>(se[0] / num_elems) * 65025.f;
+  out[0] = y; out[1] = z; out[2] = res; out[3] = bpp; out[4] = mse;
+  out[5] = lmbda * mse + bpp;
+}
+
 __global__ void sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n, double* out) {
   float acc = 0.f;
   double dacc = 0.0;
@@ -273,6 +288,18 @@ int hyres_reduce_sqdiff(const float* a, const float* b, int64_t n, double* out, 
   if (n == 0) return HYRES_OK;
   hy_count_launch();
   sqdiff_kernel<<<grid_for(n, kBlock * 8, 148 * 4), kBlock, 0, static_cast<cudaStream_t>(stream_v)>>>(a, b, n, out);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_rd_loss_finalize(const double* sum_log2_y, const double* sum_log2_z, const double* sum_sq_err,
+                           const float* jpeg_bpp, double num_pixels, double num_elems, float lmbda, float* out6,
+                           void* stream_v) {
+  if (!sum_log2_y || !sum_log2_z || !sum_sq_err || !out6 || num_pixels <= 0 || num_elems <= 0)
+    return hy_fail(HYRES_ERR_ARG, "rd_loss_finalize: bad argument");
+  hy_count_launch();
+  rd_loss_finalize_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_v)>>>(sum_log2_y, sum_log2_z, sum_sq_err, jpeg_bpp,
+                                                                            num_pixels, num_elems, lmbda, out6);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }

@@ -556,6 +556,14 @@ __global__ void __launch_bounds__(1024) jpeg_file_size_kernel(const uint32_t* __
   }
 }
 
+// bits per pixel of the batch = 8 * sum(file sizes) / pixels, as the fp32 the reference's Python float becomes
+__global__ void jpeg_bpp_kernel(const int64_t* __restrict__ sizes, int B, double pixels, float* __restrict__ bpp) {
+  if (threadIdx.x != 0) return;
+  int64_t tot = 0;
+  for (int i = 0; i < B; ++i) tot += sizes[i];
+  bpp[0] = static_cast<float>(static_cast<double>(tot) * 8.0 / pixels);
+}
+
 inline int64_t align256(int64_t v) { return (v + 255) & ~static_cast<int64_t>(255); }
 
 struct Workspace {
@@ -597,6 +605,14 @@ int64_t hyres_jpeg_scan_words(int H, int W) {
 }
 
 int hyres_jpeg_header_bytes(void) { return kHeaderBytes; }
+
+int hyres_jpeg_bpp(const int64_t* sizes, int B, int64_t pixels, float* bpp, void* stream_) {
+  if (!sizes || !bpp || B < 1 || pixels < 1) return hy_fail(HYRES_ERR_ARG, "jpeg_bpp: bad argument");
+  hy_count_launch();
+  jpeg_bpp_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>(sizes, B, static_cast<double>(pixels), bpp);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
 
 int hyres_jpeg_forward(const float* x, int B, int H, int W, int quality, void* workspace, float* decoded,
                        int64_t* sizes, uint32_t* scan_words, int64_t* scan_bits, void* stream_) {

@@ -89,9 +89,7 @@ class TurboJPEGCompression(nn.Module):
         """CUDA ``[B,3,H,W]`` -> (decoded fp32 ``[B,3,H,W]``, bpp as a 0-d fp32 CUDA tensor); no host sync."""
         from . import ops
         r = ops.jpeg_forward(self._rgb(x), self.quality)
-        N, _, H, W = x.shape
-        bpp = (r["sizes"].sum().double() * 8.0 / (N * H * W)).float()
-        return r["decoded"], bpp
+        return r["decoded"], r["bpp"]
 
     def compress_device(self, x):
         """CUDA ``[B,3,H,W]`` -> (list of ``io.BytesIO`` JPEG files, decoded fp32 ``[B,3,H,W]`` on the device):

@@ -390,17 +390,17 @@ class RateDistortionLoss(nn.Module):
         dev = output["x_hat"].device
         acc = torch.zeros(3, dtype=torch.float64, device=dev)
         if stats is not None:
-            acc[0:2] = stats
+            sum_y, sum_z = stats[0:1], stats[1:2]
         else:
-            ops.reduce_log2(output["likelihoods"]["y"].contiguous(), acc[0:1])
-            ops.reduce_log2(output["likelihoods"]["z"].contiguous(), acc[1:2])
+            sum_y, sum_z = acc[0:1], acc[1:2]
+            ops.reduce_log2(output["likelihoods"]["y"].contiguous(), sum_y)
+            ops.reduce_log2(output["likelihoods"]["z"].contiguous(), sum_z)
         ops.reduce_sqdiff(output["x_hat"].contiguous(), target.to(dev, torch.float32).contiguous(), acc[2:3])
-        out = {}
-        out["y_bpp_loss"] = (-acc[0] / num_pixels).float()
-        out["z_bpp_loss"] = (-acc[1] / num_pixels).float()
-        out["residual_bpp_loss"] = out["y_bpp_loss"] + out["z_bpp_loss"]
-        jpeg_bpp = output.get("jpeg_bpp_loss", torch.zeros((), device=dev))
-        out["bpp_loss"] = out["residual_bpp_loss"] + jpeg_bpp
-        out["mse_loss"] = (acc[2] / output["x_hat"].numel()).float() * 255 ** 2
-        out["loss"] = self.lmbda * out["mse_loss"] + out["bpp_loss"]
+        jpeg_bpp = output.get("jpeg_bpp_loss")
+        if jpeg_bpp is not None:
+            jpeg_bpp = jpeg_bpp.to(dev, torch.float32).reshape(())
+        # one launch for the scalar arithmetic of rd_loss.py:23-44 (the float operations in the reference's order)
+        r = ops.rd_loss_finalize(sum_y, sum_z, acc[2:3], jpeg_bpp, num_pixels, output["x_hat"].numel(), self.lmbda)
+        out = {"y_bpp_loss": r[0], "z_bpp_loss": r[1], "residual_bpp_loss": r[2], "bpp_loss": r[3], "mse_loss": r[4],
+               "loss": r[5]}
         return out

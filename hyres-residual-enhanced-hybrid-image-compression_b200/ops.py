@@ -497,6 +497,14 @@ def reduce_sqdiff(a, b, out):
     L.check(L.lib().hyres_reduce_sqdiff(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream()), "hyres_reduce_sqdiff")
 
 
+def rd_loss_finalize(sum_y, sum_z, sum_se, jpeg_bpp, num_pixels, num_elems, lmbda):
+    """-> fp32 [6] = y_bpp, z_bpp, residual_bpp, bpp, mse * 255^2, loss (src/losses/rd_loss.py:23-44), one launch."""
+    out = torch.empty(6, dtype=torch.float32, device=sum_y.device)
+    L.check(L.lib().hyres_rd_loss_finalize(_ptr(sum_y), _ptr(sum_z), _ptr(sum_se), _ptr(jpeg_bpp), float(num_pixels),
+                                           float(num_elems), float(lmbda), _ptr(out), _stream()), "hyres_rd_loss_finalize")
+    return out
+
+
 def reduce_log2(x, out):
     L.check(L.lib().hyres_reduce_log2(_ptr(x), x.numel(), _ptr(out), _stream()), "hyres_reduce_log2")
 
@@ -543,6 +551,10 @@ def jpeg_forward(x, quality, want_decoded=True, want_sizes=True, want_scan=False
                                        _ptr(ws["words"]) if need_scan else C.c_void_p(0), _ptr(nbits), _stream()),
             "hyres_jpeg_forward")
     out = {"decoded": dec, "sizes": sizes, "nbits": nbits}
+    if want_sizes:
+        bpp = torch.empty((), dtype=torch.float32, device=x.device)
+        L.check(L.lib().hyres_jpeg_bpp(_ptr(sizes), B, B * H * W, _ptr(bpp), _stream()), "hyres_jpeg_bpp")
+        out["bpp"] = bpp
     if want_scan:
         out["words"] = ws["words"].view(B, ws["wpi"])
     return out

@@ -271,6 +271,9 @@ int hyres_jpeg_header_bytes(void);
 int hyres_jpeg_forward(const float* x, int B, int H, int W, int quality, void* workspace,
                        float* decoded, int64_t* sizes, uint32_t* scan_words, int64_t* scan_bits,
                        void* stream);
+/* bpp[0] = 8 * sum(sizes[0..B)) / pixels as fp32 (device): `jpeg_bpp` of TurboJPEGCompression.forward
+ * (models/utils/turbo_jpeg_compression.py:66-71) without a host round trip. */
+int hyres_jpeg_bpp(const int64_t* sizes, int B, int64_t pixels, float* bpp, void* stream);
 /* Host: the complete JPEG file of one image (markers + stuffed scan + EOI) from its scan bits. */
 int hyres_jpeg_assemble(const uint32_t* scan_words_host, int64_t nbits, int H, int W, int quality,
                         uint8_t* out, int64_t cap, int64_t* len);
@@ -285,6 +288,12 @@ int hyres_nhwc_bf16_to_nchw_f32(const void* in, float* out, int B, int C, int H,
 /* sum((a-b)^2) and sum(log2(x)) accumulated into a device double. */
 int hyres_reduce_sqdiff(const float* a, const float* b, int64_t n, double* out, void* stream);
 int hyres_reduce_log2(const float* x, int64_t n, double* out, void* stream);
+/* RateDistortionLoss.forward (src/losses/rd_loss.py:23-44, alpha = 0) from the three device sums:
+ * out6 = [y_bpp, z_bpp, residual_bpp, bpp, mse * 255^2, lambda * mse + bpp] (fp32, device).
+ * jpeg_bpp: device fp32 scalar or NULL. */
+int hyres_rd_loss_finalize(const double* sum_log2_y, const double* sum_log2_z, const double* sum_sq_err,
+                           const float* jpeg_bpp, double num_pixels, double num_elems, float lmbda,
+                           float* out6, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* Entropy coder (host). Byte-identical to compressai's rANS64 interface.      */
