@@ -39,7 +39,7 @@ LMBDA = 0.008
 # anchor pass of the parameter head K = 384)
 MAC_PER_PX_CONV = 483_234  # codec forward 370 624 + MultiScaleRefine 112 610
 RU_MAC_PER_POS = 128 * 64 + 9 * 64 * 64 + 64 * 128  # one fused ResidualUnit, per position
-RU_DRAM_BYTES_PER_LAUNCH = 762_350_592  # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_full.md
+RU_DRAM_BYTES_PER_LAUNCH = 761_778_944  # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_full.md
 
 
 def load_peaks():
