@@ -119,12 +119,6 @@ __device__ __forceinline__ void mul2(float& a, float& b, float s) {
       : "+f"(a), "+f"(b)
       : "f"(s));
 }
-__device__ __forceinline__ float act_fn(float v, int act, float slope) {
-  if (act == HYRES_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == HYRES_ACT_PRELU) return v >= 0.f ? v : v * slope;
-  if (act == HYRES_ACT_CLAMP01) return fminf(fmaxf(v, 0.f), 1.f);
-  return v;
-}
 __device__ __forceinline__ void unpack16(const uint4& a, const uint4& b, float (&f)[16]) {
   const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll

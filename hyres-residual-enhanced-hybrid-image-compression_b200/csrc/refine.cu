@@ -82,6 +82,27 @@ __global__ void se_scale_down_kernel(const __nv_bfloat16* __restrict__ feat, con
   __shared__ float s_scale[64];
   __shared__ float s_hidden[16];
   const int b = blockIdx.y;
+  const int bw = W / 4, bh = H / 4;
+  const int64_t nblk = static_cast<int64_t>(bw) * bh * 8;
+  const int64_t img = static_cast<int64_t>(b) * H * W;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  // the 16 loads of this thread's (first) block are in flight while the block evaluates the SE gate: the two tiny
+  // matrix-vector products are ~130 dependent L2 accesses, which otherwise precede every block's first load
+  uint4 u[4][4];
+  auto load_block = [&](int64_t tt) {
+    const int g = static_cast<int>(tt & 7);
+    const int64_t blk = tt >> 3;
+    const int bj = static_cast<int>(blk % bw), bi = static_cast<int>(blk / bw);
+#pragma unroll
+    for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 4; ++dx) {
+        const int64_t pix = img + static_cast<int64_t>(bi * 4 + dy) * W + (bj * 4 + dx);
+        u[dy][dx] = __ldg(reinterpret_cast<const uint4*>(feat + pix * 64) + g);
+      }
+  };
+  if (t < nblk) load_block(t);
   if (threadIdx.x < Cr) {
     float a = 0.f;
     for (int c = 0; c < 64; ++c) a += fc1[threadIdx.x * 64 + c] * pooled[b * 64 + c];
@@ -94,11 +115,7 @@ __global__ void se_scale_down_kernel(const __nv_bfloat16* __restrict__ feat, con
     s_scale[threadIdx.x] = 1.f / (1.f + expf(-a));
   }
   __syncthreads();
-  const int bw = W / 4, bh = H / 4;
-  const int64_t nblk = static_cast<int64_t>(bw) * bh * 8;
-  const int64_t img = static_cast<int64_t>(b) * H * W;
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < nblk;
-       t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  for (; t < nblk; t += stride) {
     const int g = static_cast<int>(t & 7);
     const int64_t blk = t >> 3;
     const int bj = static_cast<int>(blk % bw), bi = static_cast<int>(blk / bw);
@@ -117,9 +134,8 @@ __global__ void se_scale_down_kernel(const __nv_bfloat16* __restrict__ feat, con
 #pragma unroll
       for (int dx = 0; dx < 4; ++dx) {
         const int64_t pix = img + static_cast<int64_t>(bi * 4 + dy) * W + (bj * 4 + dx);
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(feat + pix * 64) + g);
         float f[8];
-        unpack8(u, f);
+        unpack8(u[dy][dx], f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) f[k] = round_bf16(f[k] * sc[k]);
         reinterpret_cast<uint4*>(feat_s + pix * 64)[g] = pack8(f);
@@ -130,6 +146,7 @@ __global__ void se_scale_down_kernel(const __nv_bfloat16* __restrict__ feat, con
         }
       }
     }
+    if (t + stride < nblk) load_block(t + stride);  // next block of this thread, under the stores of this one
     const int Wh = W / 2, Wq = W / 4;
     const int64_t img_h = static_cast<int64_t>(b) * (H / 2) * Wh, img_q = static_cast<int64_t>(b) * (H / 4) * Wq;
 #pragma unroll
@@ -413,7 +430,9 @@ int hyres_refine_se_scale_down(const void* feat, const float* pooled, const floa
   if (C != 64 || Cr < 1 || Cr > 16) return hy_fail(HYRES_ERR_UNSUPPORTED, "se_scale_down: C must be 64, Cr <= 16");
   if ((H & 3) || (W & 3)) return hy_fail(HYRES_ERR_ARG, "se_scale_down: H and W must be multiples of 4");
   const int64_t nblk = static_cast<int64_t>(H / 4) * (W / 4) * 8;
-  int gx = static_cast<int>(std::min<int64_t>((nblk + kThreads - 1) / kThreads, 148 * 8));
+  // one resident wave (148 SMs x 8 blocks of 256 threads) over all images: the SE gate is evaluated once per block
+  const int per_img = std::max(1, (148 * 8) / B);
+  int gx = static_cast<int>(std::min<int64_t>((nblk + kThreads - 1) / kThreads, per_img));
   hy_count_launch();
   se_scale_down_kernel<<<dim3(gx, B), kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
       static_cast<const __nv_bfloat16*>(feat), pooled, fc1, fc2, Cr, static_cast<__nv_bfloat16*>(feat_s),

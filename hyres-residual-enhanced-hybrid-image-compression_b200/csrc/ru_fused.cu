@@ -55,7 +55,7 @@ constexpr uint32_t kXChunk = 23552;     // 180 rows x 128 B, padded to a multipl
 constexpr uint32_t kXBytes = kNP * 128; // bytes one TMA chunk load delivers
 constexpr uint32_t kX = kWBytes;                 // x halo patch: 2 chunks (one buffer: it only feeds G1)
 constexpr uint32_t kT1 = kX + 2 * kXChunk;       // t1 patch [180][64]
-constexpr uint32_t kT2 = kT1 + kXChunk;          // t2 [128][64]
+constexpr uint32_t kT2 = kT1 + kXChunk;          // (unused since t2 lives in tensor memory; kept so the layout below is unchanged)
 constexpr uint32_t kStg = kT2 + 16384;           // skip tile in, result out: 2 chunks [128][64]
 constexpr uint32_t kBars = kStg + 32768;
 constexpr uint32_t kBias = kBars + 256;
@@ -80,11 +80,6 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
   return v;
 }
 
