@@ -54,7 +54,7 @@ def load_peaks():
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -71,7 +71,21 @@ class ClockSampler:
         except OSError:
             self.p = None
 
-    def stop(self):
+    def wait_ready(self, timeout=2.0):
+        """Block (GPU idle) until the first sample has been written, so the timed region is covered from its start."""
+        t = time.perf_counter()
+        while self.p is not None and time.perf_counter() - t < timeout:
+            try:
+                if os.path.getsize(self.f.name) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.01)
+
+    def stop(self, t0=None, t1=None):
+        """Median SM clock / throttle reasons of the samples whose time stamp lies in [t0, t1] (datetime; the timed
+        region); if fewer than three fall inside, of all samples
+        -- `window` says which."""
         if self.p is None:
             return None
         self.p.terminate()
@@ -81,25 +95,25 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        import datetime
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.f.read().splitlines():
             c = [t.strip() for t in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(c[1]), float(c[2]), [n for n, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.f.name)
-        if not sm:
+        if not rows:
             return None
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
+        use, window = (inside, "timed region") if len(inside) >= 3 else (rows, "timed region + the idle wait before it")
+        return {"sm_mhz": statistics.median(r[1] for r in use), "sm_max_mhz": max(r[2] for r in use),
+                "reasons": sorted({n for r in use for n in r[3]}), "samples": len(use), "window": window}
 
 
 def oracle_step_factory(sample_images, threads):
@@ -150,7 +164,8 @@ def workload_config(n):
             "batch_per_gpu": BATCH, "height": H, "width": W, "global_batch": BATCH * n, "lambda": LMBDA,
             "sharding": "by image, no data-path collective; 4-double statistics all-reduce",
             "l2": "inputs + activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
-            "weights": "random init, seed 1926"}
+            "weights": "random init, seed 1926",
+            "launch": "timed steps replayed from a CUDA graph of one step (bench.py --no-graph: eager launches)"}
 
 
 def codec_cfg3(net, dev, reps=3):
@@ -185,10 +200,11 @@ def codec_cfg3(net, dev, reps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -233,19 +249,44 @@ def main():
     with torch.no_grad():
         for _ in range(args.warmup):
             step_resident()
-        barrier()
+        # The timed steps are replayed from a CUDA graph of one step (the same launches on the same buffers; under
+        # capture the two AttentionBlock branches at 1/8 resolution also overlap on two streams).  --no-graph, or a
+        # failed capture, times eager launches instead.
+        graph, lo = None, None
+        l0 = lib.hyres_launch_count()
+        if not args.no_graph:
+            try:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    lo = step_resident()
+                for _ in range(2):
+                    graph.replay()
+            except Exception as exc:  # noqa: BLE001
+                print(f"bench: CUDA graph capture failed ({type(exc).__name__}: {exc}); timing eager launches", file=sys.stderr)
+                graph = None
+        if graph is None:
+            l0 = lib.hyres_launch_count()
+            lo = step_resident()
+        launches = lib.hyres_launch_count() - l0  # kernels of ONE step (counted at capture / at the eager call)
+        import datetime
         sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
         sampler.start()
-        l0 = lib.hyres_launch_count()
+        sampler.wait_ready()  # nvidia-smi needs ~0.1 s to deliver its first sample
+        barrier()
+        t_start = datetime.datetime.now()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            lo = step_resident()
+            if graph is not None:
+                graph.replay()
+            else:
+                lo = step_resident()
         e1.record()
         barrier()
+        t_end = datetime.datetime.now()
         ms_local = e0.elapsed_time(e1) / args.steps
-        launches = (lib.hyres_launch_count() - l0) // args.steps
-        clocks = sampler.stop()
+        clocks = sampler.stop(t_start, t_end)
         ms = D.max_over_ranks(ms_local, dev)
         loss_val = float(lo["loss"])
 

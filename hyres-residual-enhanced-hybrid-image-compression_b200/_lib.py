@@ -32,6 +32,7 @@ class ConvIO(C.Structure):
         ("f32_sb", C.c_int64), ("f32_sh", C.c_int64), ("f32_sw", C.c_int64), ("f32_sc", C.c_int64),
         ("mt_hint", C.c_int), ("ld_x0", C.c_int), ("x0_square", C.c_int),
         ("out_pad", C.c_int), ("up_t2", C.c_void_p), ("up_t3", C.c_void_p),
+        ("cta_limit", C.c_int),
     ]
 
 

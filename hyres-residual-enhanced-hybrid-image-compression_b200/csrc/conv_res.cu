@@ -70,6 +70,7 @@ struct alignas(64) ResParams {
   int32_t pf_extra;  // L2 prefetch distance beyond the ring, in tiles; < 0: no prefetch
   int32_t up, u_bytes, t2_off, t3_off;  // up-add mode (see conv_res_try_run)
   int32_t decoupled, stg_base_off, stg_per_grp;  // result staging outside the TMA ring (1 or 2 buffers per epilogue group)
+  int32_t cta_limit;  // > 0: at most this many CTAs
   long long* trace;  // optional: clock64 stamps of CTA 0 (tools/experiments/res_trace.py), 16 slots per tile
   const float* bias;
   const float* pixscale;
@@ -660,7 +661,7 @@ const void* up_table() {
 
 // Launch with the epilogue variant of p.epi / p.act.
 int res_dispatch(const ResParams& p, int smem, cudaStream_t stream) {
-  const int grid = std::min(p.ntiles, num_sms());
+  const int grid = std::min(p.ntiles, p.cta_limit > 0 ? std::min(p.cta_limit, num_sms()) : num_sms());
   const int threads = p.a_square ? kThreadsSq : kThreads;
   hy_count_launch();
   // the combinations the codec uses are compiled straight-line; anything else runs the generic instance
@@ -816,6 +817,7 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   p.cout = c->cout;
   p.epi = io->epi; p.act = io->act; p.slope = io->slope;
   p.bias = c->d_bias;
+  p.cta_limit = io->cta_limit;
   p.pixscale = io->pixscale;
   p.out_f32 = io->out_f32;
   p.f32_sb = io->f32_sb; p.f32_sh = io->f32_sh; p.f32_sw = io->f32_sw; p.f32_sc = io->f32_sc;

@@ -917,7 +917,7 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
     HY_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     smem_set = true;
   }
-  const int grid = std::min(p.nitems, num_sms());
+  const int grid = std::min(p.nitems, io->cta_limit > 0 ? std::min(io->cta_limit, num_sms()) : num_sms());
   hy_count_launch();
   HY_CUDA(hy_launch_pdl(conv_tc_kernel, grid, kThreads, smem, stream, p));
   return HYRES_OK;

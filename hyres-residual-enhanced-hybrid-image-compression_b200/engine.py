@@ -16,6 +16,8 @@ element-wise work folded into conv epilogues:
 
 Activations are NHWC bf16; y, z, the entropy parameters and the final images stay fp32.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -60,6 +62,17 @@ def _gdn(m):
     return _Bound(get, kind=HYRES_CONV)
 
 
+_NO_BRANCH_STREAMS = bool(os.environ.get("HYRES_NO_BRANCH_STREAMS"))
+_side = {}
+
+
+def _side_stream(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _side:
+        _side[key] = torch.cuda.Stream(device=dev)
+    return _side[key]
+
+
 class _RU:
     """1x1 -> ReLU -> 3x3 -> ReLU -> 1x1 (+skip [+ReLU]): ResidualUnit and ResidualBottleneckBlock."""
 
@@ -71,12 +84,12 @@ class _RU:
     def layers(self):
         return [self.c1, self.c2, self.c3]
 
-    def __call__(self, x, out_sq=False):
+    def __call__(self, x, out_sq=False, cta_limit=0):
         if self.fused and not out_sq:
             return ops.ru_fused(x, self.c1.layer, self.c2.layer, self.c3.layer, self.final_act == ACT_RELU)
-        a, _, _ = self.c1(x, act=ACT_RELU)
-        b, _, _ = self.c2(a, act=ACT_RELU)
-        o, sq, _ = self.c3(b, epi=EPI_ADD, aux0=x, act=self.final_act, out_sq=out_sq)
+        a, _, _ = self.c1(x, act=ACT_RELU, cta_limit=cta_limit)
+        b, _, _ = self.c2(a, act=ACT_RELU, cta_limit=cta_limit)
+        o, sq, _ = self.c3(b, epi=EPI_ADD, aux0=x, act=self.final_act, out_sq=out_sq, cta_limit=cta_limit)
         return (o, sq) if out_sq else o
 
 
@@ -101,12 +114,46 @@ class _Attn:
         return out + [self.gate]
 
     def __call__(self, x, out_f32=None):
+        # under CUDA-graph capture only: replayed, the two branches overlap (1-2 % of a step); launched eagerly the
+        # host issues the 18 small kernels more slowly than they run and the split grids just halve each layer's SMs
+        if not self.a[0].fused and not _NO_BRANCH_STREAMS and torch.cuda.is_current_stream_capturing():
+            return self._two_streams(x, out_f32)
         a = x
         for r in self.a:
             a = r(a)
         b = x
         for r in self.b:
             b = r(b)
+        o16, _, o32 = self.gate(b, epi=EPI_GATE, aux0=x, aux1=a, out_f32=out_f32)
+        return (o16, o32) if out_f32 else o16
+
+    def _two_streams(self, x, out_f32):
+        """The C = 192 blocks (1/8 resolution: 768 tiles a layer, 5 per SM, latency-bound launches of 15-40 us): the
+        two independent branches run side by side on two streams, each layer on half of the SMs, so one branch's
+        prologues / tails / tile-count rounding hide under the other's tiles.  Fork and join are events, so the step
+        stays CUDA-graph capturable."""
+        cur = torch.cuda.current_stream(x.device)
+        side = _side_stream(x.device)
+        half = max(1, ops.sm_count() // 2)
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        side.wait_event(fork)
+        a = b = x
+        # launches alternate between the streams layer by layer, so both always have queued work
+        for ra, rb in zip(self.a, self.b):
+            with torch.cuda.stream(side):
+                ta, _, _ = ra.c1(a, act=ACT_RELU, cta_limit=half)
+            tb, _, _ = rb.c1(b, act=ACT_RELU, cta_limit=half)
+            with torch.cuda.stream(side):
+                ua, _, _ = ra.c2(ta, act=ACT_RELU, cta_limit=half)
+            ub, _, _ = rb.c2(tb, act=ACT_RELU, cta_limit=half)
+            with torch.cuda.stream(side):
+                a, _, _ = ra.c3(ua, epi=EPI_ADD, aux0=a, act=ra.final_act, cta_limit=half)
+            b, _, _ = rb.c3(ub, epi=EPI_ADD, aux0=b, act=rb.final_act, cta_limit=half)
+        a.record_stream(cur)  # allocated on the side stream, consumed by the gate on the main stream
+        join = torch.cuda.Event()
+        join.record(side)
+        cur.wait_event(join)
         o16, _, o32 = self.gate(b, epi=EPI_GATE, aux0=x, aux1=a, out_f32=out_f32)
         return (o16, o32) if out_f32 else o16
 

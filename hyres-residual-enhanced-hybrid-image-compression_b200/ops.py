@@ -13,6 +13,10 @@ from ._lib import (ACT_CLAMP01, ACT_NONE, ACT_PRELU, ACT_RELU, EPI_ADD, EPI_GATE
                    EPI_IGDN, EPI_LINEAR, EPI_PIXSCALE, HYRES_CONV, HYRES_DECONV_K5S2)
 
 
+def sm_count():
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -96,7 +100,7 @@ class ConvLayer:
 
     def __call__(self, x0, x1=None, epi=EPI_LINEAR, act=ACT_NONE, slope=0.0, aux0=None, aux1=None,
                  pixscale=None, out_bf16=True, out_sq=False, out_f32=None, mt=0, x0_square=False, out_pad=0,
-                 up_t2=None, up_t3=None):
+                 up_t2=None, up_t3=None, cta_limit=0):
         """Run the layer.
 
         out_bf16 / out_sq: True (allocate), False, or a preallocated NHWC tensor (its last
@@ -177,6 +181,7 @@ class ConvLayer:
             io.out_f32 = view.data_ptr()
             io.f32_sb, io.f32_sh, io.f32_sw, io.f32_sc = view.stride()
         io.mt_hint = mt
+        io.cta_limit = int(cta_limit)
         io.x0_square = 1 if x0_square else 0
         keep += [o16, osq, o32]
         if ConvLayer._prof is not None:

@@ -20,6 +20,10 @@ class _Slot:
         self.result_host = torch.zeros(3, dtype=torch.float64).pin_memory()
         self.stats = torch.zeros(2, dtype=torch.float64, device=dev)
         self.used = False
+        self.graph = None       # CUDA graph of forward + loss on this slot's static buffers (device JPEG batches)
+        self.graph_shape = None
+        self.graph_key = None
+        self.eager_runs = 0
 
 
 class HostPipeline:
@@ -28,8 +32,13 @@ class HostPipeline:
     memory.  Yields, in order, one dict per batch with the host floats ``loss``, ``bpp_loss``, ``mse_loss``
     (``src/losses/rd_loss.py:18-44``)."""
 
-    def __init__(self, model, criterion, depth=2):
+    def __init__(self, model, criterion, depth=2, use_graph=True):
+        """``use_graph``: after one eager pass per slot, forward + loss of a slot are replayed from a CUDA graph
+        captured on the slot's static device buffers (same kernels, same results; the AttentionBlock branches at
+        1/8 resolution additionally overlap on two captured streams).  Falls back to eager launches if the capture
+        fails or when a batch carries an injected JPEG result."""
         self.model, self.criterion = model, criterion
+        self.use_graph = use_graph
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
             raise RuntimeError("HostPipeline needs the model on a CUDA sm_100 device (no CPU fallback)")
@@ -48,6 +57,7 @@ class HostPipeline:
     def _stage(self, slot, x_host, jd_host):
         if slot.x is None or slot.x.shape != x_host.shape:
             slot.x = torch.empty(x_host.shape, dtype=torch.float32, device=self.dev)
+            slot.graph = None  # captured on the old buffer
         if jd_host is not None and (slot.jd is None or slot.jd.shape != jd_host.shape):
             slot.jd = torch.empty(jd_host.shape, dtype=torch.float32, device=self.dev)
         if slot.used:
@@ -59,19 +69,46 @@ class HostPipeline:
             slot.ready.record(self.copy_stream)
         self.h2d_bytes += x_host.numel() * 4 + (jd_host.numel() * 4 if jd_host is not None else 0)
 
-    def _launch(self, slot, jd_host, jpeg_bpp):
-        cur = torch.cuda.current_stream(self.dev)
-        cur.wait_event(slot.ready)
+    def _body(self, slot, jpeg):
         slot.stats.zero_()
-        jpeg = None if jd_host is None else (slot.jd, jpeg_bpp)
         out = self.model(slot.x, jpeg=jpeg, stats=slot.stats)
         lo = self.criterion(out, slot.x, stats=slot.stats)
         slot.result_dev.copy_(torch.stack([lo["loss"].double(), lo["bpp_loss"].double(), lo["mse_loss"].double()]))
+
+    def _launch(self, slot, jd_host, jpeg_bpp):
+        cur = torch.cuda.current_stream(self.dev)
+        cur.wait_event(slot.ready)
+        graphable = self.use_graph and jd_host is None and not self.model.training
+        if graphable and slot.graph is not None and slot.graph_key != self._weights_key():
+            slot.graph = None  # parameters changed since the capture: the packed weights must be refreshed eagerly
+        if graphable and slot.graph is not None and slot.graph_shape == tuple(slot.x.shape):
+            slot.graph.replay()
+        else:
+            self._body(slot, None if jd_host is None else (slot.jd, jpeg_bpp))
+            slot.eager_runs += 1
+            if graphable and slot.graph is None and slot.eager_runs >= 1:
+                self._capture(slot)
         slot.free.record(cur)
         slot.result_host.copy_(slot.result_dev, non_blocking=True)
         slot.done.record(cur)
         slot.used = True
         self.d2h_bytes += 24
+
+    def _weights_key(self):
+        return sum(p._version for p in self.model.parameters())
+
+    def _capture(self, slot):
+        """Capture forward + loss on the slot's buffers; the eager pass just launched has produced this batch's
+        result already, the graph serves the following batches."""
+        try:
+            g = torch.cuda.CUDAGraph()
+            keep = slot.result_dev.clone()
+            with torch.cuda.graph(g):
+                self._body(slot, None)
+            slot.result_dev.copy_(keep)  # capture does not execute; keep the eager result for this batch
+            slot.graph, slot.graph_shape, slot.graph_key = g, tuple(slot.x.shape), self._weights_key()
+        except Exception:  # noqa: BLE001 -- capture is an optimisation; eager launches stay correct
+            slot.graph, self.use_graph = None, False
 
     @staticmethod
     def _collect(slot):

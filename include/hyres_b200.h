@@ -128,6 +128,8 @@ typedef struct {
    * The interpolation runs on the tensor cores (two small GEMMs per tile). NULL = off. */
   const void* up_t2;
   const void* up_t3;
+  int cta_limit; /* > 0: launch at most this many CTAs (the persistent kernels use one per SM); lets two
+                    independent layers -- the branches of an AttentionBlock -- share the GPU on two streams */
 } hyres_conv_io;
 
 int hyres_conv_out_size(const hyres_conv* c, int H, int W, int* OH, int* OW);
