@@ -259,6 +259,41 @@ def test_host_pipeline_matches_direct_calls(nets, oracle):
     assert list(pipe.run(iter([]))) == []
 
 
+def test_host_pipeline_graph_replay_equals_eager_launches(nets, oracle):
+    """Batches without an injected JPEG result run the device JPEG stage; after one eager pass per slot the pipeline
+    replays a CUDA graph of forward + loss.  Results must equal the eager pipeline's to the last bit, the graphs must
+    be dropped when a parameter changes, and a new batch shape must fall back to eager launches."""
+    import hyres_b200
+    _, pnet = nets
+    crit = hyres_b200.RateDistortionLoss(lmbda=0.008)
+    batches = [oracle.synthetic_image(2, 64, 96, seed=60 + k).pin_memory() for k in range(7)]
+    eager = list(hyres_b200.HostPipeline(pnet, crit, use_graph=False).run(iter(batches)))
+    pipe = hyres_b200.HostPipeline(pnet, crit)
+    got = list(pipe.run(iter(batches)))
+    assert got == eager
+    assert all(s.graph is not None for s in pipe.slots), "no CUDA graph was captured"
+    # direct calls agree too (device JPEG stage inside forward)
+    with torch.no_grad():
+        stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+        out = pnet(batches[3].cuda(), stats=stats)
+        lo = crit(out, batches[3].cuda(), stats=stats)
+    assert float(lo["loss"]) == got[3]["loss"]
+    # a parameter update invalidates the captured graphs (the packed weights are refreshed on the eager path)
+    p = pnet.refine.fusion[2].bias
+    with torch.no_grad():
+        p.add_(0.25)
+    try:
+        changed = list(pipe.run(iter(batches[:3])))
+        ref = list(hyres_b200.HostPipeline(pnet, crit, use_graph=False).run(iter(batches[:3])))
+        assert changed == ref and changed[0]["loss"] != got[0]["loss"]
+    finally:
+        with torch.no_grad():
+            p.sub_(0.25)
+    # another shape: slots are re-staged and run eagerly first
+    other = [oracle.synthetic_image(1, 96, 64, seed=70 + k).pin_memory() for k in range(3)]
+    assert list(pipe.run(iter(other))) == list(hyres_b200.HostPipeline(pnet, crit, use_graph=False).run(iter(other)))
+
+
 def test_full_size_properties_cfg4_refine(nets, oracle):
     """BASELINE.json configs[3] shape (MultiScaleRefine on frozen-codec output, batch 32 of 512x512): the refine
     engine alone, fed x0 = jpeg + r_hat.  Size-independent properties: x0 is the exact fp32 sum; images are
