@@ -32,6 +32,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+OUT = sys.stdout  # where the JSON line goes (main() re-points it at the real stdout before fd 1 is redirected)
 
 H, W, BATCH = 512, 768, 16
 LMBDA = 0.008
@@ -148,14 +149,14 @@ def run_reference(args, rank):
     dt = (time.perf_counter() - t0) / args.steps
     v = px / dt / 1e6
     sample = f"{sample_images} synthetic {W}x{H} image per step (of the {BATCH}-image batch), full forward (CPU JPEG stage included) + RD loss, fp32"
-    print(json.dumps({
+    print(file=OUT, flush=True, *[json.dumps({
         "impl": "reference", "metric": "hyres_forward_mpixel_per_s", "value": v, "unit": "Mpixel/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })])
 
 
 def workload_config(n):
@@ -209,6 +210,12 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its version banner there
+    # when the first communicator is created) is sent to stderr
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -373,7 +380,7 @@ def main():
         line["cpu_baseline"] = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
                                 "sample": f"1 synthetic {W}x{H} image (1/16 of the batch), full forward (CPU JPEG stage "
                                           f"included) + RD loss, fp32 oracle, mean of {n} after 1 warm-up"}
-    print(json.dumps(line))
+    print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
 
