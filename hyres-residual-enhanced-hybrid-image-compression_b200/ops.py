@@ -517,32 +517,23 @@ def reduce_log2(x, out):
 # ---------------------------------------------------------------------------------------------
 # JPEG stage on the device (models/utils/turbo_jpeg_compression.py:17-40,62-77)
 # ---------------------------------------------------------------------------------------------
-_jpeg_ws = {}
-
-
 def _jpeg_buffers(dev, B, H, W, want_scan):
-    key = (dev.index, B, H, W)
-    ws = _jpeg_ws.get(key)
-    if ws is None:
-        n = L.lib().hyres_jpeg_workspace_bytes(B, H, W)
-        if n <= 0:
-            raise ValueError(f"jpeg_forward: unsupported size {H}x{W} (H must be a multiple of 8, W of 16)")
-        if len(_jpeg_ws) > 8:
-            _jpeg_ws.clear()
-        ws = {"ws": torch.empty(n, dtype=torch.uint8, device=dev)}
-        _jpeg_ws[key] = ws
-    if want_scan and "words" not in ws:
-        wpi = L.lib().hyres_jpeg_scan_words(H, W)
-        ws["wpi"] = wpi
-        ws["words"] = torch.empty(B * wpi, dtype=torch.int32, device=dev)
+    """Scratch of one call, from torch's caching allocator (under CUDA-graph capture: from the graph's pool, so a
+    replayed graph never sees memory that a later call reuses)."""
+    n = L.lib().hyres_jpeg_workspace_bytes(B, H, W)
+    if n <= 0:
+        raise ValueError(f"jpeg_forward: unsupported size {H}x{W} (H must be a multiple of 8, W of 16)")
+    ws = {"ws": torch.empty(n, dtype=torch.uint8, device=dev)}
+    if want_scan:
+        ws["wpi"] = L.lib().hyres_jpeg_scan_words(H, W)
+        ws["words"] = torch.empty(B * ws["wpi"], dtype=torch.int32, device=dev)
     return ws
 
 
 def jpeg_forward(x, quality, want_decoded=True, want_sizes=True, want_scan=False):
     """x fp32 NCHW [B,3,H,W] in [0,1] on the device -> dict(decoded fp32 NCHW, sizes int64 [B] (file bytes),
     words int32 [B, words_per_image] + nbits int64 [B] (the entropy-coded scans, big-endian bit strings)).
-    Bit-exact with libjpeg-turbo's 4:2:2 baseline round trip (tests/test_gpu_jpeg.py).  The scan buffer is a cached
-    scratch tensor: consume ``words`` before the next call with the same shape."""
+    Bit-exact with libjpeg-turbo's 4:2:2 baseline round trip (tests/test_gpu_jpeg.py)."""
     _f32c(x, "x")
     B, C3, H, W = x.shape
     if C3 != 3:
