@@ -280,6 +280,7 @@ def test_host_pipeline_graph_replay_equals_eager_launches(nets, oracle):
     assert float(lo["loss"]) == got[3]["loss"]
     # a parameter update invalidates the captured graphs (the packed weights are refreshed on the eager path)
     p = pnet.refine.fusion[2].bias
+    saved = p.detach().clone()
     with torch.no_grad():
         p.add_(0.25)
     try:
@@ -288,7 +289,7 @@ def test_host_pipeline_graph_replay_equals_eager_launches(nets, oracle):
         assert changed == ref and changed[0]["loss"] != got[0]["loss"]
     finally:
         with torch.no_grad():
-            p.sub_(0.25)
+            p.copy_(saved)  # bit-exact restore for the tests that follow
     # another shape: slots are re-staged and run eagerly first
     other = [oracle.synthetic_image(1, 96, 64, seed=70 + k).pin_memory() for k in range(3)]
     assert list(pipe.run(iter(other))) == list(hyres_b200.HostPipeline(pnet, crit, use_graph=False).run(iter(other)))
