@@ -752,8 +752,6 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   p.store_bf16 = io->out_bf16 ? 1 : 0;
   p.a_square = io->x0_square ? 1 : 0;
   {
-    static const int pf = [] { const char* e = getenv("HYRES_RES_PF"); return e ? atoi(e) : 0; }();
-    p.pf_extra = pf;
     // HYRES_RES_TRACE=<device pointer, hex>: 64 x 16 clock64 stamps of CTA 0 (tools/experiments/res_trace.py)
     const char* e = getenv("HYRES_RES_TRACE");
     p.trace = e ? reinterpret_cast<long long*>(strtoull(e, nullptr, 16)) : nullptr;
@@ -798,6 +796,13 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   if (NA < 2) return HYRES_OK;
   NA = std::min(NA, kMaxStages);
   p.NA = NA;
+  {
+    // L2 prefetch of the tiles beyond the ring pays only when the ring is shallow (gate: two stages, GDN: three); with a deep
+    // ring the prefetch operations queue in front of the loads the MMAs are waiting for (measured: 1x1 64->64 at
+    // 16x512x768 0.296 -> 0.259 ms, channel statistics 0.321 -> 0.242 ms without it).  HYRES_RES_PF overrides.
+    static const char* e = getenv("HYRES_RES_PF");
+    p.pf_extra = e ? atoi(e) : (NA <= 3 ? 0 : -1);
+  }
   p.stg_base_off = NA * stage;
   p.w_bytes = static_cast<int>(w_bytes);
   p.nslots = nslots;
@@ -879,8 +884,10 @@ extern "C" int hyres_refine_stats3_tc(const void* f1, const void* s2_padded, con
   p.epi = HYRES_EPI_STATS; p.act = HYRES_ACT_NONE;
   p.out_f32 = stats;
   {
-    static const int pf = [] { const char* e = getenv("HYRES_RES_PF"); return e ? atoi(e) : 0; }();
-    p.pf_extra = pf;
+    static const char* e = getenv("HYRES_RES_PF");
+    p.pf_extra = e ? atoi(e) : -1;  // deep ring: no L2 prefetch (see conv_res_try_run)
+    const char* tr = getenv("HYRES_RES_TRACE");
+    p.trace = tr ? reinterpret_cast<long long*>(strtoull(tr, nullptr, 16)) : nullptr;
   }
   int rc = encode_map4(&p.mapA, f1, 64, 64, B, H, W, kTW, kTH);
   if (rc != HYRES_OK) return rc;
