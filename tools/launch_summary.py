@@ -22,7 +22,7 @@ for k, t in step:
     a[0] += 1
     a[1] += t
 tot = sum(t for _, t in step)
-out = ["# r01: ncu launch list of one bench step (`bench.py --steps 1 --warmup 3 --no-cpu-baseline`, workload configs[1])", "",
+out = ["# r01: ncu launch list of one bench step (`bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph`, workload configs[1])", "",
        "source: `profiles/r01_launches.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none`), one complete step of the run",
        "(from one `jpeg_color_fwd_kernel` launch to the next).  Per-launch times under ncu are serialised and cold-cache: compare the SHARES with",
        "`bench.py`'s live CUDA-event numbers, not the absolutes.  `conv_res_kernel<EPI, ACT>`: EPI 0 linear, 1 add, 2 gate, 3 GDN, 4 IGDN,",
