@@ -89,6 +89,11 @@ def make(case):
         out = torch.empty_like(x)
         return (lambda: ops.ru_fused(x, c1, c2, c3, True, out=out),
                 2.0 * B * 256 * 384 * (128 * 64 + 576 * 64 + 64 * 128), 2 * x.numel() * 2)
+    if case == "c3x3_96":
+        L = ops.ConvLayer(w(96, 96, 3), bias(96), pad=1)
+        x = rnd(B, 64, 96, 96)
+        out = torch.empty_like(x)
+        return lambda: L(x, act=ACT_RELU, out_bf16=out, mt=MT), 2.0 * B * 64 * 96 * 96 * 864, 2 * x.numel() * 2
     if case == "ru192":
         c1 = ops.ConvLayer(w(96, 192, 1), bias(96))
         c2 = ops.ConvLayer(w(96, 96, 3), bias(96), pad=1)
