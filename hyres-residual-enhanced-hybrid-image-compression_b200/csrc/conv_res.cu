@@ -793,7 +793,11 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   const int stg_bytes = p.decoupled ? 2 * p.stg_per_grp * p.nchunk_out * 16384 : 0;
   const int fixed = fixed0 + stg_bytes;
   int NA = (kSmemLimit - fixed) / stage;
-  if (NA < 2) return HYRES_OK;
+  // a single stage (no load / compute overlap) is still accepted for the gate at C = 192: its three operand tiles
+  // (144 KB) leave room for one stage only, and the streaming kernel's per-thread global loads of the two epilogue
+  // operands are far slower (measured 115 us against ~35 us for 16x64x96x192)
+  static const bool allow1 = getenv("HYRES_RES_NO_NA1") == nullptr;
+  if (NA < 2 && !(NA == 1 && need1 && allow1)) return HYRES_OK;
   NA = std::min(NA, kMaxStages);
   p.NA = NA;
   {

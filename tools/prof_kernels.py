@@ -37,6 +37,11 @@ def make(case):
         x, a0, a1 = rnd(B, 256, 384, 128), rnd(B, 256, 384, 128), rnd(B, 256, 384, 128)
         out = torch.empty_like(x)
         return lambda: L(x, epi=EPI_GATE, aux0=a0, aux1=a1, out_bf16=out), 2.0 * B * 256 * 384 * 128 * 128, 4 * x.numel() * 2
+    if case == "gate192":
+        L = ops.ConvLayer(w(192, 192, 1), bias(192))
+        x, a0, a1 = rnd(B, 64, 96, 192), rnd(B, 64, 96, 192), rnd(B, 64, 96, 192)
+        out = torch.empty_like(x)
+        return lambda: L(x, epi=EPI_GATE, aux0=a0, aux1=a1, out_bf16=out), 2.0 * B * 64 * 96 * 192 * 192, 4 * x.numel() * 2
     if case == "gdn":
         L = ops.ConvLayer(w(128, 128, 1).abs(), bias(128).abs() + 0.5)
         x = rnd(B, 256, 384, 128)
