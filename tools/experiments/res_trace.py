@@ -14,10 +14,12 @@ for case in (sys.argv[1] if len(sys.argv) > 1 else "fus0lin").split(","):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    t = buf.cpu().view(64, 16)
+    t = buf.cpu().view(64, 16).clone()
+    buf.zero_()
     names = {0: "ld", 1: "m:A", 2: "m:accfree", 3: "m:iss", 4: "e:top", 5: "e:acc", 6: "e:chunks", 8: "s:rel"}
     print("==", case)
-    for it in range(20, 30):
+    have = [i for i in range(63) if int(t[i, 3]) and int(t[i + 1, 3])]
+    for it in (have[20:30] if len(have) > 30 else have[:10]):
         base = int(t[it, 3])
         ev = sorted((int(t[it, k]) - base, names[k]) for k in names)
         print(f"tile {it} (MMA-issue period {int(t[it + 1, 3]) - base}): " + "  ".join(f"{n}@{c}" for c, n in ev))
