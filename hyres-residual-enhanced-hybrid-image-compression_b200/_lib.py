@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libhyres_b200.so")
 HYRES_CONV, HYRES_DECONV_K5S2 = 0, 1
 EPI_LINEAR, EPI_ADD, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_PIXSCALE = range(6)
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_CLAMP01 = range(4)
+SPLIT_COPY, SPLIT_ADD, SPLIT_GATE, SPLIT_GDN, SPLIT_IGDN, SPLIT_SQUARE, SPLIT_ROUND_CHAN = range(7)
 
 
 class HyresError(RuntimeError):
@@ -33,6 +34,8 @@ class ConvIO(C.Structure):
         ("mt_hint", C.c_int), ("ld_x0", C.c_int), ("x0_square", C.c_int),
         ("out_pad", C.c_int), ("up_t2", C.c_void_p), ("up_t3", C.c_void_p),
         ("cta_limit", C.c_int),
+        ("split_mode", C.c_int), ("aux0_f32", C.c_void_p), ("aux1_f32", C.c_void_p),
+        ("out_split", C.c_void_p), ("out_nsplit", C.c_int), ("split_square", C.c_int),
     ]
 
 
@@ -56,6 +59,7 @@ SIGNATURES = {
     "hyres_last_error": (C.c_char_p, []),
     "hyres_launch_count": (C.c_longlong, []),
     "hyres_conv_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hyres_conv_create_split": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
     "hyres_conv_update": (_i, [_vp, _vp, _vp]),
     "hyres_conv_destroy": (None, [_vp]),
     "hyres_conv_macs_per_pos": (_i64, [_vp]),
@@ -73,6 +77,9 @@ SIGNATURES = {
     "hyres_gc_indexes": (_i, [_vp, _vp, _i, _f, _vp, _i, _i, _i, _i, _vp]),
     "hyres_gc_dequant": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_add_to_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "hyres_split_f32": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
+    "hyres_residual_im2col5s2_split": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_symbols_to_nhwc_f32": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_eb_forward": (_i, [_vp, _vp, _vp, _i, _u64, _f, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_eb_dequant": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_se_pool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -11,7 +11,8 @@
 
 #include "hyres_b200.h"
 
-constexpr int kMaxTaps = 5;   // vertical taps per patch
+constexpr int kMaxRows = 5;   // vertical taps (kernel rows) per patch
+constexpr int kMaxTaps = 16;  // B tiles per patch: kernel rows x weight parts of a split-precision layer
 
 struct TapGroup {
   int32_t src;      // 0: x0, 1: x1
@@ -22,16 +23,31 @@ struct TapGroup {
   int32_t ntaps;    // B tiles consumed against this patch
   int32_t kslot0;   // first 64-wide K slot in the packed weights
   int32_t tap_row[kMaxTaps];  // row shift (in patch rows) of each tap
+  int32_t tap_acc[kMaxTaps];  // accumulator of each tap (split-precision layers keep the leading products apart)
 };
 
 struct hyres_conv {
   int kind, cin0, cin1, w_cin_total, cout, R, S, stride, pad, dil;
   int BN, cout_pad, ktot, nphase, extra_rows;
+  // split-precision layers (fp32-equivalent arithmetic on the bf16 tensor cores): the input tensor carries
+  // nsplit bf16 parts of every fp32 activation ([.., nsplit*cin], part p in channels [p*cin, (p+1)*cin)), the
+  // weights are packed as nsplit bf16 parts, and part i of the activations meets parts 0 .. nsplit-1-i of the
+  // weights (3 products for nsplit = 2, 6 for nsplit = 3); every product accumulates into the same fp32 TMEM tile.
+  int nsplit = 1;
+  // Accumulators per output tile of a split layer.  The tensor core truncates when it adds into an fp32
+  // accumulator (about 0.05 ulp of bias per MMA, measured: tools/check_precise.py), so a chain of 1 200 MMAs
+  // drifts by ~60 ulp.  The leading products (part 0 x part 0, K/16 MMAs) therefore get accumulators of their
+  // own (round robin over nacc - 1 of them) and the 2^-8 / 2^-16 sized cross products share the last one, whose
+  // ulp is 2^8 smaller; the epilogue adds the accumulators in fp32 (round to nearest).
+  int nacc = 1;
+  int bn_cap = 256;  // widest N block (TMEM: nacc * block width <= 512 columns)
+  int lead_mmas = 0; // K / 16 of the longest leading-product chain
+  int acc_mask[4] = {1, 1, 1, 1};  // per phase: accumulators that receive at least one MMA
   int ph_begin[4], ph_count[4];
   std::vector<TapGroup> groups;
   std::vector<uint8_t> tap_mask;
   // k-slot -> (src, chunk, r, s) for weight packing
-  struct Slot { int src, chunk, r, s; };
+  struct Slot { int src, chunk, r, s, wpart; };
   std::vector<Slot> slots;
   TapGroup* d_groups = nullptr;
   __nv_bfloat16* d_w = nullptr;

@@ -61,6 +61,12 @@ struct alignas(64) ConvParams {
   int32_t MT, NA, NB;
   int32_t a_stage_bytes, b_stage_bytes, patch_rows;
   int32_t tmem_cols, acc_cols, nbuf, acc_empty_count, fast_epi;
+  int32_t nacc, acc_stride;  // split-precision layers: accumulators per tile, TMEM columns between them
+  int32_t acc_mask[4];       // per phase: which accumulators hold a sum
+  int32_t split_epi, split_mode, out_nsplit, split_square;
+  const float* aux0_f32;
+  const float* aux1_f32;
+  __nv_bfloat16* out_split;
   int32_t cout;              // live output channels
   int32_t epi, act;
   float slope;
@@ -220,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         hy::mbar_wait(acc_empty + 8 * buf, (use & 1u) ^ 1u);
         hy::tc_fence_after();
         const uint32_t d_item = tmem_base + buf * p.acc_cols;
-        uint32_t first = 0;  // becomes 1 after the first k-step (accumulate flag)
+        uint32_t used = 0;  // bit a: accumulator a already holds a partial sum (accumulate flag)
         for (int g = 0; g < g_count; ++g) {
           const TapGroup tg = p.groups[g_begin + g];
           hy::mbar_wait(a_full + 8 * sa, pa);
@@ -231,14 +237,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             hy::tc_fence_after();
             const uint64_t b_d = hy::desc_u64(b_base + sb * p.b_stage_bytes);
             const uint64_t a_d = hy::desc_u64(a_stage + p.groups[g_begin + g].tap_row[t] * (kTileW * 128));
+            const int acc = p.nacc > 1 ? p.groups[g_begin + g].tap_acc[t] : 0;
+            const uint32_t first = (used >> acc) & 1u;
             for (int sub = 0; sub < p.MT; ++sub) {
               const uint64_t a_sub = a_d + ((sub * (kSubH * kTileW * 128)) >> 4);
-              const uint32_t d_tmem = d_item + sub * p.bn_max;
+              const uint32_t d_tmem = d_item + acc * p.acc_stride + sub * p.bn_max;
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 hy::umma_issue<2>(d_tmem, a_sub + 2 * k, b_d + 2 * k, idesc, first | static_cast<uint32_t>(k), leader);
             }
-            first = 1;
+            used |= 1u << acc;
             hy::umma_commit_mode<2>(b_empty + 8 * sb, leader);
             if (++sb == p.NB) { sb = 0; pb ^= 1u; }
           }
@@ -281,6 +289,102 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int nsub = (p.MT - sub0 + sub_step - 1) / sub_step;
       const int total = nsub * nchunk;
       const uint32_t t_item = t_lane + buf * p.acc_cols;
+      if (p.split_epi) {
+        // split-precision layer: v = sum of the tile's accumulators (cross products first, fp32 round to nearest)
+        // + bias, the fp32 element-wise stage (skip / gate / GDN), ReLU -> fp32 row and / or its bf16 parts
+        const float lo = p.act == HYRES_ACT_RELU ? 0.f : -3.402823466e38f;
+        const int nch = it.bn >> 5;
+        const int steps = nsub * nch;
+        const uint32_t mask = static_cast<uint32_t>(p.acc_mask[it.phase]);
+        hy::mbar_wait(acc_full + 8 * buf, use & 1u);
+        hy::tc_fence_after();
+        for (int q = 0; q < steps; ++q) {
+          const int si = q / nch;
+          const int sub = sub0 + si * sub_step;
+          const int cb = (q - si * nch) << 5;
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          for (int a = p.nacc - 1; a >= 0; --a) {
+            if (!((mask >> a) & 1u)) continue;
+            uint32_t r[32];
+            hy::tmem_ld32(t_item + a * p.acc_stride + sub * p.bn_max + cb, r);
+            hy::tmem_ld_fence32(r);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+          }
+          if (q + 1 == steps) {
+            hy::tc_fence_before();
+            hy::mbar_arrive(acc_empty + 8 * buf);
+          }
+          const int n = it.n0 + cb;
+          const int hv = it.h0 + sub * kSubH + ti, wv = it.w0 + tj;
+          if (hv >= p.OHv || wv >= p.OWv || n >= p.cout) continue;
+          const int oh = hv * p.out_mul + ph_p, ow = wv * p.out_mul + ph_q;
+          const long long opix = (static_cast<long long>(it.b_img) * p.OH + oh) * p.OW + ow;
+          const float4* bq = reinterpret_cast<const float4*>(p.bias + n);
+          const float4* x0 = reinterpret_cast<const float4*>(p.aux0_f32 + opix * p.cout + n);
+          const float4* x1 = reinterpret_cast<const float4*>(p.aux1_f32 + opix * p.cout + n);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(bq + i);
+            float4 t = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+            if (p.split_mode == HYRES_SPLIT_ADD) {
+              const float4 a = __ldg(x0 + i);
+              t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+            } else if (p.split_mode == HYRES_SPLIT_GATE) {
+              const float4 a = __ldg(x0 + i), g = __ldg(x1 + i);
+              t.x = g.x * (1.f / (1.f + expf(-t.x))) + a.x;
+              t.y = g.y * (1.f / (1.f + expf(-t.y))) + a.y;
+              t.z = g.z * (1.f / (1.f + expf(-t.z))) + a.z;
+              t.w = g.w * (1.f / (1.f + expf(-t.w))) + a.w;
+            } else if (p.split_mode == HYRES_SPLIT_GDN) {
+              const float4 a = __ldg(x0 + i);
+              t.x = a.x * (1.f / sqrtf(t.x)); t.y = a.y * (1.f / sqrtf(t.y));
+              t.z = a.z * (1.f / sqrtf(t.z)); t.w = a.w * (1.f / sqrtf(t.w));
+            } else if (p.split_mode == HYRES_SPLIT_IGDN) {
+              const float4 a = __ldg(x0 + i);
+              t.x = a.x * sqrtf(t.x); t.y = a.y * sqrtf(t.y); t.z = a.z * sqrtf(t.z); t.w = a.w * sqrtf(t.w);
+            }
+            v[4 * i] = fmaxf(t.x, lo); v[4 * i + 1] = fmaxf(t.y, lo);
+            v[4 * i + 2] = fmaxf(t.z, lo); v[4 * i + 3] = fmaxf(t.w, lo);
+          }
+          if (p.out_f32) {
+            float* o = p.out_f32 + it.b_img * p.f32_sb + oh * p.f32_sh + ow * p.f32_sw + n * p.f32_sc;
+            if (n + 32 <= p.cout && p.f32_sc == 1) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (n + i < p.cout) o[i * p.f32_sc] = v[i];
+            }
+          }
+          if (p.out_split) {  // cout is a multiple of 32 here (checked by the entry point)
+            if (p.split_square) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] *= v[i];
+            }
+            __nv_bfloat16* o = p.out_split + opix * (static_cast<long long>(p.out_nsplit) * p.cout) + n;
+            for (int part = 0; part < p.out_nsplit; ++part) {
+              uint32_t w[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+                v[2 * i] -= __bfloat162float(h0);      // exact: the residual of a round-to-nearest bf16
+                v[2 * i + 1] -= __bfloat162float(h1);
+                w[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<uint4*>(o + static_cast<long long>(part) * p.cout)[i] =
+                    make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            }
+          }
+        }
+        continue;
+      }
       if (p.fast_epi) {
         // bias (+ReLU) -> bf16 / fp32 rows: 32 accumulator columns per step, TMEM loads double buffered
         const float lo = p.act == HYRES_ACT_RELU ? 0.f : -3.402823466e38f;
@@ -537,74 +641,104 @@ void build_plan(hyres_conv* c) {
   c->slots.clear();
   auto live = [&](int r, int s) { return c->tap_mask.empty() || c->tap_mask[r * c->S + s] != 0; };
   const int nsrc = c->cin1 > 0 ? 2 : 1;
+  const int P = c->nsplit;
   int extra = 0;
-  auto add_group = [&](int src, int c_off, int dw, int hpar, const std::vector<std::pair<int, int>>& taps,
-                       int chunk, int s) {
-    // taps: (row offset in view rows, r)
-    if (taps.empty()) return;
-    int mn = taps[0].first, mx = taps[0].first;
-    for (auto& t : taps) { mn = std::min(mn, t.first); mx = std::max(mx, t.first); }
+  int lead = 0, phase_mask = 0;
+  // One group = one activation patch (input part `part`, 64-channel chunk, kernel column) and the B tiles that
+  // meet it: every live kernel row, times the weight parts 0 .. P-1-part of a split-precision layer (the small
+  // products are issued first).
+  auto add_group = [&](int src, int c_off, int dw, int hpar, const std::vector<std::pair<int, int>>& rows,
+                       int chunk, int s, int part) {
+    // rows: (row offset in view rows, r)
+    if (rows.empty()) return;
+    int mn = rows[0].first, mx = rows[0].first;
+    for (auto& t : rows) { mn = std::min(mn, t.first); mx = std::max(mx, t.first); }
     TapGroup g{};
     g.src = src; g.c_off = c_off; g.dw = dw; g.dh = mn; g.hpar = hpar;
-    g.ntaps = static_cast<int>(taps.size());
     g.kslot0 = static_cast<int>(c->slots.size());
-    for (size_t i = 0; i < taps.size(); ++i) {
-      g.tap_row[i] = taps[i].first - mn;
-      c->slots.push_back({src, chunk, taps[i].second, s});
-    }
+    int n = 0;
+    for (int wpart = P - 1 - part; wpart >= 0; --wpart)
+      for (size_t i = 0; i < rows.size(); ++i) {
+        g.tap_row[n] = rows[i].first - mn;
+        // leading products round robin over the first nacc - 1 accumulators, cross products into the last
+        int acc = 0;
+        if (c->nacc > 1) acc = (part == 0 && wpart == 0) ? (lead++ % (c->nacc - 1)) : c->nacc - 1;
+        g.tap_acc[n++] = acc;
+        phase_mask |= 1 << acc;
+        c->slots.push_back({src, chunk, rows[i].second, s, wpart});
+      }
+    g.ntaps = n;
     extra = std::max(extra, mx - mn);
     c->groups.push_back(g);
   };
   if (c->kind == HYRES_CONV && c->stride == 1) {
     c->nphase = 1;
     c->ph_begin[0] = 0;
-    for (int src = 0; src < nsrc; ++src) {
-      const int cin = src ? c->cin1 : c->cin0;
-      for (int ch = 0; ch < (cin + 63) / 64; ++ch)
-        for (int s = 0; s < c->S; ++s) {
-          std::vector<std::pair<int, int>> taps;
-          for (int r = 0; r < c->R; ++r)
-            if (live(r, s)) taps.push_back({r * c->dil - c->pad, r});
-          add_group(src, ch * 64, s * c->dil - c->pad, 0, taps, ch, s);
-        }
-    }
+    for (int part = P - 1; part >= 0; --part)
+      for (int src = 0; src < nsrc; ++src) {
+        const int cin = src ? c->cin1 : c->cin0;
+        for (int ch = 0; ch < (cin + 63) / 64; ++ch)
+          for (int s = 0; s < c->S; ++s) {
+            std::vector<std::pair<int, int>> rows;
+            for (int r = 0; r < c->R; ++r)
+              if (live(r, s)) rows.push_back({r * c->dil - c->pad, r});
+            add_group(src, part * cin + ch * 64, s * c->dil - c->pad, 0, rows, ch, s, part);
+          }
+      }
     c->ph_count[0] = static_cast<int>(c->groups.size());
+    c->acc_mask[0] = phase_mask;
   } else if (c->kind == HYRES_CONV && c->stride == 2) {
     c->nphase = 1;
     c->ph_begin[0] = 0;
-    for (int ch = 0; ch < (c->cin0 + 63) / 64; ++ch)
-      for (int s = 0; s < c->S; ++s) {
-        const int ds = s - c->pad;
-        const int q = ds & 1;
-        const int wq = (ds - q) / 2;
-        for (int par = 0; par < 2; ++par) {
-          std::vector<std::pair<int, int>> taps;
-          for (int r = 0; r < c->R; ++r) {
-            const int dr = r - c->pad;
-            if ((dr & 1) != par || !live(r, s)) continue;
-            taps.push_back({(dr - par) / 2, r});
+    for (int part = P - 1; part >= 0; --part)
+      for (int ch = 0; ch < (c->cin0 + 63) / 64; ++ch)
+        for (int s = 0; s < c->S; ++s) {
+          const int ds = s - c->pad;
+          const int q = ds & 1;
+          const int wq = (ds - q) / 2;
+          for (int par = 0; par < 2; ++par) {
+            std::vector<std::pair<int, int>> rows;
+            for (int r = 0; r < c->R; ++r) {
+              const int dr = r - c->pad;
+              if ((dr & 1) != par || !live(r, s)) continue;
+              rows.push_back({(dr - par) / 2, r});
+            }
+            add_group(0, q * P * c->cin0 + part * c->cin0 + ch * 64, wq, par, rows, ch, s, part);
           }
-          add_group(0, q * c->cin0 + ch * 64, wq, par, taps, ch, s);
         }
-      }
     c->ph_count[0] = static_cast<int>(c->groups.size());
+    c->acc_mask[0] = phase_mask;
   } else {  // HYRES_DECONV_K5S2
     c->nphase = 4;
     for (int ph = 0; ph < 4; ++ph) {
       const int pp = ph >> 1, qq = ph & 1;
       c->ph_begin[ph] = static_cast<int>(c->groups.size());
-      for (int ch = 0; ch < (c->cin0 + 63) / 64; ++ch)
-        for (int s = qq; s < 5; s += 2) {
-          std::vector<std::pair<int, int>> taps;
-          for (int r = pp; r < 5; r += 2) taps.push_back({(pp + 2 - r) / 2, r});
-          add_group(0, ch * 64, (qq + 2 - s) / 2, 0, taps, ch, s);
-        }
+      lead = 0;
+      phase_mask = 0;
+      for (int part = P - 1; part >= 0; --part)
+        for (int ch = 0; ch < (c->cin0 + 63) / 64; ++ch)
+          for (int s = qq; s < 5; s += 2) {
+            std::vector<std::pair<int, int>> rows;
+            for (int r = pp; r < 5; r += 2) rows.push_back({(pp + 2 - r) / 2, r});
+            add_group(0, part * c->cin0 + ch * 64, (qq + 2 - s) / 2, 0, rows, ch, s, part);
+          }
       c->ph_count[ph] = static_cast<int>(c->groups.size()) - c->ph_begin[ph];
+      c->acc_mask[ph] = phase_mask;
     }
   }
   c->extra_rows = extra;
   c->ktot = static_cast<int>(c->slots.size()) * 64;
   c->macs_per_pos = static_cast<int64_t>(c->ktot) * c->cout_pad / (c->nphase);
+}
+
+// bf16 part `part` of an fp32 value: v = p0 + p1 + p2 (+ an error below 2^-24 |v|), each part rounded to nearest.
+inline __nv_bfloat16 split_part(float v, int part) {
+  __nv_bfloat16 b = __float2bfloat16(v);
+  for (int i = 0; i < part; ++i) {
+    v -= __bfloat162float(b);
+    b = __float2bfloat16(v);
+  }
+  return b;
 }
 
 void pack_weights(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16>& out) {
@@ -623,7 +757,7 @@ void pack_weights(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16
           v = w[(static_cast<size_t>(ci) * c->cout + n) * RS + sl.r * c->S + sl.s];
         else
           v = w[(static_cast<size_t>(n) * c->w_cin_total + ci) * RS + sl.r * c->S + sl.s];
-        out[static_cast<size_t>(n) * c->ktot + ks * 64 + cc] = __float2bfloat16(v);
+        out[static_cast<size_t>(n) * c->ktot + ks * 64 + cc] = split_part(v, sl.wpart);
       }
     }
   }
@@ -637,7 +771,7 @@ int upload_weights(hyres_conv* c, const float* weight, const float* bias) {
   if (bias) std::copy(bias, bias + c->cout, b.begin());
   HY_CUDA(cudaMemcpy(c->d_bias, b.data(), b.size() * sizeof(float), cudaMemcpyHostToDevice));
   c->h_bias = b;
-  if (conv_sc_applicable(c)) {
+  if (c->nsplit == 1 && conv_sc_applicable(c)) {
     conv_sc_pack(c, weight, packed);
     if (!c->d_w_tap) HY_CUDA(cudaMalloc(&c->d_w_tap, packed.size() * sizeof(__nv_bfloat16)));
     HY_CUDA(cudaMemcpy(c->d_w_tap, packed.data(), packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
@@ -709,7 +843,15 @@ extern "C" {
 int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout, int R, int S,
                       int stride, int pad, int dil, const float* weight, const float* bias,
                       const uint8_t* tap_mask) {
+  return hyres_conv_create_split(out, kind, cin0, cin1, w_cin_total, cout, R, S, stride, pad, dil, weight, bias,
+                                 tap_mask, 1);
+}
+
+int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout, int R, int S,
+                            int stride, int pad, int dil, const float* weight, const float* bias,
+                            const uint8_t* tap_mask, int nsplit) {
   if (!out || !weight) return hy_fail(HYRES_ERR_ARG, "conv_create: null argument");
+  if (nsplit < 1 || nsplit > 3) return hy_fail(HYRES_ERR_ARG, "conv_create: nsplit must be 1, 2 or 3");
   if (kind != HYRES_CONV && kind != HYRES_DECONV_K5S2) return hy_fail(HYRES_ERR_ARG, "conv_create: bad kind");
   if (cin0 <= 0 || cin1 < 0 || cout <= 0 || (cin0 % 8) || (cin1 % 8))
     return hy_fail(HYRES_ERR_ARG, "conv_create: channel counts must be positive multiples of 8");
@@ -720,7 +862,7 @@ int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_
     if (stride != 1 && stride != 2) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv: stride must be 1 or 2");
     if (stride == 2 && (dil != 1 || cin1 != 0 || pad != R / 2 || R != S))
       return hy_fail(HYRES_ERR_UNSUPPORTED, "conv stride 2: needs dil=1, pad=k/2, one input");
-    if (R > kMaxTaps || S > 7 || dil < 1) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv: kernel too large");
+    if (R > kMaxRows || S > 7 || dil < 1) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv: kernel too large");
     if (stride == 1 && 2 * pad != dil * (R - 1))
       return hy_fail(HYRES_ERR_UNSUPPORTED, "conv stride 1: only 'same' padding");
   }
@@ -729,9 +871,25 @@ int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_
   c->kind = kind; c->cin0 = cin0; c->cin1 = cin1;
   c->w_cin_total = w_cin_total > 0 ? w_cin_total : cin0 + cin1;
   c->cout = cout; c->R = R; c->S = S; c->stride = stride; c->pad = pad; c->dil = dil;
+  c->nsplit = nsplit;
   if (tap_mask) c->tap_mask.assign(tap_mask, tap_mask + R * S);
   c->BN = choose_bn(cout);
   c->cout_pad = (cout + c->BN - 1) / c->BN * c->BN;
+  if (nsplit > 1) {
+    // one accumulator for the cross products plus one per ~72 leading MMAs (K / 16) of the longest chain, at most 3
+    static const int nacc_env = [] { const char* e = getenv("HYRES_SPLIT_NACC"); return e ? atoi(e) : 0; }();
+    int live = 0;
+    for (int i = 0; i < R * S; ++i) live += (!tap_mask || tap_mask[i]) ? 1 : 0;
+    if (kind == HYRES_DECONV_K5S2) live = 9;  // the largest sub-pixel phase
+    const int lead = live * ((cin0 + 63) / 64 + (cin1 + 63) / 64) * 4;
+    c->lead_mmas = lead;
+    // short chains (K <= 256: at most 96 MMAs with the cross products) stay below one ulp in a single accumulator
+    int nacc = lead <= 16 ? 1 : 1 + std::min(3, (lead + 71) / 72);
+    if (nacc_env >= 1 && nacc_env <= 4) nacc = nacc_env;
+    c->nacc = nacc;
+    c->bn_cap = nacc <= 2 ? 256 : 128;
+    if (c->cout_pad > c->bn_cap && (c->cout_pad % 64)) { c->nacc = 2; c->bn_cap = 256; }  // N blocks are multiples of 64
+  }
   build_plan(c);
   if (c->groups.empty()) { delete c; return hy_fail(HYRES_ERR_ARG, "conv_create: no live taps"); }
   cudaError_t e;
@@ -789,20 +947,38 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   // layers whose weights fit in shared memory run on the persistent resident-weights kernel
   const bool res_only = io->out_pad != 0 || io->up_t2 != nullptr || io->up_t3 != nullptr;
   static const bool no_sc = getenv("HYRES_NO_SC") != nullptr;
-  if (!no_sc && !res_only) {
+  const bool split = c->nsplit > 1;  // split-precision layers run on the streaming kernel only
+  if (split && (res_only || io->x0_square || io->epi != HYRES_EPI_LINEAR || io->out_bf16 || io->out_sq))
+    return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: split-precision layers take the linear epilogue and write fp32 / parts");
+  if (split) {
+    if (io->act != HYRES_ACT_NONE && io->act != HYRES_ACT_RELU)
+      return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: split-precision layers support ReLU only");
+    if (!io->out_f32 && !io->out_split) return hy_fail(HYRES_ERR_ARG, "conv_run: split layer without an output");
+    if (io->out_split && (io->out_nsplit < 1 || io->out_nsplit > 3 || (c->cout % 32)))
+      return hy_fail(HYRES_ERR_ARG, "conv_run: out_split needs 1..3 parts and a multiple of 32 output channels");
+    const int m = io->split_mode;
+    if (m != HYRES_SPLIT_COPY && m != HYRES_SPLIT_ADD && m != HYRES_SPLIT_GATE && m != HYRES_SPLIT_GDN && m != HYRES_SPLIT_IGDN)
+      return hy_fail(HYRES_ERR_ARG, "conv_run: bad split_mode");
+    if (m != HYRES_SPLIT_COPY && !io->aux0_f32) return hy_fail(HYRES_ERR_ARG, "conv_run: aux0_f32 missing");
+    if (m == HYRES_SPLIT_GATE && !io->aux1_f32) return hy_fail(HYRES_ERR_ARG, "conv_run: aux1_f32 missing");
+    if (m != HYRES_SPLIT_COPY && (c->cout % 32)) return hy_fail(HYRES_ERR_ARG, "conv_run: fused split stage needs a multiple of 32 output channels");
+  } else if (io->out_split || io->split_mode) {
+    return hy_fail(HYRES_ERR_ARG, "conv_run: out_split / split_mode need a split-precision layer");
+  }
+  if (!no_sc && !res_only && !split) {
     int handled = 0;
     const int rc = conv_sc_try_run(c, io, stream, &handled);
     if (rc != HYRES_OK || handled) return rc;
   }
   static const bool no_res = getenv("HYRES_NO_RES") != nullptr;
-  if (!no_res) {
+  if (!no_res && !split) {
     int handled = 0;
     const int rc = conv_res_try_run(c, io, stream, &handled);
     if (rc != HYRES_OK || handled) return rc;
   }
   if (io->x0_square) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: x0_square is only available on resident-weight 1x1 layers");
   if (res_only) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: out_pad / up-add are only available on resident-weight layers");
-  if (io->ld_x0 && io->ld_x0 != c->cin0) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: strided x0 is only available on resident-weight layers");
+  if (io->ld_x0 && io->ld_x0 != c->nsplit * c->cin0) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: strided x0 is only available on resident-weight layers");
 
   ConvParams p;
   memset(&p, 0, sizeof p);
@@ -814,7 +990,8 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   p.nphase = c->nphase;
 
   // N blocks: <= 256 output channels each, balanced, multiples of the weight TMA box
-  static const int bn_cap = [] { const char* e = getenv("HYRES_TC_BNMAX"); const int v = e ? atoi(e) : 0; return (v >= 64 && v <= 256 && v % 64 == 0) ? v : 256; }();
+  static const int bn_cap_env = [] { const char* e = getenv("HYRES_TC_BNMAX"); const int v = e ? atoi(e) : 0; return (v >= 64 && v <= 256 && v % 64 == 0) ? v : 256; }();
+  const int bn_cap = std::min(bn_cap_env, c->bn_cap);
   if (c->cout_pad <= bn_cap || (c->cout_pad <= 256 && c->cout_pad % 64)) {
     p.n_blocks = 1; p.nb_n0[0] = 0; p.nb_bn[0] = c->cout_pad;
   } else {
@@ -845,13 +1022,22 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   auto items_for = [&](int mt) {
     return static_cast<long long>(io->B) * tiles_w * ((p.OHv + kSubH * mt - 1) / (kSubH * mt)) * c->nphase * p.n_blocks;
   };
+  const int nacc = c->nacc;
+  if (nacc * p.bn_max > 512) return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: split layer too wide for its accumulators");
+  p.nacc = nacc;
   int mt = io->mt_hint;
   if (mt != 1 && mt != 2 && mt != 4) mt = (p.bn_max * 2 <= 512 && items_for(2) >= 2LL * num_sms()) ? 2 : 1;
-  while (mt > 1 && mt * p.bn_max > 512) mt >>= 1;
+  while (mt > 1 && nacc * mt * p.bn_max > 512) mt >>= 1;
+  // few MMAs per tile: the fused fp32 epilogue of a split layer dominates, so keep two accumulator buffers and let
+  // the two epilogue groups drain one tile each under the next tile's MMAs
+  if (split && c->lead_mmas <= 16)
+    while (mt > 1 && 2 * nacc * mt * p.bn_max > 512) mt >>= 1;
   p.MT = mt;
-  p.acc_cols = mt * p.bn_max;
+  p.acc_stride = mt * p.bn_max;
+  p.acc_cols = nacc * p.acc_stride;
   p.nbuf = 2 * p.acc_cols <= 512 ? 2 : 1;
-  p.acc_empty_count = p.nbuf == 2 ? 128 : 256;
+  p.acc_empty_count = (p.nbuf == 2 || mt == 1) ? 128 : 256;
+  for (int i = 0; i < 4; ++i) p.acc_mask[i] = c->acc_mask[i];
   int cols = 32;
   while (cols < p.nbuf * p.acc_cols) cols <<= 1;
   p.tmem_cols = cols;
@@ -899,13 +1085,17 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   p.pixscale = io->pixscale;
   p.out_bf16 = static_cast<__nv_bfloat16*>(io->out_bf16); p.ld_out = io->ld_out;
   p.out_sq = static_cast<__nv_bfloat16*>(io->out_sq); p.ld_sq = io->ld_sq;
+  p.split_epi = split ? 1 : 0;
+  p.split_mode = io->split_mode; p.out_nsplit = io->out_nsplit; p.split_square = io->split_square;
+  p.aux0_f32 = io->aux0_f32; p.aux1_f32 = io->aux1_f32;
+  p.out_split = static_cast<__nv_bfloat16*>(io->out_split);
   p.out_f32 = io->out_f32;
   p.f32_sb = io->f32_sb; p.f32_sh = io->f32_sh; p.f32_sw = io->f32_sw; p.f32_sc = io->f32_sc;
 
   const int s2 = (c->kind == HYRES_CONV && c->stride == 2) ? 1 : 0;
-  int rc = encode_act_map(&p.mapA0, io->x0, c->cin0, io->B, io->H, io->W, s2, p.patch_rows);
+  int rc = encode_act_map(&p.mapA0, io->x0, c->nsplit * c->cin0, io->B, io->H, io->W, s2, p.patch_rows);
   if (rc != HYRES_OK) return rc;
-  if (c->cin1 > 0) rc = encode_act_map(&p.mapA1, io->x1, c->cin1, io->B, io->H, io->W, 0, p.patch_rows);
+  if (c->cin1 > 0) rc = encode_act_map(&p.mapA1, io->x1, c->nsplit * c->cin1, io->B, io->H, io->W, 0, p.patch_rows);
   else p.mapA1 = p.mapA0;
   if (rc != HYRES_OK) return rc;
   rc = encode_w_map(&p.mapB, c->d_w, c->ktot, c->cout_pad, p.b_box_rows);

@@ -461,7 +461,7 @@ int encode_act4d(CUtensorMap* m, const void* ptr, int C, int ld, int B, int H, i
 
 bool is_conv(const hyres_conv* c, int cin, int cout, int k) {
   return c && c->kind == HYRES_CONV && c->cin0 == cin && c->cin1 == 0 && c->cout == cout && c->R == k && c->S == k &&
-         c->stride == 1 && c->dil == 1 && c->pad == k / 2 && c->tap_mask.empty();
+         c->stride == 1 && c->dil == 1 && c->pad == k / 2 && c->tap_mask.empty() && c->nsplit == 1;
 }
 
 }  // namespace

@@ -63,6 +63,7 @@ def _gdn(m):
 
 
 _NO_BRANCH_STREAMS = bool(os.environ.get("HYRES_NO_BRANCH_STREAMS"))
+_PRECISE_UNFUSED = bool(os.environ.get("HYRES_PRECISE_UNFUSED"))
 _side = {}
 
 
@@ -288,6 +289,173 @@ class CodecEngine:
         t, _, _ = self.gs7(t, epi=EPI_IGDN, aux0=t, x0_square=True)
         _, _, x = self.gs8(t, out_bf16=False, out_f32="nchw", act=ACT_CLAMP01 if clamp else ACT_NONE)
         return x  # fp32 NCHW [B,3,H,W]
+
+
+class _PT:
+    """An activation of the split-precision trunk: fp32 NHWC tensor + its bf16 parts ([..., nsplit*C])."""
+    __slots__ = ("f32", "sp")
+
+    def __init__(self, f32, sp):
+        self.f32, self.sp = f32, sp
+
+
+class PreciseTrunk:
+    """The entropy-critical half of ``LightWeightCheckerboard`` -- g_a, h_a, h_s, context_prediction,
+    param_aggregation (models/checkerboard.py:35-45,61-88) -- at fp32-equivalent precision.
+
+    These layers decide the integer symbols and CDF indexes (models/checkerboard.py:159-165), which must equal the
+    fp32 reference's; a bf16 trunk flips a few per cent of them.  Here activations stay fp32 in HBM, every
+    convolution is a split-bf16 product on the tensor cores (``ops.ConvLayer(nsplit=3)``: 6 bf16 MMAs per MAC, fp32
+    accumulation in TMEM, error ~2^-22 relative) and the element-wise work between two convolutions (ReLU, skip,
+    gate, GDN) is IEEE fp32 (``ops.split_f32``).  ``compress`` / ``decompress`` always run this trunk; ``forward``
+    uses it when the model's ``precision`` is "fp32x3"."""
+
+    def __init__(self, model, nsplit=3):
+        self.model, self.P = model, nsplit
+        M = model.M
+        P = nsplit
+
+        def cv(m):
+            return _Bound(_wb(m), kind=HYRES_CONV, stride=m.stride[0], pad=m.padding[0], dil=m.dilation[0], nsplit=P)
+
+        def dc(m):
+            return _Bound(_wb(m), kind=HYRES_DECONV_K5S2, nsplit=P)
+
+        def gd(m):
+            return _Bound(m.effective, kind=HYRES_CONV, nsplit=P)
+
+        def ru(c1, c2, c3):
+            return [cv(c1), cv(c2), cv(c3)]
+
+        def ru_unit(u):
+            return ru(u.conv[0], u.conv[2], u.conv[4])
+
+        def rbb(r):
+            return ru(r.conv1, r.conv2, r.conv3)
+
+        def attn(m):
+            return dict(a=[ru_unit(u) for u in m.conv_a], b=[ru_unit(m.conv_b[i]) for i in range(3)],
+                        gate=cv(m.conv_b[3]))
+
+        ga = model.g_a
+
+        def ga0():
+            w = ga[0].weight  # [N,3,5,5] -> [N,128,1,1], k = (r*5+s)*3 + c
+            w2 = torch.zeros(w.shape[0], 128, 1, 1, dtype=torch.float32)
+            w2[:, :75, 0, 0] = w.detach().float().cpu().permute(0, 2, 3, 1).reshape(w.shape[0], 75)
+            return w2, ga[0].bias
+
+        self.ga0 = _Bound(ga0, kind=HYRES_CONV, nsplit=P)
+        self.ga1, self.ga2, self.ga3, self.ga4 = gd(ga[1]), rbb(ga[2]), attn(ga[3]), cv(ga[4])
+        self.ga5, self.ga6, self.ga7, self.ga8 = gd(ga[5]), rbb(ga[6]), cv(ga[7]), attn(ga[8])
+        self.ha = [cv(model.h_a[0]), cv(model.h_a[2]), cv(model.h_a[4])]
+        self.hs = [dc(model.h_s[0]), dc(model.h_s[2]), cv(model.h_s[4])]
+        cp = model.context_prediction
+        mask = (cp.mask[0, 0] != 0).to(torch.uint8)
+        self.ctx = _Bound(_wb(cp), kind=HYRES_CONV, stride=1, pad=cp.padding[0], dil=1, tap_mask=mask, nsplit=P)
+        pa = model.param_aggregation
+        self.head0_anchor = _Bound(_wb(pa[0]), kind=HYRES_CONV, cin0=2 * M, cin1=0, nsplit=P)
+        self.head0_full = _Bound(_wb(pa[0]), kind=HYRES_CONV, cin0=2 * M, cin1=2 * M, nsplit=P)
+        self.head1, self.head2 = cv(pa[2]), cv(pa[4])
+        self._versions = None
+
+    def _all_bound(self):
+        out = [self.ga0, self.ga1, self.ga4, self.ga5, self.ga7, self.ctx, self.head0_anchor, self.head0_full,
+               self.head1, self.head2] + self.ha + self.hs + self.ga2 + self.ga6
+        for blk in (self.ga3, self.ga8):
+            for r in blk["a"] + blk["b"]:
+                out += r
+            out.append(blk["gate"])
+        return out
+
+    def sync(self, force=False):
+        key = tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+        if force or (self._versions is not None and key != self._versions):
+            for b in self._all_bound():
+                b.refresh()
+        self._versions = key
+
+    # -- building blocks --
+    def _conv(self, layer, x_sp, x1_sp=None, relu=False, mode=ops.SPLIT_COPY, aux0=None, aux1=None, want_f32=False,
+              want_split=True, square=False):
+        """bf16 parts in -> _PT(fp32 NHWC or None, bf16 parts or None); bias, the fp32 element-wise stage that
+        follows the convolution (skip / gate / GDN), ReLU and the split of the result all run in the epilogue."""
+        if _PRECISE_UNFUSED:  # experiment: convolution -> fp32, element-wise stage + split as a second kernel
+            _, _, o = layer(x_sp, x1_sp, act=ACT_RELU if (relu and mode == ops.SPLIT_COPY) else ACT_NONE,
+                            out_bf16=False, out_f32="nhwc")
+            if mode == ops.SPLIT_COPY and not square:
+                f, sp = ops.split_f32(o, nsplit=self.P, want_f32=True, want_split=want_split)
+                return _PT(f, sp)
+            if mode == ops.SPLIT_COPY:  # square: parts of o*o, fp32 o
+                _, sp = ops.split_f32(o, mode=ops.SPLIT_SQUARE, nsplit=self.P)
+                return _PT(o, sp)
+            f, sp = ops.split_f32(o, mode=mode, aux0=aux0, aux1=aux1, relu=relu, nsplit=self.P, want_f32=True,
+                                  want_split=want_split)
+            return _PT(f, sp)
+        _, sp, o = layer(x_sp, x1_sp, act=ACT_RELU if relu else ACT_NONE, out_bf16=False,
+                         out_f32="nhwc" if want_f32 else None, split_mode=mode, aux0_f32=aux0, aux1_f32=aux1,
+                         out_split=True if want_split else None, split_square=square)
+        return _PT(o, sp)
+
+    def split(self, x32, want_f32=True, **kw):
+        f, sp = ops.split_f32(x32, nsplit=self.P, want_f32=want_f32, **kw)
+        return _PT(f, sp)
+
+    def _ru(self, x, layers, final_relu):
+        c1, c2, c3 = layers
+        a = self._conv(c1, x.sp, relu=True)
+        b = self._conv(c2, a.sp, relu=True)
+        return self._conv(c3, b.sp, mode=ops.SPLIT_ADD, aux0=x.f32, relu=final_relu, want_f32=True)
+
+    def _attn(self, x, blk):
+        a = x
+        for r in blk["a"]:
+            a = self._ru(a, r, True)
+        b = x
+        for r in blk["b"]:
+            b = self._ru(b, r, True)
+        return self._conv(blk["gate"], b.sp, mode=ops.SPLIT_GATE, aux0=x.f32, aux1=a.f32, want_f32=True)
+
+    def _conv_gdn(self, conv, gdn, x_sp, inverse=False):
+        """conv -> (I)GDN: the conv writes its fp32 result and the parts of its square, the 1x1 gamma GEMM over
+        those ends in x * rsqrt(.) (or x * sqrt(.))."""
+        t = self._conv(conv, x_sp, want_f32=True, square=True)
+        return self._conv(gdn, t.sp, mode=ops.SPLIT_IGDN if inverse else ops.SPLIT_GDN, aux0=t.f32, want_f32=True)
+
+    # -- stages --
+    def g_a(self, x, jpeg=None):
+        """x (and optionally jpeg): fp32 NCHW -> (y as _PT [B,H/8,W/8,M], residual fp32 NCHW or x)."""
+        residual, a = ops.residual_im2col5s2_split(x, jpeg, nsplit=self.P)
+        t = self._conv_gdn(self.ga0, self.ga1, a)
+        t = self._ru(t, self.ga2, False)
+        t = self._attn(t, self.ga3)
+        t = self._conv_gdn(self.ga4, self.ga5, t.sp)
+        t = self._ru(t, self.ga6, False)
+        t = self._conv(self.ga7, t.sp, want_f32=True)
+        return self._attn(t, self.ga8), residual
+
+    def h_a(self, y):
+        t = self._conv(self.ha[0], y.sp, relu=True)
+        t = self._conv(self.ha[1], t.sp, relu=True)
+        return self._conv(self.ha[2], t.sp, want_f32=True, want_split=False).f32  # z fp32 NHWC
+
+    def h_s(self, zhat32):
+        t = self.split(zhat32, want_f32=False)
+        t = self._conv(self.hs[0], t.sp, relu=True)
+        t = self._conv(self.hs[1], t.sp, relu=True)
+        return self._conv(self.hs[2], t.sp)  # latent parts [B,h,w,P*2M]
+
+    def head(self, latent, ctx=None):
+        if ctx is None:
+            t = self._conv(self.head0_anchor, latent.sp, relu=True)
+        else:
+            t = self._conv(self.head0_full, latent.sp, ctx.sp, relu=True)
+        t = self._conv(self.head1, t.sp, relu=True)
+        return self._conv(self.head2, t.sp, want_f32=True, want_split=False).f32  # fp32 NHWC [B,h,w,2M]: scales | means
+
+    def context(self, yq32):
+        t = self.split(yq32, want_f32=False)
+        return self._conv(self.ctx, t.sp)
 
 
 class RefineEngine:

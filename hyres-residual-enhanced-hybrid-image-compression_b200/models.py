@@ -24,7 +24,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .engine import CodecEngine, RefineEngine
+from .engine import CodecEngine, PreciseTrunk, RefineEngine
 from .entropy import EntropyBottleneck, GaussianConditional
 from .jpeg import TurboJPEGCompression
 from .layers import (AttentionBlock, CheckboardMaskedConv2d, GDN, MultiScaleRefine, Quantizer,
@@ -118,7 +118,16 @@ class LightWeightCheckerboard(CompressionModel):
         self.param_aggregation = nn.Sequential(conv1x1(4 * M, 640), nn.ReLU(inplace=True), conv1x1(640, 512),
                                                nn.ReLU(inplace=True), conv1x1(512, 2 * M))
         self._engine = None
+        self._precise = {}
         self._noise_calls = 0
+        # Arithmetic of the entropy-critical trunk (g_a, h_a, h_s, context, parameter head):
+        #   "bf16"   plain bf16 tensor-core convolutions with bf16 activations (fastest; symbols agree with the
+        #            fp32 reference only to a few per cent, so it is offered for forward / training only);
+        #   "fp32x3" fp32 activations, split-bf16 products (6 MMAs per MAC): fp32-equivalent, symbols and CDF
+        #            indexes equal the fp32 reference's except at numerical ties;  "fp32x2": 3 MMAs, ~2^-16.
+        # compress / decompress produce and consume bitstreams, so they default to the fp32-equivalent trunk.
+        self.precision = "bf16"
+        self.codec_precision = "fp32x3"
 
     # -- engine plumbing --
     def engine(self):
@@ -131,6 +140,17 @@ class LightWeightCheckerboard(CompressionModel):
             self._engine = CodecEngine(self)
         self._engine.sync()
         return self._engine
+
+    def precise(self, mode):
+        """The split-precision trunk for ``mode`` ("fp32x2" / "fp32x3"), built lazily."""
+        if mode not in ("fp32x2", "fp32x3"):
+            raise ValueError(f"unknown precision {mode!r}: expected 'bf16', 'fp32x2' or 'fp32x3'")
+        self.engine()
+        pt = self._precise.get(mode)
+        if pt is None:
+            pt = self._precise[mode] = PreciseTrunk(self, nsplit=int(mode[-1]))
+        pt.sync()
+        return pt
 
     def _seed(self):
         self._noise_calls += 1
@@ -161,6 +181,8 @@ class LightWeightCheckerboard(CompressionModel):
         eng = self.engine()
         x = x.contiguous().float()
         training = self.training
+        if self.precision != "bf16":
+            return self._forward_precise(x, noisequant, stats, _jpeg)
         y16, y32, residual = eng.g_a(x, _jpeg)
         z32 = eng.h_a(y16)
         ebp, med = eng.eb_params()
@@ -181,6 +203,34 @@ class LightWeightCheckerboard(CompressionModel):
             out["_residual"] = residual
         return out
 
+    def _forward_precise(self, x, noisequant, stats, _jpeg):
+        """``forward`` with the analysis / hyper / parameter networks on the fp32-equivalent trunk (g_s stays bf16)."""
+        eng, pt = self.engine(), self.precise(self.precision)
+        training = self.training
+        y, residual = pt.g_a(x, _jpeg)
+        z32 = pt.h_a(y)
+        ebp, med = eng.eb_params()
+        out_noise = training and noisequant
+        eb = ops.eb_forward(z32, ebp, med, lik_noise=training, out_noise=out_noise, seed=self._seed(),
+                            lik_bound=self.entropy_bottleneck.likelihood_bound, want_zhat_nchw=out_noise,
+                            sum_log2=None if stats is None else stats[1:2])
+        if out_noise:
+            zhat32 = eb["zhat_nchw"].permute(0, 2, 3, 1).contiguous()
+        else:
+            zhat32, _ = ops.split_f32(z32, mode=ops.SPLIT_ROUND_CHAN, chan=med, want_f32=True, want_split=False)
+        latent = pt.h_s(zhat32)
+        pa = pt.head(latent)
+        yqa32, _ = ops.gc_quant_pass(y.f32, pa, 0, noise=noisequant, seed=self._seed(), want_bf16=False)
+        ctx = pt.context(yqa32)
+        pna = pt.head(latent, ctx)
+        yqna32, _ = ops.gc_quant_pass(y.f32, pna, 1, noise=noisequant, seed=self._seed(), want_bf16=False)
+        y_hat16, lik_y = ops.gc_merge_likelihood(y.f32, pa, pna, yqa32, yqna32, noise=training, seed=self._seed(),
+                                                 sum_log2=None if stats is None else stats[0:1])
+        out = {"x_hat": eng.g_s(y_hat16), "likelihoods": {"y": lik_y, "z": eb["lik"]}}
+        if _jpeg is not None:
+            out["_residual"] = residual
+        return out
+
     # -- symbols of both passes (GPU part of compress) --
     def encode_symbols(self, x, _jpeg=None):
         """GPU front-end of ``compress``: returns the integer streams the entropy coder consumes,
@@ -191,6 +241,21 @@ class LightWeightCheckerboard(CompressionModel):
         x = x.contiguous().float()
         table = self._scale_table(x.device)
         bound = float(self.gaussian_conditional.scale_bound.item())
+        if self.codec_precision != "bf16":
+            pt = self.precise(self.codec_precision)
+            y, _ = pt.g_a(x, _jpeg)
+            z32 = pt.h_a(y)
+            ebp, med = eng.eb_params()
+            eb = ops.eb_forward(z32, ebp, med, want_lik=False, want_symbols=True)
+            zhat32, _ = ops.split_f32(z32, mode=ops.SPLIT_ROUND_CHAN, chan=med, want_f32=True, want_split=False)
+            latent = pt.h_s(zhat32)
+            pa = pt.head(latent)
+            sym_a, idx_a, yqa32, _ = ops.gc_symbols(y.f32, pa, 0, table, bound, want_bf16=False)
+            ctx = pt.context(yqa32)
+            pna = pt.head(latent, ctx)
+            sym_na, idx_na, _, _ = ops.gc_symbols(y.f32, pna, 1, table, bound, want_f32=False, want_bf16=False)
+            return {"sym_z": eb["symbols"], "sym_a": sym_a, "idx_a": idx_a, "sym_na": sym_na, "idx_na": idx_na,
+                    "y": y.f32, "z": z32, "params_a": pa, "params_na": pna}
         y16, y32, _ = eng.g_a(x, _jpeg, want_residual=False)
         z32 = eng.h_a(y16)
         ebp, med = eng.eb_params()
@@ -227,13 +292,22 @@ class LightWeightCheckerboard(CompressionModel):
         out_size = (B, ebm._quantized_cdf.size(0), int(shape[0]), int(shape[1]))
         sym_z = ebm.decode_symbols(strings[1], ebm._build_indexes(out_size)).to(dev)
         _, med = eng.eb_params()
-        latent = eng.h_s(ops.eb_dequant(sym_z.contiguous(), med))
-        pa = eng.head(latent)
+        if self.codec_precision != "bf16":
+            pt = self.precise(self.codec_precision)
+            latent = pt.h_s(ops.symbols_to_nhwc_f32(sym_z.contiguous(), med))
+            head, context = pt.head, pt.context
+            ctx_in = 0  # the context conv reads the fp32 dequantised anchors
+        else:
+            latent = eng.h_s(ops.eb_dequant(sym_z.contiguous(), med))
+            head, context = eng.head, eng.context
+            ctx_in = 1  # ... or their bf16 copy
+        pa = head(latent)
         idx_a = ops.gc_indexes(pa, table, self.M, bound)
         sym_a = gc.decode_symbols(strings[0][0], idx_a).to(dev, non_blocking=True)
-        yqa32, yqa16 = ops.gc_dequant(sym_a.contiguous(), pa)
-        ctx = eng.context(yqa16)
-        pna = eng.head(latent, ctx)
+        yqa = ops.gc_dequant(sym_a.contiguous(), pa, want_bf16=bool(ctx_in))
+        yqa32 = yqa[0]
+        ctx = context(yqa[ctx_in])
+        pna = head(latent, ctx)
         idx_na = ops.gc_indexes(pna, table, self.M, bound)
         sym_na = gc.decode_symbols(strings[0][1], idx_na).to(dev, non_blocking=True)
         yqna32, _ = ops.gc_dequant(sym_na.contiguous(), pna, want_bf16=False)
@@ -261,11 +335,14 @@ class LightWeightCheckerboard(CompressionModel):
         out = super().load_state_dict(state_dict)
         if self._engine is not None:
             self._engine.sync(force=True)
+        for pt in self._precise.values():
+            pt.sync(force=True)
         return out
 
     def _apply(self, fn, *a, **k):
         out = super()._apply(fn, *a, **k)
         self._engine = None  # device / dtype moved: rebuild the packed layers lazily
+        self._precise = {}
         return out
 
     @classmethod

@@ -10,7 +10,8 @@ import torch
 
 from . import _lib as L
 from ._lib import (ACT_CLAMP01, ACT_NONE, ACT_PRELU, ACT_RELU, EPI_ADD, EPI_GATE, EPI_GDN,
-                   EPI_IGDN, EPI_LINEAR, EPI_PIXSCALE, HYRES_CONV, HYRES_DECONV_K5S2)
+                   EPI_IGDN, EPI_LINEAR, EPI_PIXSCALE, HYRES_CONV, HYRES_DECONV_K5S2, SPLIT_ADD, SPLIT_COPY,
+                   SPLIT_GATE, SPLIT_GDN, SPLIT_IGDN, SPLIT_ROUND_CHAN, SPLIT_SQUARE)
 
 
 def sm_count():
@@ -52,7 +53,9 @@ class ConvLayer:
         return sum(a.elapsed_time(b) for a, b in ev), len(ev)
 
     def __init__(self, weight, bias=None, kind=HYRES_CONV, stride=1, pad=0, dil=1, cin0=None,
-                 cin1=0, tap_mask=None):
+                 cin1=0, tap_mask=None, nsplit=1):
+        """nsplit > 1: split-precision layer (hyres_conv_create_split): inputs are the bf16 parts produced by
+        ``split_f32`` ([B,H,W,nsplit*cin]), the result is fp32 (``out_f32``) with fp32-equivalent accuracy."""
         w = weight.detach().to("cpu", torch.float32).contiguous()
         b = None if bias is None else bias.detach().to("cpu", torch.float32).contiguous()
         if kind == HYRES_DECONV_K5S2:
@@ -61,7 +64,7 @@ class ConvLayer:
             cout, cin_total, R, S = w.shape
         if cin0 is None:
             cin0 = cin_total
-        self.kind, self.cin0, self.cin1, self.cout = kind, cin0, cin1, cout
+        self.kind, self.cin0, self.cin1, self.cout, self.nsplit = kind, cin0, cin1, cout, nsplit
         self.R, self.S, self.stride, self.pad, self.dil = R, S, stride, pad, dil
         self._w_shape = tuple(w.shape)
         mask = None
@@ -69,8 +72,8 @@ class ConvLayer:
             mask = tap_mask.detach().to("cpu", torch.uint8).contiguous()
         h = C.c_void_p()
         lib = L.lib()
-        L.check(lib.hyres_conv_create(C.byref(h), kind, cin0, cin1, cin_total, cout, R, S, stride,
-                                      pad, dil, _ptr(w), _ptr(b), _ptr(mask)), "hyres_conv_create")
+        L.check(lib.hyres_conv_create_split(C.byref(h), kind, cin0, cin1, cin_total, cout, R, S, stride,
+                                            pad, dil, _ptr(w), _ptr(b), _ptr(mask), nsplit), "hyres_conv_create")
         self._h = h
 
     def update(self, weight, bias=None):
@@ -100,7 +103,8 @@ class ConvLayer:
 
     def __call__(self, x0, x1=None, epi=EPI_LINEAR, act=ACT_NONE, slope=0.0, aux0=None, aux1=None,
                  pixscale=None, out_bf16=True, out_sq=False, out_f32=None, mt=0, x0_square=False, out_pad=0,
-                 up_t2=None, up_t3=None, cta_limit=0):
+                 up_t2=None, up_t3=None, cta_limit=0, split_mode=SPLIT_COPY, aux0_f32=None, aux1_f32=None,
+                 out_split=None, split_square=False):
         """Run the layer.
 
         out_bf16 / out_sq: True (allocate), False, or a preallocated NHWC tensor (its last
@@ -111,15 +115,19 @@ class ConvLayer:
         out_pad: > 0 allocates (or expects) the bf16 output as [B, OH+2p, OW+2p, C] and stores into its interior.
         up_t2 / up_t3: padded bf16 [B, OH/2+2, OW/2+2, 64] / [B, OH/4+2, OW/4+2, 64]; their bilinear x2 / x4
         up-samplings are added to the accumulator before the epilogue (MultiScaleRefine fusion).
+        Split-precision layers (nsplit > 1): ``split_mode`` / ``aux0_f32`` / ``aux1_f32`` fuse the fp32
+        element-wise stage into the epilogue and ``out_split`` (True or a tensor [B,OH,OW,nsplit*cout]) receives the
+        bf16 parts of the result (of its square with ``split_square``); the parts tensor is returned in the ``sq``
+        slot.
         Returns (bf16, sq, f32) with None for absent outputs.
         """
         _chk_nhwc(x0, "x0")
         B, H, W, c0 = x0.shape
-        if c0 != self.cin0:
-            raise ValueError(f"x0 has {c0} channels, layer expects {self.cin0}")
+        if c0 != self.nsplit * self.cin0:
+            raise ValueError(f"x0 has {c0} channels, layer expects {self.nsplit} x {self.cin0}")
         if self.cin1:
             _chk_nhwc(x1, "x1")
-            if tuple(x1.shape) != (B, H, W, self.cin1):
+            if tuple(x1.shape) != (B, H, W, self.nsplit * self.cin1):
                 raise ValueError("x1 shape mismatch")
         OH, OW = self.out_size(H, W)
         dev = x0.device
@@ -180,6 +188,24 @@ class ConvLayer:
                 raise ValueError("out_f32 view must be fp32 [B,OH,OW,>=cout]")
             io.out_f32 = view.data_ptr()
             io.f32_sb, io.f32_sh, io.f32_sw, io.f32_sc = view.stride()
+        if out_split is not None and out_split is not False:
+            if self.nsplit == 1:
+                raise ValueError("out_split needs a split-precision layer")
+            if out_split is True:
+                out_split = torch.empty((B, OH, OW, self.nsplit * self.cout), dtype=torch.bfloat16, device=dev)
+            if (out_split.dtype != torch.bfloat16 or not out_split.is_contiguous()
+                    or tuple(out_split.shape) != (B, OH, OW, self.nsplit * self.cout)):
+                raise ValueError("out_split: expected contiguous bf16 [B,OH,OW,nsplit*cout]")
+            io.out_split, io.out_nsplit, io.split_square = out_split.data_ptr(), self.nsplit, 1 if split_square else 0
+            osq = out_split
+        io.split_mode = int(split_mode)
+        for t, nm in ((aux0_f32, "aux0_f32"), (aux1_f32, "aux1_f32")):
+            if t is not None:
+                if t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != (B, OH, OW, self.cout):
+                    raise ValueError(f"{nm}: expected contiguous fp32 [B,OH,OW,cout]")
+        io.aux0_f32 = aux0_f32.data_ptr() if aux0_f32 is not None else 0
+        io.aux1_f32 = aux1_f32.data_ptr() if aux1_f32 is not None else 0
+        keep += [aux0_f32, aux1_f32]
         io.mt_hint = mt
         io.cta_limit = int(cta_limit)
         io.x0_square = 1 if x0_square else 0
@@ -307,6 +333,57 @@ def conv3ch(layer, ksize, stride, a, b=None, sign=1, want_sum=True, act=ACT_NONE
     else:
         run()
     return src, out
+
+
+def split_f32(x, mode=SPLIT_COPY, aux0=None, aux1=None, chan=None, relu=False, nsplit=3, want_f32=False,
+              want_split=True):
+    """Element-wise stage of the split-precision trunk (csrc/precise.cu).  x, aux0, aux1: fp32 NHWC [..., C];
+    chan: fp32 [C].  -> (v fp32 or None, bf16 parts [..., nsplit*C] or None); COPY without ReLU returns x itself
+    as the fp32 result."""
+    _f32c(x, "x")
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    for t, nm in ((aux0, "aux0"), (aux1, "aux1")):
+        if t is not None:
+            _f32c(t, nm)
+            if t.shape != x.shape:
+                raise ValueError(f"split_f32: {nm} shape mismatch")
+    if chan is not None:
+        _f32c(chan, "chan")
+        if chan.numel() != Cc:
+            raise ValueError("split_f32: chan must have C entries")
+    trivial = mode == SPLIT_COPY and not relu
+    o32 = torch.empty_like(x) if (want_f32 and not trivial) else None
+    osp = torch.empty(x.shape[:-1] + (nsplit * Cc,), dtype=torch.bfloat16, device=x.device) if want_split else None
+    if o32 is not None or osp is not None:
+        L.check(L.lib().hyres_split_f32(_ptr(x), rows, Cc, mode, _ptr(aux0), _ptr(aux1), _ptr(chan), 1 if relu else 0,
+                                        _ptr(o32), _ptr(osp), nsplit, _stream()), "hyres_split_f32")
+    return (x if (want_f32 and trivial) else o32), osp
+
+
+def residual_im2col5s2_split(x, jpeg=None, nsplit=3):
+    """x, jpeg: fp32 NCHW [B,3,H,W] -> (residual fp32 NCHW or x, bf16 parts [B,H/2,W/2,nsplit*128])."""
+    _f32c(x, "x")
+    B, Cc, H, W = x.shape
+    if Cc != 3:
+        raise ValueError("expected 3 channels")
+    res = None
+    if jpeg is not None:
+        _f32c(jpeg, "jpeg")
+        res = torch.empty_like(x)
+    a = torch.empty((B, H // 2, W // 2, nsplit * 128), dtype=torch.bfloat16, device=x.device)
+    L.check(L.lib().hyres_residual_im2col5s2_split(_ptr(x), _ptr(jpeg), _ptr(res), _ptr(a), nsplit, B, H, W,
+                                                   _stream()), "hyres_residual_im2col5s2_split")
+    return (res if res is not None else x), a
+
+
+def symbols_to_nhwc_f32(symbols, chan=None):
+    """int32 [B,C,h,w] (+ per-channel fp32 offset) -> fp32 NHWC [B,h,w,C]."""
+    B, Cc, h, w = symbols.shape
+    out = torch.empty((B, h, w, Cc), dtype=torch.float32, device=symbols.device)
+    L.check(L.lib().hyres_symbols_to_nhwc_f32(_ptr(symbols), _ptr(chan), _ptr(out), B, h, w, Cc, _stream()),
+            "hyres_symbols_to_nhwc_f32")
+    return out
 
 
 def final_clamp(x0, refined):

@@ -93,6 +93,17 @@ typedef struct hyres_conv hyres_conv;
 int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout,
                       int R, int S, int stride, int pad, int dil, const float* weight,
                       const float* bias, const uint8_t* tap_mask);
+/* Split-precision variant (fp32-equivalent arithmetic on the bf16 tensor cores) for the layers that decide
+ * integer symbols and CDF indexes -- g_a, h_a, h_s, context_prediction, param_aggregation
+ * (models/checkerboard.py:35-45,61-88), whose fp32 results the reference rounds at
+ * models/checkerboard.py:159-165. nsplit = 1 is hyres_conv_create. nsplit = 2 / 3: the layer's inputs are bf16
+ * NHWC tensors [B,H,W,nsplit*cin] holding nsplit bf16 parts of every fp32 activation (part p in channels
+ * [p*cin,(p+1)*cin), see hyres_split_f32); the weights are packed as nsplit parts as well and part i of the
+ * activations is multiplied with parts 0..nsplit-1-i of the weights (3 / 6 tensor-core products per MAC), all
+ * accumulated in one fp32 TMEM tile. Such layers take HYRES_EPI_LINEAR (+ bias, ReLU) and write out_f32 only. */
+int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout,
+                            int R, int S, int stride, int pad, int dil, const float* weight,
+                            const float* bias, const uint8_t* tap_mask, int nsplit);
 /* Re-pack new weights into an existing layer (same geometry). */
 int hyres_conv_update(hyres_conv* c, const float* weight, const float* bias);
 void hyres_conv_destroy(hyres_conv* c);
@@ -130,6 +141,17 @@ typedef struct {
   const void* up_t3;
   int cta_limit; /* > 0: launch at most this many CTAs (the persistent kernels use one per SM); lets two
                     independent layers -- the branches of an AttentionBlock -- share the GPU on two streams */
+  /* Split-precision layers only (hyres_conv_create_split, nsplit > 1): the fp32 element-wise stage that follows
+   * the convolution, fused into its epilogue.  v = split_mode(acc + bias, aux0_f32, aux1_f32) (HYRES_SPLIT_COPY /
+   * _ADD / _GATE / _GDN / _IGDN, see hyres_split_f32), then `act` (none / ReLU).  v goes to out_f32 (optional) and,
+   * as out_nsplit bf16 parts, to out_split [B,OH,OW,out_nsplit*cout] (optional); split_square != 0 stores the
+   * parts of v*v instead (the x^2 operand of the GDN that follows).  aux*: fp32 NHWC [B,OH,OW,cout], dense. */
+  int split_mode;
+  const float* aux0_f32;
+  const float* aux1_f32;
+  void* out_split;
+  int out_nsplit;
+  int split_square;
 } hyres_conv_io;
 
 int hyres_conv_out_size(const hyres_conv* c, int H, int W, int* OH, int* OW);
@@ -213,6 +235,31 @@ int hyres_gc_dequant(const int32_t* symbols, const float* params, float* yq_f32,
                      int B, int h, int w, int M, void* stream);
 /* y_hat = a + b (fp32 NHWC in, bf16 NHWC out). models/checkerboard.py:234 */
 int hyres_add_to_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------- */
+/* Split-precision trunk: fp32 element-wise work between two split convolutions */
+/* ------------------------------------------------------------------------- */
+#define HYRES_SPLIT_COPY 0       /* v = in                                                      */
+#define HYRES_SPLIT_ADD 1        /* v = in + aux0           (ResidualUnit / RBB skip)           */
+#define HYRES_SPLIT_GATE 2       /* v = aux1 * sigmoid(in) + aux0  (models/layers/attention.py:44-47) */
+#define HYRES_SPLIT_GDN 3        /* v = aux0 * (1 / sqrt(in))      (compressai GDN)             */
+#define HYRES_SPLIT_IGDN 4       /* v = aux0 * sqrt(in)                                         */
+#define HYRES_SPLIT_SQUARE 5     /* v = in * in             (the GDN operand x^2)               */
+#define HYRES_SPLIT_ROUND_CHAN 6 /* v = round(in - chan[c]) + chan[c]  (models/checkerboard.py:99-101) */
+/* in, aux0, aux1: fp32 [rows][C] (NHWC rows); chan: fp32 [C]. v (then ReLU if relu != 0) is written as fp32
+ * (out_f32, optional) and as nsplit bf16 parts [rows][nsplit*C] (out_split, optional): part 0 = bf16(v),
+ * part 1 = bf16(v - part 0), part 2 = bf16(v - part 0 - part 1). IEEE fp32 arithmetic throughout. */
+int hyres_split_f32(const float* in, int64_t rows, int C, int mode, const float* aux0, const float* aux1,
+                    const float* chan, int relu, float* out_f32, void* out_split, int nsplit, void* stream);
+/* residual = x - jpeg (fp32 NCHW; jpeg may be NULL: x is the residual) and the 5x5/stride-2 im2col of the
+ * residual as nsplit bf16 parts [B,H/2,W/2,nsplit*128] (k = (r*5+s)*3+c within a part, 75 live): g_a.0 as a
+ * split 1x1 GEMM. models/hyres.py:48,96 + models/checkerboard.py:36 */
+int hyres_residual_im2col5s2_split(const float* x, const float* jpeg, float* residual, void* a_out, int nsplit,
+                                   int B, int H, int W, void* stream);
+/* out[b,i,j,c] = float(symbols[b,c,i,j]) + chan[c] (chan may be NULL): decoded integer symbols in the coder's
+ * (B,C,h,w) order -> fp32 NHWC (EntropyBottleneck.dequantize, compressai; models/checkerboard.py:206). */
+int hyres_symbols_to_nhwc_f32(const int32_t* symbols, const float* chan, float* out, int B, int h, int w, int C,
+                              void* stream);
 
 /* EntropyBottleneck. z: fp32 NHWC [B,h,w,C]. `eb_params`: fp32 [C][58] =
  * softplus(matrices) (3,9,9,9,3), biases (3,3,3,3,1), tanh(factors) (3,3,3,3);

@@ -1,14 +1,15 @@
 """The drop-in model API on the GPU (LightWeightCheckerboard / ResidualJPEGCompression of
 hyres_b200) against the CPU oracle on the same seeded weights and inputs.
 
-Stated tolerances: the convolution trunk stores activations in bf16 with
-fp32 accumulation, so float outputs are compared with the oracle's bf16-storage mode at
-  x_hat / residual_hat : 3e-2 of the output range (max abs),
-  y, z, entropy params : 2e-2 / 5e-2 of their range,
-  rate (bpp)           : 1 % relative,
-and integer streams are compared by match fraction here (they are bit-exact *given identical
-float inputs*: tests/test_gpu_kernels.py).  Encoder and decoder of the product are bit-consistent
-with each other: decompress(compress(x)) reproduces forward(x) exactly."""
+Two arithmetic modes of the entropy-critical trunk (models.LightWeightCheckerboard.precision / codec_precision):
+  "fp32x3" (compress / decompress default): compared with the oracle's fp32 mode -- the reference's semantics --
+           y, z, entropy params to 5e-5 of their range, integer streams >= 0.999 equal end to end (every mismatch a
+           numerical tie or its consequence: tests/test_gpu_precise.py has the stage-by-stage accounting);
+  "bf16"   (forward default): activations stored in bf16 with fp32 accumulation, compared with the oracle's
+           bf16-storage mode at x_hat / residual_hat 3e-2 of the output range (max abs), y, z, entropy params
+           2e-2 / 5e-2 / 8e-2 of their range, rate 1 % relative, integer streams by match fraction.
+g_s and MultiScaleRefine run in bf16 in both modes (x_hat: 3e-2 abs).  Encoder and decoder of the product are
+bit-consistent with each other: decompress(compress(x)) reproduces forward(x) exactly when both use one mode."""
 import pytest
 import torch
 
@@ -33,11 +34,30 @@ def test_codec_stages_vs_oracle(nets, oracle, B, H, W):
     x = oracle.synthetic_image(B, H, W, seed=9)
     jpeg_dec, _ = onet.jpeg(x)
     residual = x - jpeg_dec
+    nchw = lambda t: t.permute(0, 3, 1, 2).float().cpu()  # noqa: E731
+    # fp32-equivalent trunk (the codec default) against the reference's fp32 semantics
+    assert pnet.residual_model.codec_precision == "fp32x3"
     with torch.no_grad():
         s = pnet.residual_model.encode_symbols(residual.cuda())
-        with oracle.precision("bf16"):
+        with oracle.precision("fp32"):
             oc = onet.residual_model.compress(residual, return_intermediates=True)
-    nchw = lambda t: t.permute(0, 3, 1, 2).float().cpu()  # noqa: E731
+    assert _rel(nchw(s["y"]), oc["_y"]) < 5e-5
+    assert _rel(nchw(s["z"]), oc["_z"]) < 5e-5
+    assert _rel(nchw(s["params_a"]), oc["_anchor_params"]) < 5e-5
+    for k, lo in (("sym_z", 1.0), ("sym_a", 0.9999), ("idx_a", 0.9999), ("sym_na", 0.999), ("idx_na", 0.995)):
+        got, want = s[k].cpu(), oc["_" + k].int()
+        match = (got == want).float().mean().item()
+        assert match >= lo, f"{k}: {match}"
+        assert (got - want).abs().max().item() <= 1
+    # plain bf16 trunk against the oracle's bf16-storage mode
+    pnet.residual_model.codec_precision = "bf16"
+    try:
+        with torch.no_grad():
+            s = pnet.residual_model.encode_symbols(residual.cuda())
+            with oracle.precision("bf16"):
+                oc = onet.residual_model.compress(residual, return_intermediates=True)
+    finally:
+        pnet.residual_model.codec_precision = "fp32x3"
     assert _rel(nchw(s["y"]), oc["_y"]) < 2e-2
     assert _rel(nchw(s["z"]), oc["_z"]) < 2e-2
     assert _rel(nchw(s["params_a"]), oc["_anchor_params"]) < 5e-2
@@ -105,7 +125,11 @@ def test_compress_decompress_roundtrip_and_self_consistency(nets, oracle):
         (sa, sna), sz = c["strings"]
         assert len(sa) == len(sna) == len(sz) == B and all(isinstance(t, bytes) for t in sa + sna + sz)
         d = codec.decompress(c["strings"], c["shape"])
-        f = codec(residual)
+        codec.precision = codec.codec_precision  # forward on the trunk the codec uses
+        try:
+            f = codec(residual)
+        finally:
+            codec.precision = "bf16"
     assert d["x_hat"].shape == (B, 3, H, W)
     assert torch.equal(d["x_hat"], f["x_hat"].clamp(0, 1))  # Q3, and encoder/decoder bit-consistency
     # the strings decode to exactly the symbols the encoder produced
@@ -130,7 +154,7 @@ def test_wrapper_compress_decompress(nets, oracle):
         c = pnet.compress(x.cuda())
         assert "jpeg_buffers" in c and len(c["jpeg_buffers"]) == 1
         d = pnet.decompress(c)
-        with oracle.precision("bf16"):
+        with oracle.precision("fp32"):
             oc = onet.compress(x, jpeg_buffers=c["jpeg_buffers"])
             od = onet.decompress(oc)
     assert d["x_hat"].shape == x.shape and 0 <= d["x_hat"].min() and d["x_hat"].max() <= 1
@@ -203,7 +227,11 @@ def test_full_size_properties_cfg3_tile(nets, oracle):
     with torch.no_grad():
         c = codec.compress(tiles)
         d = codec.decompress(c["strings"], c["shape"])
-        f = codec(tiles)
+        codec.precision = codec.codec_precision
+        try:
+            f = codec(tiles)
+        finally:
+            codec.precision = "bf16"
     assert torch.equal(d["x_hat"], f["x_hat"].clamp(0, 1))
     nbytes = sum(len(s) for grp in (c["strings"][0][0], c["strings"][0][1], c["strings"][1]) for s in grp)
     assert all(len(s) % 4 == 0 and len(s) >= 8 for s in c["strings"][1])
