@@ -1,25 +1,28 @@
 #!/usr/bin/env python
-"""Headline benchmark of the HyRES residual-codec hot path (BASELINE.json metric).
+"""Headline benchmark of the HyRES residual-codec hot path (BASELINE.json metric: enc+dec Mpixel/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload codec|forward]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1]): full ResidualJPEGCompression forward + rate-distortion loss on
-a batch of 16 synthetic 768x512 images per GPU (N=128, M=192, random-init weights, seed 1926).
-One step = one pass of the hot path over one batch, JPEG stage included on both arms: on the B200 arm
-it runs on the device (csrc/jpeg.cu, bit-exact with libjpeg-turbo), on the reference arm it is the
-per-image libjpeg-turbo loop the reference runs on the CPU (models/utils/turbo_jpeg_compression.py).
+Workload `codec` (default; BASELINE.json configs[2]): ResidualJPEGCompression.compress + .decompress of one
+2048x1408 CLIC-shape image per GPU per step, as eight 704x512 tiles (tier T-A of SURVEY section 8e) -- JPEG q=1
+stage, residual codec with the fp32-equivalent (split-bf16) entropy trunk, rANS strings out (host threads) and
+back in, synthesis + MultiScaleRefine.  Steps run through hyres_b200.CodecPipeline (several images in flight on
+worker threads / CUDA streams; every image still goes through the public compress / decompress).
 
-  value : Mpixel/s with inputs resident in HBM (CUDA events on the launch stream, max over ranks)
-  e2e   : Mpixel/s through the public API with pinned HOST inputs, H2D copies and the D2H read of
-          the loss inside the timed region
-  roofline     : the dominant kernel, ru_fused_kernel (tensor bound): its algorithmic FLOPs per launch / its
-                 average CUDA-event launch time; `all_tensor_kernels` = canonical FLOPs of the step / summed
-                 time of every tcgen05 launch
-  cpu_baseline : the CPU oracle (the reference's PyTorch semantics, fp32) on a bounded sample
+  value : Mpixel/s, inputs resident in HBM, x_hat left on the device (the strings do cross the host: that is the path)
+  e2e   : Mpixel/s with pinned HOST images in and x_hat back in pinned HOST memory, all copies inside the timed region
+  roofline     : the dominant kernel of this workload, conv_tc_kernel on the split-precision layers (tensor bound):
+                 algorithmic FLOPs of those layers / their summed CUDA-event launch time (6 tensor-core products per
+                 algorithmic MAC are executed: `executed` says what the tensor pipe actually sustained)
+  forward      : the round-1 headline kept beside it -- BASELINE.json configs[1], full forward + RD loss, batch 16 of
+                 768x512, bf16 trunk -- with the roofline of its dominant kernel (ru_fused_kernel)
+  cpu_baseline : the CPU oracle (the reference's PyTorch semantics, fp32) compress + decompress on a bounded sample
 
-`--impl reference` times that CPU path alone, on every host core, for the driver's ratio.
+Under torchrun every rank runs its own images (weak scaling) and the step's statistics (stream bytes, squared
+error, pixels) are all-reduced over NCCL inside the timed step.  `--impl reference` times the CPU path alone, on
+every host core, for the driver's ratio.  `--workload forward` prints the forward line instead.
 """
 import argparse
 import json
@@ -43,14 +46,19 @@ RU_MAC_PER_POS = 128 * 64 + 9 * 64 * 64 + 64 * 128  # one fused ResidualUnit, pe
 RU_DRAM_BYTES_PER_LAUNCH = 761_778_944  # dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_ncu_full.md
 
 
+CODEC_TILES, CODEC_H, CODEC_W = 8, 704, 512  # one 2048x1408 image as a 2x4 grid of tiles
+# canonical algorithmic work of compress + decompress, SURVEY.md section 8d: encode 215 488 + decode 322 642 MAC/px
+MAC_PER_PX_ENCDEC = 538_130
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as fh:
             d = json.load(fh)
-        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))), hbm=float(d["hbm_gbs"]),
-                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
-    return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md, sustained)")
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops"))), burst=float(d["bf16_tflops"]),
+                    hbm=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1400.0, burst=1660.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler:
@@ -133,6 +141,47 @@ def oracle_step_factory(sample_images, threads):
     return step, sample_images * H * W
 
 
+def oracle_codec_step_factory(tiles, threads):
+    """The reference's CPU compress + decompress (models/hyres.py:79-134 through the oracle restatement, fp32,
+    its C rANS coder, libjpeg-turbo for the JPEG stage) on `tiles` 704x512 tiles."""
+    import torch
+    from oracle import hyres_oracle as O
+    torch.set_num_threads(threads)
+    net = O.make_model(seed=1926, wrapper=True)
+    x = O.synthetic_image(tiles, CODEC_H, CODEC_W, seed=7)
+
+    def step():
+        with torch.no_grad(), O.precision("fp32"):
+            c = net.compress(x)
+            d = net.decompress(c)
+            return float(d["x_hat"].mean())
+    return step, tiles * CODEC_H * CODEC_W
+
+
+def run_reference_codec(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    step, px = oracle_codec_step_factory(1, cores)
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    v = px / dt / 1e6
+    sample = (f"1 synthetic {CODEC_W}x{CODEC_H} tile per step (of the {CODEC_TILES}-tile image), compress + decompress "
+              "(CPU JPEG stage, fp32 convolutions on all cores, single-threaded C rANS per string as in the reference)")
+    print(file=OUT, flush=True, *[json.dumps({
+        "impl": "reference", "metric": "hyres_encdec_mpixel_per_s", "value": v, "unit": "Mpixel/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": codec_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    })])
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's own CPU implementation of the path (here: the oracle port,
     because compressai is not installable -- DESIGN.md section 3), all host threads, rank 0 only."""
@@ -159,94 +208,187 @@ def run_reference(args, rank):
     })])
 
 
+def codec_config(n, workers=None):
+    c = {"workload": "BASELINE.json configs[2]: ResidualJPEGCompression.compress + .decompress (JPEG q=1 stage, residual "
+                     "codec N=128 M=192 with checkerboard two-pass symbols + CDF indexes, rANS strings, MultiScaleRefine) of "
+                     "one 2048x1408 synthetic image per GPU per step as eight 704x512 tiles (tier T-A)",
+         "tiles_per_gpu": CODEC_TILES, "height": CODEC_H, "width": CODEC_W, "global_tiles": CODEC_TILES * n,
+         "trunk_precision": "fp32x3 (split-bf16, fp32-equivalent) for g_a/h_a/h_s/context/parameter head; bf16 for g_s/refine",
+         "sharding": "by image (tile set) per rank, no data-path collective; per-step NCCL all-reduce of 4 doubles "
+                     "(stream bytes, squared error, pixels, images) inside the timed step",
+         "l2": "inputs + activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+         "weights": "random init, seed 1926",
+         "timing": "host wall clock between device-wide synchronizes (max over ranks): a step alternates kernels on "
+                   "several streams with host rANS threads, so stream-local CUDA events cannot bracket it"}
+    if workers is not None:
+        c["images_in_flight"] = workers
+    return c
+
+
 def workload_config(n):
     return {"workload": "BASELINE.json configs[1]: ResidualJPEGCompression (JPEG q=1 stage + residual codec "
                         "N=128 M=192 + MultiScaleRefine) forward + RD loss, batch 16 of 768x512 synthetic images per GPU",
             "batch_per_gpu": BATCH, "height": H, "width": W, "global_batch": BATCH * n, "lambda": LMBDA,
-            "sharding": "by image, no data-path collective; 4-double statistics all-reduce",
+            "sharding": "by image, no data-path collective; the 4-double statistics all-reduce (sum log2 lik_y, sum log2 "
+                        "lik_z, squared error, pixels) runs over NCCL after every step, inside the timed region",
             "l2": "inputs + activations per step (>2 GB) exceed the 126 MB L2; no explicit flush",
             "weights": "random init, seed 1926",
             "launch": "timed steps replayed from a CUDA graph of one step (bench.py --no-graph: eager launches)"}
 
 
-def codec_cfg3(net, dev, reps=3):
-    """BASELINE.json configs[2] on one GPU: compress + decompress (strings out and back, host rANS included) of one
-    2048x1408 image as eight 704x512 tiles (tier T-A of SURVEY section 8e).  Extra evidence next to the headline."""
-    import torch
-    from hyres_b200 import synthetic
-    tiles, h, w = 8, 704, 512
-    x = synthetic.synthetic_image(tiles, h, w, seed=7)
-    xd = x.to(dev)
-    with torch.no_grad():
-        for _ in range(2):
-            d = net.decompress(net.compress(xd))
-        t_enc = t_dec = 0.0
-        for _ in range(reps):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            c = net.compress(xd)  # device JPEG encoder + residual codec; decompress decodes the JPEG files on the CPU
-            torch.cuda.synchronize()
-            t1 = time.perf_counter()
-            d = net.decompress(c)
-            torch.cuda.synchronize()
-            t_enc += t1 - t0
-            t_dec += time.perf_counter() - t1
-    px = tiles * h * w
-    nbytes = sum(len(s) for grp in (c["strings"][0][0], c["strings"][0][1], c["strings"][1]) for s in grp)
-    return {"workload": "compress + decompress, 8 tiles of 704x512 (one 2048x1408 image), JPEG stage and host rANS included",
-            "enc_ms": t_enc / reps * 1e3, "dec_ms": t_dec / reps * 1e3, "encdec_mpixel_per_s": px * reps / (t_enc + t_dec) / 1e6,
-            "residual_bpp": 8.0 * nbytes / px, "host_cores": os.cpu_count(), "x_hat_shape": list(d["x_hat"].shape)}
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-
-    rank = int(os.environ.get("RANK", "0"))
-    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its version banner there
-    # when the first communicator is created) is sent to stderr
-    global OUT
-    sys.stdout.flush()
-    OUT = os.fdopen(os.dup(1), "w")
-    os.dup2(2, 1)
-    if args.impl == "reference":
-        run_reference(args, rank)
-        return
-
+def bench_codec(args, net, dev, rank, world, lib, peaks):
+    """compress + decompress of one 8-tile image per step through CodecPipeline.  Returns the JSON line (rank 0)."""
+    import datetime
     import torch
     import hyres_b200
-    from hyres_b200 import _lib, dist as D, ops, synthetic
+    from hyres_b200 import dist as D, ops, synthetic
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA sm_100 device: the hot path has no CPU fallback")
-    rank, world, local = D.init_from_env()
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    lib = _lib.lib()
-    _lib.check(lib.hyres_device_check(local), "hyres_device_check")
+    workers = args.in_flight
+    tiles, h, w = CODEC_TILES, CODEC_H, CODEC_W
+    px_step = tiles * h * w
+    # a few distinct images per rank, cycled (the JPEG stage and the coder see different data every step)
+    hosts = [synthetic.synthetic_image(tiles, h, w, seed=7 + 17 * rank + k).pin_memory() for k in range(4)]
+    devs = [t.to(dev) for t in hosts]
+    pipe = hyres_b200.CodecPipeline(net, workers=workers, reuse_host_buffers=True)
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)  # stream bytes, squared error, pixels, images
 
-    torch.manual_seed(1926)
-    net = hyres_b200.ResidualJPEGCompression(jpeg_quality=1)
-    net.update(force=True)
-    net = net.to(dev).eval()
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def run(n, resident):
+        """n steps; every result is consumed (its stream size and reconstruction error enter the step statistics,
+        which are all-reduced across ranks: the bpp / MSE a multi-GPU job reports)."""
+        src = devs if resident else hosts
+        last = None
+        for k, (c, x_hat) in enumerate(pipe.roundtrip((src[i % len(src)] for i in range(n)), to_host=not resident)):
+            nbytes = pipe._stream_bytes(c)
+            ref = devs[k % len(devs)]
+            xh = x_hat if resident else x_hat.to(dev, non_blocking=True)
+            se = (xh - ref).double().pow(2).sum()
+            stats.copy_(torch.stack([torch.tensor(float(nbytes), dtype=torch.float64, device=dev), se,
+                                     torch.tensor(float(px_step), dtype=torch.float64, device=dev),
+                                     torch.tensor(1.0, dtype=torch.float64, device=dev)]))
+            D.reduce_stats(stats)
+            last = stats.clone()
+        torch.cuda.synchronize()
+        return last
+
+    with torch.no_grad():
+        run(max(args.warmup, workers + 1), True)
+        l0 = lib.hyres_launch_count()
+        sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else dev.index)
+        sampler.start()
+        sampler.wait_ready()
+        barrier()
+        t_start = datetime.datetime.now()
+        t0 = time.perf_counter()
+        g = run(args.steps, True)
+        barrier()
+        ms_local = (time.perf_counter() - t0) * 1e3 / args.steps
+        t_end = datetime.datetime.now()
+        clocks = sampler.stop(t_start, t_end)
+        launches = lib.hyres_launch_count() - l0
+        ms = D.max_over_ranks(ms_local, dev)
+
+        # ---- end to end: pinned host images in, x_hat back in pinned host memory ----
+        run(workers + 1, False)
+        barrier()
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
+        t0 = time.perf_counter()
+        ge = run(args.steps, False)
+        barrier()
+        e2e_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, dev)
+        h2d, d2h = pipe.h2d_bytes // args.steps, pipe.d2h_bytes // args.steps
+
+        # ---- one un-pipelined compress / decompress: latency of the single public calls + per-launch conv times ----
+        prof = None
+        if rank == 0:
+            x = devs[0]
+            net.decompress(net.compress(x))  # this thread's stream: warm the allocator before timing single calls
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            c = net.compress(x)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            net.decompress(c)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            ops.ConvLayer.profile_begin()
+            c = net.compress(x)
+            net.decompress(c)
+            conv_ms, conv_n = ops.ConvLayer.profile_end()
+            rows = ops.ConvLayer.last_profile
+            split = [r for r in rows if r.get("nsplit", 1) > 1]
+            prof = dict(enc_ms=(t1 - t0) * 1e3, dec_ms=(t2 - t1) * 1e3, conv_ms=conv_ms, conv_n=conv_n,
+                        split_ms=sum(r["ms"] for r in split), split_n=len(split),
+                        split_flops=2.0 * sum(r["alg_macs"] for r in split),
+                        split_products=6 if net.residual_model.codec_precision == "fp32x3" else 3)
+    pipe.close()
+    if rank != 0:
+        return None
+    value = world * px_step / (ms * 1e-3) / 1e6
+    gbytes, gse, gpx, gimg = [float(v) for v in g.tolist()]
+    achieved = prof["split_flops"] / (prof["split_ms"] * 1e-3) / 1e12
+    line = {
+        "metric": "hyres_encdec_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 tensor-core products, fp32 accumulation; the entropy-critical trunk carries "
+                                      "fp32 activations as 3 bf16 parts (fp32-equivalent); symbols int32",
+        "data": "synthetic", "config": codec_config(world, workers),
+        "e2e": {"value": world * px_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "h2d / d2h count the image in and the reconstruction out; the symbol / index tensors cross PCIe "
+                        "on top of that in both arms (resident and e2e), because the entropy coder runs on the host"},
+        "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(1, args.steps),
+        "clocks": clocks,
+        "global_stats": {"bpp": 8.0 * gbytes / gpx, "mse_255": gse / (gpx * 3) * 255 ** 2, "images": gimg,
+                         "note": "last step, all-reduced over ranks (NCCL) inside the timed loop"},
+        "single_call_latency": {"compress_ms": prof["enc_ms"], "decompress_ms": prof["dec_ms"],
+                                "note": "one un-pipelined public compress() / decompress() of the 8-tile image"},
+        "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel on the %d split-precision (fp32x3) layers of one compress + "
+                                                  "decompress" % prof["split_n"],
+                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                     "traffic": None, "executed": achieved * prof["split_products"],
+                     "executed_frac": achieved * prof["split_products"] / peaks["tflops"],
+                     "ms_per_step": prof["split_ms"], "peak_source": peaks["source"],
+                     "note": "achieved counts ALGORITHMIC FLOPs (one MAC per weight tap); each is executed as %d bf16 "
+                             "tensor-core products so that symbols equal the fp32 reference's, `executed` is what the "
+                             "tensor pipe sustains" % prof["split_products"],
+                     "all_tensor_kernels": {"launches": prof["conv_n"], "ms_per_step": prof["conv_ms"],
+                                            "achieved": 2.0 * MAC_PER_PX_ENCDEC * px_step / (prof["conv_ms"] * 1e-3) / 1e12},
+                     "step_tflops": 2.0 * MAC_PER_PX_ENCDEC * px_step / (ms * 1e-3) / 1e12},
+    }
+    return line
+
+
+def bench_forward(args, net, dev, rank, world, lib, peaks, steps):
+    """BASELINE.json configs[1]: forward + RD loss, batch 16 of 768x512 (the round-1 headline).  Returns a dict."""
+    import datetime
+    import torch
+    import hyres_b200
+    from hyres_b200 import dist as D, ops, synthetic
+
     crit = hyres_b200.RateDistortionLoss(lmbda=LMBDA)
-
     x_host = synthetic.synthetic_image(BATCH, H, W, seed=1926 + rank).pin_memory()
     x_dev = x_host.to(dev)
     px_step = BATCH * H * W
     stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    gstats = torch.zeros(4, dtype=torch.float64, device=dev)
+    se = torch.zeros(1, dtype=torch.float64, device=dev)
 
     def step_resident():
         stats.zero_()
         out = net(x_dev, stats=stats)  # JPEG stage (device) + residual codec + refine
-        return crit(out, x_dev, stats=stats)
+        lo = crit(out, x_dev, stats=stats)
+        # the four sums a multi-GPU job reduces: sum log2 lik_y, sum log2 lik_z, squared error, pixels
+        se.zero_()
+        ops.reduce_sqdiff(out["x_hat"], x_dev, se)
+        gstats[0:2].copy_(stats)
+        gstats[2:3].copy_(se)
+        gstats[3].fill_(float(px_step))
+        return lo
 
     def barrier():
         if world > 1:
@@ -256,9 +398,6 @@ def main():
     with torch.no_grad():
         for _ in range(args.warmup):
             step_resident()
-        # The timed steps are replayed from a CUDA graph of one step (the same launches on the same buffers; under
-        # capture the two AttentionBlock branches at 1/8 resolution also overlap on two streams).  --no-graph, or a
-        # failed capture, times eager launches instead.
         graph, lo = None, None
         l0 = lib.hyres_launch_count()
         if not args.no_graph:
@@ -275,32 +414,31 @@ def main():
         if graph is None:
             l0 = lib.hyres_launch_count()
             lo = step_resident()
-        launches = lib.hyres_launch_count() - l0  # kernels of ONE step (counted at capture / at the eager call)
-        import datetime
-        sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+        launches = lib.hyres_launch_count() - l0
+        red = gstats.clone()
+        sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else dev.index)
         sampler.start()
-        sampler.wait_ready()  # nvidia-smi needs ~0.1 s to deliver its first sample
+        sampler.wait_ready()
         barrier()
         t_start = datetime.datetime.now()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             if graph is not None:
                 graph.replay()
             else:
                 lo = step_resident()
+            red.copy_(gstats)
+            D.reduce_stats(red)  # NCCL all-reduce of the step's four sums, on the same stream, every step
         e1.record()
         barrier()
         t_end = datetime.datetime.now()
-        ms_local = e0.elapsed_time(e1) / args.steps
+        ms_local = e0.elapsed_time(e1) / steps
         clocks = sampler.stop(t_start, t_end)
         ms = D.max_over_ranks(ms_local, dev)
         loss_val = float(lo["loss"])
+        glob = D.rd_from_stats(red, LMBDA, jpeg_bpp=0.0)
 
-        # ---- end to end through the public API with host buffers ----
-        # hyres_b200.HostPipeline: every step's x leaves pinned host memory inside the timed region (on a copy
-        # stream, under the previous step's kernels), the JPEG stage runs on the device, and every step's loss
-        # is read back.
         pipe = hyres_b200.HostPipeline(net, crit)
 
         def host_batches(n):
@@ -312,52 +450,47 @@ def main():
         barrier()
         pipe.h2d_bytes = pipe.d2h_bytes = 0
         t0 = time.perf_counter()
-        e2e_results = list(pipe.run(host_batches(args.steps)))
+        e2e_results = list(pipe.run(host_batches(steps)))
         torch.cuda.synchronize()
-        e2e_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3 / args.steps, dev)
-        h2d = pipe.h2d_bytes // args.steps
-        d2h = pipe.d2h_bytes // args.steps
+        e2e_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps, dev)
+        h2d = pipe.h2d_bytes // steps
+        d2h = pipe.d2h_bytes // steps
         e2e_loss = e2e_results[-1]["loss"]
 
-        # ---- roofline of the dominant kernel: per-launch CUDA events around every conv launch ----
         conv_ms, conv_n = None, 0
         if rank == 0:
             ops.ConvLayer.profile_begin()
             step_resident()
             torch.cuda.synchronize()
             conv_ms, conv_n = ops.ConvLayer.profile_end()
-
     if rank != 0:
-        torch.distributed.destroy_process_group()
-        return
-    peaks = load_peaks()
+        return None
     value = world * px_step / (ms * 1e-3) / 1e6
     flops_step = 2.0 * MAC_PER_PX_CONV * px_step
     all_tc = flops_step / (conv_ms * 1e-3) / 1e12 if conv_ms else None
-    # dominant kernel: ru_fused_kernel (the 14 C=128 ResidualUnit / ResidualBottleneckBlock instances at H/2).
-    # algorithmic MACs per position = 128*64 + 576*64 + 64*128; traffic per launch from the
-    # ncu --set full capture of the same shape (profiles/r01_ncu_full.md): dram read + write.
     ru = [r for r in ops.ConvLayer.last_profile if r["kind"] == "ru" and r["H"] == H // 2]
     ru_flops = 2.0 * RU_MAC_PER_POS * BATCH * (H // 2) * (W // 2)
     ru_ms = sum(r["ms"] for r in ru) / len(ru) if ru else None
     achieved = ru_flops / (ru_ms * 1e-3) / 1e12 if ru_ms else None
-    line = {
+    return {
         "metric": "hyres_forward_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "steps": steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
         "e2e": {"value": world * px_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": int(launches) * args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "forward + RD loss: the step's result is the loss (24 bytes back); x_hat stays on the device"},
+        "gpu_launches": int(launches) * steps,
         "gpu_launches_per_step": int(launches),
         "clocks": clocks,
+        "global_stats": {"bpp_residual": float(glob["residual_bpp_loss"]), "mse_255": float(glob["mse_loss"]),
+                         "note": "all-reduced over ranks (NCCL) after every timed step"},
         "roofline": {"bound": "tensor", "kernel": "ru_fused_kernel (fused 1x1 -> 3x3 -> 1x1 + skip at 16x256x384x128, "
                                                   "%d launches per step)" % len(ru),
-                     "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                     "frac": achieved / peaks["tflops"] if achieved else None,
+                     "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
+                     "frac": achieved / peaks["burst"] if achieved else None,
+                     "frac_of_sustained": achieved / peaks["tflops"] if achieved else None,
                      "traffic": RU_DRAM_BYTES_PER_LAUNCH, "algorithmic_bytes": 2 * BATCH * (H // 2) * (W // 2) * 128 * 2,
-                     "ms_per_launch": ru_ms, "peak_source": peaks["source"],
-                     "note": "N = 64 tcgen05.mma is bound by shared-memory operand fetch at 2/3 of the dense peak "
-                             "(profiles/r01_microbench.md); the kernel is shared-memory-bandwidth bound",
+                     "ms_per_launch": ru_ms, "peak_source": peaks["source"] + "; per-launch timing -> burst peak",
                      "share_of_step": (ru_ms * len(ru)) / ms_local if ru_ms else None,
                      "all_tensor_kernels": {"launches": conv_n, "ms_per_step": conv_ms, "achieved": all_tc,
                                             "frac": all_tc / peaks["tflops"] if all_tc else None,
@@ -366,11 +499,74 @@ def main():
                      "step_frac": flops_step / (ms * 1e-3) / 1e12 / peaks["tflops"]},
         "loss": loss_val, "e2e_loss": e2e_loss,
     }
-    if world == 1:
-        line["codec_cfg3"] = codec_cfg3(net, dev)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="codec", choices=["codec", "forward"])
+    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("HYRES_CODEC_IN_FLIGHT", "4")),
+                    help="images in flight in the codec pipeline (worker threads / CUDA streams)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-forward", action="store_true", help="codec workload: skip the forward sub-benchmark")
+    ap.add_argument("--no-graph", action="store_true", help="forward: time eager launches instead of CUDA-graph replays")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    # stdout carries exactly one JSON line: everything else that writes to fd 1 (NCCL prints its version banner there
+    # when the first communicator is created) is sent to stderr
+    global OUT
+    sys.stdout.flush()
+    OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    if args.impl == "reference":
+        (run_reference_codec if args.workload == "codec" else run_reference)(args, rank)
+        return
+
+    import torch
+    import hyres_b200
+    from hyres_b200 import _lib, dist as D
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA sm_100 device: the hot path has no CPU fallback")
+    rank, world, local = D.init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lib = _lib.lib()
+    _lib.check(lib.hyres_device_check(local), "hyres_device_check")
+
+    torch.manual_seed(1926)
+    net = hyres_b200.ResidualJPEGCompression(jpeg_quality=1)
+    net.update(force=True)
+    net = net.to(dev).eval()
+    peaks = load_peaks()
+
+    if args.workload == "forward":
+        line = bench_forward(args, net, dev, rank, world, lib, peaks, args.steps)
+    else:
+        line = bench_codec(args, net, dev, rank, world, lib, peaks)
+        if not args.no_forward:
+            fwd = bench_forward(args, net, dev, rank, world, lib, peaks, max(10, args.steps))
+            if line is not None:
+                line["forward"] = {k: fwd[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "e2e",
+                                                       "gpu_launches_per_step", "roofline", "global_stats", "loss",
+                                                       "config")}
+    if rank != 0:
+        torch.distributed.destroy_process_group()
+        return
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        step, px = oracle_step_factory(1, cores)
+        if args.workload == "forward":
+            step, px = oracle_step_factory(1, cores)
+            what = f"1 synthetic {W}x{H} image (1/16 of the batch), full forward (CPU JPEG stage included) + RD loss"
+        else:
+            step, px = oracle_codec_step_factory(1, cores)
+            what = (f"1 synthetic {CODEC_W}x{CODEC_H} tile (1/8 of the image), compress + decompress (CPU JPEG stage, "
+                    "single-threaded C rANS per string as in the reference)")
         step()
         t0 = time.perf_counter()
         n = 3
@@ -378,8 +574,7 @@ def main():
             step()
         dt = (time.perf_counter() - t0) / n
         line["cpu_baseline"] = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-                                "sample": f"1 synthetic {W}x{H} image (1/16 of the batch), full forward (CPU JPEG stage "
-                                          f"included) + RD loss, fp32 oracle, mean of {n} after 1 warm-up"}
+                                "sample": what + f", fp32 oracle, mean of {n} after 1 warm-up"}
     print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -9,4 +9,5 @@ from .models import (LightWeightCheckerboard, RateDistortionLoss, ResidualJPEGCo
 from .layers import AttentionBlock, CheckboardMaskedConv2d, MultiScaleRefine, conv1x1, conv3x3  # noqa: F401
 from .jpeg import TurboJPEGCompression  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
+from .codec_pipeline import CodecPipeline  # noqa: F401
 from . import container  # noqa: F401

@@ -1,0 +1,128 @@
+"""Throughput pipeline for compress / decompress (models/hyres.py:79-134, models/checkerboard.py:167-240).
+
+One ``compress`` or ``decompress`` call is a chain GPU -> host -> GPU -> host -> GPU: the two rANS passes run on
+host threads and the second pass needs the first pass's symbols (context model).  Called back to back, the GPU
+idles while the host codes and the host idles while the GPU convolves.  ``CodecPipeline`` keeps several batches
+in flight, each on its own worker thread and CUDA stream: the coder calls (ctypes, GIL released) of one batch
+overlap the kernels and PCIe copies of the others.  Every batch still goes through the model's public
+``compress`` / ``decompress``, so the strings are exactly what single calls return.
+"""
+import threading
+from collections import deque
+from concurrent.futures import ThreadPoolExecutor
+
+import torch
+
+
+class CodecPipeline:
+    def __init__(self, model, workers=3, reuse_host_buffers=False):
+        """model: ``ResidualJPEGCompression`` (or ``LightWeightCheckerboard``) on a CUDA sm_100 device.
+        ``reuse_host_buffers``: decoded images come back in a per-worker ring of pinned buffers (no 35 MB
+        ``pin_memory`` per batch); a yielded ``x_hat`` is then valid until the next result is taken from the iterator."""
+        self.model = model
+        self.dev = next(model.parameters()).device
+        if self.dev.type != "cuda":
+            raise RuntimeError("CodecPipeline needs the model on a CUDA sm_100 device (no CPU fallback)")
+        self.workers = max(1, int(workers))
+        self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="hyres-codec")
+        self._tls = threading.local()
+        self._lock = threading.Lock()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._wrapper = hasattr(model, "residual_model")
+        self.reuse_host_buffers = bool(reuse_host_buffers)
+        # build the packed layers (and their weight uploads) once, outside the worker threads
+        codec = model.residual_model if self._wrapper else model
+        codec.engine()
+        if codec.codec_precision != "bf16":
+            codec.precise(codec.codec_precision)
+        if self._wrapper:
+            model.refine_engine()
+
+    def close(self):
+        self._pool.shutdown(wait=True)
+
+    def _stream(self):
+        s = getattr(self._tls, "stream", None)
+        if s is None:
+            s = self._tls.stream = torch.cuda.Stream(device=self.dev)
+        return s
+
+    def _host_buffer(self, like):
+        if not self.reuse_host_buffers:
+            return torch.empty(like.shape, dtype=like.dtype).pin_memory()
+        ring = self._tls.__dict__.setdefault("ring", {})
+        key = (tuple(like.shape), like.dtype)
+        ent = ring.get(key)
+        if ent is None:
+            # a worker can finish at most `workers` more jobs before the consumer asks for the next result
+            ent = ring[key] = [[torch.empty(like.shape, dtype=like.dtype).pin_memory() for _ in range(self.workers + 2)], 0]
+        ent[1] = (ent[1] + 1) % (self.workers + 2)
+        return ent[0][ent[1]]
+
+    def _count(self, h2d=0, d2h=0):
+        with self._lock:
+            self.h2d_bytes += h2d
+            self.d2h_bytes += d2h
+
+    @staticmethod
+    def _stream_bytes(c):
+        n = sum(len(s) for grp in (c["strings"][0][0], c["strings"][0][1], c["strings"][1]) for s in grp)
+        for b in c.get("jpeg_buffers", ()):
+            n += b.getbuffer().nbytes
+        return n
+
+    # -- jobs (run on a worker thread, on that worker's stream) --
+    @torch.no_grad()
+    def _compress_job(self, x):
+        torch.cuda.set_device(self.dev)
+        with torch.cuda.stream(self._stream()):
+            if not x.is_cuda:
+                self._count(h2d=x.numel() * x.element_size())
+                x = x.to(self.dev, non_blocking=True)
+            c = self.model.compress(x)
+            torch.cuda.current_stream().synchronize()
+        return c
+
+    @torch.no_grad()
+    def _decompress_job(self, c, to_host):
+        torch.cuda.set_device(self.dev)
+        with torch.cuda.stream(self._stream()):
+            d = self.model.decompress(c) if self._wrapper else self.model.decompress(c["strings"], c["shape"])
+            x_hat = d["x_hat"]
+            if to_host:
+                host = self._host_buffer(x_hat)
+                host.copy_(x_hat, non_blocking=True)
+                self._count(d2h=x_hat.numel() * x_hat.element_size())
+                x_hat = host
+            torch.cuda.current_stream().synchronize()
+        return x_hat
+
+    def _roundtrip_job(self, x, to_host):
+        c = self._compress_job(x)
+        return c, self._decompress_job(c, to_host)
+
+    def _ordered(self, jobs):
+        """Submit jobs keeping ``workers`` in flight; yield results in submission order."""
+        pending = deque()
+        for fn, args in jobs:
+            pending.append(self._pool.submit(fn, *args))
+            while len(pending) > self.workers:
+                yield pending.popleft().result()
+        while pending:
+            yield pending.popleft().result()
+
+    # -- public --
+    def compress(self, batches):
+        """batches: iterable of fp32 ``[B,3,H,W]`` tensors (pinned host or device) -> iterator of the dicts
+        ``model.compress`` returns, in order."""
+        return self._ordered((self._compress_job, (x,)) for x in batches)
+
+    def decompress(self, compressed, to_host=True):
+        """compressed: iterable of dicts from ``compress`` -> iterator of ``x_hat`` (pinned host tensors, or device
+        tensors with ``to_host=False``), in order."""
+        return self._ordered((self._decompress_job, (c, to_host)) for c in compressed)
+
+    def roundtrip(self, batches, to_host=True):
+        """compress followed by decompress of every batch -> iterator of (compressed dict, x_hat)."""
+        return self._ordered((self._roundtrip_job, (x, to_host)) for x in batches)

@@ -115,8 +115,8 @@ def encode_batch(symbols, indexes, tables, threads=None):
         return [outs[i][: lens[i]].tobytes() for i in range(count)]
 
 
-def decode_batch(strings, indexes, tables, threads=None):
-    """strings: list of bytes; indexes int32 [count, n] -> int32 [count, n]."""
+def decode_batch(strings, indexes, tables, threads=None, out=None):
+    """strings: list of bytes; indexes int32 [count, n] -> int32 [count, n] (``out``: preallocated result)."""
     ix = _i32(indexes)
     count, n = ix.shape
     if len(strings) != count:
@@ -124,7 +124,10 @@ def decode_batch(strings, indexes, tables, threads=None):
     if count == 0:
         return np.empty((0, n), dtype=np.int32)
     bufs = [np.frombuffer(s, dtype=np.uint8) for s in strings]
-    out = np.empty((count, n), dtype=np.int32)
+    if out is None:
+        out = np.empty((count, n), dtype=np.int32)
+    elif out.shape != (count, n) or out.dtype != np.int32 or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("decode_batch: `out` must be a C-contiguous int32 [count, n] array")
     bp = (C.c_void_p * count)(*[b.ctypes.data for b in bufs])
     ip = (C.c_void_p * count)(*[ix[i].ctypes.data for i in range(count)])
     op = (C.c_void_p * count)(*[out[i].ctypes.data for i in range(count)])

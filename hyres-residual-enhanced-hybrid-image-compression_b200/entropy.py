@@ -11,6 +11,8 @@ by ``hyres_pmf_to_quantized_cdf``.
 import math
 
 import numpy as np
+import threading
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -88,7 +90,7 @@ class EntropyModel(nn.Module):
         return self._tables_cache[1]
 
     # -- coding of already-quantised symbols --
-    _pinned = {}
+    _tls = threading.local()  # pinned staging buffers are per thread: CodecPipeline runs one batch per worker thread
 
     @classmethod
     def _host_i32(cls, t, slot):
@@ -101,11 +103,12 @@ class EntropyModel(nn.Module):
         if not t.is_cuda:
             return t.contiguous().numpy()
         key = (slot, t.numel())
-        buf = cls._pinned.get(key)
+        pinned = cls._tls.__dict__.setdefault("pinned", {})
+        buf = pinned.get(key)
         if buf is None:
-            if len(cls._pinned) > 16:
-                cls._pinned.clear()
-            buf = cls._pinned[key] = torch.empty(t.numel(), dtype=torch.int32).pin_memory()
+            if len(pinned) > 16:
+                pinned.clear()
+            buf = pinned[key] = torch.empty(t.numel(), dtype=torch.int32).pin_memory()
         view = buf.view(B, -1)
         view.copy_(t, non_blocking=True)
         torch.cuda.current_stream(t.device).synchronize()
@@ -134,8 +137,21 @@ class EntropyModel(nn.Module):
             k += a.shape[0]
         return res
 
-    def decode_symbols(self, strings, indexes):
-        """-> int32 CPU tensor shaped like ``indexes`` (pinned when the indexes came from the GPU)."""
+    @classmethod
+    def _pinned_i32(cls, slot, n):
+        pinned = cls._tls.__dict__.setdefault("pinned", {})
+        key = (slot, n)
+        buf = pinned.get(key)
+        if buf is None:
+            if len(pinned) > 16:
+                pinned.clear()
+            buf = pinned[key] = torch.empty(n, dtype=torch.int32).pin_memory()
+        return buf
+
+    def decode_symbols(self, strings, indexes, slot=None):
+        """-> int32 CPU tensor shaped like ``indexes`` (pinned when the indexes came from the GPU).  ``slot``: decode
+        into this thread's cached pinned buffer of that name instead of a fresh allocation (pinning 35 MB per pass
+        costs milliseconds); the result is then only valid until the same thread decodes into the slot again."""
         if not isinstance(strings, (tuple, list)):
             raise ValueError("Invalid `strings` parameter type.")
         if len(strings) != indexes.size(0):
@@ -143,6 +159,10 @@ class EntropyModel(nn.Module):
         if indexes.dim() < 2:
             raise ValueError("Invalid `indexes` size. Expected a tensor with at least 2 dimensions.")
         ix = self._host_i32(indexes, ("d", 0))
+        if slot is not None and indexes.is_cuda:
+            buf = self._pinned_i32(("o", slot), ix.size)
+            coder.decode_batch(list(strings), ix, self.tables(), out=buf.numpy().reshape(ix.shape))
+            return buf.view(indexes.shape)
         out = coder.decode_batch(list(strings), ix, self.tables())
         res = torch.from_numpy(out).reshape(indexes.shape)
         return res.pin_memory() if indexes.is_cuda else res

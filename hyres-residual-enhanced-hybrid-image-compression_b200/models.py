@@ -291,6 +291,7 @@ class LightWeightCheckerboard(CompressionModel):
         B = len(strings[1])
         out_size = (B, ebm._quantized_cdf.size(0), int(shape[0]), int(shape[1]))
         sym_z = ebm.decode_symbols(strings[1], ebm._build_indexes(out_size)).to(dev)
+        slot = "y" if dev.type == "cuda" else None  # both passes decode into one cached pinned buffer per thread
         _, med = eng.eb_params()
         if self.codec_precision != "bf16":
             pt = self.precise(self.codec_precision)
@@ -303,13 +304,13 @@ class LightWeightCheckerboard(CompressionModel):
             ctx_in = 1  # ... or their bf16 copy
         pa = head(latent)
         idx_a = ops.gc_indexes(pa, table, self.M, bound)
-        sym_a = gc.decode_symbols(strings[0][0], idx_a).to(dev, non_blocking=True)
+        sym_a = gc.decode_symbols(strings[0][0], idx_a, slot=slot).to(dev, non_blocking=True)
         yqa = ops.gc_dequant(sym_a.contiguous(), pa, want_bf16=bool(ctx_in))
         yqa32 = yqa[0]
         ctx = context(yqa[ctx_in])
         pna = head(latent, ctx)
         idx_na = ops.gc_indexes(pna, table, self.M, bound)
-        sym_na = gc.decode_symbols(strings[0][1], idx_na).to(dev, non_blocking=True)
+        sym_na = gc.decode_symbols(strings[0][1], idx_na, slot=slot).to(dev, non_blocking=True)
         yqna32, _ = ops.gc_dequant(sym_na.contiguous(), pna, want_bf16=False)
         y_hat16 = ops.add_to_bf16(yqa32, yqna32)
         x_hat = eng.g_s(y_hat16, clamp=True)  # Q3

@@ -70,6 +70,9 @@ class ConvLayer:
         mask = None
         if tap_mask is not None:
             mask = tap_mask.detach().to("cpu", torch.uint8).contiguous()
+        # algorithmic MACs per OUTPUT position (live taps only; a transposed k5 s2 layer touches 25/4 taps on average)
+        taps = int(mask.sum()) if mask is not None else R * S
+        self.alg_macs_per_out = (cin0 + cin1) * cout * taps / (4.0 if kind == HYRES_DECONV_K5S2 else 1.0)
         h = C.c_void_p()
         lib = L.lib()
         L.check(lib.hyres_conv_create_split(C.byref(h), kind, cin0, cin1, cin_total, cout, R, S, stride,
@@ -218,7 +221,8 @@ class ConvLayer:
             ConvLayer._prof.append((e0, e1))
             ConvLayer._prof_info.append(dict(kind=self.kind, cin=self.cin0 + self.cin1, cout=self.cout, k=self.R,
                                              stride=self.stride, dil=self.dil, B=B, H=H, W=W, OH=OH, OW=OW,
-                                             epi=epi, f32=o32 is not None, sq=osq is not None))
+                                             epi=epi, f32=o32 is not None, sq=osq is not None, nsplit=self.nsplit,
+                                             alg_macs=self.alg_macs_per_out * B * OH * OW))
         else:
             L.check(L.lib().hyres_conv_run(self._h, C.byref(io), _stream()), "hyres_conv_run")
         return o16, osq, o32

@@ -349,3 +349,34 @@ def test_full_size_properties_cfg4_refine(nets, oracle):
         with oracle.precision("bf16"):
             want = onet.refine((js + rs).cpu())
     assert _rel(got.cpu(), want) < 3e-2
+
+
+def test_codec_pipeline_matches_direct_calls(nets, oracle):
+    """hyres_b200.CodecPipeline (several batches in flight on worker threads / CUDA streams) returns, in order,
+    exactly the strings and reconstructions of back-to-back public compress() / decompress() calls, from pinned
+    host batches and from device batches."""
+    import hyres_b200
+    _, pnet = nets
+    batches = [oracle.synthetic_image(2, 64, 96, seed=80 + k).pin_memory() for k in range(7)]
+    want = []
+    with torch.no_grad():
+        for x in batches:
+            c = pnet.compress(x.cuda())
+            want.append((c, pnet.decompress(c)["x_hat"].cpu()))
+    pipe = hyres_b200.CodecPipeline(pnet, workers=3)
+    try:
+        got = list(pipe.roundtrip(iter(batches)))
+        assert len(got) == len(want)
+        for (c, x_hat), (wc, wx) in zip(got, want):
+            assert c["strings"] == wc["strings"] and tuple(c["shape"]) == tuple(wc["shape"])
+            assert [b.getvalue() for b in c["jpeg_buffers"]] == [b.getvalue() for b in wc["jpeg_buffers"]]
+            assert not x_hat.is_cuda and x_hat.is_pinned() and torch.equal(x_hat, wx)
+        assert pipe.h2d_bytes == 7 * 2 * 3 * 64 * 96 * 4 and pipe.d2h_bytes == pipe.h2d_bytes
+        # device batches in, device reconstructions out; separate compress / decompress stages
+        cs = list(pipe.compress(x.cuda() for x in batches[:3]))
+        xs = list(pipe.decompress(iter(cs), to_host=False))
+        for x_hat, (_, wx) in zip(xs, want[:3]):
+            assert x_hat.is_cuda and torch.equal(x_hat.cpu(), wx)
+        assert list(pipe.roundtrip(iter([]))) == []
+    finally:
+        pipe.close()
