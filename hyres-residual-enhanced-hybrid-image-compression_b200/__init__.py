@@ -11,3 +11,4 @@ from .jpeg import TurboJPEGCompression  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
 from .codec_pipeline import CodecPipeline  # noqa: F401
 from . import container  # noqa: F401
+from .export import export_model, load_exported  # noqa: F401

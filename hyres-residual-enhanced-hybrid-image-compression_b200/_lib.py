@@ -61,14 +61,15 @@ SIGNATURES = {
     "hyres_conv_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "hyres_conv_create_split": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
     "hyres_conv_update": (_i, [_vp, _vp, _vp]),
+    "hyres_conv_packed_elems": (_i64, [_vp, _i]),
+    "hyres_conv_export_packed": (_i, [_vp, _vp, _vp, _vp]),
+    "hyres_conv_import_packed": (_i, [_vp, _vp, _vp, _vp]),
     "hyres_conv_destroy": (None, [_vp]),
     "hyres_conv_macs_per_pos": (_i64, [_vp]),
     "hyres_conv_out_size": (_i, [_vp, _i, _i, C.POINTER(_i), C.POINTER(_i)]),
     "hyres_conv_run": (_i, [_vp, C.POINTER(ConvIO), _vp]),
     "hyres_ru_supported": (_i, [_vp, _vp, _vp]),
     "hyres_ru_run": (_i, [_vp, _vp, _vp, C.POINTER(RuIO), _vp]),
-    "hyres_residual_im2col5s2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "hyres_addback_im2col3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_conv3ch_run": (_i, [_vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "hyres_final_clamp": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hyres_gc_quant_pass": (_i, [_vp, _vp, _i, _i, _u64, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -84,8 +85,6 @@ SIGNATURES = {
     "hyres_eb_dequant": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_se_pool": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_se_scale_down": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "hyres_refine_up_concat_stats": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "hyres_refine_stats3": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_stats3_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "hyres_replicate_border": (_i, [_vp, _i, _i, _i, _i, _vp]),
     "hyres_refine_spatial_att": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp]),

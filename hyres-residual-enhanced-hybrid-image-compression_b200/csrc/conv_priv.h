@@ -52,6 +52,7 @@ struct hyres_conv {
   TapGroup* d_groups = nullptr;
   __nv_bfloat16* d_w = nullptr;
   __nv_bfloat16* d_w_tap = nullptr;  // tap-major packing for the three-output-channel layers (conv_sc.cu)
+  int64_t w_tap_elems = 0;
   float* d_bias = nullptr;
   std::vector<float> h_bias;  // host copy (cout_pad entries): kernels that take the bias as launch parameters
   int64_t macs_per_pos = 0;
@@ -87,4 +88,5 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
 // conv_sc.cu: layers with three output channels as one tap-major GEMM per tile plus a gather epilogue.
 bool conv_sc_applicable(const hyres_conv* c);
 void conv_sc_pack(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16>& out);
+int64_t conv_sc_packed_elems(const hyres_conv* c);
 int conv_sc_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream, int* handled);

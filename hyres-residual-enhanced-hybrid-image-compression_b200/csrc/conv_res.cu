@@ -614,11 +614,11 @@ int encode_map4(CUtensorMap* m, const void* ptr, int C, int ld, int B, int H, in
 
 template <int EPI, int ACT>
 cudaError_t launch_res(int grid, int threads, int smem, cudaStream_t stream, const ResParams& p) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static HyPerDevice attr;
+  if (!attr.done()) {
     const cudaError_t e = cudaFuncSetAttribute(conv_res_kernel<EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr.mark();
   }
   return hy_launch_pdl(conv_res_kernel<EPI, ACT>, grid, threads, smem, stream, p);
 }

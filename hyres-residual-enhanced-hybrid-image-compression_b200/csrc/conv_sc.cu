@@ -285,10 +285,10 @@ int launch(const ScParams& p, cudaStream_t stream) {
   constexpr int smem = ((C::KCH * C::N * 128 + 1023) & ~1023) + C::NA * C::KCH * kChunk + (32768 - kChunk) +
                        2 * ((kNP * NJ * 4 + 127) / 128 * 128) + 256 + 1024;
   static_assert(smem <= 227 * 1024, "conv_sc: shared memory budget");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static HyPerDevice attr;
+  if (!attr.done()) {
     HY_CUDA(cudaFuncSetAttribute(conv_sc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr.mark();
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();
@@ -304,6 +304,10 @@ bool conv_sc_applicable(const hyres_conv* c) {
   if (c->cout != 3 || c->cin1 != 0 || !c->tap_mask.empty()) return false;
   if (c->kind == HYRES_DECONV_K5S2) return c->cin0 == 128;
   return c->kind == HYRES_CONV && c->R == 3 && c->S == 3 && c->stride == 1 && c->dil == 1 && c->pad == 1 && c->cin0 == 64;
+}
+
+int64_t conv_sc_packed_elems(const hyres_conv* c) {
+  return static_cast<int64_t>(c->kind == HYRES_DECONV_K5S2 ? 80 : 32) * c->cin0;
 }
 
 void conv_sc_pack(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16>& out) {

@@ -773,7 +773,10 @@ int upload_weights(hyres_conv* c, const float* weight, const float* bias) {
   c->h_bias = b;
   if (c->nsplit == 1 && conv_sc_applicable(c)) {
     conv_sc_pack(c, weight, packed);
-    if (!c->d_w_tap) HY_CUDA(cudaMalloc(&c->d_w_tap, packed.size() * sizeof(__nv_bfloat16)));
+    if (!c->d_w_tap) {
+      c->w_tap_elems = static_cast<int64_t>(packed.size());
+      HY_CUDA(cudaMalloc(&c->d_w_tap, packed.size() * sizeof(__nv_bfloat16)));
+    }
     HY_CUDA(cudaMemcpy(c->d_w_tap, packed.data(), packed.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
   }
   return HYRES_OK;
@@ -828,12 +831,15 @@ int encode_w_map(CUtensorMap* m, const void* ptr, int ktot, int cout_pad, int bn
 }
 
 int num_sms() {
-  static int n = 0;
+  static std::atomic<int> cache[64];  // per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::atomic<int>& slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -850,7 +856,7 @@ int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_
 int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout, int R, int S,
                             int stride, int pad, int dil, const float* weight, const float* bias,
                             const uint8_t* tap_mask, int nsplit) {
-  if (!out || !weight) return hy_fail(HYRES_ERR_ARG, "conv_create: null argument");
+  if (!out) return hy_fail(HYRES_ERR_ARG, "conv_create: null argument");
   if (nsplit < 1 || nsplit > 3) return hy_fail(HYRES_ERR_ARG, "conv_create: nsplit must be 1, 2 or 3");
   if (kind != HYRES_CONV && kind != HYRES_DECONV_K5S2) return hy_fail(HYRES_ERR_ARG, "conv_create: bad kind");
   if (cin0 <= 0 || cin1 < 0 || cout <= 0 || (cin0 % 8) || (cin1 % 8))
@@ -898,9 +904,43 @@ int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int 
   if (e == cudaSuccess) e = cudaMalloc(&c->d_w, static_cast<size_t>(c->cout_pad) * c->ktot * sizeof(__nv_bfloat16));
   if (e == cudaSuccess) e = cudaMalloc(&c->d_bias, c->cout_pad * sizeof(float));
   if (e != cudaSuccess) { hyres_conv_destroy(c); return hy_fail(HYRES_ERR_CUDA, cudaGetErrorString(e)); }
-  int rc = upload_weights(c, weight, bias);
-  if (rc != HYRES_OK) { hyres_conv_destroy(c); return rc; }
+  if (conv_sc_applicable(c) && c->nsplit == 1) {
+    c->w_tap_elems = conv_sc_packed_elems(c);
+    e = cudaMalloc(&c->d_w_tap, c->w_tap_elems * sizeof(__nv_bfloat16));
+    if (e != cudaSuccess) { hyres_conv_destroy(c); return hy_fail(HYRES_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  // weight == NULL: an empty layer whose packed operands arrive through hyres_conv_import_packed
+  if (weight) {
+    int rc = upload_weights(c, weight, bias);
+    if (rc != HYRES_OK) { hyres_conv_destroy(c); return rc; }
+  } else {
+    c->h_bias.assign(c->cout_pad, 0.f);
+  }
   *out = c;
+  return HYRES_OK;
+}
+
+int64_t hyres_conv_packed_elems(const hyres_conv* c, int which) {
+  if (!c) return 0;
+  if (which == 0) return static_cast<int64_t>(c->cout_pad) * c->ktot;
+  if (which == 1) return c->d_w_tap ? static_cast<int64_t>(c->w_tap_elems) : 0;
+  return which == 2 ? c->cout_pad : 0;
+}
+
+int hyres_conv_export_packed(const hyres_conv* c, void* w, void* w_tap, float* bias) {
+  if (!c || !w || !bias || (c->d_w_tap && !w_tap)) return hy_fail(HYRES_ERR_ARG, "conv_export_packed: null argument");
+  HY_CUDA(cudaMemcpy(w, c->d_w, static_cast<size_t>(c->cout_pad) * c->ktot * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost));
+  if (c->d_w_tap) HY_CUDA(cudaMemcpy(w_tap, c->d_w_tap, c->w_tap_elems * sizeof(__nv_bfloat16), cudaMemcpyDeviceToHost));
+  HY_CUDA(cudaMemcpy(bias, c->d_bias, c->cout_pad * sizeof(float), cudaMemcpyDeviceToHost));
+  return HYRES_OK;
+}
+
+int hyres_conv_import_packed(hyres_conv* c, const void* w, const void* w_tap, const float* bias) {
+  if (!c || !w || !bias || (c->d_w_tap && !w_tap)) return hy_fail(HYRES_ERR_ARG, "conv_import_packed: null argument");
+  HY_CUDA(cudaMemcpy(c->d_w, w, static_cast<size_t>(c->cout_pad) * c->ktot * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  if (c->d_w_tap) HY_CUDA(cudaMemcpy(c->d_w_tap, w_tap, c->w_tap_elems * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice));
+  HY_CUDA(cudaMemcpy(c->d_bias, bias, c->cout_pad * sizeof(float), cudaMemcpyHostToDevice));
+  c->h_bias.assign(bias, bias + c->cout_pad);
   return HYRES_OK;
 }
 
@@ -1102,10 +1142,10 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   if (rc != HYRES_OK) return rc;
 
   const int smem = smem_need();
-  static bool smem_set = false;
-  if (!smem_set) {
+  static HyPerDevice attr;
+  if (!attr.done()) {
     HY_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    smem_set = true;
+    attr.mark();
   }
   const int grid = std::min(p.nitems, io->cta_limit > 0 ? std::min(io->cta_limit, num_sms()) : num_sms());
   hy_count_launch();

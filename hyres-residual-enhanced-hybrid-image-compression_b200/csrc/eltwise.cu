@@ -1,5 +1,5 @@
-// HBM-bound kernels of the HyRES hot path: residual / add-back / clamp, im2col for the
-// two 3-channel convolutions, NHWC<->NCHW layout changes, and loss reductions.
+// HBM-bound kernels of the HyRES hot path: the final clamp, NHWC<->NCHW layout changes and loss
+// reductions (the residual / add-back arithmetic is fused into the first-layer kernels, conv_c3.cu).
 // All are coalesced and vectorised; none stages through shared memory unless it
 // transposes.  Reference call sites are cited per entry point in include/hyres_b200.h.
 #include <cstdint>
@@ -17,26 +17,6 @@ inline int grid_for(int64_t n, int per_block, int cap = 148 * 16) {
   if (g < 1) g = 1;
   if (g > cap) g = cap;
   return static_cast<int>(g);
-}
-
-// out = a - b  or  a + b   (fp32, float4 body + scalar tail)
-template <int SIGN>
-__global__ void addsub_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
-                              int64_t n) {
-  const int64_t n4 = n >> 2;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
-    const float4 x = __ldg(reinterpret_cast<const float4*>(a) + i);
-    const float4 y = __ldg(reinterpret_cast<const float4*>(b) + i);
-    float4 r;
-    r.x = SIGN > 0 ? x.x + y.x : x.x - y.x;
-    r.y = SIGN > 0 ? x.y + y.y : x.y - y.y;
-    r.z = SIGN > 0 ? x.z + y.z : x.z - y.z;
-    r.w = SIGN > 0 ? x.w + y.w : x.w - y.w;
-    reinterpret_cast<float4*>(o)[i] = r;
-  }
-  for (int64_t i = (n4 << 2) + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
-    o[i] = SIGN > 0 ? a[i] + b[i] : a[i] - b[i];
 }
 
 __global__ void final_clamp_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o,
@@ -57,48 +37,6 @@ __global__ void final_clamp_kernel(const float* __restrict__ a, const float* __r
     o[i] = fminf(fmaxf(a[i] + b[i], 0.f), 1.f);
 }
 
-// im2col of a 3-channel fp32 NCHW image into bf16 rows of KPAD entries:
-//   A[b, i, j, (r*K + s)*3 + c] = x[b, c, i*STRIDE + r - PAD, j*STRIDE + s - PAD]  (0 outside)
-// One thread writes 8 consecutive k (16 B), so a warp writes 512 contiguous bytes.
-template <int K, int STRIDE, int PAD, int KPAD>
-__global__ void im2col3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int H, int W,
-                               int OH, int OW) {
-  constexpr int G = KPAD / 8;
-  const int64_t total = static_cast<int64_t>(B) * OH * OW * G;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  const int64_t plane = static_cast<int64_t>(H) * W;
-  for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < total; t += stride) {
-    const int g = static_cast<int>(t % G);
-    int64_t pix = t / G;
-    const int j = static_cast<int>(pix % OW);
-    pix /= OW;
-    const int i = static_cast<int>(pix % OH);
-    const int b = static_cast<int>(pix / OH);
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = g * 8 + e;
-      float val = 0.f;
-      if (k < K * K * 3) {
-        const int c = k % 3;
-        const int rs = k / 3;
-        const int r = rs / K, s = rs % K;
-        const int ih = i * STRIDE + r - PAD, iw = j * STRIDE + s - PAD;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-          val = __ldg(x + (static_cast<int64_t>(b) * 3 + c) * plane + static_cast<int64_t>(ih) * W + iw);
-      }
-      v[e] = val;
-    }
-    uint4 o;
-    o.x = hy::pack_bf16(v[0], v[1]);
-    o.y = hy::pack_bf16(v[2], v[3]);
-    o.z = hy::pack_bf16(v[4], v[5]);
-    o.w = hy::pack_bf16(v[6], v[7]);
-    reinterpret_cast<uint4*>(a)[t] = o;
-  }
-}
-
-// [B][C][HW] fp32 -> [B][HW][C] bf16 and the reverse directions, 32x32 tiles through smem.
 template <typename TIn, typename TOut>
 __global__ void transpose_tiles(const TIn* __restrict__ in, TOut* __restrict__ out, int rows, int cols) {
   // in: [batch][rows][cols] -> out: [batch][cols][rows]
@@ -140,7 +78,7 @@ __device__ __forceinline__ void block_accumulate(double v, double* out) {
   if (threadIdx.x < 32) {
     double s = threadIdx.x < kBlock / 32 ? part[threadIdx.x] : 0.0;
     s = hy::warp_sum_d(s);
-    if (threadIdx.x == 0) atomicAdd(out, s);
+    if (threadIdx.x == 0) hy::atomic_add_exact(out, s);
   }
 }
 
@@ -187,50 +125,6 @@ __global__ void log2_kernel(const float* __restrict__ x, int64_t n, double* out)
 }  // namespace
 
 extern "C" {
-
-int hyres_residual_im2col5s2(const float* x, const float* jpeg, float* residual, void* a_out, int B, int H, int W,
-                             void* stream_v) {
-  if (!x || B <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return hy_fail(HYRES_ERR_ARG, "residual_im2col5s2: bad argument");
-  if (jpeg && !residual) return hy_fail(HYRES_ERR_ARG, "residual_im2col5s2: residual buffer required with jpeg");
-  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
-  const int64_t n = static_cast<int64_t>(B) * 3 * H * W;
-  const float* src = x;
-  if (jpeg) {
-    hy_count_launch();
-    addsub_kernel<-1><<<grid_for(n, kBlock * 4), kBlock, 0, st>>>(x, jpeg, residual, n);
-    src = residual;
-  }
-  if (a_out) {
-    const int64_t t = static_cast<int64_t>(B) * (H / 2) * (W / 2) * 16;
-    hy_count_launch();
-    im2col3_kernel<5, 2, 2, 128><<<grid_for(t, kBlock, 148 * 32), kBlock, 0, st>>>(
-        src, static_cast<__nv_bfloat16*>(a_out), B, H, W, H / 2, W / 2);
-  }
-  HY_CUDA(cudaGetLastError());
-  return HYRES_OK;
-}
-
-int hyres_addback_im2col3(const float* jpeg, const float* r_hat, float* x0, void* a_out, int B, int H, int W,
-                          void* stream_v) {
-  if (!r_hat || B <= 0 || H <= 0 || W <= 0) return hy_fail(HYRES_ERR_ARG, "addback_im2col3: bad argument");
-  if (jpeg && !x0) return hy_fail(HYRES_ERR_ARG, "addback_im2col3: x0 buffer required with jpeg");
-  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
-  const int64_t n = static_cast<int64_t>(B) * 3 * H * W;
-  const float* src = r_hat;
-  if (jpeg) {
-    hy_count_launch();
-    addsub_kernel<1><<<grid_for(n, kBlock * 4), kBlock, 0, st>>>(jpeg, r_hat, x0, n);
-    src = x0;
-  }
-  if (a_out) {
-    const int64_t t = static_cast<int64_t>(B) * H * W * 8;
-    hy_count_launch();
-    im2col3_kernel<3, 1, 1, 64><<<grid_for(t, kBlock, 148 * 32), kBlock, 0, st>>>(
-        src, static_cast<__nv_bfloat16*>(a_out), B, H, W, H, W);
-  }
-  HY_CUDA(cudaGetLastError());
-  return HYRES_OK;
-}
 
 int hyres_final_clamp(const float* x0, const float* refined, float* x_hat, int64_t n, void* stream_v) {
   if (!x0 || !refined || !x_hat || n < 0) return hy_fail(HYRES_ERR_ARG, "final_clamp: bad argument");

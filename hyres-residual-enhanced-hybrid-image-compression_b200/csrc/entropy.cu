@@ -161,7 +161,7 @@ __global__ void gc_merge_likelihood_kernel(const float* __restrict__ y, const fl
     if (threadIdx.x == 0) {
       double s = 0.0;
       for (int k = 0; k < kThreads / 32; ++k) s += part[k];
-      atomicAdd(sum_log2, s);
+      hy::atomic_add_exact(sum_log2, s);
     }
   }
 }
@@ -322,7 +322,7 @@ __global__ void eb_forward_kernel(const float* __restrict__ z, const EbChan* __r
     if (threadIdx.x == 0) {
       double s = 0.0;
       for (int k = 0; k < kThreads / 32; ++k) s += part[k];
-      atomicAdd(sum_log2, s);
+      hy::atomic_add_exact(sum_log2, s);
     }
   }
 }

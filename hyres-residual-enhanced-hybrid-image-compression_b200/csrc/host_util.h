@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <cstdint>
 #include <cstdlib>
 
 int hy_fail(int code, const char* msg);
@@ -15,6 +17,20 @@ void hy_count_launch();
     cudaError_t _e = (expr);                                            \
     if (_e != cudaSuccess) return hy_fail(-2, cudaGetErrorString(_e));  \
   } while (0)
+
+// One-time initialisation per DEVICE (function attributes such as the dynamic shared-memory opt-in are per device,
+// and one process may drive several GPUs): `done` says whether the current device has been initialised, `mark`
+// records it after the initialisation succeeded (two threads racing both initialise; that is harmless).
+struct HyPerDevice {
+  std::atomic<uint64_t> mask{0};
+  static uint64_t bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+  }
+  bool done() const { return (mask.load(std::memory_order_acquire) & bit()) != 0; }
+  void mark() { mask.fetch_or(bit(), std::memory_order_release); }
+};
 
 // Launch with the programmatic-stream-serialization attribute (see pdl_wait in common.cuh); HYRES_NO_PDL=1
 // falls back to plain stream order.

@@ -193,6 +193,7 @@ int decode_one(const uint8_t* in, int64_t in_len, const int32_t* indexes, int64_
         val = static_cast<int32_t>(dec_get_bits(x, src, kBypassBits));
         n_bypass += val;
       }
+      if (n_bypass > 8) return HYRES_ERR_ARG;  // more than 32 raw bits: malformed stream
       uint32_t raw = 0;
       for (int32_t j = 0; j < n_bypass; ++j) {
         val = static_cast<int32_t>(dec_get_bits(x, src, kBypassBits));

@@ -166,197 +166,6 @@ __global__ void se_scale_down_kernel(const __nv_bfloat16* __restrict__ feat, con
   }
 }
 
-// PyTorch bilinear, align_corners=False: src = scale*(dst+0.5)-0.5 clamped at 0.
-__device__ __forceinline__ void bilinear_coord(int dst, float scale, int n, int& i0, int& i1, float& l1) {
-  float src = scale * (static_cast<float>(dst) + 0.5f) - 0.5f;
-  if (src < 0.f) src = 0.f;
-  i0 = static_cast<int>(src);
-  i1 = i0 + (i0 < n - 1 ? 1 : 0);
-  l1 = src - static_cast<float>(i0);
-}
-
-__device__ __forceinline__ void bilinear8(const __nv_bfloat16* __restrict__ src, int64_t img, int Ws, int y0, int y1,
-                                          int x0, int x1, float ly, float lx, int g, float (&o)[8]) {
-  float a[8], b[8], c[8], d[8];
-  unpack8(__ldg(reinterpret_cast<const uint4*>(src + (img + static_cast<int64_t>(y0) * Ws + x0) * 64) + g), a);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(src + (img + static_cast<int64_t>(y0) * Ws + x1) * 64) + g), b);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(src + (img + static_cast<int64_t>(y1) * Ws + x0) * 64) + g), c);
-  unpack8(__ldg(reinterpret_cast<const uint4*>(src + (img + static_cast<int64_t>(y1) * Ws + x1) * 64) + g), d);
-  const float hy0 = 1.f - ly, hx0 = 1.f - lx;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) o[k] = hy0 * (hx0 * a[k] + lx * b[k]) + ly * (hx0 * c[k] + lx * d[k]);
-}
-
-// multi[..., 64:128] = up2(f2), multi[..., 128:192] = up4(f3); stats = (mean, max) over 192 channels.
-// One thread: a 2x2 block of output positions x one 8-channel group; 8 lanes cover the 64 channels of a block.
-// The block shares its sources (3x3 of f2, 2x2 of f3 instead of 4 + 4 per position) and, with
-// align_corners=False, its interpolation weights are constants: x2 -> (.25,.75) / (.75,.25),
-// x4 -> (.375,.625) (.125,.875) / (.875,.125) (.625,.375).  Clamping the neighbour index at the image border
-// reproduces PyTorch's clamp of the source coordinate (both taps then read the same row / column).
-// acc += w * unpack(u), as packed fp32 pairs; NP bf16 pairs per vector
-template <int NP>
-__device__ __forceinline__ void fma_pairs(float (&acc)[2 * NP], const uint32_t (&q)[NP], float w) {
-#pragma unroll
-  for (int i = 0; i < NP; ++i) {
-    asm("{\n\t"
-        ".reg .b64 a, x, ww;\n\t"
-        "mov.b64 a, {%0, %1};\n\t"
-        "mov.b64 x, {%2, %3};\n\t"
-        "mov.b64 ww, {%4, %4};\n\t"
-        "fma.rn.f32x2 a, x, ww, a;\n\t"
-        "mov.b64 {%0, %1}, a;\n\t"
-        "}"
-        : "+f"(acc[2 * i]), "+f"(acc[2 * i + 1])
-        : "f"(hy::bf16_lo(q[i])), "f"(hy::bf16_hi(q[i])), "f"(w));
-  }
-}
-__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
-  uint32_t r;
-  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
-  return r;
-}
-template <int NP> struct VecOf;
-template <> struct VecOf<4> { using type = uint4; };
-template <> struct VecOf<2> { using type = uint2; };
-template <int NP>
-__device__ __forceinline__ void ldv(const __nv_bfloat16* p, uint32_t (&q)[NP]) {
-  const typename VecOf<NP>::type v = __ldg(reinterpret_cast<const typename VecOf<NP>::type*>(p));
-  memcpy(q, &v, sizeof v);
-}
-template <int NP>
-__device__ __forceinline__ void stv(__nv_bfloat16* p, const uint32_t (&q)[NP]) {
-  typename VecOf<NP>::type v;
-  memcpy(&v, q, sizeof v);
-  *reinterpret_cast<typename VecOf<NP>::type*>(p) = v;
-}
-
-// NP: bf16 pairs per thread (4 -> 8 channels, 8 lanes per block; 2 -> 4 channels, 16 lanes per block)
-template <int NP>
-__global__ void __launch_bounds__(kThreads, 3) up_concat_stats_kernel(const __nv_bfloat16* __restrict__ f2,
-                                                                      const __nv_bfloat16* __restrict__ f3,
-                                                                      const __nv_bfloat16* f1, int ld1,
-                                                                      __nv_bfloat16* multi,
-                                                                      float* __restrict__ stats, int H, int W,
-                                                                      int64_t nblk_total) {
-  // f1: the full-resolution 64 channels, pixel stride ld1 (the concat variant passes multi / 192);
-  // multi == nullptr: statistics only, the up-sampled channels are not materialised
-  constexpr int LPB = 32 / NP;   // lanes per 2x2 block
-  constexpr int CH = 2 * NP;     // channels per thread
-  const int64_t total = nblk_total * LPB;
-  const int Wh = W / 2, Hh = H / 2, Wq = W / 4, Hq = H / 4;
-  const int lane = threadIdx.x & 31;
-  // warp-uniform loop bound: every lane of a warp stays in the loop for the shuffles
-  for (int64_t base = blockIdx.x * static_cast<int64_t>(blockDim.x) + (threadIdx.x - lane); base < total;
-       base += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t t = base + lane;
-    const bool live = t < total;
-    const int64_t tt = live ? t : total - 1;
-    const int g = static_cast<int>(tt % LPB);
-    const int64_t blk = tt / LPB;
-    const int n = static_cast<int>(blk % Wh);           // block column == f2 column
-    const int m = static_cast<int>((blk / Wh) % Hh);    // block row == f2 row
-    const int b = static_cast<int>(blk / (static_cast<int64_t>(Wh) * Hh));
-    // ---- sources ----
-    const int r2[3] = {max(m - 1, 0), m, min(m + 1, Hh - 1)};
-    const int c2[3] = {max(n - 1, 0), n, min(n + 1, Wh - 1)};
-    const int64_t img2 = static_cast<int64_t>(b) * Hh * Wh;
-    uint32_t S[3][3][NP];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int c = 0; c < 3; ++c) ldv<NP>(f2 + (img2 + static_cast<int64_t>(r2[a]) * Wh + c2[c]) * 64 + g * CH, S[a][c]);
-    const int iq = m >> 1, jq = n >> 1, mo = m & 1, no = n & 1;
-    const int r3[2] = {mo ? iq : max(iq - 1, 0), mo ? min(iq + 1, Hq - 1) : iq};
-    const int c3[2] = {no ? jq : max(jq - 1, 0), no ? min(jq + 1, Wq - 1) : jq};
-    const int64_t img3 = static_cast<int64_t>(b) * Hq * Wq;
-    uint32_t Q[2][2][NP];
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int c = 0; c < 2; ++c) ldv<NP>(f3 + (img3 + static_cast<int64_t>(r3[a]) * Wq + c3[c]) * 64 + g * CH, Q[a][c]);
-    const int64_t img = static_cast<int64_t>(b) * H * W;
-    uint32_t F1[2][2][NP];
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx)
-        ldv<NP>(f1 + (img + static_cast<int64_t>(2 * m + dy) * W + 2 * n + dx) * ld1 + g * CH, F1[dy][dx]);
-    // weight of the second (lower / right) tap: x2 -> .75 (even output) / .25 (odd); x4 by (block parity, offset)
-    const float l3y[2] = {mo ? 0.125f : 0.625f, mo ? 0.375f : 0.875f};
-    const float l3x[2] = {no ? 0.125f : 0.625f, no ? 0.375f : 0.875f};
-    float ps[4];      // per-position partial channel sum
-    uint32_t pm[4];   // per-position partial channel max, packed bf16 pair
-#pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-#pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const float ly = dy ? 0.25f : 0.75f, lx = dx ? 0.25f : 0.75f;
-        float v2[CH], v3[CH];
-#pragma unroll
-        for (int k = 0; k < CH; ++k) v2[k] = v3[k] = 0.f;
-        fma_pairs<NP>(v2, S[dy][dx], (1.f - ly) * (1.f - lx));
-        fma_pairs<NP>(v2, S[dy][dx + 1], (1.f - ly) * lx);
-        fma_pairs<NP>(v2, S[dy + 1][dx], ly * (1.f - lx));
-        fma_pairs<NP>(v2, S[dy + 1][dx + 1], ly * lx);
-        const float my = l3y[dy], mx = l3x[dx];
-        fma_pairs<NP>(v3, Q[0][0], (1.f - my) * (1.f - mx));
-        fma_pairs<NP>(v3, Q[0][1], (1.f - my) * mx);
-        fma_pairs<NP>(v3, Q[1][0], my * (1.f - mx));
-        fma_pairs<NP>(v3, Q[1][1], my * mx);
-        uint32_t u2[NP], u3[NP];
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-          u2[k] = hy::pack_bf16(v2[2 * k], v2[2 * k + 1]);
-          u3[k] = hy::pack_bf16(v3[2 * k], v3[2 * k + 1]);
-        }
-        if (live && multi) {
-          __nv_bfloat16* o = multi + (img + static_cast<int64_t>(2 * m + dy) * W + 2 * n + dx) * 192 + g * CH;
-          stv<NP>(o + 64, u2);
-          stv<NP>(o + 128, u3);
-        }
-        // statistics of the stored (bf16) values: max exactly on the packed pairs, sum in fp32
-        uint32_t mx2 = F1[dy][dx][0];
-        float acc[CH];
-#pragma unroll
-        for (int k = 0; k < CH; ++k) acc[k] = 0.f;
-#pragma unroll
-        for (int k = 0; k < NP; ++k) mx2 = max_bf16x2(mx2, max_bf16x2(F1[dy][dx][k], max_bf16x2(u2[k], u3[k])));
-        fma_pairs<NP>(acc, F1[dy][dx], 1.f);
-        fma_pairs<NP>(acc, u2, 1.f);
-        fma_pairs<NP>(acc, u3, 1.f);
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < CH; ++k) sum += acc[k];
-        ps[dy * 2 + dx] = sum;
-        pm[dy * 2 + dx] = mx2;
-      }
-    }
-    // ---- reduce over the LPB lanes of the block (aligned groups), halving the positions in the first two rounds ----
-    const bool hiA = (lane & (LPB / 2)) != 0;  // keeps positions 2,3 (else 0,1)
-    float s0, s1;
-    uint32_t m0, m1;
-    s0 = (hiA ? ps[2] : ps[0]) + __shfl_xor_sync(0xffffffffu, hiA ? ps[0] : ps[2], LPB / 2);
-    s1 = (hiA ? ps[3] : ps[1]) + __shfl_xor_sync(0xffffffffu, hiA ? ps[1] : ps[3], LPB / 2);
-    m0 = max_bf16x2(hiA ? pm[2] : pm[0], __shfl_xor_sync(0xffffffffu, hiA ? pm[0] : pm[2], LPB / 2));
-    m1 = max_bf16x2(hiA ? pm[3] : pm[1], __shfl_xor_sync(0xffffffffu, hiA ? pm[1] : pm[3], LPB / 2));
-    const bool hiB = (lane & (LPB / 4)) != 0;  // keeps the second of the pair
-    float sum = (hiB ? s1 : s0) + __shfl_xor_sync(0xffffffffu, hiB ? s0 : s1, LPB / 4);
-    uint32_t mm = max_bf16x2(hiB ? m1 : m0, __shfl_xor_sync(0xffffffffu, hiB ? m0 : m1, LPB / 4));
-#pragma unroll
-    for (int o = LPB / 8; o > 0; o >>= 1) {
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      mm = max_bf16x2(mm, __shfl_xor_sync(0xffffffffu, mm, o));
-    }
-    if (live && (lane & (LPB / 4 - 1)) == 0) {
-      const int pos = (hiA ? 2 : 0) + (hiB ? 1 : 0);  // dy * 2 + dx
-      const int64_t pix = img + static_cast<int64_t>(2 * m + (pos >> 1)) * W + 2 * n + (pos & 1);
-      reinterpret_cast<float2*>(stats)[pix] = make_float2(sum * (1.f / 192.f), fmaxf(hy::bf16_lo(mm), hy::bf16_hi(mm)));
-    }
-  }
-}
-
-// Fills the one-pixel border of a padded NHWC tensor [B,Hp,Wp,C] with the nearest interior pixel (corners included),
-// so that a bilinear read that steps outside the image sees the clamped source PyTorch would use.
 __global__ void replicate_border_kernel(uint4* __restrict__ t, int B, int Hp, int Wp, int c8) {
   const int per_img = 2 * Wp + 2 * (Hp - 2);
   const int64_t total = static_cast<int64_t>(B) * per_img * c8;
@@ -453,36 +262,6 @@ int hyres_refine_se_scale_down(const void* feat, const float* pooled, const floa
   se_scale_down_kernel<<<dim3(gx, B), kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
       static_cast<const __nv_bfloat16*>(feat), pooled, fc1, fc2, Cr, static_cast<__nv_bfloat16*>(feat_s),
       static_cast<__nv_bfloat16*>(feat_h), static_cast<__nv_bfloat16*>(feat_q), H, W);
-  HY_CUDA(cudaGetLastError());
-  return HYRES_OK;
-}
-
-int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi, float* stats, int B, int H, int W, int C,
-                                 void* stream_v) {
-  if (!f2 || !f3 || !multi || !stats || B <= 0) return hy_fail(HYRES_ERR_ARG, "up_concat_stats: bad argument");
-  if (C != 64) return hy_fail(HYRES_ERR_UNSUPPORTED, "up_concat_stats: C must be 64");
-  if ((H & 3) || (W & 3)) return hy_fail(HYRES_ERR_ARG, "up_concat_stats: H and W must be multiples of 4");
-  const int64_t nblk = static_cast<int64_t>(B) * (H / 2) * (W / 2);
-  int gx = static_cast<int>(std::min<int64_t>((nblk * 16 + kThreads - 1) / kThreads, 148 * 24));
-  hy_count_launch();
-  up_concat_stats_kernel<2><<<gx, kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
-      static_cast<const __nv_bfloat16*>(f2), static_cast<const __nv_bfloat16*>(f3),
-      static_cast<const __nv_bfloat16*>(multi), 192, static_cast<__nv_bfloat16*>(multi), stats, H, W, nblk);
-  HY_CUDA(cudaGetLastError());
-  return HYRES_OK;
-}
-
-int hyres_refine_stats3(const void* f1, const void* f2, const void* f3, float* stats, int B, int H, int W, int C,
-                        void* stream_v) {
-  if (!f1 || !f2 || !f3 || !stats || B <= 0) return hy_fail(HYRES_ERR_ARG, "stats3: bad argument");
-  if (C != 64) return hy_fail(HYRES_ERR_UNSUPPORTED, "stats3: C must be 64");
-  if ((H & 3) || (W & 3)) return hy_fail(HYRES_ERR_ARG, "stats3: H and W must be multiples of 4");
-  const int64_t nblk = static_cast<int64_t>(B) * (H / 2) * (W / 2);
-  int gx = static_cast<int>(std::min<int64_t>((nblk * 16 + kThreads - 1) / kThreads, 148 * 24));
-  hy_count_launch();
-  up_concat_stats_kernel<2><<<gx, kThreads, 0, static_cast<cudaStream_t>(stream_v)>>>(
-      static_cast<const __nv_bfloat16*>(f2), static_cast<const __nv_bfloat16*>(f3),
-      static_cast<const __nv_bfloat16*>(f1), 64, nullptr, stats, H, W, nblk);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }

@@ -509,11 +509,11 @@ int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c
   }
   const int smem = kSmemUsed + 1024;
   static const int cs = [] { const char* e = getenv("HYRES_RU_CS"); const int v = e ? atoi(e) : 0; return v == 4 ? 4 : 2; }();
-  static bool attr_set = false;
-  if (!attr_set) {
+  static HyPerDevice attr;
+  if (!attr.done()) {
     HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     HY_CUDA(cudaFuncSetAttribute(ru_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+    attr.mark();
   }
   const int grid = std::min(p.ntiles, num_sms());
   hy_count_launch();

@@ -411,6 +411,8 @@ class ResidualJPEGCompression(CompressionModel):
         return out
 
     def decompress(self, compressed_data):
+        from . import container
+        container.check_trunk(compressed_data, self.residual_model.codec_precision)
         jpeg_buffers = compressed_data["jpeg_buffers"]
         strings, shape = compressed_data["strings"], compressed_data["shape"]
         device = next(self.parameters()).device

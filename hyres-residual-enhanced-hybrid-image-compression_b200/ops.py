@@ -32,6 +32,14 @@ def _chk_nhwc(t, name, dtype=torch.bfloat16):
                          f"cuda={t.is_cuda} contiguous={t.is_contiguous()}")
 
 
+# Deployment export (export.py): while PACKED_COLLECT is a dict every new ConvLayer stores its packed device operands
+# in it, keyed by a digest of (geometry, weights, bias); while PACKED_CACHE is a dict a new ConvLayer whose digest is
+# found there is created empty and filled from the stored operands instead of being packed again.
+PACKED_COLLECT = None
+PACKED_CACHE = None
+PACKED_STATS = {"imported": 0, "packed": 0}  # layers filled from exported operands / packed from fp32 weights
+
+
 class ConvLayer:
     """One packed convolution layer (weights live in the library, bf16 K-major)."""
 
@@ -75,9 +83,38 @@ class ConvLayer:
         self.alg_macs_per_out = (cin0 + cin1) * cout * taps / (4.0 if kind == HYRES_DECONV_K5S2 else 1.0)
         h = C.c_void_p()
         lib = L.lib()
+        key = None
+        if PACKED_COLLECT is not None or PACKED_CACHE is not None:
+            import hashlib
+            d = hashlib.sha1(repr((kind, cin0, cin1, cin_total, cout, R, S, stride, pad, dil, nsplit)).encode())
+            d.update(w.numpy().tobytes())
+            d.update(b.numpy().tobytes() if b is not None else b"-")
+            d.update(mask.numpy().tobytes() if mask is not None else b"-")
+            key = d.hexdigest()
+        cached = PACKED_CACHE.get(key) if PACKED_CACHE is not None else None
         L.check(lib.hyres_conv_create_split(C.byref(h), kind, cin0, cin1, cin_total, cout, R, S, stride,
-                                            pad, dil, _ptr(w), _ptr(b), _ptr(mask), nsplit), "hyres_conv_create")
+                                            pad, dil, _ptr(w) if cached is None else C.c_void_p(0), _ptr(b), _ptr(mask),
+                                            nsplit), "hyres_conv_create")
         self._h = h
+        if cached is not None:
+            pw, pt, pb = cached
+            sizes = [lib.hyres_conv_packed_elems(h, i) for i in range(3)]
+            if [pw.numel(), pt.numel(), pb.numel()] != sizes:
+                raise ValueError("ConvLayer: exported operands do not match this layer's packing")
+            L.check(lib.hyres_conv_import_packed(h, _ptr(pw), _ptr(pt) if pt.numel() else C.c_void_p(0), _ptr(pb)),
+                    "hyres_conv_import_packed")
+            PACKED_STATS["imported"] += 1
+        else:
+            PACKED_STATS["packed"] += 1
+        if cached is not None:
+            pass
+        elif PACKED_COLLECT is not None:
+            pw = torch.empty(lib.hyres_conv_packed_elems(h, 0), dtype=torch.bfloat16)
+            pt = torch.empty(lib.hyres_conv_packed_elems(h, 1), dtype=torch.bfloat16)
+            pb = torch.empty(lib.hyres_conv_packed_elems(h, 2), dtype=torch.float32)
+            L.check(lib.hyres_conv_export_packed(h, _ptr(pw), _ptr(pt) if pt.numel() else C.c_void_p(0), _ptr(pb)),
+                    "hyres_conv_export_packed")
+            PACKED_COLLECT[key] = (pw, pt, pb)
 
     def update(self, weight, bias=None):
         w = weight.detach().to("cpu", torch.float32).contiguous()
@@ -271,36 +308,6 @@ def _f32c(t, name):
     if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
         raise ValueError(f"{name}: expected contiguous CUDA fp32 tensor")
     return t
-
-
-def residual_im2col5s2(x, jpeg=None, want_residual=True):
-    """x, jpeg: fp32 NCHW [B,3,H,W].  Returns (residual fp32 NCHW or x, A bf16 [B,H/2,W/2,128])."""
-    _f32c(x, "x")
-    B, C, H, W = x.shape
-    if C != 3:
-        raise ValueError("expected 3 channels")
-    res = None
-    if jpeg is not None:
-        _f32c(jpeg, "jpeg")
-        res = torch.empty_like(x)
-    a = torch.empty((B, H // 2, W // 2, 128), dtype=torch.bfloat16, device=x.device)
-    L.check(L.lib().hyres_residual_im2col5s2(_ptr(x), _ptr(jpeg), _ptr(res), _ptr(a), B, H, W, _stream()),
-            "hyres_residual_im2col5s2")
-    return (res if res is not None else x), a
-
-
-def addback_im2col3(r_hat, jpeg=None):
-    """x0 = jpeg + r_hat (or r_hat), A bf16 [B,H,W,64] = 3x3 im2col of x0."""
-    _f32c(r_hat, "r_hat")
-    B, C, H, W = r_hat.shape
-    x0 = None
-    if jpeg is not None:
-        _f32c(jpeg, "jpeg")
-        x0 = torch.empty_like(r_hat)
-    a = torch.empty((B, H, W, 64), dtype=torch.bfloat16, device=r_hat.device)
-    L.check(L.lib().hyres_addback_im2col3(_ptr(jpeg), _ptr(r_hat), _ptr(x0), _ptr(a), B, H, W, _stream()),
-            "hyres_addback_im2col3")
-    return (x0 if x0 is not None else r_hat), a
 
 
 def conv3ch(layer, ksize, stride, a, b=None, sign=1, want_sum=True, act=ACT_NONE, slope=0.0, out=None):
@@ -504,31 +511,10 @@ def refine_se_scale_down(feat, fc1, fc2):
     return fs, fh, fq, pooled
 
 
-def refine_up_concat_stats(f2, f3, multi):
-    """multi bf16 [B,H,W,192] holds branch 1 in [..., :64]; fills [64:192] and returns stats [B,H,W,2]."""
-    B, H, W, C3 = multi.shape
-    stats = torch.empty((B, H, W, 2), dtype=torch.float32, device=multi.device)
-    L.check(L.lib().hyres_refine_up_concat_stats(_ptr(f2), _ptr(f3), _ptr(multi), _ptr(stats), B, H, W, C3 // 3,
-                                                 _stream()), "hyres_refine_up_concat_stats")
-    return stats
-
-
-def refine_stats3(f1, f2, f3):
-    """Channel mean / max over the virtual concat [f1 | up2(f2) | up4(f3)] (bf16 NHWC, 64 channels each) -> fp32
-    [B,H,W,2], without materialising the up-sampled channels."""
-    _chk_nhwc(f1, "f1"), _chk_nhwc(f2, "f2"), _chk_nhwc(f3, "f3")
-    B, H, W, Cc = f1.shape
-    if tuple(f2.shape) != (B, H // 2, W // 2, Cc) or tuple(f3.shape) != (B, H // 4, W // 4, Cc):
-        raise ValueError("refine_stats3: f2 / f3 must be the half / quarter resolution tensors")
-    stats = torch.empty((B, H, W, 2), dtype=torch.float32, device=f1.device)
-    L.check(L.lib().hyres_refine_stats3(_ptr(f1), _ptr(f2), _ptr(f3), _ptr(stats), B, H, W, Cc, _stream()),
-            "hyres_refine_stats3")
-    return stats
-
-
 def refine_stats3_tc(f1, s2p, s3p):
-    """As refine_stats3, on the tensor cores: s2p / s3p are the half / quarter resolution tensors padded by one
-    replicated pixel ([B,H/2+2,W/2+2,64] / [B,H/4+2,W/4+2,64])."""
+    """Channel mean / max over the virtual concat [f1 | up2(f2) | up4(f3)] (bf16 NHWC, 64 channels each) -> fp32
+    [B,H,W,2] on the tensor cores, without materialising the up-sampled channels: s2p / s3p are the half / quarter
+    resolution tensors padded by one replicated pixel ([B,H/2+2,W/2+2,64] / [B,H/4+2,W/4+2,64])."""
     _chk_nhwc(f1, "f1"), _chk_nhwc(s2p, "s2p"), _chk_nhwc(s3p, "s3p")
     B, H, W, Cc = f1.shape
     if Cc != 64 or tuple(s2p.shape) != (B, H // 2 + 2, W // 2 + 2, 64) or tuple(s3p.shape) != (B, H // 4 + 2, W // 4 + 2, 64):

@@ -104,6 +104,13 @@ int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_
 int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout,
                             int R, int S, int stride, int pad, int dil, const float* weight,
                             const float* bias, const uint8_t* tap_mask, int nsplit);
+/* Deployment export (the analogue of src/updata.py:50-78, which saves the CDF tables next to the weights): the
+ * packed device operands of a layer -- K-major bf16 weights (which = 0), the tap-major copy the 3-output-channel
+ * kernel reads (which = 1, 0 elements for other layers) and the padded fp32 bias (which = 2) -- can be copied
+ * out once and copied back into a layer created with weight == NULL, so a deployment never re-packs. */
+int64_t hyres_conv_packed_elems(const hyres_conv* c, int which);
+int hyres_conv_export_packed(const hyres_conv* c, void* w_bf16, void* w_tap_bf16, float* bias);
+int hyres_conv_import_packed(hyres_conv* c, const void* w_bf16, const void* w_tap_bf16, const float* bias);
 /* Re-pack new weights into an existing layer (same geometry). */
 int hyres_conv_update(hyres_conv* c, const float* weight, const float* bias);
 void hyres_conv_destroy(hyres_conv* c);
@@ -180,17 +187,6 @@ int hyres_ru_run(const hyres_conv* c1, const hyres_conv* c2, const hyres_conv* c
 /* Memory-bound kernels                                                       */
 /* ------------------------------------------------------------------------- */
 
-/* residual = x - jpeg (fp32 NCHW out, may be NULL) and the 5x5/stride-2 im2col
- * of the residual as bf16 [B,H/2,W/2,128] (k = (r*5+s)*3+c, 75 live) that feeds
- * g_a.0 as a 1x1 GEMM. jpeg may be NULL (x is already the residual).
- * models/hyres.py:48,96 + models/checkerboard.py:36 */
-int hyres_residual_im2col5s2(const float* x, const float* jpeg, float* residual, void* a_out,
-                             int B, int H, int W, void* stream);
-/* x0 = jpeg + r_hat (fp32 NCHW out) and the 3x3 im2col of x0 as bf16
- * [B,H,W,64] (k = (r*3+s)*3+c, 27 live) feeding refine.conv_in.
- * models/hyres.py:62,127 + models/layers/enhancement.py:60 */
-int hyres_addback_im2col3(const float* jpeg, const float* r_hat, float* x0, void* a_out, int B,
-                          int H, int W, void* stream);
 /* The two 3-channel first-layer convolutions fused with the residual arithmetic around them
  * (no im2col tensor in HBM; the im2col row is built on chip):
  *   src = a + sign * b        (fp32 NCHW [B,3,H,W]; b may be NULL)
@@ -200,7 +196,7 @@ int hyres_addback_im2col3(const float* jpeg, const float* r_hat, float* x0, void
  * models/checkerboard.py:36, cout 128) or ksize 3 / stride 1 (refine.conv_in + PReLU on
  * x0 = jpeg + r_hat: models/hyres.py:62,127 + models/layers/enhancement.py:60,89, cout 64).
  * `c` is the layer created as the 1x1 GEMM over the im2col ordering k = (r*ksize+s)*3 + c
- * (cin 128 / 64, zero beyond 75 / 27), exactly what the im2col entry points above feed. */
+ * (cin 128 / 64, zero beyond 75 / 27). */
 int hyres_conv3ch_run(hyres_conv* c, int ksize, int stride, const float* a, const float* b, int sign,
                       float* sum_out, void* out_bf16, int ld_out, int B, int H, int W, int act,
                       float slope, void* stream);
@@ -281,14 +277,8 @@ int hyres_refine_se_pool(const void* feat, float* scratch, float* pooled /*[B,C]
 int hyres_refine_se_scale_down(const void* feat, const float* pooled, const float* fc1,
                                const float* fc2, int C, int Cr, void* feat_s, void* feat_h,
                                void* feat_q, int B, int H, int W, void* stream);
-int hyres_refine_up_concat_stats(const void* f2, const void* f3, void* multi /*[B,H,W,3C]*/,
-                                 float* stats /*[B,H,W,2]*/, int B, int H, int W, int C,
-                                 void* stream);
-/* The same channel mean / max over the virtual concat [f1 | up2(f2) | up4(f3)] without materialising it
- * (the fusion conv then up-samples on the tensor cores: hyres_conv_io.up_t2 / up_t3). f1: [B,H,W,C]. */
-int hyres_refine_stats3(const void* f1, const void* f2, const void* f3, float* stats /*[B,H,W,2]*/,
-                        int B, int H, int W, int C, void* stream);
-/* The tensor-core version (the product path): s2 / s3 are bf16 NHWC tensors padded by one replicated
+/* Channel mean / max over the virtual concat [f1 | up2(s2) | up4(s3)] (models/layers/enhancement.py:101-106,
+ * 15-21) without materialising it: s2 / s3 are bf16 NHWC tensors padded by one replicated
  * pixel, [B,H/2+2,W/2+2,64] / [B,H/4+2,W/4+2,64]; the bilinear up-samplings are GEMMs with a constant
  * interpolation matrix, the epilogue reduces over the channels. H, W multiples of 32. */
 int hyres_refine_stats3_tc(const void* f1, const void* s2_padded, const void* s3_padded, float* stats,

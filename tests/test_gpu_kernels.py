@@ -110,24 +110,15 @@ def test_noise_quantiser_statistics(pcodec):
 
 
 def test_residual_addback_clamp_exact(build_lib):
-    """K5 (models/hyres.py:48,62,66-67): fp32 elementwise, bit-exact; the fused im2col operands are
-    the bf16 roundings of the same values."""
+    """K5 (models/hyres.py:48,62,66-67): fp32 elementwise, bit-exact (the residual and the add-back are produced by
+    the fused first-layer kernels, conv_c3.cu -- tests/test_gpu_conv.py::test_conv3ch_fused_first_layer -- and by
+    the split-precision im2col, tests/test_gpu_precise.py)."""
     from hyres_b200 import ops
     g = torch.Generator().manual_seed(2)
     x = torch.rand(2, 3, 64, 96, generator=g).cuda()
     j = torch.rand(2, 3, 64, 96, generator=g).cuda()
-    res, a = ops.residual_im2col5s2(x, j)
-    assert torch.equal(res, x - j)
-    pad = torch.nn.functional.pad(res, (2, 2, 2, 2))
-    cols = torch.nn.functional.unfold(pad, 5, stride=2)  # [B, 3*25, L], channel-major (c, r, s)
-    cols = cols.reshape(2, 3, 25, 32, 48).permute(0, 3, 4, 2, 1).reshape(2, 32, 48, 75)  # k = (r*5+s)*3 + c
-    assert torch.equal(a[..., :75], cols.bfloat16())
-    assert float(a[..., 75:].abs().max()) == 0.0
     r_hat = torch.randn(2, 3, 64, 96, generator=g).cuda() * 0.1
-    x0, a3 = ops.addback_im2col3(r_hat, j)
-    assert torch.equal(x0, j + r_hat)
-    cols = torch.nn.functional.unfold(x0, 3, padding=1).reshape(2, 3, 9, 64, 96).permute(0, 3, 4, 2, 1).reshape(2, 64, 96, 27)
-    assert torch.equal(a3[..., :27], cols.bfloat16())
+    x0 = j + r_hat
     refined = torch.randn(2, 3, 64, 96, generator=g).cuda()
     assert torch.equal(ops.final_clamp(x0, refined), torch.clamp(x0 + refined, 0, 1))
     acc = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -176,20 +167,18 @@ def test_refine_memory_ops_vs_oracle(build_lib, oracle_net):
     torch.testing.assert_close(nchw(fh), half, rtol=2e-2, atol=2e-2)
     torch.testing.assert_close(nchw(fq), quarter, rtol=2e-2, atol=2e-2)
     # upsample + concat + channel mean/max statistics + 7x7 attention
-    f1 = torch.randn(2, 32, 48, 64, generator=g).bfloat16().cuda()
-    f2 = torch.randn(2, 16, 24, 64, generator=g).bfloat16().cuda()
-    f3 = torch.randn(2, 8, 12, 64, generator=g).bfloat16().cuda()
-    multi = torch.empty(2, 32, 48, 192, dtype=torch.bfloat16, device="cuda")
-    multi[..., :64] = f1
-    stats = ops.refine_up_concat_stats(f2, f3, multi)
+    f1 = torch.randn(2, 32, 64, 64, generator=g).bfloat16().cuda()
+    f2 = torch.randn(2, 16, 32, 64, generator=g).bfloat16().cuda()
+    f3 = torch.randn(2, 8, 16, 64, generator=g).bfloat16().cuda()
+    pad1 = lambda t: F.pad(nchw(t), (1, 1, 1, 1), mode="replicate").permute(0, 2, 3, 1).bfloat16().contiguous().cuda()  # noqa: E731
+    stats = ops.refine_stats3_tc(f1, pad1(f2), pad1(f3))
     with torch.no_grad():
-        up2 = F.interpolate(nchw(f2), size=(32, 48), mode="bilinear", align_corners=False)
-        up3 = F.interpolate(nchw(f3), size=(32, 48), mode="bilinear", align_corners=False)
+        up2 = F.interpolate(nchw(f2), size=(32, 64), mode="bilinear", align_corners=False)
+        up3 = F.interpolate(nchw(f3), size=(32, 64), mode="bilinear", align_corners=False)
         cat = torch.cat([nchw(f1), up2, up3], 1).bfloat16().float()
         want_att = rf.spatial_att(cat)[:, 0]
-    torch.testing.assert_close(nchw(multi), cat, rtol=1e-2, atol=1e-2)
     torch.testing.assert_close(stats[..., 0].cpu(), cat.mean(1), rtol=1e-3, atol=2e-3)
-    torch.testing.assert_close(stats[..., 1].cpu(), cat.max(1)[0], rtol=1e-2, atol=1e-2)
+    torch.testing.assert_close(stats[..., 1].cpu(), cat.max(1)[0], rtol=2e-2, atol=2e-2)
     w7 = rf.spatial_att.conv.weight.detach().reshape(-1).cuda().contiguous()
     att = ops.refine_spatial_att(stats, w7)
     torch.testing.assert_close(att.cpu(), want_att, rtol=1e-2, atol=1e-2)

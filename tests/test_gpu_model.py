@@ -380,3 +380,35 @@ def test_codec_pipeline_matches_direct_calls(nets, oracle):
         assert list(pipe.roundtrip(iter([]))) == []
     finally:
         pipe.close()
+
+
+def test_export_and_load_prepacked_model(nets, oracle, tmp_path):
+    """hyres_b200.export_model / load_exported (the src/updata.py:50-78 step): CDF tables in the state dict plus the
+    packed device operands of every layer; the loaded model re-packs nothing and reproduces strings and
+    reconstructions bit for bit.  A changed weight falls back to packing from the state dict."""
+    import hyres_b200
+    from hyres_b200 import ops
+    _, pnet = nets
+    x = oracle.synthetic_image(2, 64, 96, seed=90).cuda()
+    path = tmp_path / "hyres_export.pt"
+    blob = hyres_b200.export_model(pnet, str(path), update=False)
+    assert blob["format"] == 1 and len(blob["packed"]) > 100
+    assert "residual_model.gaussian_conditional._quantized_cdf" in blob["state_dict"]
+    with torch.no_grad():
+        c = pnet.compress(x)
+        want = pnet.decompress(c)["x_hat"]
+        before = dict(ops.PACKED_STATS)
+        net2 = hyres_b200.load_exported(str(path))
+        assert ops.PACKED_STATS["packed"] == before["packed"]  # nothing was packed from fp32 weights
+        # (layers with identical weights -- the freshly initialised GDN gammas -- share one exported entry)
+        assert ops.PACKED_STATS["imported"] - before["imported"] >= len(blob["packed"])
+        c2 = net2.compress(x)
+        assert c2["strings"] == c["strings"]
+        assert torch.equal(net2.decompress(c2)["x_hat"], want)
+        assert torch.equal(net2(x)["x_hat"], pnet(x)["x_hat"])
+        # a checkpoint whose weights moved since the export: the stale operands are ignored for that layer
+        blob["state_dict"]["refine.fusion.2.bias"] = blob["state_dict"]["refine.fusion.2.bias"] + 0.25
+        before = dict(ops.PACKED_STATS)
+        net3 = hyres_b200.load_exported(blob)
+        assert ops.PACKED_STATS["packed"] - before["packed"] == 1
+        assert not torch.equal(net3.decompress(c)["x_hat"], want)

@@ -56,24 +56,6 @@ def test_upadd_conv_matches_interpolate_then_conv(build_lib, B, H, W):
     assert (_nchw(h) - ref_cat).abs().max().item() < 4e-2
 
 
-def test_stats3_equals_the_concat_kernels_statistics(build_lib):
-    from hyres_b200 import ops
-    g = torch.Generator().manual_seed(3)
-    B, H, W = 2, 32, 48
-    f1 = torch.randn(B, H, W, 64, generator=g).bfloat16().cuda()
-    f2 = torch.randn(B, H // 2, W // 2, 64, generator=g).bfloat16().cuda()
-    f3 = torch.randn(B, H // 4, W // 4, 64, generator=g).bfloat16().cuda()
-    multi = torch.empty(B, H, W, 192, dtype=torch.bfloat16, device="cuda")
-    multi[..., :64] = f1
-    a = ops.refine_up_concat_stats(f2, f3, multi)
-    b = ops.refine_stats3(f1, f2, f3)
-    assert torch.equal(a, b)
-    cat = torch.cat([_nchw(f1), F.interpolate(_nchw(f2), scale_factor=2, mode="bilinear", align_corners=False),
-                     F.interpolate(_nchw(f3), scale_factor=4, mode="bilinear", align_corners=False)], 1)
-    assert torch.allclose(b[..., 0], cat.mean(1), atol=2e-3)
-    assert torch.allclose(b[..., 1], cat.amax(1), atol=2e-2)
-
-
 def test_upadd_rejects_layers_it_cannot_run(build_lib):
     from hyres_b200 import ops
     from hyres_b200._lib import HyresError
@@ -89,8 +71,9 @@ def test_upadd_rejects_layers_it_cannot_run(build_lib):
 
 @pytest.mark.parametrize("B,H,W", [(1, 32, 32), (2, 64, 96)])
 def test_tensor_core_stats_match_the_elementwise_kernel(build_lib, B, H, W):
-    """hyres_refine_stats3_tc (bilinear up-sampling as GEMMs, channel fold in the epilogue) against the elementwise
-    kernel and PyTorch: mean within 1e-3 (fp32 summation order), max within one bf16 ulp of O(1) values (2e-2)."""
+    """hyres_refine_stats3_tc (bilinear up-sampling as GEMMs, channel fold in the epilogue) against PyTorch's
+    bilinear interpolation of the concat: mean within 2e-3 (fp32 summation order), max within one bf16 ulp of O(1)
+    values (2e-2)."""
     from hyres_b200 import ops
     g = torch.Generator().manual_seed(11)
     f1 = torch.randn(B, H, W, 64, generator=g).bfloat16().cuda()
@@ -98,10 +81,7 @@ def test_tensor_core_stats_match_the_elementwise_kernel(build_lib, B, H, W):
     f3 = torch.randn(B, H // 4, W // 4, 64, generator=g).bfloat16().cuda()
     f2p = F.pad(_nchw(f2), (1, 1, 1, 1), mode="replicate").permute(0, 2, 3, 1).bfloat16().contiguous()
     f3p = F.pad(_nchw(f3), (1, 1, 1, 1), mode="replicate").permute(0, 2, 3, 1).bfloat16().contiguous()
-    a = ops.refine_stats3(f1, f2, f3)
     b = ops.refine_stats3_tc(f1, f2p, f3p)
-    assert torch.allclose(a[..., 0], b[..., 0], atol=1e-3)
-    assert torch.allclose(a[..., 1], b[..., 1], atol=2e-2)
     cat = torch.cat([_nchw(f1), F.interpolate(_nchw(f2), scale_factor=2, mode="bilinear", align_corners=False),
                      F.interpolate(_nchw(f3), scale_factor=4, mode="bilinear", align_corners=False)], 1)
     assert torch.allclose(b[..., 0], cat.mean(1), atol=2e-3)

@@ -149,3 +149,15 @@ def test_container_roundtrip_and_errors(build_lib):
             container.unpack(bad)
     with pytest.raises(ValueError):
         container.pack({"strings": [[[b"a"], [b"b", b"c"]], [b"z"]], "shape": (1, 1)})
+    # the header records which trunk arithmetic made the strings; a mismatching decoder is refused
+    assert "trunk" not in d
+    for tag, want in (("fp32x3", "fp32"), ("fp32x2", "fp32"), ("bf16", "bf16")):
+        dt = container.unpack(container.pack(c, trunk=tag))
+        assert dt["trunk"] == want and dt["strings"] == c["strings"]
+        assert container.pack(dt) == container.pack(c, trunk=tag)  # the tag survives a second round trip
+    container.check_trunk(container.unpack(container.pack(c, trunk="fp32x3")), "fp32x2")
+    container.check_trunk(d, "bf16")  # untagged: accepted
+    with pytest.raises(ValueError):
+        container.check_trunk(container.unpack(container.pack(c, trunk="bf16")), "fp32x3")
+    with pytest.raises(ValueError):
+        container.pack(c, trunk="fp64")

@@ -37,8 +37,16 @@ def main():
     for r in rows:
         taps = r["k"] * r["k"]
         opos = r["B"] * r["OH"] * r["OW"]
-        macs = opos * r["cin"] * r["cout"] * taps / (4 if r["kind"] == 1 else 1)
+        if r["kind"] == "ru":  # fused 1x1 -> 3x3 -> 1x1 bottleneck: C -> C/2 -> C/2 -> C
+            c, m = r["cin"], r["cin"] // 2
+            macs = opos * (c * m + 9 * m * m + m * c)
+        elif r["kind"] == "c3":  # 3-input-channel first layers
+            macs = opos * 3 * r["cout"] * taps
+        else:  # ConvLayer rows carry their algorithmic MACs (live taps only; deconv = 25/4 taps per output)
+            macs = r.get("alg_macs", opos * r["cin"] * r["cout"] * taps / (4 if r["kind"] == 1 else 1))
         byts = r["B"] * r["H"] * r["W"] * r["cin"] * 2 + opos * r["cout"] * (4 if r["f32"] else 2)
+        if r["kind"] == "c3":
+            byts = r["B"] * r["H"] * r["W"] * 3 * 4 * 2 + opos * r["cout"] * 2
         r["tflops"] = 2 * macs / r["ms"] / 1e9
         r["gbs"] = byts / r["ms"] / 1e6
         key = (r["kind"], r["cin"], r["cout"], r["k"], r["stride"], r["dil"], r["H"], r["W"], r["epi"], r["f32"], r["sq"])
@@ -51,7 +59,7 @@ def main():
     print(f"{'kind cin->cout k s d  HxW epi f32 sq':48s} {'n':>3s} {'ms':>8s} {'share':>6s} {'TF/s':>7s} {'GB/s':>7s}")
     for key, g in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
         kind, cin, cout, k, s, d, Hh, Ww, epi, f32, sq = key
-        name = f"{'dc' if kind else 'cv'} {cin}->{cout} k{k} s{s} d{d} {Hh}x{Ww} e{epi} {int(f32)} {int(sq)}"
+        name = f"{kind if isinstance(kind, str) else ('dc' if kind else 'cv')} {cin}->{cout} k{k} s{s} d{d} {Hh}x{Ww} e{epi} {int(f32)} {int(sq)}"
         print(f"{name:48s} {g['n']:3d} {g['ms']:8.3f} {g['ms'] / tot:6.1%} {2 * g['macs'] / g['ms'] / 1e9:7.1f} {g['bytes'] / g['ms'] / 1e6:7.0f}")
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as fh:

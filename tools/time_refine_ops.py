@@ -24,12 +24,12 @@ def timeit(fn, n=10):
 
 
 def main():
-    f2 = torch.randn(B, H // 2, W // 2, 64, device="cuda").bfloat16()
-    f3 = torch.randn(B, H // 4, W // 4, 64, device="cuda").bfloat16()
-    multi = torch.randn(B, H, W, 192, device="cuda").bfloat16()
-    ms = timeit(lambda: ops.refine_up_concat_stats(f2, f3, multi))
-    gb = B * H * W * (128 + 256 + 8 + 40) / 1e9
-    print(f"up_concat_stats {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+    f1 = torch.randn(B, H, W, 64, device="cuda").bfloat16()
+    f2p = torch.randn(B, H // 2 + 2, W // 2 + 2, 64, device="cuda").bfloat16()
+    f3p = torch.randn(B, H // 4 + 2, W // 4 + 2, 64, device="cuda").bfloat16()
+    ms = timeit(lambda: ops.refine_stats3_tc(f1, f2p, f3p))
+    gb = B * H * W * (128 + 32 + 8 + 8) / 1e9
+    print(f"stats3_tc {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
     feat = torch.randn(B, H, W, 64, device="cuda").bfloat16()
     fc1, fc2 = torch.randn(4, 64, device="cuda") * 0.1, torch.randn(64, 4, device="cuda") * 0.1
     ms = timeit(lambda: ops.refine_se_scale_down(feat, fc1, fc2))
