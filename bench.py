@@ -501,17 +501,85 @@ def bench_forward(args, net, dev, rank, world, lib, peaks, steps):
     }
 
 
+TRAIN_BATCH, TRAIN_H, TRAIN_W = 16, 256, 256
+
+
+def train_config(n):
+    return {"workload": "BASELINE.json configs[4]: training step (forward + backward, lambda = 0.008 RD loss, gradient "
+                        "clipping, Adam + auxiliary Adam) on a batch of 16 synthetic 256x256 crops per GPU, noise quantiser",
+            "batch_per_gpu": TRAIN_BATCH, "height": TRAIN_H, "width": TRAIN_W, "global_batch": TRAIN_BATCH * n,
+            "lambda": LMBDA, "precision": "bf16 tensor-core convolutions (forward, data gradient, weight gradient), "
+                                          "bf16 activations / gradients between layers, fp32 master weights and Adam",
+            "parallelism": f"dp{n}: one process per GPU, gradients all-reduced over NCCL in 8 MB buckets launched from "
+                           "autograd hooks during backward (replaces nn.DataParallel, src/training.py:211-212)",
+            "weights": "random init, seed 1926"}
+
+
+def bench_train(args, dev, rank, world, lib, peaks, steps):
+    """One optimisation step per timed step (src/utils/engine.py:29-90).  Returns a dict (rank 0) or None."""
+    import torch
+    import hyres_b200
+    from hyres_b200 import dist as D, synthetic, train as T
+
+    torch.manual_seed(1926)
+    net = hyres_b200.ResidualJPEGCompression(jpeg_quality=1)
+    net.update(force=True)
+    net = net.to(dev)
+    trainer = T.Trainer(net, lmbda=LMBDA, lr=1e-4, aux_lr=1e-3, clip_max_norm=1.0)
+    x_host = synthetic.synthetic_image(TRAIN_BATCH, TRAIN_H, TRAIN_W, seed=11 + rank).pin_memory()
+    x_dev = x_host.to(dev)
+    px_step = TRAIN_BATCH * TRAIN_H * TRAIN_W
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        r = trainer.step(x_dev)
+    l0 = lib.hyres_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = trainer.step(x_dev)
+    e1.record()
+    barrier()
+    ms = D.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+    launches = (lib.hyres_launch_count() - l0) // steps
+    loss = float(r["loss"])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = trainer.step(x_host.to(dev, non_blocking=True))
+        loss_e2e = float(r["loss"])  # the step's result is read back every step
+    torch.cuda.synchronize()
+    e2e_ms = D.max_over_ranks((time.perf_counter() - t0) * 1e3 / steps, dev)
+    if rank != 0:
+        return None
+    flops = 3 * 2.0 * MAC_PER_PX_CONV * px_step  # forward + data gradient + weight gradient of every convolution
+    return {"metric": "hyres_train_mpixel_per_s", "value": world * px_step / (ms * 1e-3) / 1e6, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": steps, "ms_per_step": ms, "scaling": "weak", "config": train_config(world),
+            "e2e": {"value": world * px_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches_per_step": int(launches),
+            "weight_gradient": "tcgen05 (csrc/wgrad.cu)" if T.wgrad_native_active() else "ATen convolution_backward (cuDNN)",
+            "step_tflops": flops / (ms * 1e-3) / 1e12, "step_frac": flops / (ms * 1e-3) / 1e12 / peaks["tflops"],
+            "loss": loss, "loss_e2e": loss_e2e}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="codec", choices=["codec", "forward"])
+    ap.add_argument("--workload", default="codec", choices=["codec", "forward", "train"])
     ap.add_argument("--in-flight", type=int, default=int(os.environ.get("HYRES_CODEC_IN_FLIGHT", "4")),
                     help="images in flight in the codec pipeline (worker threads / CUDA streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="codec workload: skip the forward sub-benchmark")
+    ap.add_argument("--no-train", action="store_true", help="codec workload: skip the training-step sub-benchmark")
     ap.add_argument("--no-graph", action="store_true", help="forward: time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -547,6 +615,11 @@ def main():
 
     if args.workload == "forward":
         line = bench_forward(args, net, dev, rank, world, lib, peaks, args.steps)
+    elif args.workload == "train":
+        line = bench_train(args, dev, rank, world, lib, peaks, args.steps)
+        if line is not None:
+            line.update({"warmup": args.warmup, "higher_is_better": True, "vs_baseline": None, "dtype": "bf16",
+                         "data": "synthetic"})
     else:
         line = bench_codec(args, net, dev, rank, world, lib, peaks)
         if not args.no_forward:
@@ -555,26 +628,35 @@ def main():
                 line["forward"] = {k: fwd[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "e2e",
                                                        "gpu_launches_per_step", "roofline", "global_stats", "loss",
                                                        "config")}
+        if not args.no_train:
+            del net
+            torch.cuda.empty_cache()
+            tr = bench_train(args, dev, rank, world, lib, peaks, max(5, min(args.steps, 10)))
+            if line is not None:
+                line["train"] = tr
     if rank != 0:
         torch.distributed.destroy_process_group()
         return
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        if args.workload == "forward":
+        if args.workload == "train":
+            step, px, what = None, 0, ""
+        elif args.workload == "forward":
             step, px = oracle_step_factory(1, cores)
             what = f"1 synthetic {W}x{H} image (1/16 of the batch), full forward (CPU JPEG stage included) + RD loss"
         else:
             step, px = oracle_codec_step_factory(1, cores)
             what = (f"1 synthetic {CODEC_W}x{CODEC_H} tile (1/8 of the image), compress + decompress (CPU JPEG stage, "
                     "single-threaded C rANS per string as in the reference)")
-        step()
-        t0 = time.perf_counter()
-        n = 3
-        for _ in range(n):
+        if step is not None:
             step()
-        dt = (time.perf_counter() - t0) / n
-        line["cpu_baseline"] = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
-                                "sample": what + f", fp32 oracle, mean of {n} after 1 warm-up"}
+            t0 = time.perf_counter()
+            n = 3
+            for _ in range(n):
+                step()
+            dt = (time.perf_counter() - t0) / n
+            line["cpu_baseline"] = {"value": px / dt / 1e6, "unit": "Mpixel/s", "cores": cores, "kind": "port",
+                                    "sample": what + f", fp32 oracle, mean of {n} after 1 warm-up"}
     print(json.dumps(line), file=OUT, flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()

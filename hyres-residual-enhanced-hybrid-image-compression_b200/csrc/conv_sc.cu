@@ -325,7 +325,7 @@ void conv_sc_pack(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16
 
 int conv_sc_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream, int* handled) {
   *handled = 0;
-  if (!c->d_w_tap || !conv_sc_applicable(c)) return HYRES_OK;
+  if (!c->d_w_tap || !c->w_tap_valid || !conv_sc_applicable(c)) return HYRES_OK;
   if (io->out_bf16 || io->out_sq || !io->out_f32 || io->epi != HYRES_EPI_LINEAR) return HYRES_OK;
   if (io->act != HYRES_ACT_NONE && io->act != HYRES_ACT_CLAMP01) return HYRES_OK;
   if (io->x0_square || (io->ld_x0 && io->ld_x0 != c->cin0)) return HYRES_OK;

@@ -763,6 +763,38 @@ void pack_weights(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16
   }
 }
 
+// Device-side packing (training: the weights change every step and live on the GPU): one thread per packed element.
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                                    const hyres_conv::Slot* __restrict__ slots, int cout, int cout_pad, int ktot,
+                                    int cin0, int cin1, int w_cin_total, int RS, int S, int deconv) {
+  const long long total = static_cast<long long>(cout_pad) * ktot;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx / ktot);
+    const int k = static_cast<int>(idx - static_cast<long long>(n) * ktot);
+    const hyres_conv::Slot sl = slots[k >> 6];
+    const int cc = k & 63;
+    const int cin_src = sl.src ? cin1 : cin0;
+    float v = 0.f;
+    if (n < cout && sl.chunk * 64 + cc < cin_src) {
+      const int ci = (sl.src ? cin0 : 0) + sl.chunk * 64 + cc;
+      v = deconv ? w[(static_cast<size_t>(ci) * cout + n) * RS + sl.r * S + sl.s]
+                 : w[(static_cast<size_t>(n) * w_cin_total + ci) * RS + sl.r * S + sl.s];
+    }
+    __nv_bfloat16 b = __float2bfloat16_rn(v);
+    for (int i = 0; i < sl.wpart; ++i) {
+      v -= __bfloat162float(b);
+      b = __float2bfloat16_rn(v);
+    }
+    out[idx] = b;
+  }
+}
+
+__global__ void pad_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int cout, int cout_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cout_pad) out[i] = (b && i < cout) ? b[i] : 0.f;
+}
+
 int upload_weights(hyres_conv* c, const float* weight, const float* bias) {
   std::vector<__nv_bfloat16> packed;
   pack_weights(c, weight, packed);
@@ -946,12 +978,35 @@ int hyres_conv_import_packed(hyres_conv* c, const void* w, const void* w_tap, co
 
 int hyres_conv_update(hyres_conv* c, const float* weight, const float* bias) {
   if (!c || !weight) return hy_fail(HYRES_ERR_ARG, "conv_update: null argument");
+  c->w_tap_valid = true;
   return upload_weights(c, weight, bias);
+}
+
+int hyres_conv_update_device(hyres_conv* c, const float* weight_dev, const float* bias_dev, void* stream_v) {
+  if (!c || !weight_dev) return hy_fail(HYRES_ERR_ARG, "conv_update_device: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  if (!c->d_slots) {
+    HY_CUDA(cudaMalloc(&c->d_slots, c->slots.size() * sizeof(hyres_conv::Slot)));
+    HY_CUDA(cudaMemcpy(c->d_slots, c->slots.data(), c->slots.size() * sizeof(hyres_conv::Slot), cudaMemcpyHostToDevice));
+  }
+  const long long total = static_cast<long long>(c->cout_pad) * c->ktot;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8));
+  hy_count_launch();
+  pack_weights_kernel<<<grid, 256, 0, st>>>(weight_dev, c->d_w, c->d_slots, c->cout, c->cout_pad, c->ktot, c->cin0,
+                                           c->cin1, c->w_cin_total, c->R * c->S, c->S,
+                                           c->kind == HYRES_DECONV_K5S2 ? 1 : 0);
+  HY_CUDA(cudaGetLastError());
+  hy_count_launch();
+  pad_bias_kernel<<<(c->cout_pad + 255) / 256, 256, 0, st>>>(bias_dev, c->d_bias, c->cout, c->cout_pad);
+  HY_CUDA(cudaGetLastError());
+  c->w_tap_valid = false;  // the tap-major copy of a three-output-channel layer is not refreshed: use the generic kernel
+  return HYRES_OK;
 }
 
 void hyres_conv_destroy(hyres_conv* c) {
   if (!c) return;
   if (c->d_groups) cudaFree(c->d_groups);
+  if (c->d_slots) cudaFree(c->d_slots);
   if (c->d_w) cudaFree(c->d_w);
   if (c->d_w_tap) cudaFree(c->d_w_tap);
   if (c->d_bias) cudaFree(c->d_bias);

@@ -64,17 +64,22 @@ class ConvLayer:
                  cin1=0, tap_mask=None, nsplit=1):
         """nsplit > 1: split-precision layer (hyres_conv_create_split): inputs are the bf16 parts produced by
         ``split_f32`` ([B,H,W,nsplit*cin]), the result is fp32 (``out_f32``) with fp32-equivalent accuracy."""
-        w = weight.detach().to("cpu", torch.float32).contiguous()
+        if isinstance(weight, (tuple, list, torch.Size)):
+            # shape only: an empty layer whose operands arrive later (update_device: training; import: deployment)
+            w, wshape = None, tuple(int(v) for v in weight)
+        else:
+            w = weight.detach().to("cpu", torch.float32).contiguous()
+            wshape = tuple(w.shape)
         b = None if bias is None else bias.detach().to("cpu", torch.float32).contiguous()
         if kind == HYRES_DECONV_K5S2:
-            cin_total, cout, R, S = w.shape
+            cin_total, cout, R, S = wshape
         else:
-            cout, cin_total, R, S = w.shape
+            cout, cin_total, R, S = wshape
         if cin0 is None:
             cin0 = cin_total
         self.kind, self.cin0, self.cin1, self.cout, self.nsplit = kind, cin0, cin1, cout, nsplit
         self.R, self.S, self.stride, self.pad, self.dil = R, S, stride, pad, dil
-        self._w_shape = tuple(w.shape)
+        self._w_shape = wshape
         mask = None
         if tap_mask is not None:
             mask = tap_mask.detach().to("cpu", torch.uint8).contiguous()
@@ -84,14 +89,14 @@ class ConvLayer:
         h = C.c_void_p()
         lib = L.lib()
         key = None
-        if PACKED_COLLECT is not None or PACKED_CACHE is not None:
+        if w is not None and (PACKED_COLLECT is not None or PACKED_CACHE is not None):
             import hashlib
             d = hashlib.sha1(repr((kind, cin0, cin1, cin_total, cout, R, S, stride, pad, dil, nsplit)).encode())
             d.update(w.numpy().tobytes())
             d.update(b.numpy().tobytes() if b is not None else b"-")
             d.update(mask.numpy().tobytes() if mask is not None else b"-")
             key = d.hexdigest()
-        cached = PACKED_CACHE.get(key) if PACKED_CACHE is not None else None
+        cached = PACKED_CACHE.get(key) if (PACKED_CACHE is not None and key is not None) else None
         L.check(lib.hyres_conv_create_split(C.byref(h), kind, cin0, cin1, cin_total, cout, R, S, stride,
                                             pad, dil, _ptr(w) if cached is None else C.c_void_p(0), _ptr(b), _ptr(mask),
                                             nsplit), "hyres_conv_create")
@@ -108,7 +113,7 @@ class ConvLayer:
             PACKED_STATS["packed"] += 1
         if cached is not None:
             pass
-        elif PACKED_COLLECT is not None:
+        elif PACKED_COLLECT is not None and key is not None:
             pw = torch.empty(lib.hyres_conv_packed_elems(h, 0), dtype=torch.bfloat16)
             pt = torch.empty(lib.hyres_conv_packed_elems(h, 1), dtype=torch.bfloat16)
             pb = torch.empty(lib.hyres_conv_packed_elems(h, 2), dtype=torch.float32)
@@ -122,6 +127,18 @@ class ConvLayer:
             raise ValueError("ConvLayer.update: weight shape changed")
         b = None if bias is None else bias.detach().to("cpu", torch.float32).contiguous()
         L.check(L.lib().hyres_conv_update(self._h, _ptr(w), _ptr(b)), "hyres_conv_update")
+
+    def update_device(self, weight, bias=None):
+        """Re-pack from fp32 CUDA tensors with a kernel on the current stream (no host round trip)."""
+        w = weight.detach()
+        if tuple(w.shape) != self._w_shape or not w.is_cuda or w.dtype != torch.float32 or not w.is_contiguous():
+            raise ValueError("ConvLayer.update_device: expected a contiguous fp32 CUDA weight of the original shape")
+        b = None
+        if bias is not None:
+            b = bias.detach()
+            if not b.is_cuda or b.dtype != torch.float32 or b.numel() != self.cout or not b.is_contiguous():
+                raise ValueError("ConvLayer.update_device: bias must be a contiguous fp32 CUDA vector of cout entries")
+        L.check(L.lib().hyres_conv_update_device(self._h, _ptr(w), _ptr(b), _stream()), "hyres_conv_update_device")
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -272,6 +289,12 @@ class ConvLayer:
             raise ValueError(f"{name}: expected [B={B},OH={OH},OW={OW},C] channel-contiguous, got {tuple(t.shape)}")
         if t.stride(1) != OW * t.stride(2) or t.stride(0) != OH * OW * t.stride(2):
             raise ValueError(f"{name}: pixel stride must be uniform (a channel slice of a dense NHWC tensor)")
+
+
+def wgrad_supported(tc):
+    """True when the tcgen05 weight-gradient kernel (csrc/wgrad.cu) covers this training convolution."""
+    fn = getattr(L.lib(), "hyres_wgrad_supported", None)
+    return bool(fn is not None and fn(tc.fwd._h))
 
 
 def ru_supported(c1, c2, c3):

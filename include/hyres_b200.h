@@ -113,6 +113,9 @@ int hyres_conv_export_packed(const hyres_conv* c, void* w_bf16, void* w_tap_bf16
 int hyres_conv_import_packed(hyres_conv* c, const void* w_bf16, const void* w_tap_bf16, const float* bias);
 /* Re-pack new weights into an existing layer (same geometry). */
 int hyres_conv_update(hyres_conv* c, const float* weight, const float* bias);
+/* The same from DEVICE fp32 tensors, packed by a kernel on `stream` (training: optimizer.step() changes the
+ * weights every iteration, src/utils/engine.py:56-84; nothing crosses PCIe). bias_dev may be NULL. */
+int hyres_conv_update_device(hyres_conv* c, const float* weight_dev, const float* bias_dev, void* stream);
 void hyres_conv_destroy(hyres_conv* c);
 /* MACs per output position the packed layer executes (padded K and N included). */
 int64_t hyres_conv_macs_per_pos(const hyres_conv* c);

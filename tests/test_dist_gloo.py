@@ -96,3 +96,58 @@ def test_rd_from_stats_matches_loss(oracle):
     got = D.rd_from_stats(stats, 0.008, jpeg_bpp=0.25)
     for k in ("y_bpp_loss", "z_bpp_loss", "bpp_loss", "mse_loss", "loss"):
         assert math.isclose(float(got[k]), float(want[k]), rel_tol=1e-5), k
+
+
+def _bucket_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hyres_b200.train import GradBuckets
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(40, 300), torch.nn.Tanh(), torch.nn.Linear(300, 7))
+    unused = torch.nn.Parameter(torch.zeros(5))  # receives no gradient: must not stall the reduction
+    params = list(net.parameters()) + [unused]
+    buckets = GradBuckets(params, bucket_bytes=4096)  # several small buckets
+    out = []
+    for step in range(2):
+        for p in params:
+            p.grad = None
+        x = torch.full((3, 40), float(rank + 1 + step))
+        net(x).square().sum().backward()
+        local = [p.grad.numpy().copy() for p in net.parameters()]
+        buckets.finish()
+        out.append((local, [p.grad.numpy().copy() for p in net.parameters()]))
+    assert unused.grad is None
+    q.put((rank, out, len(buckets.buckets)))
+    dist.destroy_process_group()
+
+
+def test_gradient_buckets_average_over_two_ranks():
+    """hyres_b200.train.GradBuckets (gradient all-reduce launched from autograd hooks; replaces nn.DataParallel,
+    src/training.py:211-212): after finish() every rank holds the mean of the ranks' gradients, in several buckets,
+    across consecutive steps, with a parameter that never receives a gradient."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, q), daemon=True) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        rank, out, nb = q.get(timeout=120)
+        res[rank] = out
+        assert nb >= 2
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for step in range(2):
+        mean = [(a + b) / 2 for a, b in zip(res[0][step][0], res[1][step][0])]
+        for r in range(2):
+            for got, want in zip(res[r][step][1], mean):
+                torch.testing.assert_close(torch.from_numpy(got), torch.from_numpy(want), rtol=1e-6, atol=1e-7)
