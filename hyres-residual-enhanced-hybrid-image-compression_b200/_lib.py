@@ -62,6 +62,9 @@ SIGNATURES = {
     "hyres_conv_create_split": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
     "hyres_conv_update": (_i, [_vp, _vp, _vp]),
     "hyres_conv_update_device": (_i, [_vp, _vp, _vp, _vp]),
+    "hyres_wgrad_supported": (_i, [_vp]),
+    "hyres_wgrad_workspace_bytes": (_i64, [_vp, _i, _i, _i]),
+    "hyres_wgrad_run": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "hyres_conv_packed_elems": (_i64, [_vp, _i]),
     "hyres_conv_export_packed": (_i, [_vp, _vp, _vp, _vp]),
     "hyres_conv_import_packed": (_i, [_vp, _vp, _vp, _vp]),

@@ -291,10 +291,37 @@ class ConvLayer:
             raise ValueError(f"{name}: pixel stride must be uniform (a channel slice of a dense NHWC tensor)")
 
 
+def _wgrad_plan(tc):
+    """The convolution whose weight gradient equals this training node's, and whether input / output-gradient swap
+    roles (transposed convolution: the weight gradient of its stride-2 data-gradient convolution)."""
+    if tc.kind == HYRES_DECONV_K5S2:
+        return tc.dgrad_layer(), True
+    return tc.wgrad_layer(), False
+
+
 def wgrad_supported(tc):
     """True when the tcgen05 weight-gradient kernel (csrc/wgrad.cu) covers this training convolution."""
-    fn = getattr(L.lib(), "hyres_wgrad_supported", None)
-    return bool(fn is not None and fn(tc.fwd._h))
+    layer, _ = _wgrad_plan(tc)
+    return bool(L.lib().hyres_wgrad_supported(layer._h))
+
+
+def conv_wgrad(tc, x, g16, want_bias=True):
+    """x: the node's input, g16: gradient of its output (both bf16 NHWC) -> (dW fp32 in the parameter's layout,
+    db fp32 or None)."""
+    layer, swap = _wgrad_plan(tc)
+    inp, gout = (g16, x) if swap else (x, g16)
+    _chk_nhwc(inp, "wgrad input"), _chk_nhwc(gout, "wgrad output gradient")
+    B, H, W, _ = inp.shape
+    lib = L.lib()
+    nbytes = lib.hyres_wgrad_workspace_bytes(layer._h, B, H, W)
+    if nbytes <= 0:
+        raise ValueError("conv_wgrad: unsupported layer")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=inp.device)
+    dw = torch.empty(tc.w_shape, dtype=torch.float32, device=inp.device)
+    L.check(lib.hyres_wgrad_run(layer._h, _ptr(inp), _ptr(gout), B, H, W, _ptr(dw), _ptr(ws), _stream()),
+            "hyres_wgrad_run")
+    db = torch.sum(g16, dim=(0, 1, 2), dtype=torch.float32) if want_bias else None
+    return dw, db
 
 
 def ru_supported(c1, c2, c3):

@@ -47,6 +47,7 @@ class TrainConv:
         self.tap_mask = tap_mask
         self.fwd = ops.ConvLayer(self.w_shape, None, kind=kind, stride=stride, pad=pad, dil=dil, tap_mask=tap_mask)
         self._dgrad = None
+        self._unmasked = None
         if kind == HYRES_DECONV_K5S2:
             self.cin, self.cout = w_shape[0], w_shape[1]
         else:
@@ -64,6 +65,18 @@ class TrainConv:
                 self._dgrad = ops.ConvLayer((self.cin, self.cout, R, S), None, kind=HYRES_CONV, stride=1, pad=self.pad,
                                             dil=self.dil, tap_mask=mask)
         return self._dgrad
+
+    def wgrad_layer(self):
+        """The layer whose tap table drives the weight-gradient kernel.  A masked convolution uses the unmasked
+        geometry: the reference masks ``weight.data`` (models/layers/checkerboard.py:47), not the gradient, so dead
+        taps do receive a gradient -- it never moves the forward pass (they are re-masked on every call) but it
+        enters ``clip_grad_norm_`` (src/utils/engine.py:71) and therefore the size of every other update."""
+        if self.tap_mask is None:
+            return self.fwd
+        if self._unmasked is None:
+            self._unmasked = ops.ConvLayer(self.w_shape, None, kind=self.kind, stride=self.stride, pad=self.pad,
+                                           dil=self.dil)
+        return self._unmasked
 
     def dgrad_weight(self, w):
         if self.kind == HYRES_DECONV_K5S2 or self.stride == 2:

@@ -120,6 +120,19 @@ void hyres_conv_destroy(hyres_conv* c);
 /* MACs per output position the packed layer executes (padded K and N included). */
 int64_t hyres_conv_macs_per_pos(const hyres_conv* c);
 
+/* Weight gradient of the convolution `c` (training: loss.backward() through the nn.Conv2d / nn.ConvTranspose2d
+ * modules of models/checkerboard.py:35-88, src/utils/engine.py:50-53) on the tensor cores:
+ *   dw[co][ci][r][s] = sum_pos gout[pos][co] * x[pos*stride + tap][ci]      (fp32, PyTorch weight layout of `c`)
+ * x: bf16 NHWC [B,H,W,cin] (the layer's input), gout: bf16 NHWC [B,OH,OW,cout] (gradient of its output).
+ * Supported: HYRES_CONV layers with one input (any kernel / stride / dilation / tap mask the forward supports);
+ * masked taps receive zero.  A transposed convolution's weight gradient is this call on its data-gradient
+ * convolution (stride 2, same weight tensor) with x := the transposed layer's output gradient and gout := its
+ * input.  `workspace`: hyres_wgrad_workspace_bytes() bytes of device memory. */
+int hyres_wgrad_supported(const hyres_conv* c);
+int64_t hyres_wgrad_workspace_bytes(const hyres_conv* c, int B, int H, int W);
+int hyres_wgrad_run(hyres_conv* c, const void* x, const void* gout, int B, int H, int W, float* dw, void* workspace,
+                    void* stream);
+
 typedef struct {
   const void* x0; /* bf16 NHWC [B,H,W,cin0] */
   const void* x1; /* bf16 NHWC [B,H,W,cin1] or NULL */
