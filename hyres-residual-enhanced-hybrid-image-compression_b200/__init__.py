@@ -10,5 +10,5 @@ from .layers import AttentionBlock, CheckboardMaskedConv2d, MultiScaleRefine, co
 from .jpeg import TurboJPEGCompression  # noqa: F401
 from .pipeline import HostPipeline  # noqa: F401
 from .codec_pipeline import CodecPipeline  # noqa: F401
-from . import container  # noqa: F401
+from . import container, spatial  # noqa: F401
 from .export import export_model, load_exported  # noqa: F401

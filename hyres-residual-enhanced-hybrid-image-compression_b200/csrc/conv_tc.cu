@@ -296,12 +296,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int nch = it.bn >> 5;
         const int steps = nsub * nch;
         const uint32_t mask = static_cast<uint32_t>(p.acc_mask[it.phase]);
+        // geometry of chunk q (32 output channels of one position) and the address of its skip / GDN operand
+        auto chunk = [&](int q, int& sub, int& cb, int& oh, int& ow, long long& opix) -> bool {
+          const int si = q / nch;
+          sub = sub0 + si * sub_step;
+          cb = (q - si * nch) << 5;
+          const int hv = it.h0 + sub * kSubH + ti, wv = it.w0 + tj;
+          oh = hv * p.out_mul + ph_p;
+          ow = wv * p.out_mul + ph_q;
+          opix = (static_cast<long long>(it.b_img) * p.OH + oh) * p.OW + ow;
+          return hv < p.OHv && wv < p.OWv && it.n0 + cb < p.cout;
+        };
+        const bool has_aux = p.split_mode != HYRES_SPLIT_COPY;
+        // the operand of chunk q + 1 is requested before chunk q's accumulators are read, the first one before the
+        // accumulators are even complete: one global-load latency per tile instead of one per chunk
+        float4 ax[8], an[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ax[i] = an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto fetch = [&](int q, float4 (&dst)[8]) {
+          int sub, cb, oh, ow; long long opix;
+          if (!has_aux || q >= steps || !chunk(q, sub, cb, oh, ow, opix)) return;
+          const float4* g = reinterpret_cast<const float4*>(p.aux0_f32 + opix * p.cout + it.n0 + cb);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dst[i] = __ldg(g + i);
+        };
+        fetch(0, ax);
         hy::mbar_wait(acc_full + 8 * buf, use & 1u);
         hy::tc_fence_after();
         for (int q = 0; q < steps; ++q) {
-          const int si = q / nch;
-          const int sub = sub0 + si * sub_step;
-          const int cb = (q - si * nch) << 5;
+          int sub, cb, oh, ow; long long opix;
+          const bool valid = chunk(q, sub, cb, oh, ow, opix);
+          fetch(q + 1, an);
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -318,32 +343,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             hy::mbar_arrive(acc_empty + 8 * buf);
           }
           const int n = it.n0 + cb;
-          const int hv = it.h0 + sub * kSubH + ti, wv = it.w0 + tj;
-          if (hv >= p.OHv || wv >= p.OWv || n >= p.cout) continue;
-          const int oh = hv * p.out_mul + ph_p, ow = wv * p.out_mul + ph_q;
-          const long long opix = (static_cast<long long>(it.b_img) * p.OH + oh) * p.OW + ow;
+          if (valid) {
           const float4* bq = reinterpret_cast<const float4*>(p.bias + n);
-          const float4* x0 = reinterpret_cast<const float4*>(p.aux0_f32 + opix * p.cout + n);
           const float4* x1 = reinterpret_cast<const float4*>(p.aux1_f32 + opix * p.cout + n);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b4 = __ldg(bq + i);
             float4 t = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
+            const float4 a = ax[i];
             if (p.split_mode == HYRES_SPLIT_ADD) {
-              const float4 a = __ldg(x0 + i);
               t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
             } else if (p.split_mode == HYRES_SPLIT_GATE) {
-              const float4 a = __ldg(x0 + i), g = __ldg(x1 + i);
+              const float4 g = __ldg(x1 + i);
               t.x = g.x * (1.f / (1.f + expf(-t.x))) + a.x;
               t.y = g.y * (1.f / (1.f + expf(-t.y))) + a.y;
               t.z = g.z * (1.f / (1.f + expf(-t.z))) + a.z;
               t.w = g.w * (1.f / (1.f + expf(-t.w))) + a.w;
             } else if (p.split_mode == HYRES_SPLIT_GDN) {
-              const float4 a = __ldg(x0 + i);
               t.x = a.x * (1.f / sqrtf(t.x)); t.y = a.y * (1.f / sqrtf(t.y));
               t.z = a.z * (1.f / sqrtf(t.z)); t.w = a.w * (1.f / sqrtf(t.w));
             } else if (p.split_mode == HYRES_SPLIT_IGDN) {
-              const float4 a = __ldg(x0 + i);
               t.x = a.x * sqrtf(t.x); t.y = a.y * sqrtf(t.y); t.z = a.z * sqrtf(t.z); t.w = a.w * sqrtf(t.w);
             }
             v[4 * i] = fmaxf(t.x, lo); v[4 * i + 1] = fmaxf(t.y, lo);
@@ -382,6 +401,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
             }
           }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) ax[i] = an[i];
         }
         continue;
       }

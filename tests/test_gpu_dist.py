@@ -84,3 +84,50 @@ def test_two_rank_global_stats_equal_single_process(build_lib, tmp_path):
     for k in ("y_bpp_loss", "z_bpp_loss", "bpp_loss", "mse_loss", "loss"):
         assert got[k] == pytest.approx(float(lo[k]), rel=2e-6), (k, got, float(lo[k]))
     print(json.dumps(got))
+
+
+SPATIAL_WORKER = r'''
+import json, os, sys, hashlib
+sys.path.insert(0, sys.argv[1])
+import torch
+import hyres_b200
+from hyres_b200 import dist as D, spatial, synthetic
+use_nccl = torch.cuda.device_count() >= 2
+rank, world, local = D.init_from_env(backend="nccl" if use_nccl else "gloo")
+dev = torch.device("cuda", local if use_nccl else 0)
+torch.cuda.set_device(dev)
+from oracle import hyres_oracle as O  # test infrastructure: weights with lively symbol statistics
+net = hyres_b200.ResidualJPEGCompression(jpeg_quality=1)
+net.load_state_dict(O.make_model(seed=1926, wrapper=True, lively=True).state_dict())
+net = net.to(dev).eval()
+x = synthetic.synthetic_image(1, 576, 768, seed=8).to(dev)
+with torch.no_grad():
+    c = spatial.compress_sharded(net, x, rows=1, cols=2, halo=256)
+    if rank == 0:
+        whole = net.compress(x)
+        same = c["strings"] == whole["strings"]
+        print("RESULT " + json.dumps({"same": bool(same), "bytes": sum(len(s) for s in c["strings"][0][0])}))
+    else:
+        assert c is None
+torch.distributed.destroy_process_group()
+'''
+
+
+def test_two_rank_spatial_sharding_gives_the_whole_image_strings(build_lib, tmp_path):
+    """hyres_b200.spatial.compress_sharded with two ranks (one tile + halo each, integers all-reduced) against the
+    single-rank whole-image compress()."""
+    script = tmp_path / "spatial_worker.py"
+    script.write_text(SPATIAL_WORKER)
+    port = _free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=900) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+    line = [ln for ln in outs[0][0].splitlines() if ln.startswith("RESULT ")][0]
+    got = json.loads(line[len("RESULT "):])
+    assert got["same"] and got["bytes"] > 1000, got

@@ -412,3 +412,31 @@ def test_export_and_load_prepacked_model(nets, oracle, tmp_path):
         net3 = hyres_b200.load_exported(blob)
         assert ops.PACKED_STATS["packed"] - before["packed"] == 1
         assert not torch.equal(net3.decompress(c)["x_hat"], want)
+
+
+def test_spatially_sharded_compress_is_byte_identical_to_whole_image(nets, oracle):
+    """SURVEY 8e tier T-B: one image coded tile by tile with halos (as 4 emulated ranks and as one rank owning all
+    tiles) gives the integers and the strings of the whole-image compress(), bit for bit; without the halo it does
+    not (that is tier T-A: independent tiles)."""
+    from hyres_b200 import spatial
+    _, pnet = nets
+    codec = pnet.residual_model
+    x = oracle.synthetic_image(1, 768, 1024, seed=101).cuda()
+    with torch.no_grad():
+        whole = pnet.compress(x)
+        jd, _ = pnet.jpeg.forward_device(x)
+        res = x - jd
+        ref = codec.encode_symbols(res)
+        parts = [spatial.encode_symbols_sharded(codec, res, 2, 2, ranks=(r, 4)) for r in range(4)]
+        for k in ("sym_z", "sym_a", "idx_a", "sym_na", "idx_na"):
+            got = sum(p[k] for p in parts)  # what the all-reduce computes: every element has one writer
+            assert torch.equal(got, ref[k]), k
+        sharded = spatial.compress_sharded(pnet, x, rows=2, cols=2)
+        assert sharded["strings"] == whole["strings"] and tuple(sharded["shape"]) == tuple(whole["shape"])
+        assert [b.getvalue() for b in sharded["jpeg_buffers"]] == [b.getvalue() for b in whole["jpeg_buffers"]]
+        assert torch.equal(pnet.decompress(sharded)["x_hat"], pnet.decompress(whole)["x_hat"])
+        no_halo = spatial.encode_symbols_sharded(codec, res, 2, 2, halo=0, ranks=(0, 1))
+        assert not torch.equal(no_halo["sym_a"], ref["sym_a"])
+    wins = spatial.spatial_windows(1408, 2048, 2, 4)
+    assert len(wins) == 8 and wins[0] == ((0, 704, 0, 512), (0, 960, 0, 768))
+    assert all(v % 32 == 0 for t, w in wins for v in t + w)

@@ -1,41 +1,59 @@
 #!/usr/bin/env python
-"""ncu launch list (csv of `--metrics gpu__time_duration.sum`) of a bench run -> per-kernel table of ONE step
-(from one jpeg_color_fwd_kernel launch to the next).   python tools/launch_summary.py in.csv out.md"""
+"""ncu launch list (csv of `--metrics gpu__time_duration.sum`) -> per-kernel table.
+
+    python tools/launch_summary.py in.csv out.md --title "..." [--step-marker jpeg_color_fwd]
+
+With --step-marker the table covers ONE step (from one launch of the marker kernel to the next; the last complete
+one); without it every captured launch is aggregated (pipelined workloads interleave their steps)."""
+import argparse
 import collections
 import csv
 import re
-import sys
 
-src, dst = sys.argv[1], sys.argv[2]
-with open(src) as f:
+ap = argparse.ArgumentParser()
+ap.add_argument("src")
+ap.add_argument("dst")
+ap.add_argument("--title", default="ncu launch list")
+ap.add_argument("--note", default="")
+ap.add_argument("--step-marker", default=None)
+a = ap.parse_args()
+with open(a.src) as f:
     lines = [l for l in f if l.startswith('"')]
 rd = csv.reader(lines)
 hdr = next(rd)
 ix = {h: i for i, h in enumerate(hdr)}
-L = [(r[ix["Kernel Name"]], float(r[ix["Metric Value"]])) for r in rd]
-starts = [i for i, (k, _) in enumerate(L) if "jpeg_color_fwd" in k]
-step = L[starts[-2]:starts[-1]]
+unit = None
+L = []
+for r in rd:
+    unit = r[ix["Metric Unit"]] if "Metric Unit" in ix else "ns"
+    v = float(r[ix["Metric Value"]].replace(",", ""))
+    L.append((r[ix["Kernel Name"]], v * (1e3 if unit in ("us", "usecond") else 1.0)))
+if a.step_marker:
+    starts = [i for i, (k, _) in enumerate(L) if a.step_marker in k]
+    sel = L[starts[-2]:starts[-1]]
+    scope = f"one complete step (from one `{a.step_marker}` launch to the next)"
+else:
+    sel = L
+    scope = f"all {len(L)} captured launches"
 agg = collections.OrderedDict()
-for k, t in step:
-    name = re.sub(r"\(.*", "", k).replace("void ", "").replace("<unnamed>::", "")[:60]
-    a = agg.setdefault(name, [0, 0.0])
-    a[0] += 1
-    a[1] += t
-tot = sum(t for _, t in step)
-out = ["# r01: ncu launch list of one bench step (`bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-graph`, workload configs[1])", "",
-       "source: `profiles/r01_launches.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none`), one complete step of the run",
-       "(from one `jpeg_color_fwd_kernel` launch to the next).  Per-launch times under ncu are serialised and cold-cache: compare the SHARES with",
-       "`bench.py`'s live CUDA-event numbers, not the absolutes.  `conv_res_kernel<EPI, ACT>`: EPI 0 linear, 1 add, 2 gate, 3 GDN, 4 IGDN,",
-       "5 pixel scale (+ tensor-core up-add), 6 channel statistics; ACT 0 none, 1 ReLU, 2 PReLU.", "",
-       "| kernel | launches / step | us / step | share |", "|---|---|---|---|"]
+for k, t in sel:
+    name = re.sub(r"\(.*", "", k).replace("void ", "").replace("<unnamed>::", "")[:70]
+    e = agg.setdefault(name, [0, 0.0])
+    e[0] += 1
+    e[1] += t
+tot = sum(t for _, t in sel)
+out = [f"# {a.title}", "", f"source: `{a.src}` (`ncu --metrics gpu__time_duration.sum --clock-control none`), {scope}.",
+       "Per-launch times under ncu are serialised and cold-cache: compare the SHARES with the live CUDA-event numbers of "
+       "`bench.py`, not the absolutes.", a.note, "",
+       "| kernel | launches | us | share |", "|---|---|---|---|"]
 tn, tt = 0, 0.0
 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    if k.startswith("at::"):
+    if k.startswith("at::") or k.startswith("std::enable_if") or "elementwise" in k or "cub::" in k:
         tn += n
         tt += t
         continue
     out.append(f"| `{k}` | {n} | {t / 1e3:.1f} | {100 * t / tot:.1f}% |")
-out.append(f"| `(torch elementwise / copy / fill)` | {tn} | {tt / 1e3:.1f} | {100 * tt / tot:.1f}% |")
-out.append(f"| total | {len(step)} | {tot / 1e3:.1f} | 100% |")
-open(dst, "w").write("\n".join(out) + "\n")
-print("\n".join(out[-3:]))
+out.append(f"| `(torch element-wise / copy / fill / reduce)` | {tn} | {tt / 1e3:.1f} | {100 * tt / tot:.1f}% |")
+out.append(f"| total | {len(sel)} | {tot / 1e3:.1f} | 100% |")
+open(a.dst, "w").write("\n".join(out) + "\n")
+print("\n".join(out[-12:]))
