@@ -8,6 +8,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdio>
 
 #define HYRES_OK 0
 #define HYRES_ERR_ARG -1
@@ -57,7 +58,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ff) == 0 && (clock64() - t0) > 4000000000LL) __trap();
+    if ((++spins & 0x3ff) == 0 && (clock64() - t0) > 4000000000LL) {
+      printf("hyres: mbarrier wait timed out: block %d of %d (%d threads), thread %d, barrier 0x%x parity %u\n",
+             blockIdx.x, gridDim.x, blockDim.x, threadIdx.x, bar, parity);
+      __trap();
+    }
   }
 }
 

@@ -74,7 +74,6 @@ __global__ void __launch_bounds__(kThreads, KS == 3 ? 3 : 2) conv_c3_kernel(cons
   constexpr uint32_t kPatchBytes = (3 * RH * RW * 2 + 127) / 128 * 128;  // bf16
   static_assert(KLIVE + 2 <= NK16 * 16, "two spare K columns carry the bias");
 
-  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
@@ -104,6 +103,10 @@ __global__ void __launch_bounds__(kThreads, KS == 3 ? 3 : 2) conv_c3_kernel(cons
   hy::tc_fence_before();
   __syncthreads();
   hy::tc_fence_after();
+  // Dependents (the next kernel of this stream) may be scheduled from here on -- only AFTER this CTA owns its
+  // tensor memory: a dependent that lands on the same SM allocates TMEM in its prologue and then waits for this
+  // grid to finish, so it must never be able to take the columns this CTA still has to allocate.
+  hy::pdl_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   hy::pdl_wait();  // (the weight / bias loads below are cheap; everything dependent comes after this)

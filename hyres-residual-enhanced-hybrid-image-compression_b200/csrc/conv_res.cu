@@ -136,7 +136,6 @@ template <int EPI, int ACT>
 __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_constant__ ResParams p) {
   const int epi = EPI >= 0 ? EPI : p.epi;
   const int act = ACT >= 0 ? ACT : p.act;
-  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
@@ -152,8 +151,15 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
   const uint32_t A_READY = A_EMPTY + 8 * kMaxStages;
   const uint32_t ACC_FULL = A_READY + 8 * kMaxStages;
   const uint32_t ACC_EMPTY = ACC_FULL + 16;
-  const uint32_t STAGED = ACC_EMPTY + 16;  // [2]: a group's result tile is staged (and its operands consumed)
-  const uint32_t STG_FREE = STAGED + 16;   // [2][2]: decoupled mode: a staging buffer of the group has been read by its store
+  // STAGED[2]: an epilogue group's result tile is staged (and its operands consumed); STAGED_ACK[2]: the group's store
+  // warp has seen that.  The group waits for the acknowledgement of tile k - 1 before it signals tile k, so the
+  // barrier can never complete two phases while the store warp is still busy with an earlier tile (under memory
+  // pressure from kernels of other streams its TMA-store read wait can outlast two epilogues; a waiter that misses a
+  // phase never wakes up -- seen as a watchdog trap when compress and decompress ran concurrently on several streams).
+  const uint32_t STAGED = ACC_EMPTY + 16;
+  const uint32_t STAGED_ACK = STAGED + 16;
+  const uint32_t STG_FREE = STAGED_ACK + 16;  // [2][2]: decoupled mode: a staging buffer of the group has been read by its store
+  const bool store_role = p.store_bf16 || !p.decoupled;  // otherwise the store warps have nothing to send or release
   const uint32_t tmem_slot = STG_FREE + 32;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform by construction
   const int lane = threadIdx.x & 31;
@@ -170,9 +176,12 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
     for (int i = 0; i < 2; ++i) {
       hy::mbar_init(ACC_FULL + 8 * i, 1);
       hy::mbar_init(ACC_EMPTY + 8 * i, 128);
-      hy::mbar_init(STAGED + 8 * i, 128);
       hy::mbar_init(STG_FREE + 16 * i, 1);
       hy::mbar_init(STG_FREE + 16 * i + 8, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      hy::mbar_init(STAGED + 8 * i, 128);
+      hy::mbar_init(STAGED_ACK + 8 * i, 1);
     }
     hy::mbar_fence_init();
     // the weights do not depend on the predecessor kernel: their load starts before the dependency wait
@@ -207,6 +216,10 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
   hy::tc_fence_before();
   __syncthreads();
   hy::tc_fence_after();
+  // Dependents (the next kernel of this stream) may be scheduled from here on -- only AFTER this CTA owns its
+  // tensor memory: a dependent that lands on the same SM allocates TMEM in its prologue and then waits for this
+  // grid to finish, so it must never be able to take the columns this CTA still has to allocate.
+  hy::pdl_launch_dependents();
   uint32_t tmem_base_v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
@@ -324,7 +337,7 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
     // One per epilogue group: waits until the group has staged a tile, sends it with a TMA store and releases the
     // stage once the store has read it.  (Measured with the clock64 trace: when a thread of the group did this,
     // its warp -- and through the group barrier the whole group -- lost ~880 clk per tile waiting for the store.)
-    if (lane == 0) {
+    if (lane == 0 && store_role) {
       const int grp = warp - 10;
       for (int it = grp;; it += 2) {
         const int t = blockIdx.x + it * static_cast<int>(gridDim.x);
@@ -336,6 +349,7 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
         const int sk = p.stg_per_grp == 2 ? ((it >> 1) & 1) : 0;  // staging buffer of this tile (decoupled mode)
         const uint32_t src = p.decoupled ? stg_base + (grp * p.stg_per_grp + sk) * p.nchunk_out * 16384 : sb + p.o_off;
         hy::mbar_wait(STAGED + 8 * grp, (it >> 1) & 1);
+        hy::mbar_arrive(STAGED_ACK + 8 * grp);
         if (p.store_bf16) {
           for (int c = 0; c < p.nchunk_out; ++c) hy::tma_store_4d(&p.mapOut, src + c * 16384, c * 64, w0, h0, b_img);
           hy::tma_store_commit();
@@ -576,7 +590,10 @@ __global__ void __launch_bounds__(kThreadsSq, 1) conv_res_kernel(const __grid_co
       hy::mbar_arrive(ACC_EMPTY + 8 * grp);
       if (row == 0) RES_STAMP(it, 6);  // chunks done
       if (p.store_bf16) hy::fence_async_smem();
-      hy::mbar_arrive(STAGED + 8 * grp);  // this thread's part is staged and its operands are consumed
+      if (store_role) {  // this thread's part is staged and its operands are consumed
+        if (it >= 2) hy::mbar_wait(STAGED_ACK + 8 * grp, ((it >> 1) - 1) & 1);  // the store warp took the previous tile
+        hy::mbar_arrive(STAGED + 8 * grp);
+      }
     }
   }
 
@@ -785,7 +802,7 @@ int conv_res_try_run(hyres_conv* c, const hyres_conv_io* io, cudaStream_t stream
   p.stage_bytes = stage;
   p.stage_tx_bytes = p.nchunk_in * PH * PW * 128 + (need0 ? p.nchunk_out * 16384 : 0) + (need1 ? p.nchunk_out * 16384 : 0) +
                      (up ? (kT2Rows + kT3Rows) * 128 : 0);
-  const int fixed0 = static_cast<int>(w_bytes) + p.u_bytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+  const int fixed0 = static_cast<int>(w_bytes) + p.u_bytes + 1024 /*bias*/ + 512 /*barriers*/ + 1024 /*alignment*/;
   // two staging buffers per group when the ring keeps >= 3 stages next to them: the group then never waits for the
   // read of its previous store (~1000 clk)
   p.stg_per_grp = 1;
@@ -878,7 +895,7 @@ extern "C" int hyres_refine_stats3_tc(const void* f1, const void* s2_padded, con
   p.t3_off = p.t2_off + (kT2Rows * 128 + 1023) / 1024 * 1024;
   p.stage_bytes = p.t3_off + kT3Rows * 128;
   p.stage_tx_bytes = p.a_chunk_bytes + (kT2Rows + kT3Rows) * 128;
-  const int fixed = p.u_bytes + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment*/;
+  const int fixed = p.u_bytes + 1024 /*bias*/ + 512 /*barriers*/ + 1024 /*alignment*/;
   p.NA = std::min((kSmemLimit - fixed) / p.stage_bytes, kMaxStages);
   p.stg_base_off = p.NA * p.stage_bytes;
   p.stg_per_grp = 1;

@@ -59,7 +59,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sc_kernel(const __grid_const
   constexpr int ACCW = 2 * C::N;                       // two 128-row blocks cover the 180-position patch
   constexpr int TMEM_COLS = 2 * ACCW <= 128 ? 128 : (2 * ACCW <= 256 ? 256 : 512);
 
-  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t w_base = base;
@@ -94,6 +93,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_sc_kernel(const __grid_const
   hy::tc_fence_before();
   __syncthreads();
   hy::tc_fence_after();
+  // Dependents (the next kernel of this stream) may be scheduled from here on -- only AFTER this CTA owns its
+  // tensor memory: a dependent that lands on the same SM allocates TMEM in its prologue and then waits for this
+  // grid to finish, so it must never be able to take the columns this CTA still has to allocate.
+  hy::pdl_launch_dependents();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   hy::pdl_wait();  // everything above is independent of the predecessor kernel

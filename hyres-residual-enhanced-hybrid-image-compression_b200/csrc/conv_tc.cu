@@ -114,7 +114,6 @@ struct Item {
 // item boundaries; the accumulators are double buffered in TMEM whenever 2 * MT * BN <= 512 columns,
 // and two epilogue warp groups drain them while the next item's MMAs are issued.
 __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
-  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -159,6 +158,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   hy::tc_fence_before();
   __syncthreads();
   hy::tc_fence_after();
+  // Dependents (the next kernel of this stream) may be scheduled from here on -- only AFTER this CTA owns its
+  // tensor memory: a dependent that lands on the same SM allocates TMEM in its prologue and then waits for this
+  // grid to finish, so it must never be able to take the columns this CTA still has to allocate.
+  hy::pdl_launch_dependents();
   uint32_t tmem_base_v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
@@ -291,42 +294,72 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t t_item = t_lane + buf * p.acc_cols;
       if (p.split_epi) {
         // split-precision layer: v = sum of the tile's accumulators (cross products first, fp32 round to nearest)
-        // + bias, the fp32 element-wise stage (skip / gate / GDN), ReLU -> fp32 row and / or its bf16 parts
+        // + bias, the fp32 element-wise stage (skip / gate / GDN), ReLU -> fp32 row and / or its bf16 parts.
+        // TMEM hands every thread one position (row) of 32 channels; global memory wants a warp to touch few
+        // 128-byte lines per instruction.  Each epilogue warp therefore owns a 4.5 KB shared-memory tile through
+        // which operands and results are transposed: global accesses use the "line layout" (instruction j, lane l ->
+        // row 4j + l/8, 16-byte piece l%8: four rows of 128 B per instruction instead of 32 scattered pieces).
         const float lo = p.act == HYRES_ACT_RELU ? 0.f : -3.402823466e38f;
         const int nch = it.bn >> 5;
         const int steps = nsub * nch;
         const uint32_t mask = static_cast<uint32_t>(p.acc_mask[it.phase]);
-        // geometry of chunk q (32 output channels of one position) and the address of its skip / GDN operand
-        auto chunk = [&](int q, int& sub, int& cb, int& oh, int& ow, long long& opix) -> bool {
+        float* stg = reinterpret_cast<float*>(smem_raw + (bar_base + 512 - hy::smem_u32(smem_raw))) + warp * (32 * 36);
+        const int qrow = lane >> 3, qpc = lane & 7;  // line layout
+        const bool coalesced = p.f32_sc == 1 && (p.cout & 31) == 0;
+        // output pixel of local row `rl` (0..31) of this warp, sub-tile `sub`
+        auto rowpix = [&](int sub, int rl, long long& opix) -> bool {
+          const int r = (warp & 3) * 32 + rl;
+          const int hv = it.h0 + sub * kSubH + (r >> 3), wv = it.w0 + (r & 7);
+          opix = (static_cast<long long>(it.b_img) * p.OH + (hv * p.out_mul + ph_p)) * p.OW + (wv * p.out_mul + ph_q);
+          return hv < p.OHv && wv < p.OWv;
+        };
+        auto chunk_of = [&](int q, int& sub, int& cb) {
           const int si = q / nch;
           sub = sub0 + si * sub_step;
           cb = (q - si * nch) << 5;
-          const int hv = it.h0 + sub * kSubH + ti, wv = it.w0 + tj;
-          oh = hv * p.out_mul + ph_p;
-          ow = wv * p.out_mul + ph_q;
-          opix = (static_cast<long long>(it.b_img) * p.OH + oh) * p.OW + ow;
-          return hv < p.OHv && wv < p.OWv && it.n0 + cb < p.cout;
         };
         const bool has_aux = p.split_mode != HYRES_SPLIT_COPY;
-        // the operand of chunk q + 1 is requested before chunk q's accumulators are read, the first one before the
-        // accumulators are even complete: one global-load latency per tile instead of one per chunk
-        float4 ax[8], an[8];
+        // operand of chunk q in the line layout; chunk q + 1 is requested before chunk q's accumulators are read
+        auto fetch = [&](const float* src, int q, float4 (&dst)[8]) {
+          if (q >= steps) return;
+          int sub, cb;
+          chunk_of(q, sub, cb);
+          if (it.n0 + cb >= p.cout) return;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ax[i] = an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        auto fetch = [&](int q, float4 (&dst)[8]) {
-          int sub, cb, oh, ow; long long opix;
-          if (!has_aux || q >= steps || !chunk(q, sub, cb, oh, ow, opix)) return;
-          const float4* g = reinterpret_cast<const float4*>(p.aux0_f32 + opix * p.cout + it.n0 + cb);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) dst[i] = __ldg(g + i);
+          for (int j = 0; j < 8; ++j) {
+            long long opix;
+            dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rowpix(sub, 4 * j + qrow, opix))
+              dst[j] = __ldg(reinterpret_cast<const float4*>(src + opix * p.cout + it.n0 + cb) + qpc);
+          }
         };
-        fetch(0, ax);
+        // line layout -> the warp's tile; every thread then reads its own row (8 float4 = 32 channels) from there
+        auto stage = [&](const float4 (&src)[8]) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(stg + (4 * j + qrow) * 36 + qpc * 4) = src[j];
+          __syncwarp();
+        };
+        float4 an[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_aux && coalesced) fetch(p.aux0_f32, 0, an);
         hy::mbar_wait(acc_full + 8 * buf, use & 1u);
         hy::tc_fence_after();
         for (int q = 0; q < steps; ++q) {
-          int sub, cb, oh, ow; long long opix;
-          const bool valid = chunk(q, sub, cb, oh, ow, opix);
-          fetch(q + 1, an);
+          int sub, cb;
+          chunk_of(q, sub, cb);
+          long long opix;
+          const bool valid_row = rowpix(sub, lane, opix);
+          const int n = it.n0 + cb;
+          const bool aux_staged = has_aux && coalesced;
+          if (aux_staged) {
+            stage(an);
+            fetch(p.aux0_f32, q + 1, an);
+          }
+          const bool row_ok = valid_row && n < p.cout;
+          const float4* g0 = reinterpret_cast<const float4*>(p.aux0_f32 + opix * p.cout + n);  // used when !aux_staged
+          const float4* g1 = reinterpret_cast<const float4*>(p.aux1_f32 + opix * p.cout + n);  // gate only
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -342,19 +375,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             hy::tc_fence_before();
             hy::mbar_arrive(acc_empty + 8 * buf);
           }
-          const int n = it.n0 + cb;
-          if (valid) {
+          if (n >= p.cout) continue;  // warp-uniform
           const float4* bq = reinterpret_cast<const float4*>(p.bias + n);
-          const float4* x1 = reinterpret_cast<const float4*>(p.aux1_f32 + opix * p.cout + n);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 b4 = __ldg(bq + i);
             float4 t = make_float4(v[4 * i] + b4.x, v[4 * i + 1] + b4.y, v[4 * i + 2] + b4.z, v[4 * i + 3] + b4.w);
-            const float4 a = ax[i];
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (aux_staged) a = *reinterpret_cast<const float4*>(stg + lane * 36 + i * 4);
+            else if (has_aux && row_ok) a = __ldg(g0 + i);
             if (p.split_mode == HYRES_SPLIT_ADD) {
               t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
             } else if (p.split_mode == HYRES_SPLIT_GATE) {
-              const float4 g = __ldg(x1 + i);
+              const float4 g = row_ok ? __ldg(g1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
               t.x = g.x * (1.f / (1.f + expf(-t.x))) + a.x;
               t.y = g.y * (1.f / (1.f + expf(-t.y))) + a.y;
               t.z = g.z * (1.f / (1.f + expf(-t.z))) + a.z;
@@ -369,12 +402,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             v[4 * i + 2] = fmaxf(t.z, lo); v[4 * i + 3] = fmaxf(t.w, lo);
           }
           if (p.out_f32) {
-            float* o = p.out_f32 + it.b_img * p.f32_sb + oh * p.f32_sh + ow * p.f32_sw + n * p.f32_sc;
-            if (n + 32 <= p.cout && p.f32_sc == 1) {
+            if (coalesced) {
+              __syncwarp();
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                reinterpret_cast<float4*>(o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
+                *reinterpret_cast<float4*>(stg + lane * 36 + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                long long op;
+                if (rowpix(sub, 4 * j + qrow, op))
+                  reinterpret_cast<float4*>(p.out_f32 + op * p.f32_sw + n)[qpc] =
+                      *reinterpret_cast<const float4*>(stg + (4 * j + qrow) * 36 + qpc * 4);
+              }
+            } else if (valid_row) {
+              float* o = p.out_f32 + it.b_img * p.f32_sb + (opix / p.OW % p.OH) * p.f32_sh + (opix % p.OW) * p.f32_sw + n * p.f32_sc;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (n + i < p.cout) o[i * p.f32_sc] = v[i];
@@ -385,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
               for (int i = 0; i < 32; ++i) v[i] *= v[i];
             }
-            __nv_bfloat16* o = p.out_split + opix * (static_cast<long long>(p.out_nsplit) * p.cout) + n;
+            uint4* stg4 = reinterpret_cast<uint4*>(stg);
             for (int part = 0; part < p.out_nsplit; ++part) {
               uint32_t w[16];
 #pragma unroll
@@ -395,15 +437,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 v[2 * i + 1] -= __bfloat162float(h1);
                 w[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
               }
+              __syncwarp();
 #pragma unroll
-              for (int i = 0; i < 4; ++i)
-                reinterpret_cast<uint4*>(o + static_cast<long long>(part) * p.cout)[i] =
-                    make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+              for (int i = 0; i < 4; ++i) stg4[lane * 5 + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+              __syncwarp();
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {  // instruction j, lane l -> row 8j + l/4, 16-byte piece l%4: 8 rows of 64 B
+                const int rl = 8 * j + (lane >> 2), pc = lane & 3;
+                long long op;
+                if (rowpix(sub, rl, op))
+                  reinterpret_cast<uint4*>(p.out_split + op * (static_cast<long long>(p.out_nsplit) * p.cout) +
+                                           static_cast<long long>(part) * p.cout + n)[pc] = stg4[rl * 5 + pc];
+              }
             }
           }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) ax[i] = an[i];
         }
         continue;
       }
@@ -1168,7 +1215,8 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
     total_groups += c->ph_count[ph];
     for (int g = 0; g < c->ph_count[ph]; ++g) total_btiles += c->groups[c->ph_begin[ph] + g].ntaps;
   }
-  const int fixed = 512 /*barriers*/ + 1024 /*alignment*/;
+  // split layers: eight 4.5 KB transposition tiles for the epilogue warps behind the barrier block
+  const int fixed = 512 /*barriers*/ + 1024 /*alignment*/ + (split ? 8 * 32 * 36 * 4 : 0);
   const double taps_per_group = static_cast<double>(total_btiles) / total_groups;
   p.NA = 2; p.NB = 2;
   auto smem_need = [&]() { return p.NA * p.a_stage_bytes + p.NB * p.b_stage_bytes + fixed; };

@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
   constexpr int kEpiThreads = 128 * CS;
   constexpr int kThreads = kEpiThreads + 96;
   constexpr int kWarpLoad = 4 * CS, kWarpMma = 4 * CS + 1, kWarpStore = 4 * CS + 2;  // one warp each
-  hy::pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   auto bar = [&](int i) { return base + kBars + 8u * i; };
@@ -155,6 +154,10 @@ __global__ void __launch_bounds__(128 * CS + 96, 1) ru_fused_kernel(const __grid
   hy::tc_fence_before();
   __syncthreads();
   hy::tc_fence_after();
+  // Dependents (the next kernel of this stream) may be scheduled from here on -- only AFTER this CTA owns its
+  // tensor memory: a dependent that lands on the same SM allocates TMEM in its prologue and then waits for this
+  // grid to finish, so it must never be able to take the columns this CTA still has to allocate.
+  hy::pdl_launch_dependents();
   uint32_t tmem_base_v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base_v) : "r"(tmem_slot));
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
