@@ -525,7 +525,7 @@ def bench_train(args, dev, rank, world, lib, peaks, steps):
     net = hyres_b200.ResidualJPEGCompression(jpeg_quality=1)
     net.update(force=True)
     net = net.to(dev)
-    trainer = T.Trainer(net, lmbda=LMBDA, lr=1e-4, aux_lr=1e-3, clip_max_norm=1.0)
+    trainer = T.Trainer(net, lmbda=LMBDA, lr=1e-4, aux_lr=1e-3, clip_max_norm=1.0, capturable=not args.no_graph)
     x_host = synthetic.synthetic_image(TRAIN_BATCH, TRAIN_H, TRAIN_W, seed=11 + rank).pin_memory()
     x_dev = x_host.to(dev)
     px_step = TRAIN_BATCH * TRAIN_H * TRAIN_W
@@ -537,6 +537,15 @@ def bench_train(args, dev, rank, world, lib, peaks, steps):
 
     for _ in range(max(args.warmup, 3)):
         r = trainer.step(x_dev)
+    graphed = False
+    l0 = lib.hyres_launch_count()
+    if not args.no_graph:
+        try:
+            trainer.capture(x_dev, warmup=1)
+            graphed = True
+        except Exception as exc:  # noqa: BLE001
+            print(f"bench: training-step capture failed ({type(exc).__name__}: {exc}); timing eager launches", file=sys.stderr)
+    launches_captured = lib.hyres_launch_count() - l0
     l0 = lib.hyres_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -547,6 +556,8 @@ def bench_train(args, dev, rank, world, lib, peaks, steps):
     barrier()
     ms = D.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
     launches = (lib.hyres_launch_count() - l0) // steps
+    if graphed:  # replayed launches are not counted by the library: one captured step (after its eager warm-up step)
+        launches = launches_captured // 2
     loss = float(r["loss"])
     barrier()
     t0 = time.perf_counter()
@@ -563,6 +574,7 @@ def bench_train(args, dev, rank, world, lib, peaks, steps):
             "e2e": {"value": world * px_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches_per_step": int(launches),
+            "launch": "whole step replayed from a CUDA graph" if graphed else "eager launches",
             "weight_gradient": "tcgen05 (csrc/wgrad.cu)" if T.wgrad_native_active() else "ATen convolution_backward (cuDNN)",
             "step_tflops": flops / (ms * 1e-3) / 1e12, "step_frac": flops / (ms * 1e-3) / 1e12 / peaks["tflops"],
             "loss": loss, "loss_e2e": loss_e2e}

@@ -62,6 +62,8 @@ SIGNATURES = {
     "hyres_conv_create_split": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i]),
     "hyres_conv_update": (_i, [_vp, _vp, _vp]),
     "hyres_conv_update_device": (_i, [_vp, _vp, _vp, _vp]),
+    "hyres_colsum_workspace_bytes": (_i64, [_i64, _i]),
+    "hyres_colsum_bf16": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "hyres_wgrad_supported": (_i, [_vp]),
     "hyres_wgrad_workspace_bytes": (_i64, [_vp, _i, _i, _i]),
     "hyres_wgrad_run": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -51,6 +51,7 @@ struct hyres_conv {
   std::vector<Slot> slots;
   TapGroup* d_groups = nullptr;
   Slot* d_slots = nullptr;           // device copy of `slots` (hyres_conv_update_device packs on the GPU)
+  void* d_wg_items = nullptr;        // weight-gradient work items of this layer's plan (wgrad.cu), uploaded once
   bool w_tap_valid = true;           // false once the weights were re-packed on the device (d_w_tap is stale)
   __nv_bfloat16* d_w = nullptr;
   __nv_bfloat16* d_w_tap = nullptr;  // tap-major packing for the three-output-channel layers (conv_sc.cu)

@@ -1076,6 +1076,7 @@ void hyres_conv_destroy(hyres_conv* c) {
   if (!c) return;
   if (c->d_groups) cudaFree(c->d_groups);
   if (c->d_slots) cudaFree(c->d_slots);
+  if (c->d_wg_items) cudaFree(c->d_wg_items);
   if (c->d_w) cudaFree(c->d_w);
   if (c->d_w_tap) cudaFree(c->d_w_tap);
   if (c->d_bias) cudaFree(c->d_bias);

@@ -301,8 +301,7 @@ int64_t hyres_wgrad_workspace_bytes(const hyres_conv* c, int B, int H, int W) {
   hyres_conv_out_size(c, H, W, &OH, &OW);
   const int ntiles = B * ((OH + kTileH - 1) / kTileH) * ((OW + kTileW - 1) / kTileW);
   const int split = choose_split(pl, ntiles);
-  return static_cast<int64_t>(split) * pl.n_kslots * pl.n_co_blocks * 128 * 64 * 4 +
-         static_cast<int64_t>(pl.items.size()) * sizeof(WgItem) + 256;
+  return static_cast<int64_t>(split) * pl.n_kslots * pl.n_co_blocks * 128 * 64 * 4;
 }
 
 int hyres_wgrad_run(hyres_conv* c, const void* x, const void* gout, int B, int H, int W, float* dw, void* workspace,
@@ -329,12 +328,14 @@ int hyres_wgrad_run(hyres_conv* c, const void* x, const void* gout, int B, int H
   p.stage_bytes = pl.stage_bytes;
   p.nstage = pl.nstage;
   p.groups = c->d_groups + c->ph_begin[0];
-  // workspace: [items table | partial sums]
-  uint8_t* ws = static_cast<uint8_t*>(workspace);
-  const size_t items_bytes = (pl.items.size() * sizeof(WgItem) + 255) / 256 * 256;
-  HY_CUDA(cudaMemcpyAsync(ws, pl.items.data(), pl.items.size() * sizeof(WgItem), cudaMemcpyHostToDevice, st));
-  p.items = reinterpret_cast<const WgItem*>(ws);
-  p.partial = reinterpret_cast<float*>(ws + items_bytes);
+  // the plan's item table lives with the layer (uploaded on first use: a step that is being captured into a CUDA
+  // graph must not copy from pageable host memory); workspace = partial sums
+  if (!c->d_wg_items) {
+    HY_CUDA(cudaMalloc(&c->d_wg_items, pl.items.size() * sizeof(WgItem)));
+    HY_CUDA(cudaMemcpy(c->d_wg_items, pl.items.data(), pl.items.size() * sizeof(WgItem), cudaMemcpyHostToDevice));
+  }
+  p.items = static_cast<const WgItem*>(c->d_wg_items);
+  p.partial = static_cast<float*>(workspace);
   if (!c->d_slots) {
     HY_CUDA(cudaMalloc(&c->d_slots, c->slots.size() * sizeof(hyres_conv::Slot)));
     HY_CUDA(cudaMemcpy(c->d_slots, c->slots.data(), c->slots.size() * sizeof(hyres_conv::Slot), cudaMemcpyHostToDevice));
@@ -358,6 +359,79 @@ int hyres_wgrad_run(hyres_conv* c, const void* x, const void* gout, int B, int H
   hy_count_launch();
   wgrad_reduce_kernel<<<static_cast<int>(std::min<long long>((total + 255) / 256, 148 * 8)), 256, 0, st>>>(
       p.partial, c->d_slots, p.n_split, p.n_kslots, p.n_co_blocks, c->cout, c->w_cin_total, c->R * c->S, c->S, dw);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Bias gradient: db[c] = sum over rows of g[row][c] (g: bf16 [rows][C], C a multiple of 8).  HBM-bound column sums:
+// a block owns a slab of rows, a thread 8 channels (16-byte loads) of every (blockDim.y)-th row; slabs are reduced in
+// shared memory, slab partials in a second, fixed-order pass (deterministic).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ g, long long rows, int C, int rows_per_block,
+                                      float* __restrict__ partial) {
+  extern __shared__ float red[];  // [blockDim.y][C]
+  const int c8 = threadIdx.x;     // group of 8 channels
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c8 * 8 < C)
+    for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(g + r * C) + c8);
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += hy::bf16_lo(u[i]);
+        acc[2 * i + 1] += hy::bf16_hi(u[i]);
+      }
+    }
+  if (c8 * 8 < C)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.y * C + c8 * 8 + i] = acc[i];
+  __syncthreads();
+  for (int c = threadIdx.y * blockDim.x + threadIdx.x; c < C; c += blockDim.x * blockDim.y) {
+    float s = 0.f;
+    for (int y = 0; y < blockDim.y; ++y) s += red[y * C + c];
+    partial[static_cast<long long>(blockIdx.x) * C + c] = s;
+  }
+}
+
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < nblocks; ++b) s += partial[static_cast<long long>(b) * C + c];
+  out[c] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t hyres_colsum_workspace_bytes(int64_t rows, int C) {
+  if (rows <= 0 || C <= 0) return 0;
+  const int64_t nblocks = std::min<int64_t>(148 * 4, (rows + 63) / 64);
+  return nblocks * C * 4;
+}
+
+int hyres_colsum_bf16(const void* g, int64_t rows, int C, float* out, void* workspace, void* stream_v) {
+  if (!g || !out || !workspace || rows <= 0 || C <= 0 || (C % 8) || C > 2048)
+    return hy_fail(HYRES_ERR_ARG, "colsum_bf16: bad argument (C must be a multiple of 8, at most 2048)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream_v);
+  const int nblocks = static_cast<int>(std::min<int64_t>(148 * 4, (rows + 63) / 64));
+  const int rows_per_block = static_cast<int>((rows + nblocks - 1) / nblocks);
+  const int tx = C / 8;                              // threads along channels
+  const int ty = std::max(1, std::min(1024 / tx, 48 * 1024 / (C * 4)));  // row lanes (shared memory: ty * C floats)
+  hy_count_launch();
+  colsum_partial_kernel<<<nblocks, dim3(tx, ty), ty * C * 4, st>>>(static_cast<const __nv_bfloat16*>(g), rows, C,
+                                                                  rows_per_block, static_cast<float*>(workspace));
+  HY_CUDA(cudaGetLastError());
+  hy_count_launch();
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(static_cast<const float*>(workspace), nblocks, C, out);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }

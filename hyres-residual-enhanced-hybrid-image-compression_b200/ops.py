@@ -320,8 +320,20 @@ def conv_wgrad(tc, x, g16, want_bias=True):
     dw = torch.empty(tc.w_shape, dtype=torch.float32, device=inp.device)
     L.check(lib.hyres_wgrad_run(layer._h, _ptr(inp), _ptr(gout), B, H, W, _ptr(dw), _ptr(ws), _stream()),
             "hyres_wgrad_run")
-    db = torch.sum(g16, dim=(0, 1, 2), dtype=torch.float32) if want_bias else None
+    db = colsum_bf16(g16) if want_bias else None
     return dw, db
+
+
+def colsum_bf16(g):
+    """bf16 [..., C] -> fp32 [C]: sum over all leading dimensions (a layer's bias gradient)."""
+    _chk_nhwc(g, "g")
+    Cc = g.shape[-1]
+    rows = g.numel() // Cc
+    lib = L.lib()
+    ws = torch.empty(lib.hyres_colsum_workspace_bytes(rows, Cc), dtype=torch.uint8, device=g.device)
+    out = torch.empty(Cc, dtype=torch.float32, device=g.device)
+    L.check(lib.hyres_colsum_bf16(_ptr(g), rows, Cc, _ptr(out), _ptr(ws), _stream()), "hyres_colsum_bf16")
+    return out
 
 
 def ru_supported(c1, c2, c3):

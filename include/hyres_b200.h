@@ -133,6 +133,11 @@ int64_t hyres_wgrad_workspace_bytes(const hyres_conv* c, int B, int H, int W);
 int hyres_wgrad_run(hyres_conv* c, const void* x, const void* gout, int B, int H, int W, float* dw, void* workspace,
                     void* stream);
 
+/* Bias gradient db[c] = sum over rows of g[row][c] (g: bf16 [rows][C], the NHWC output gradient of a layer;
+ * C a multiple of 8): deterministic two-pass column sums. workspace: hyres_colsum_workspace_bytes() bytes. */
+int64_t hyres_colsum_workspace_bytes(int64_t rows, int C);
+int hyres_colsum_bf16(const void* g, int64_t rows, int C, float* out, void* workspace, void* stream);
+
 typedef struct {
   const void* x0; /* bf16 NHWC [B,H,W,cin0] */
   const void* x1; /* bf16 NHWC [B,H,W,cin1] or NULL */
