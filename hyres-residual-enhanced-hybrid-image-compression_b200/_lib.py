@@ -13,6 +13,7 @@ HYRES_CONV, HYRES_DECONV_K5S2 = 0, 1
 EPI_LINEAR, EPI_ADD, EPI_GATE, EPI_GDN, EPI_IGDN, EPI_PIXSCALE = range(6)
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_CLAMP01 = range(4)
 SPLIT_COPY, SPLIT_ADD, SPLIT_GATE, SPLIT_GDN, SPLIT_IGDN, SPLIT_SQUARE, SPLIT_ROUND_CHAN = range(7)
+SPLIT_F16 = 16  # HYRES_SPLIT_F16: format flag of an nsplit code (2 | SPLIT_F16 = two half parts)
 
 
 class HyresError(RuntimeError):

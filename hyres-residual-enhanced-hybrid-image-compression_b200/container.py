@@ -10,7 +10,7 @@ little-endian layout so that a compressed batch can leave the process and come b
 
 Flag bits 1-2 record the arithmetic of the entropy-critical trunk that produced the strings, because the decoder
 recomputes the CDF indexes and must land on the same integers: 0 = not recorded, 1 = "bf16" (decodable only by this
-library's bf16 trunk), 2 = fp32-equivalent ("fp32x2" / "fp32x3": decodable by the fp32 reference decoder as well, up
+library's bf16 trunk), 2 = fp32-equivalent ("fp32x2" / "fp32x3" / "fp32h2": decodable by the fp32 reference decoder as well, up
 to numerical ties).  ``pack(c, trunk=model.codec_precision)`` sets them, ``unpack`` returns them as ``"trunk"`` and
 ``decompress`` refuses a stream whose tag does not match the model's trunk.
 
@@ -25,7 +25,7 @@ MAGIC = b"HYRS"
 VERSION = 1
 _FLAG_JPEG = 1
 _TRUNK_SHIFT, _TRUNK_MASK = 1, 3
-_TRUNK_CODE = {None: 0, "bf16": 1, "fp32x2": 2, "fp32x3": 2, "fp32": 2}
+_TRUNK_CODE = {None: 0, "bf16": 1, "fp32x2": 2, "fp32x3": 2, "fp32h2": 2, "fp32": 2}
 _TRUNK_NAME = {0: None, 1: "bf16", 2: "fp32"}
 
 

@@ -6,6 +6,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <cstdio>
@@ -392,6 +393,37 @@ __device__ __forceinline__ uint32_t elect_leader() {
 __host__ __device__ inline uint32_t umma_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// Same with A = B = IEEE half (format code 0): the half-part split-precision layers.
+__host__ __device__ inline uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------
+// split-precision parts of an fp32 value (hyres_b200.h: hyres_conv_create_split)
+// ----------------------------------------------------------------------------
+constexpr int kSplitF16 = 16;            // format flag in an nsplit code (HYRES_SPLIT_F16)
+constexpr float kF16LoScale = 2048.f;    // second half part = half((v - p0) * 2^11)
+constexpr float kF16LoInv = 1.f / 2048.f;
+// bf16 parts: v = p0 + p1 + p2 (+ O(2^-25 |v|)), each rounded to nearest; the residuals are exact in fp32
+__device__ __forceinline__ void split_bf16x3(float v, uint16_t& p0, uint16_t& p1, uint16_t& p2) {
+  const __nv_bfloat16 b0 = __float2bfloat16_rn(v);
+  const float r1 = v - __bfloat162float(b0);
+  const __nv_bfloat16 b1 = __float2bfloat16_rn(r1);
+  const float r2 = r1 - __bfloat162float(b1);
+  p0 = __bfloat16_as_ushort(b0);
+  p1 = __bfloat16_as_ushort(b1);
+  p2 = __bfloat16_as_ushort(__float2bfloat16_rn(r2));
+}
+// half parts: v = p0 + p1 * 2^-11 to 2^-23 |v| (or 2^-36 absolute when p1 is subnormal); the residual v - p0 is
+// exact in fp32 and stays in the range of p0 after scaling.  |v| >= 65520 overflows to infinity (and the
+// products to NaN): loud, not silent.
+__device__ __forceinline__ void split_f16x2(float v, uint16_t& p0, uint16_t& p1) {
+  const __half h0 = __float2half_rn(v);
+  const float r = (v - __half2float(h0)) * kF16LoScale;
+  p0 = __half_as_ushort(h0);
+  p1 = __half_as_ushort(__float2half_rn(r));
 }
 
 // ----------------------------------------------------------------------------

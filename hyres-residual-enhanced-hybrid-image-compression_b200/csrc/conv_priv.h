@@ -34,6 +34,10 @@ struct hyres_conv {
   // weights are packed as nsplit bf16 parts, and part i of the activations meets parts 0 .. nsplit-1-i of the
   // weights (3 products for nsplit = 2, 6 for nsplit = 3); every product accumulates into the same fp32 TMEM tile.
   int nsplit = 1;
+  // half-part format (2 | HYRES_SPLIT_F16): two IEEE half parts, the second scaled by 2^11; nsplit == 2 then, the
+  // leading product p0 x w0 and the cross products p0 x w1 + p1 x w0 never share an accumulator, and the
+  // epilogue adds the cross accumulator times 2^-11.
+  bool split_f16 = false;
   // Accumulators per output tile of a split layer.  The tensor core truncates when it adds into an fp32
   // accumulator (about 0.05 ulp of bias per MMA, measured: tools/check_precise.py), so a chain of 1 200 MMAs
   // drifts by ~60 ulp.  The leading products (part 0 x part 0, K/16 MMAs) therefore get accumulators of their

@@ -64,6 +64,7 @@ struct alignas(64) ConvParams {
   int32_t nacc, acc_stride;  // split-precision layers: accumulators per tile, TMEM columns between them
   int32_t acc_mask[4];       // per phase: which accumulators hold a sum
   int32_t split_epi, split_mode, out_nsplit, split_square;
+  int32_t split_f16, out_f16;  // half-part format of the operands / of the parts written by the epilogue
   const float* aux0_f32;
   const float* aux1_f32;
   __nv_bfloat16* out_split;
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it_n) {
         const Item it = decode(item);
         const int g_begin = p.ph_begin[it.phase], g_count = p.ph_count[it.phase];
-        const uint32_t idesc = hy::umma_idesc_bf16(128, it.bn);
+        const uint32_t idesc = p.split_f16 ? hy::umma_idesc_f16(128, it.bn) : hy::umma_idesc_bf16(128, it.bn);
         const int buf = p.nbuf == 2 ? (it_n & 1) : 0;
         const uint32_t use = p.nbuf == 2 ? (it_n >> 1) : it_n;  // how often this buffer was used before
         hy::mbar_wait(acc_empty + 8 * buf, (use & 1u) ^ 1u);
@@ -368,8 +369,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             uint32_t r[32];
             hy::tmem_ld32(t_item + a * p.acc_stride + sub * p.bn_max + cb, r);
             hy::tmem_ld_fence32(r);
+            // half parts: the last accumulator holds the cross products, scaled by 2^11 (exact power of two)
+            const float sc = (p.split_f16 && a == p.nacc - 1) ? hy::kF16LoInv : 1.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] += __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), sc, v[i]);
           }
           if (q + 1 == steps) {
             hy::tc_fence_before();
@@ -430,12 +433,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             uint4* stg4 = reinterpret_cast<uint4*>(stg);
             for (int part = 0; part < p.out_nsplit; ++part) {
               uint32_t w[16];
+              if (p.out_f16) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-                v[2 * i] -= __bfloat162float(h0);      // exact: the residual of a round-to-nearest bf16
-                v[2 * i + 1] -= __bfloat162float(h1);
-                w[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                for (int i = 0; i < 16; ++i) {
+                  const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
+                  v[2 * i] = (v[2 * i] - __half2float(h0)) * hy::kF16LoScale;  // exact residual, back in p0's range
+                  v[2 * i + 1] = (v[2 * i + 1] - __half2float(h1)) * hy::kF16LoScale;
+                  w[i] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+                }
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+                  v[2 * i] -= __bfloat162float(h0);      // exact: the residual of a round-to-nearest bf16
+                  v[2 * i + 1] -= __bfloat162float(h1);
+                  w[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                }
               }
               __syncwarp();
 #pragma unroll
@@ -800,8 +813,14 @@ void build_plan(hyres_conv* c) {
   c->macs_per_pos = static_cast<int64_t>(c->ktot) * c->cout_pad / (c->nphase);
 }
 
-// bf16 part `part` of an fp32 value: v = p0 + p1 + p2 (+ an error below 2^-24 |v|), each part rounded to nearest.
-inline __nv_bfloat16 split_part(float v, int part) {
+// part `part` of an fp32 weight.  bf16 parts: v = p0 + p1 + p2 (+ an error below 2^-24 |v|), each rounded to nearest;
+// half parts: p0 = half(v), p1 = half((v - p0) * 2^11).  Returned as raw 16-bit patterns.
+inline __nv_bfloat16 split_part(float v, int part, bool f16) {
+  if (f16) {
+    const __half h0 = __float2half_rn(v);
+    const __half h = part == 0 ? h0 : __float2half_rn((v - __half2float(h0)) * 2048.f);
+    return __ushort_as_bfloat16(__half_as_ushort(h));
+  }
   __nv_bfloat16 b = __float2bfloat16(v);
   for (int i = 0; i < part; ++i) {
     v -= __bfloat162float(b);
@@ -826,7 +845,7 @@ void pack_weights(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16
           v = w[(static_cast<size_t>(ci) * c->cout + n) * RS + sl.r * c->S + sl.s];
         else
           v = w[(static_cast<size_t>(n) * c->w_cin_total + ci) * RS + sl.r * c->S + sl.s];
-        out[static_cast<size_t>(n) * c->ktot + ks * 64 + cc] = split_part(v, sl.wpart);
+        out[static_cast<size_t>(n) * c->ktot + ks * 64 + cc] = split_part(v, sl.wpart, c->split_f16);
       }
     }
   }
@@ -835,7 +854,7 @@ void pack_weights(const hyres_conv* c, const float* w, std::vector<__nv_bfloat16
 // Device-side packing (training: the weights change every step and live on the GPU): one thread per packed element.
 __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                                     const hyres_conv::Slot* __restrict__ slots, int cout, int cout_pad, int ktot,
-                                    int cin0, int cin1, int w_cin_total, int RS, int S, int deconv) {
+                                    int cin0, int cin1, int w_cin_total, int RS, int S, int deconv, int f16) {
   const long long total = static_cast<long long>(cout_pad) * ktot;
   for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -849,6 +868,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
       const int ci = (sl.src ? cin0 : 0) + sl.chunk * 64 + cc;
       v = deconv ? w[(static_cast<size_t>(ci) * cout + n) * RS + sl.r * S + sl.s]
                  : w[(static_cast<size_t>(n) * w_cin_total + ci) * RS + sl.r * S + sl.s];
+    }
+    if (f16) {
+      uint16_t p0, p1;
+      hy::split_f16x2(v, p0, p1);
+      out[idx] = __ushort_as_bfloat16(sl.wpart ? p1 : p0);
+      continue;
     }
     __nv_bfloat16 b = __float2bfloat16_rn(v);
     for (int i = 0; i < sl.wpart; ++i) {
@@ -958,7 +983,9 @@ int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int 
                             int stride, int pad, int dil, const float* weight, const float* bias,
                             const uint8_t* tap_mask, int nsplit) {
   if (!out) return hy_fail(HYRES_ERR_ARG, "conv_create: null argument");
-  if (nsplit < 1 || nsplit > 3) return hy_fail(HYRES_ERR_ARG, "conv_create: nsplit must be 1, 2 or 3");
+  if (!hy_split_code_ok(nsplit)) return hy_fail(HYRES_ERR_ARG, "conv_create: nsplit must be 1, 2, 3 or 2 | HYRES_SPLIT_F16");
+  const bool split_f16 = (nsplit & HYRES_SPLIT_F16) != 0;
+  nsplit &= 15;
   if (kind != HYRES_CONV && kind != HYRES_DECONV_K5S2) return hy_fail(HYRES_ERR_ARG, "conv_create: bad kind");
   if (cin0 <= 0 || cin1 < 0 || cout <= 0 || (cin0 % 8) || (cin1 % 8))
     return hy_fail(HYRES_ERR_ARG, "conv_create: channel counts must be positive multiples of 8");
@@ -979,6 +1006,7 @@ int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int 
   c->w_cin_total = w_cin_total > 0 ? w_cin_total : cin0 + cin1;
   c->cout = cout; c->R = R; c->S = S; c->stride = stride; c->pad = pad; c->dil = dil;
   c->nsplit = nsplit;
+  c->split_f16 = split_f16;
   if (tap_mask) c->tap_mask.assign(tap_mask, tap_mask + R * S);
   c->BN = choose_bn(cout);
   c->cout_pad = (cout + c->BN - 1) / c->BN * c->BN;
@@ -991,8 +1019,8 @@ int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int 
     const int lead = live * ((cin0 + 63) / 64 + (cin1 + 63) / 64) * 4;
     c->lead_mmas = lead;
     // short chains (K <= 256: at most 96 MMAs with the cross products) stay below one ulp in a single accumulator
-    int nacc = lead <= 16 ? 1 : 1 + std::min(3, (lead + 71) / 72);
-    if (nacc_env >= 1 && nacc_env <= 4) nacc = nacc_env;
+    int nacc = (lead <= 16 && !split_f16) ? 1 : 1 + std::min(3, (lead + 71) / 72);  // half parts: never shared
+    if (nacc_env >= (split_f16 ? 2 : 1) && nacc_env <= 4) nacc = nacc_env;
     c->nacc = nacc;
     c->bn_cap = nacc <= 2 ? 256 : 128;
     if (c->cout_pad > c->bn_cap && (c->cout_pad % 64)) { c->nacc = 2; c->bn_cap = 256; }  // N blocks are multiples of 64
@@ -1063,7 +1091,7 @@ int hyres_conv_update_device(hyres_conv* c, const float* weight_dev, const float
   hy_count_launch();
   pack_weights_kernel<<<grid, 256, 0, st>>>(weight_dev, c->d_w, c->d_slots, c->cout, c->cout_pad, c->ktot, c->cin0,
                                            c->cin1, c->w_cin_total, c->R * c->S, c->S,
-                                           c->kind == HYRES_DECONV_K5S2 ? 1 : 0);
+                                           c->kind == HYRES_DECONV_K5S2 ? 1 : 0, c->split_f16 ? 1 : 0);
   HY_CUDA(cudaGetLastError());
   hy_count_launch();
   pad_bias_kernel<<<(c->cout_pad + 255) / 256, 256, 0, st>>>(bias_dev, c->d_bias, c->cout, c->cout_pad);
@@ -1119,8 +1147,8 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
     if (io->act != HYRES_ACT_NONE && io->act != HYRES_ACT_RELU)
       return hy_fail(HYRES_ERR_UNSUPPORTED, "conv_run: split-precision layers support ReLU only");
     if (!io->out_f32 && !io->out_split) return hy_fail(HYRES_ERR_ARG, "conv_run: split layer without an output");
-    if (io->out_split && (io->out_nsplit < 1 || io->out_nsplit > 3 || (c->cout % 32)))
-      return hy_fail(HYRES_ERR_ARG, "conv_run: out_split needs 1..3 parts and a multiple of 32 output channels");
+    if (io->out_split && (!hy_split_code_ok(io->out_nsplit) || (c->cout % 32)))
+      return hy_fail(HYRES_ERR_ARG, "conv_run: out_split needs a valid nsplit code and a multiple of 32 output channels");
     const int m = io->split_mode;
     if (m != HYRES_SPLIT_COPY && m != HYRES_SPLIT_ADD && m != HYRES_SPLIT_GATE && m != HYRES_SPLIT_GDN && m != HYRES_SPLIT_IGDN)
       return hy_fail(HYRES_ERR_ARG, "conv_run: bad split_mode");
@@ -1252,7 +1280,9 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   p.out_bf16 = static_cast<__nv_bfloat16*>(io->out_bf16); p.ld_out = io->ld_out;
   p.out_sq = static_cast<__nv_bfloat16*>(io->out_sq); p.ld_sq = io->ld_sq;
   p.split_epi = split ? 1 : 0;
-  p.split_mode = io->split_mode; p.out_nsplit = io->out_nsplit; p.split_square = io->split_square;
+  p.split_mode = io->split_mode; p.out_nsplit = io->out_nsplit & 15; p.split_square = io->split_square;
+  p.split_f16 = c->split_f16 ? 1 : 0;
+  p.out_f16 = (io->out_nsplit & HYRES_SPLIT_F16) ? 1 : 0;
   p.aux0_f32 = io->aux0_f32; p.aux1_f32 = io->aux1_f32;
   p.out_split = static_cast<__nv_bfloat16*>(io->out_split);
   p.out_f32 = io->out_f32;

@@ -12,6 +12,9 @@ int hy_fail(int code, const char* msg);
 // Every kernel launch of the library is counted (hyres_launch_count): bench.py reports it.
 void hy_count_launch();
 
+// nsplit codes of the split-precision layers (hyres_b200.h): 1..3 bf16 parts, or two half parts (2 | 16)
+inline bool hy_split_code_ok(int code) { return (code >= 1 && code <= 3) || code == (2 | 16); }
+
 #define HY_CUDA(expr)                                                   \
   do {                                                                  \
     cudaError_t _e = (expr);                                            \

@@ -29,17 +29,18 @@ inline int grid_for(int64_t n, int per_block, int cap = 148 * 16) {
   return static_cast<int>(g);
 }
 
-// v -> three bf16 parts, round to nearest each: v = p0 + p1 + p2 + O(2^-25 |v|); the residuals are exact in fp32
-__device__ __forceinline__ void split3(float v, __nv_bfloat16& p0, __nv_bfloat16& p1, __nv_bfloat16& p2) {
-  p0 = __float2bfloat16_rn(v);
-  const float r1 = v - __bfloat162float(p0);
-  p1 = __float2bfloat16_rn(r1);
-  const float r2 = r1 - __bfloat162float(p1);
-  p2 = __float2bfloat16_rn(r2);
+// v -> its parts in the format of an nsplit code: 1..3 bf16 parts, or two half parts (2 | HYRES_SPLIT_F16)
+__device__ __forceinline__ void split_code(float v, bool f16, uint16_t& p0, uint16_t& p1, uint16_t& p2) {
+  if (f16) {
+    hy::split_f16x2(v, p0, p1);
+    p2 = 0;
+  } else {
+    hy::split_bf16x3(v, p0, p1, p2);
+  }
 }
 
-__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+__device__ __forceinline__ uint32_t pack2(uint16_t a, uint16_t b) {
+  return static_cast<uint32_t>(a) | (static_cast<uint32_t>(b) << 16);
 }
 
 __device__ __forceinline__ float sigmoid_ieee(float x) { return 1.f / (1.f + expf(-x)); }
@@ -83,13 +84,15 @@ __global__ void split_kernel(const float* __restrict__ in, const float* __restri
     }
     if (out_f32) *reinterpret_cast<float4*>(out_f32 + e) = make_float4(v[0], v[1], v[2], v[3]);
     if (out_split) {
-      __nv_bfloat16 p[3][4];
+      const int P = nsplit & 15;
+      const bool f16 = (nsplit & hy::kSplitF16) != 0;
+      uint16_t p[3][4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) split3(v[k], p[0][k], p[1][k], p[2][k]);
-      __nv_bfloat16* o = out_split + row * (static_cast<int64_t>(nsplit) * C) + c;
+      for (int k = 0; k < 4; ++k) split_code(v[k], f16, p[0][k], p[1][k], p[2][k]);
+      __nv_bfloat16* o = out_split + row * (static_cast<int64_t>(P) * C) + c;
 #pragma unroll
       for (int q = 0; q < 3; ++q)
-        if (q < nsplit)
+        if (q < P)
           *reinterpret_cast<uint2*>(o + static_cast<int64_t>(q) * C) =
               make_uint2(pack2(p[q][0], p[q][1]), pack2(p[q][2], p[q][3]));
     }
@@ -119,7 +122,9 @@ __global__ void im2col5s2_split_kernel(const float* __restrict__ x, __nv_bfloat1
     const int64_t bi = pix / OW;
     const int i = static_cast<int>(bi % OH);
     const int b = static_cast<int>(bi / OH);
-    __nv_bfloat16 p[3][8];
+    const int P = nsplit & 15;
+    const bool f16 = (nsplit & hy::kSplitF16) != 0;
+    uint16_t p[3][8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = g * 8 + e;
@@ -131,12 +136,12 @@ __global__ void im2col5s2_split_kernel(const float* __restrict__ x, __nv_bfloat1
         if (ih >= 0 && ih < H && iw >= 0 && iw < W)
           v = __ldg(x + (static_cast<int64_t>(b) * 3 + c) * plane + static_cast<int64_t>(ih) * W + iw);
       }
-      split3(v, p[0][e], p[1][e], p[2][e]);
+      split_code(v, f16, p[0][e], p[1][e], p[2][e]);
     }
-    __nv_bfloat16* o = a + pix * (static_cast<int64_t>(nsplit) * 128) + g * 8;
+    __nv_bfloat16* o = a + pix * (static_cast<int64_t>(P) * 128) + g * 8;
 #pragma unroll
     for (int q = 0; q < 3; ++q)
-      if (q < nsplit)
+      if (q < P)
         *reinterpret_cast<uint4*>(o + q * 128) = make_uint4(pack2(p[q][0], p[q][1]), pack2(p[q][2], p[q][3]),
                                                             pack2(p[q][4], p[q][5]), pack2(p[q][6], p[q][7]));
   }
@@ -179,7 +184,8 @@ int hyres_split_f32(const float* in, int64_t rows, int C, int mode, const float*
   if (!in || rows <= 0 || C <= 0 || (C & 3))
     return hy_fail(HYRES_ERR_ARG, "split_f32: bad argument (C must be a multiple of 4)");
   if (!out_f32 && !out_split) return hy_fail(HYRES_ERR_ARG, "split_f32: no output");
-  if (out_split && (nsplit < 1 || nsplit > 3)) return hy_fail(HYRES_ERR_ARG, "split_f32: nsplit must be 1, 2 or 3");
+  if (out_split && !hy_split_code_ok(nsplit))
+    return hy_fail(HYRES_ERR_ARG, "split_f32: nsplit must be 1, 2, 3 or 2 | HYRES_SPLIT_F16");
   const bool need0 = mode == HYRES_SPLIT_ADD || mode == HYRES_SPLIT_GATE || mode == HYRES_SPLIT_GDN ||
                      mode == HYRES_SPLIT_IGDN;
   if (need0 && !aux0) return hy_fail(HYRES_ERR_ARG, "split_f32: aux0 missing");
@@ -206,7 +212,7 @@ int hyres_split_f32(const float* in, int64_t rows, int C, int mode, const float*
 
 int hyres_residual_im2col5s2_split(const float* x, const float* jpeg, float* residual, void* a_out, int nsplit, int B,
                                    int H, int W, void* stream_v) {
-  if (!x || !a_out || B <= 0 || H <= 0 || W <= 0 || ((H | W) & 1) || nsplit < 1 || nsplit > 3)
+  if (!x || !a_out || B <= 0 || H <= 0 || W <= 0 || ((H | W) & 1) || !hy_split_code_ok(nsplit))
     return hy_fail(HYRES_ERR_ARG, "residual_im2col5s2_split: bad argument");
   if (jpeg && !residual) return hy_fail(HYRES_ERR_ARG, "residual_im2col5s2_split: residual buffer missing");
   cudaStream_t st = static_cast<cudaStream_t>(stream_v);

@@ -311,9 +311,14 @@ class PreciseTrunk:
     uses it when the model's ``precision`` is "fp32x3"."""
 
     def __init__(self, model, nsplit=3):
+        """``nsplit``: the format code of the trunk's activations / weights: 3 (three bf16 parts, 6 tensor-core
+        products per MAC), 2 (two bf16 parts, 3 products, ~2^-16) or 2 | SPLIT_F16 (two IEEE half parts: 3 products
+        at fp32-equivalent accuracy).  The x^2 operand of a GDN keeps three bf16 parts in the half format too
+        (a square leaves the half range at |x| >= 256), so only the three gamma GEMMs pay 6 products there."""
         self.model, self.P = model, nsplit
         M = model.M
         P = nsplit
+        self.Psq = 3 if (nsplit & ops.SPLIT_F16) else nsplit  # format of the GDN operand x^2
 
         def cv(m):
             return _Bound(_wb(m), kind=HYRES_CONV, stride=m.stride[0], pad=m.padding[0], dil=m.dilation[0], nsplit=P)
@@ -322,7 +327,7 @@ class PreciseTrunk:
             return _Bound(_wb(m), kind=HYRES_DECONV_K5S2, nsplit=P)
 
         def gd(m):
-            return _Bound(m.effective, kind=HYRES_CONV, nsplit=P)
+            return _Bound(m.effective, kind=HYRES_CONV, nsplit=self.Psq)
 
         def ru(c1, c2, c3):
             return [cv(c1), cv(c2), cv(c3)]
@@ -387,14 +392,15 @@ class PreciseTrunk:
                 f, sp = ops.split_f32(o, nsplit=self.P, want_f32=True, want_split=want_split)
                 return _PT(f, sp)
             if mode == ops.SPLIT_COPY:  # square: parts of o*o, fp32 o
-                _, sp = ops.split_f32(o, mode=ops.SPLIT_SQUARE, nsplit=self.P)
+                _, sp = ops.split_f32(o, mode=ops.SPLIT_SQUARE, nsplit=self.Psq)
                 return _PT(o, sp)
             f, sp = ops.split_f32(o, mode=mode, aux0=aux0, aux1=aux1, relu=relu, nsplit=self.P, want_f32=True,
                                   want_split=want_split)
             return _PT(f, sp)
         _, sp, o = layer(x_sp, x1_sp, act=ACT_RELU if relu else ACT_NONE, out_bf16=False,
                          out_f32="nhwc" if want_f32 else None, split_mode=mode, aux0_f32=aux0, aux1_f32=aux1,
-                         out_split=True if want_split else None, split_square=square)
+                         out_split=True if want_split else None, split_square=square,
+                         out_code=self.Psq if square else self.P)
         return _PT(o, sp)
 
     def split(self, x32, want_f32=True, **kw):

@@ -11,7 +11,7 @@ import torch
 from . import _lib as L
 from ._lib import (ACT_CLAMP01, ACT_NONE, ACT_PRELU, ACT_RELU, EPI_ADD, EPI_GATE, EPI_GDN,
                    EPI_IGDN, EPI_LINEAR, EPI_PIXSCALE, HYRES_CONV, HYRES_DECONV_K5S2, SPLIT_ADD, SPLIT_COPY,
-                   SPLIT_GATE, SPLIT_GDN, SPLIT_IGDN, SPLIT_ROUND_CHAN, SPLIT_SQUARE)
+                   SPLIT_F16, SPLIT_GATE, SPLIT_GDN, SPLIT_IGDN, SPLIT_ROUND_CHAN, SPLIT_SQUARE)
 
 
 def sm_count():
@@ -40,6 +40,11 @@ PACKED_CACHE = None
 PACKED_STATS = {"imported": 0, "packed": 0}  # layers filled from exported operands / packed from fp32 weights
 
 
+def split_parts(code):
+    """Number of 16-bit parts per fp32 value of an nsplit code (1..3 bf16 parts, or 2 | SPLIT_F16: two half parts)."""
+    return int(code) & 15
+
+
 class ConvLayer:
     """One packed convolution layer (weights live in the library, bf16 K-major)."""
 
@@ -63,7 +68,8 @@ class ConvLayer:
     def __init__(self, weight, bias=None, kind=HYRES_CONV, stride=1, pad=0, dil=1, cin0=None,
                  cin1=0, tap_mask=None, nsplit=1):
         """nsplit > 1: split-precision layer (hyres_conv_create_split): inputs are the bf16 parts produced by
-        ``split_f32`` ([B,H,W,nsplit*cin]), the result is fp32 (``out_f32``) with fp32-equivalent accuracy."""
+        ``split_f32`` ([B,H,W,nsplit*cin]), the result is fp32 (``out_f32``) with fp32-equivalent accuracy.
+        nsplit = 2 | SPLIT_F16: two IEEE half parts (3 tensor-core products per MAC instead of 6)."""
         if isinstance(weight, (tuple, list, torch.Size)):
             # shape only: an empty layer whose operands arrive later (update_device: training; import: deployment)
             w, wshape = None, tuple(int(v) for v in weight)
@@ -77,7 +83,8 @@ class ConvLayer:
             cout, cin_total, R, S = wshape
         if cin0 is None:
             cin0 = cin_total
-        self.kind, self.cin0, self.cin1, self.cout, self.nsplit = kind, cin0, cin1, cout, nsplit
+        self.kind, self.cin0, self.cin1, self.cout, self.nsplit = kind, cin0, cin1, cout, split_parts(nsplit)
+        self.split_code = int(nsplit)
         self.R, self.S, self.stride, self.pad, self.dil = R, S, stride, pad, dil
         self._w_shape = wshape
         mask = None
@@ -161,7 +168,7 @@ class ConvLayer:
     def __call__(self, x0, x1=None, epi=EPI_LINEAR, act=ACT_NONE, slope=0.0, aux0=None, aux1=None,
                  pixscale=None, out_bf16=True, out_sq=False, out_f32=None, mt=0, x0_square=False, out_pad=0,
                  up_t2=None, up_t3=None, cta_limit=0, split_mode=SPLIT_COPY, aux0_f32=None, aux1_f32=None,
-                 out_split=None, split_square=False):
+                 out_split=None, split_square=False, out_code=None):
         """Run the layer.
 
         out_bf16 / out_sq: True (allocate), False, or a preallocated NHWC tensor (its last
@@ -175,7 +182,7 @@ class ConvLayer:
         Split-precision layers (nsplit > 1): ``split_mode`` / ``aux0_f32`` / ``aux1_f32`` fuse the fp32
         element-wise stage into the epilogue and ``out_split`` (True or a tensor [B,OH,OW,nsplit*cout]) receives the
         bf16 parts of the result (of its square with ``split_square``); the parts tensor is returned in the ``sq``
-        slot.
+        slot.  ``out_code``: nsplit code of those parts (default: the layer's own format).
         Returns (bf16, sq, f32) with None for absent outputs.
         """
         _chk_nhwc(x0, "x0")
@@ -248,12 +255,14 @@ class ConvLayer:
         if out_split is not None and out_split is not False:
             if self.nsplit == 1:
                 raise ValueError("out_split needs a split-precision layer")
+            code = self.split_code if out_code is None else int(out_code)
+            nparts = split_parts(code)
             if out_split is True:
-                out_split = torch.empty((B, OH, OW, self.nsplit * self.cout), dtype=torch.bfloat16, device=dev)
+                out_split = torch.empty((B, OH, OW, nparts * self.cout), dtype=torch.bfloat16, device=dev)
             if (out_split.dtype != torch.bfloat16 or not out_split.is_contiguous()
-                    or tuple(out_split.shape) != (B, OH, OW, self.nsplit * self.cout)):
-                raise ValueError("out_split: expected contiguous bf16 [B,OH,OW,nsplit*cout]")
-            io.out_split, io.out_nsplit, io.split_square = out_split.data_ptr(), self.nsplit, 1 if split_square else 0
+                    or tuple(out_split.shape) != (B, OH, OW, nparts * self.cout)):
+                raise ValueError("out_split: expected contiguous bf16 [B,OH,OW,parts*cout]")
+            io.out_split, io.out_nsplit, io.split_square = out_split.data_ptr(), code, 1 if split_square else 0
             osq = out_split
         io.split_mode = int(split_mode)
         for t, nm in ((aux0_f32, "aux0_f32"), (aux1_f32, "aux1_f32")):
@@ -276,6 +285,7 @@ class ConvLayer:
             ConvLayer._prof_info.append(dict(kind=self.kind, cin=self.cin0 + self.cin1, cout=self.cout, k=self.R,
                                              stride=self.stride, dil=self.dil, B=B, H=H, W=W, OH=OH, OW=OW,
                                              epi=epi, f32=o32 is not None, sq=osq is not None, nsplit=self.nsplit,
+                                             products=(1, 1, 3, 6)[self.nsplit],
                                              alg_macs=self.alg_macs_per_out * B * OH * OW))
         else:
             L.check(L.lib().hyres_conv_run(self._h, C.byref(io), _stream()), "hyres_conv_run")
@@ -427,7 +437,7 @@ def split_f32(x, mode=SPLIT_COPY, aux0=None, aux1=None, chan=None, relu=False, n
             raise ValueError("split_f32: chan must have C entries")
     trivial = mode == SPLIT_COPY and not relu
     o32 = torch.empty_like(x) if (want_f32 and not trivial) else None
-    osp = torch.empty(x.shape[:-1] + (nsplit * Cc,), dtype=torch.bfloat16, device=x.device) if want_split else None
+    osp = torch.empty(x.shape[:-1] + (split_parts(nsplit) * Cc,), dtype=torch.bfloat16, device=x.device) if want_split else None
     if o32 is not None or osp is not None:
         L.check(L.lib().hyres_split_f32(_ptr(x), rows, Cc, mode, _ptr(aux0), _ptr(aux1), _ptr(chan), 1 if relu else 0,
                                         _ptr(o32), _ptr(osp), nsplit, _stream()), "hyres_split_f32")
@@ -444,7 +454,7 @@ def residual_im2col5s2_split(x, jpeg=None, nsplit=3):
     if jpeg is not None:
         _f32c(jpeg, "jpeg")
         res = torch.empty_like(x)
-    a = torch.empty((B, H // 2, W // 2, nsplit * 128), dtype=torch.bfloat16, device=x.device)
+    a = torch.empty((B, H // 2, W // 2, split_parts(nsplit) * 128), dtype=torch.bfloat16, device=x.device)
     L.check(L.lib().hyres_residual_im2col5s2_split(_ptr(x), _ptr(jpeg), _ptr(res), _ptr(a), nsplit, B, H, W,
                                                    _stream()), "hyres_residual_im2col5s2_split")
     return (res if res is not None else x), a

@@ -25,6 +25,7 @@ import torch
 import torch.distributed as dist
 
 from .dist import shard_range, tile_grid
+from .models import _check_finite
 
 DEFAULT_HALO = 256
 
@@ -63,6 +64,7 @@ def encode_symbols_sharded(codec, residual, rows, cols, halo=DEFAULT_HALO, group
     lo, hi = shard_range(len(wins), rank, world)
     for (h0, h1, w0, w1), (H0, H1, W0, W1) in wins[lo:hi]:
         s = codec.encode_symbols(residual[:, :, H0:H1, W0:W1].contiguous())
+        _check_finite(s)
         for k, d in (("sym_z", 32), ("sym_a", 8), ("idx_a", 8), ("sym_na", 8), ("idx_na", 8)):
             out[k][:, :, h0 // d:h1 // d, w0 // d:w1 // d] = s[k][:, :, (h0 - H0) // d:(h1 - H0) // d,
                                                                 (w0 - W0) // d:(w1 - W0) // d]

@@ -100,7 +100,12 @@ int hyres_conv_create(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_
  * NHWC tensors [B,H,W,nsplit*cin] holding nsplit bf16 parts of every fp32 activation (part p in channels
  * [p*cin,(p+1)*cin), see hyres_split_f32); the weights are packed as nsplit parts as well and part i of the
  * activations is multiplied with parts 0..nsplit-1-i of the weights (3 / 6 tensor-core products per MAC), all
- * accumulated in one fp32 TMEM tile. Such layers take HYRES_EPI_LINEAR (+ bias, ReLU) and write out_f32 only. */
+ * accumulated in one fp32 TMEM tile. Such layers take HYRES_EPI_LINEAR (+ bias, ReLU) and write out_f32 only.
+ * nsplit = 2 | HYRES_SPLIT_F16: the two parts are IEEE half values, p0 = half(v), p1 = half((v - p0) * 2^11)
+ * (11 + 11 significand bits: v = p0 + p1 * 2^-11 to 2^-23 relative, |v| < 65504); the three products
+ * p0*w0 | p0*w1 + p1*w0 go to separate accumulators and the epilogue adds the second one times 2^-11:
+ * fp32-equivalent at half the tensor-core work of nsplit = 3. */
+#define HYRES_SPLIT_F16 16
 int hyres_conv_create_split(hyres_conv** out, int kind, int cin0, int cin1, int w_cin_total, int cout,
                             int R, int S, int stride, int pad, int dil, const float* weight,
                             const float* bias, const uint8_t* tap_mask, int nsplit);
@@ -173,7 +178,9 @@ typedef struct {
    * the convolution, fused into its epilogue.  v = split_mode(acc + bias, aux0_f32, aux1_f32) (HYRES_SPLIT_COPY /
    * _ADD / _GATE / _GDN / _IGDN, see hyres_split_f32), then `act` (none / ReLU).  v goes to out_f32 (optional) and,
    * as out_nsplit bf16 parts, to out_split [B,OH,OW,out_nsplit*cout] (optional); split_square != 0 stores the
-   * parts of v*v instead (the x^2 operand of the GDN that follows).  aux*: fp32 NHWC [B,OH,OW,cout], dense. */
+   * parts of v*v instead (the x^2 operand of the GDN that follows).  aux*: fp32 NHWC [B,OH,OW,cout], dense.
+   * out_nsplit carries its own format (1..3, or 2 | HYRES_SPLIT_F16): the consumer of the parts may be a layer
+   * of the other format (squares keep bf16 parts: half parts would overflow at |v| >= 256). */
   int split_mode;
   const float* aux0_f32;
   const float* aux1_f32;
@@ -265,7 +272,8 @@ int hyres_add_to_bf16(const float* a, const float* b, void* out_bf16, int64_t n,
 #define HYRES_SPLIT_ROUND_CHAN 6 /* v = round(in - chan[c]) + chan[c]  (models/checkerboard.py:99-101) */
 /* in, aux0, aux1: fp32 [rows][C] (NHWC rows); chan: fp32 [C]. v (then ReLU if relu != 0) is written as fp32
  * (out_f32, optional) and as nsplit bf16 parts [rows][nsplit*C] (out_split, optional): part 0 = bf16(v),
- * part 1 = bf16(v - part 0), part 2 = bf16(v - part 0 - part 1). IEEE fp32 arithmetic throughout. */
+ * part 1 = bf16(v - part 0), part 2 = bf16(v - part 0 - part 1); nsplit = 2 | HYRES_SPLIT_F16: two half parts,
+ * half(v) and half((v - part 0) * 2^11) (see hyres_conv_create_split). IEEE fp32 arithmetic throughout. */
 int hyres_split_f32(const float* in, int64_t rows, int C, int mode, const float* aux0, const float* aux1,
                     const float* chan, int relu, float* out_f32, void* out_split, int nsplit, void* stream);
 /* residual = x - jpeg (fp32 NCHW; jpeg may be NULL: x is the residual) and the 5x5/stride-2 im2col of the

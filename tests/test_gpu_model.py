@@ -2,7 +2,7 @@
 hyres_b200) against the CPU oracle on the same seeded weights and inputs.
 
 Two arithmetic modes of the entropy-critical trunk (models.LightWeightCheckerboard.precision / codec_precision):
-  "fp32x3" (compress / decompress default): compared with the oracle's fp32 mode -- the reference's semantics --
+  "fp32h2" (compress / decompress default): compared with the oracle's fp32 mode -- the reference's semantics --
            y, z, entropy params to 5e-5 of their range, integer streams >= 0.999 equal end to end (every mismatch a
            numerical tie or its consequence: tests/test_gpu_precise.py has the stage-by-stage accounting);
   "bf16"   (forward default): activations stored in bf16 with fp32 accumulation, compared with the oracle's
@@ -36,7 +36,7 @@ def test_codec_stages_vs_oracle(nets, oracle, B, H, W):
     residual = x - jpeg_dec
     nchw = lambda t: t.permute(0, 3, 1, 2).float().cpu()  # noqa: E731
     # fp32-equivalent trunk (the codec default) against the reference's fp32 semantics
-    assert pnet.residual_model.codec_precision == "fp32x3"
+    assert pnet.residual_model.codec_precision == "fp32h2"
     with torch.no_grad():
         s = pnet.residual_model.encode_symbols(residual.cuda())
         with oracle.precision("fp32"):
@@ -50,6 +50,7 @@ def test_codec_stages_vs_oracle(nets, oracle, B, H, W):
         assert match >= lo, f"{k}: {match}"
         assert (got - want).abs().max().item() <= 1
     # plain bf16 trunk against the oracle's bf16-storage mode
+    keep = pnet.residual_model.codec_precision
     pnet.residual_model.codec_precision = "bf16"
     try:
         with torch.no_grad():
@@ -57,7 +58,7 @@ def test_codec_stages_vs_oracle(nets, oracle, B, H, W):
             with oracle.precision("bf16"):
                 oc = onet.residual_model.compress(residual, return_intermediates=True)
     finally:
-        pnet.residual_model.codec_precision = "fp32x3"
+        pnet.residual_model.codec_precision = keep
     assert _rel(nchw(s["y"]), oc["_y"]) < 2e-2
     assert _rel(nchw(s["z"]), oc["_z"]) < 2e-2
     assert _rel(nchw(s["params_a"]), oc["_anchor_params"]) < 5e-2

@@ -42,6 +42,34 @@ def test_split_conv_vs_float64(build_lib, idx):
     assert r["max_err"] < 3e-6 and r["rms_err"] < 4e-7, r
 
 
+@pytest.mark.parametrize("idx", range(len(check_precise.CONV_CASES)), ids=[c["name"] for c in check_precise.CONV_CASES])
+def test_split_conv_half_parts_vs_float64(build_lib, idx):
+    """The same geometries with two IEEE half parts per value (nsplit = 2 | SPLIT_F16: 3 tensor-core products per
+    MAC instead of 6): the same fp32-equivalent bar; the parts represent the input to 2^-22."""
+    r = check_precise.conv_case(idx, 18)
+    assert r["split_err"] < 2.5e-7, r
+    assert r["max_err"] < 3e-6 and r["rms_err"] < 4e-7, r
+
+
+def test_half_parts_format(build_lib):
+    """p0 = half(v), p1 = half((v - p0) * 2^11): p0 + p1 / 2^11 equals v to 2^-22 relative over the half range, to
+    2^-35 absolute below it; a value outside the range turns into a non-finite part (loud, not silent)."""
+    from hyres_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(4, 6, 6, 64, generator=g) * torch.exp(4 * torch.randn(4, 6, 6, 64, generator=g))).clamp(-6e4, 6e4)
+    x[0, 0, 0, :8] = torch.tensor([0.0, 1e-9, -3e-8, 6.0e-5, 65504.0, -65504.0, 1.0, -2.5])
+    x = x.cuda()
+    _, sp = ops.split_f32(x, nsplit=2 | ops.SPLIT_F16)
+    hp = sp.view(torch.float16).double().reshape(4, 6, 6, 2, 64)
+    back = hp[..., 0, :] + hp[..., 1, :] / 2048.0
+    err = (back - x.double()).abs()
+    assert bool((err <= x.double().abs() * 2.0 ** -22 + 2.0 ** -35).all()), float(err.max())
+    assert torch.equal(hp[..., 0, :].float(), x.half().float())
+    big = torch.full((1, 1, 1, 64), 7.0e4, device="cuda")
+    _, sp = ops.split_f32(big, nsplit=2 | ops.SPLIT_F16)
+    assert not bool(torch.isfinite(sp.view(torch.float16).float()).all())
+
+
 def test_split_conv_two_parts(build_lib):
     """nsplit = 2 (3 products per MAC): ~2^-16 relative."""
     for idx in (2, 4, 14):
@@ -107,8 +135,21 @@ def test_residual_im2col_split(build_lib):
     assert alone is res and torch.equal(a2, a)
 
 
+MODES = ["fp32x3", "fp32h2"]  # three bf16 parts (6 products per MAC) / two half parts (3 products per MAC)
+
+
+@pytest.fixture(params=MODES)
+def mode(request, nets):
+    """Run the test under each fp32-equivalent trunk; the model's default is restored afterwards."""
+    codec = nets[1].residual_model
+    keep = codec.codec_precision
+    codec.codec_precision = request.param
+    yield request.param
+    codec.codec_precision = keep
+
+
 @pytest.mark.parametrize("tag", ["codec64", "codec96x160"])
-def test_bitstream_identical_to_reference_fixture(nets, golden_weights_ok, tag):
+def test_bitstream_identical_to_reference_fixture(nets, golden_weights_ok, tag, mode):
     """From the image on: the product's compress() of the fixture's residual gives the integers and the rANS byte
     strings the reference's own models/checkerboard.py produced (tests/golden/make_golden.py), and decompress()
     of the REFERENCE's strings reproduces the reference's decoded residual to the bf16 synthesis tolerance."""
@@ -116,23 +157,47 @@ def test_bitstream_identical_to_reference_fixture(nets, golden_weights_ok, tag):
         pytest.skip("regenerated weights differ from the fixture's (different torch build)")
     _, pnet = nets
     codec = pnet.residual_model
-    assert codec.codec_precision == "fp32x3"
+    assert codec.codec_precision == mode
     g = load_golden(tag)
     residual = torch.from_numpy(g["residual"]).cuda()
     with torch.no_grad():
         s = codec.encode_symbols(residual)
         c = codec.compress(residual)
+    # every integer that differs from the reference's must sit on a numerical tie of the REFERENCE's own value
+    # (rounding tie of y - mu, or a scale on a scale-table edge); "fp32x3" has none on these fixtures
+    M = g["y"].shape[1]
+    y_f = torch.from_numpy(g["y"])
+    table = codec.gaussian_conditional.scale_table.detach().cpu()
+    bound = float(codec.gaussian_conditional.scale_bound)
+    dist = {"sym_z": None}
+    for tag2, prm in (("a", "params_a"), ("na", "params_na")):
+        pr = torch.from_numpy(g[prm])
+        dist["sym_" + tag2] = check_precise.near_tie_distance_symbols(y_f - pr[:, M:])
+        sc = pr[:, :M].clamp_min(bound)
+        dist["idx_" + tag2] = ((sc.unsqueeze(-1) - table.view(1, 1, 1, 1, -1)).abs() / table.view(1, 1, 1, 1, -1)).min(-1).values
+    mismatches = {}
     for k in ("sym_z", "sym_a", "sym_na", "idx_a", "idx_na"):
-        assert torch.equal(s[k].cpu(), torch.from_numpy(g[k].astype(np.int32))), k
-    assert c["strings"][0][0][0] == g["str_a"].tobytes()
-    assert c["strings"][0][1][0] == g["str_na"].tobytes()
+        bad = s[k].cpu() != torch.from_numpy(g[k].astype(np.int32))
+        mismatches[k] = int(bad.sum())
+        if mismatches[k]:
+            assert mode != "fp32x3", (k, mismatches)
+            assert dist[k] is not None and float(dist[k][bad].max()) < 2e-4, (k, mismatches, float(dist[k][bad].max()))
+            assert mismatches[k] <= 2, (k, mismatches)
+    print(json.dumps({"fixture": tag, "mode": mode, "mismatches_vs_reference": mismatches}))
+    if mismatches["sym_a"] == 0 and mismatches["idx_a"] == 0:
+        assert c["strings"][0][0][0] == g["str_a"].tobytes()
+        if mismatches["sym_na"] == 0 and mismatches["idx_na"] == 0:
+            assert c["strings"][0][1][0] == g["str_na"].tobytes()
     assert c["strings"][1][0] == g["str_z"].tobytes()
     assert list(c["shape"]) == list(g["shape"])
     nchw = lambda t: t.permute(0, 3, 1, 2).cpu()  # noqa: E731
     torch.testing.assert_close(nchw(s["y"]), torch.from_numpy(g["y"]), rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(nchw(s["params_a"]), torch.from_numpy(g["params_a"]), rtol=1e-4, atol=2e-5)
     torch.testing.assert_close(nchw(s["params_na"]), torch.from_numpy(g["params_na"]), rtol=1e-4, atol=2e-5)
-    # the reference's bitstream through the product's decoder
+    # the reference's bitstream through the product's decoder (a CDF index that differs desynchronises the range
+    # coder from that symbol on: the cross-decode is only defined when the integers agree)
+    if sum(mismatches.values()):
+        return
     ref_strings = [[[g["str_a"].tobytes()], [g["str_na"].tobytes()]], [g["str_z"].tobytes()]]
     with torch.no_grad():
         d = codec.decompress(ref_strings, torch.Size([int(v) for v in g["shape"]]))
@@ -141,8 +206,8 @@ def test_bitstream_identical_to_reference_fixture(nets, golden_weights_ok, tag):
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 64, 64), (2, 96, 160), (1, 256, 256)])
-def test_symbols_vs_fp32_oracle(nets, oracle, B, H, W):
-    """Product (GPU, fp32x3 trunk) against the oracle in fp32 mode on the same weights and residual."""
+def test_symbols_vs_fp32_oracle(nets, oracle, B, H, W, mode):
+    """Product (GPU, fp32-equivalent trunk) against the oracle in fp32 mode on the same weights and residual."""
     onet, pnet = nets
     x = oracle.synthetic_image(B, H, W, seed=9)
     jd, _ = onet.jpeg(x)
@@ -168,15 +233,16 @@ def test_bf16_trunk_is_not_symbol_exact(nets, oracle):
     x = oracle.synthetic_image(1, 64, 64, seed=9)
     jd, _ = onet.jpeg(x)
     codec = pnet.residual_model
+    keep = codec.codec_precision
     codec.codec_precision = "bf16"
     try:
         r = check_precise.symbol_report(codec, onet.residual_model, oracle, x - jd)
     finally:
-        codec.codec_precision = "fp32x3"
+        codec.codec_precision = keep
     assert r["end_to_end_mismatches"] > 100 and r["end_to_end"]["sym_a"]["match"] > 0.98
 
 
-def test_oracle_decodes_product_bitstream_both_passes(nets, oracle):
+def test_oracle_decodes_product_bitstream_both_passes(nets, oracle, mode):
     """Cross-implementation decode: the CPU oracle's decompress() (fp32 h_s / context / parameter head recomputed
     on the CPU, models/checkerboard.py:200-240) reads the product's three strings and recovers the product's
     symbols of BOTH passes; and the product decodes the oracle's strings."""
@@ -233,7 +299,7 @@ def test_stream_is_batch_and_launch_shape_invariant(nets, oracle):
             d1 = codec.decompress(one, c8["shape"])
             assert torch.equal(d1["x_hat"][0], d8["x_hat"][i])
     # decompress(compress(x)) == clamp(forward(x)) when forward runs the same trunk (Q3 + encoder/decoder consistency)
-    codec.precision = "fp32x3"
+    codec.precision = codec.codec_precision
     try:
         with torch.no_grad():
             f = codec(x)
@@ -252,7 +318,7 @@ def test_cfg1_golden_summary_on_gpu(nets, oracle, golden_weights_ok):
     codec = pnet.residual_model
     g = load_golden("cfg1_summary")
     x = oracle.synthetic_residual(1, 256, 256).cuda()
-    codec.precision = "fp32x3"
+    codec.precision = codec.codec_precision
     try:
         with torch.no_grad():
             f = codec(x)

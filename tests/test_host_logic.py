@@ -151,7 +151,7 @@ def test_container_roundtrip_and_errors(build_lib):
         container.pack({"strings": [[[b"a"], [b"b", b"c"]], [b"z"]], "shape": (1, 1)})
     # the header records which trunk arithmetic made the strings; a mismatching decoder is refused
     assert "trunk" not in d
-    for tag, want in (("fp32x3", "fp32"), ("fp32x2", "fp32"), ("bf16", "bf16")):
+    for tag, want in (("fp32x3", "fp32"), ("fp32h2", "fp32"), ("fp32x2", "fp32"), ("bf16", "bf16")):
         dt = container.unpack(container.pack(c, trunk=tag))
         assert dt["trunk"] == want and dt["strings"] == c["strings"]
         assert container.pack(dt) == container.pack(c, trunk=tag)  # the tag survives a second round trip

@@ -70,6 +70,44 @@ def test_batch_matches_single(build_lib, tables):
     assert coder.encode_batch(sym[:0], idx[:0], tables) == []
 
 
+@pytest.mark.parametrize("group", [2, 4])
+def test_lock_step_groups_code_the_same_bytes(build_lib, group):
+    """Two / four strings coded in lock step by one thread (csrc/rans.cpp: encode_n / decode_n; chosen when the host
+    cores are oversubscribed, forced here through HYRES_RANS_GROUP) give the bytes and symbols of single calls,
+    escapes and unequal lengths included."""
+    import os
+    import subprocess
+    import sys
+    code = r"""
+import sys
+import numpy as np
+sys.path.insert(0, %r)
+import hyres_b200
+from hyres_b200 import coder
+gc = hyres_b200.models.GaussianConditional(None)
+gc.update_scale_table(hyres_b200.get_scale_table())
+t = gc.tables()
+rng = np.random.default_rng(11)
+count, n = 7, 20000
+idx = rng.integers(0, 64, size=(count, n)).astype(np.int32)
+sym = np.round(rng.standard_normal((count, n)) * rng.choice([0.3, 2.0, 30.0], size=(count, 1))).astype(np.int32)
+sym[1, ::37] += 70000
+sym[4, ::91] -= 70000
+single = [coder.encode_with_indexes(sym[i], idx[i], t) for i in range(count)]
+assert coder.encode_batch(sym, idx, t, threads=2) == single
+assert (coder.decode_batch(single, idx, t, threads=2) == sym).all()
+# unequal lengths fall back to smaller groups
+rows_s = [sym[0], sym[1][:1000], sym[2], sym[3][:1000], sym[5]]
+rows_i = [idx[0], idx[1][:1000], idx[2], idx[3][:1000], idx[5]]
+got = coder.encode_batch([r[None] for r in rows_s], [r[None] for r in rows_i], t)
+assert got == [coder.encode_with_indexes(a, b, t) for a, b in zip(rows_s, rows_i)]
+print("ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HYRES_RANS_GROUP=str(group))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
 def test_pmf_to_quantized_cdf_matches_oracle(build_lib, oracle):
     from hyres_b200 import coder
     rng = np.random.default_rng(0)

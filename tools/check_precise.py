@@ -1,7 +1,7 @@
 """GPU check of the split-precision (fp32-equivalent) trunk.
 
 Part A (``conv_cases``): every layer geometry of the entropy-critical trunk as a split convolution
-(``ops.ConvLayer(nsplit=2|3)``) against a float64 convolution of the same fp32 operands; the error of a plain
+(``ops.ConvLayer(nsplit=2|3|18)``) against a float64 convolution of the same fp32 operands; the error of a plain
 fp32 cuDNN convolution against the same float64 result is printed beside it (that is the noise floor two fp32
 implementations of the reference differ by).
 
@@ -103,15 +103,20 @@ def conv_case(idx, nsplit):
     ref32 = _torch_ref(x0, x1, wd, bd, c, torch.float32)
     scale = float(ref64.abs().max())
     # the split of the input itself: parts must add up to the fp32 value
-    parts = s0.float().reshape(B, H, W, nsplit, cin0).sum(3)
+    if nsplit & ops.SPLIT_F16:
+        hp = s0.view(torch.float16).float().reshape(B, H, W, 2, cin0)
+        parts = hp[:, :, :, 0] + hp[:, :, :, 1] / 2048.0
+    else:
+        parts = s0.float().reshape(B, H, W, nsplit, cin0).sum(3)
     split_err = float((parts - x0).abs().max() / x0.abs().max())
     err = float((got.double() - ref64).abs().max()) / scale
     err32 = float((ref32.double() - ref64).abs().max()) / scale
     rms = float((got.double() - ref64).pow(2).mean().sqrt()) / scale
     rms32 = float((ref32.double() - ref64).pow(2).mean().sqrt()) / scale
-    tol = 3e-6 if nsplit == 3 else 2e-4
+    exact = nsplit != 2  # three bf16 parts or two half parts: fp32-equivalent
+    tol = 3e-6 if exact else 2e-4
     return dict(name=c["name"], nsplit=nsplit, max_err=err, max_err_fp32_cudnn=err32, rms_err=rms, rms_err_fp32_cudnn=rms32,
-                split_err=split_err, ok=bool(err < tol and split_err < (1e-6 if nsplit == 3 else 1e-4)))
+                split_err=split_err, ok=bool(err < tol and split_err < (1e-6 if exact else 1e-4)))
 
 
 def near_tie_distance_symbols(t):
@@ -222,7 +227,7 @@ def symbol_report(pnet, onet, oracle, x, sym_eps=2e-4, idx_eps=2e-4):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--nsplit", type=int, default=0, help="0 = both 2 and 3")
+    ap.add_argument("--nsplit", type=int, default=0, help="0 = 2, 3 and 18 (two half parts)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "precise.json"))
     ap.add_argument("--skip-model", action="store_true")
     ap.add_argument("--shapes", default="1x64x64,2x96x160,1x256x256")
@@ -231,7 +236,7 @@ def main():
     import __graft_entry__ as ge
     ge.build()
     out = dict(conv=[], model=[])
-    for ns in ([2, 3] if args.nsplit == 0 else [args.nsplit]):
+    for ns in ([2, 3, 18] if args.nsplit == 0 else [args.nsplit]):
         for i in range(len(CONV_CASES)):
             r = conv_case(i, ns)
             out["conv"].append(r)
@@ -249,7 +254,7 @@ def main():
             x = O.synthetic_image(B, H, W, seed=9)
             jd, _ = onet.jpeg(x)
             res = x - jd
-            for mode in ("bf16", "fp32x2", "fp32x3"):
+            for mode in ("bf16", "fp32x2", "fp32x3", "fp32h2"):
                 pnet.residual_model.codec_precision = mode
                 r = symbol_report(pnet.residual_model, onet.residual_model, O, res)
                 out["model"].append(r)
