@@ -32,7 +32,7 @@ def _digest():
         os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))
     ) + [os.path.join(ROOT, "include", "hyres_b200.h")]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())  # not the path: the snapshot on the GPU box lives elsewhere
         with open(f, "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()

@@ -50,12 +50,12 @@ constexpr int32_t kMaxBypass = (1 << kBypassBits) - 1;
 // Encoder entry of one (row, value): x' = ((x / freq) << 16) + x % freq + start = x + start + q * (2^16 - freq) with
 // q = x / freq = mulhi(x, rcp_freq) >> rcp_shift (Alverson's reciprocal division as used by ryg_rans' rans64.h:
 // exact for all x < 2^63; freq == 1 uses rcp = 2^64 - 1, q = x - 1 and a bias that makes up for it).
-struct EncSym {
+struct EncSym {       // 16 bytes; rows are packed back to back (row_base), not at the CDF table's stride
   uint64_t rcp_freq;
-  uint32_t freq;  // 0: invalid (zero-width bin) -> the encoder fails like the division-based one did
   uint32_t bias;
-  uint32_t cmpl_freq;
-  uint32_t rcp_shift;
+  uint16_t freq_m1;   // freq - 1 (freq in 1 .. 65535)
+  uint8_t rcp_shift;
+  uint8_t valid;      // 0: zero-width bin -> the encoder fails like the division-based one did
 };
 
 constexpr int kLutShift = 4;
@@ -65,6 +65,7 @@ constexpr int kLutSize = 1 << (kPrecision - kLutShift);
 struct RowInfo {
   int32_t last_bin;  // sizes - 2: the escape bin (max_value of the format)
   int32_t offset;
+  uint32_t base;     // first entry of the row in the packed enc / sf arrays
   uint8_t enc_ok, dec_ok;
 };
 
@@ -73,8 +74,8 @@ struct Prepared {
   int n_cdfs = 0, stride = 0;
   std::vector<RowInfo> rows;
   std::vector<int32_t> sizes, offsets;
-  std::vector<EncSym> enc;       // [n_cdfs][stride]
-  std::vector<uint32_t> sf;      // [n_cdfs][stride]: start | (freq - 1) << 16 of every bin (decoder)
+  std::vector<EncSym> enc;       // packed rows: entry row.base + value
+  std::vector<uint32_t> sf;      // packed rows: start | (freq - 1) << 16 of every bin (decoder)
   std::vector<uint16_t> lut;     // [n_cdfs][kLutSize]: the bin that contains the first value of each 16-wide bucket
   std::vector<uint8_t> enc_ok;   // row usable by the encoder (sizes within the table)
   std::vector<uint8_t> dec_ok;   // row usable by the decoder (well-formed, strictly increasing CDF)
@@ -109,8 +110,11 @@ std::shared_ptr<const Prepared> prepare(const int32_t* cdfs, int n_cdfs, int str
   P->hash = h; P->n_cdfs = n_cdfs; P->stride = stride;
   P->sizes.assign(sizes, sizes + n_cdfs);
   P->offsets.assign(offsets, offsets + n_cdfs);
-  P->enc.assign(static_cast<size_t>(n_cdfs) * stride, EncSym{0, 0, 0, 0, 0});
-  P->sf.assign(static_cast<size_t>(n_cdfs) * stride, 0u);
+  size_t total_bins = 0;
+  for (int r = 0; r < n_cdfs; ++r) total_bins += static_cast<size_t>(std::max(1, std::min(sizes[r], stride)));
+  P->enc.assign(total_bins, EncSym{0, 0, 0, 0, 0});
+  P->sf.assign(total_bins, 0u);
+  size_t base = 0;
   P->lut.assign(static_cast<size_t>(n_cdfs) * kLutSize, 0);
   P->enc_ok.assign(n_cdfs, 0);
   P->dec_ok.assign(n_cdfs, 0);
@@ -124,25 +128,24 @@ std::shared_ptr<const Prepared> prepare(const int32_t* cdfs, int n_cdfs, int str
     for (int v = 0; v < bins; ++v) {
       const uint32_t start = static_cast<uint16_t>(cdf[v]);
       const uint32_t freq = static_cast<uint16_t>(cdf[v + 1] - cdf[v]);  // as the 16-bit arithmetic of the format
-      EncSym& e = P->enc[static_cast<size_t>(r) * stride + v];
-      e.freq = freq;
+      EncSym& e = P->enc[base + v];
+      e.valid = freq != 0;
+      e.freq_m1 = static_cast<uint16_t>(freq - 1);
       if (freq >= 2) {
         uint32_t shift = 0;
         while (freq > (1u << shift)) ++shift;
         const unsigned __int128 num = (static_cast<unsigned __int128>(1) << (shift + 63)) + freq - 1;
         e.rcp_freq = static_cast<uint64_t>(num / freq);
-        e.rcp_shift = shift - 1;
+        e.rcp_shift = static_cast<uint8_t>(shift - 1);
         e.bias = start;
-        e.cmpl_freq = (1u << kPrecision) - freq;
       } else if (freq == 1) {
         e.rcp_freq = ~0ull;
         e.rcp_shift = 0;
         e.bias = start + (1u << kPrecision) - 1;
-        e.cmpl_freq = (1u << kPrecision) - 1;
       }
       const int64_t f = static_cast<int64_t>(cdf[v + 1]) - cdf[v];
       if (f < 1 || f > 65536 || cdf[v] < 0 || cdf[v] > 65535) dec_ok = false;
-      else P->sf[static_cast<size_t>(r) * stride + v] = static_cast<uint32_t>(cdf[v]) | (static_cast<uint32_t>(f - 1) << 16);
+      else P->sf[base + v] = static_cast<uint32_t>(cdf[v]) | (static_cast<uint32_t>(f - 1) << 16);
     }
     if (dec_ok) {
       int s = 0;
@@ -153,7 +156,8 @@ std::shared_ptr<const Prepared> prepare(const int32_t* cdfs, int n_cdfs, int str
       }
     }
     P->dec_ok[r] = dec_ok ? 1 : 0;
-    P->rows.push_back(RowInfo{max_value, offsets[r], P->enc_ok[r], P->dec_ok[r]});
+    P->rows.push_back(RowInfo{max_value, offsets[r], static_cast<uint32_t>(base), P->enc_ok[r], P->dec_ok[r]});
+    base += static_cast<size_t>(std::max(1, std::min(size, stride)));
   }
   std::lock_guard<std::mutex> lk(mu);
   if (cache.size() >= 8) cache.erase(cache.begin());
@@ -197,6 +201,17 @@ inline void enc_put_bits(uint64_t& x, uint32_t*& p, uint32_t val, uint32_t nbits
   x = (x << nbits) | val;
 }
 
+// f(0), f(1), ... f(N-1) with compile-time indices: the per-string states of a lock-step group stay in registers
+// (no reliance on an unroll pragma, which nvcc's host pass does not forward)
+template <typename F, int... K>
+inline __attribute__((always_inline)) void for_each_k(F&& f, std::integer_sequence<int, K...>) {
+  (f(std::integral_constant<int, K>{}), ...);
+}
+template <int N, typename F>
+inline __attribute__((always_inline)) void unrolled(F&& f) {
+  for_each_k(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
 inline uint64_t mulhi64(uint64_t a, uint64_t b) {
   return static_cast<uint64_t>((static_cast<unsigned __int128>(a) * b) >> 64);
 }
@@ -225,7 +240,7 @@ int encode_n(const int32_t* const* symbols, const int32_t* const* indexes, int64
     sinks[k] = own[k].get();
     x[k] = kRansL;
   }
-  const int n_cdfs = T.n_cdfs, stride = T.stride;
+  const int n_cdfs = T.n_cdfs;
   const RowInfo* rows = T.rows.data();
   const EncSym* enc = T.enc.data();
   constexpr int64_t kBlock = 256;  // symbols between two capacity checks (one word per symbol at most + escapes)
@@ -233,12 +248,13 @@ int encode_n(const int32_t* const* symbols, const int32_t* const* indexes, int64
     const int64_t lo = std::max<int64_t>(hi - kBlock, 0);
     for (int k = 0; k < NS; ++k) sinks[k]->room(kBlock + 64);
     for (int64_t i = hi - 1; i >= lo; --i) {
-#pragma GCC unroll 4
-      for (int k = 0; k < NS; ++k) {
+      int bad = 0;
+      unrolled<NS>([&](auto kc) __attribute__((always_inline)) {
+        constexpr int k = decltype(kc)::value;
         const int32_t ci = indexes[k][i];
-        if (static_cast<uint32_t>(ci) >= static_cast<uint32_t>(n_cdfs)) return HYRES_ERR_ARG;
+        if (static_cast<uint32_t>(ci) >= static_cast<uint32_t>(n_cdfs)) { bad = 1; return; }
         const RowInfo ri = rows[ci];
-        if (!ri.enc_ok) return HYRES_ERR_ARG;
+        if (!ri.enc_ok) { bad = 1; return; }
         int32_t value = symbols[k][i] - ri.offset;
         if (static_cast<uint32_t>(value) >= static_cast<uint32_t>(ri.last_bin)) {  // negative, or at / beyond the escape bin
           const uint32_t raw = value < 0 ? static_cast<uint32_t>(-2 * value - 1) : static_cast<uint32_t>(2 * (value - ri.last_bin));
@@ -246,12 +262,14 @@ int encode_n(const int32_t* const* symbols, const int32_t* const* indexes, int64
           value = ri.last_bin;
           sinks[k]->room(kBlock + 64);
         }
-        const EncSym& e = enc[static_cast<size_t>(ci) * stride + value];
-        if (e.freq == 0) return HYRES_ERR_ARG;
-        enc_renorm(x[k], sinks[k]->p, static_cast<uint64_t>(e.freq) << 47);  // ((L >> 16) << 32) * freq
+        const EncSym e = enc[ri.base + value];
+        if (!e.valid) { bad = 1; return; }
+        const uint32_t freq = static_cast<uint32_t>(e.freq_m1) + 1u;
+        enc_renorm(x[k], sinks[k]->p, static_cast<uint64_t>(freq) << 47);  // ((L >> 16) << 32) * freq
         const uint64_t q = mulhi64(x[k], e.rcp_freq) >> e.rcp_shift;
-        x[k] = x[k] + e.bias + q * e.cmpl_freq;
-      }
+        x[k] = x[k] + e.bias + q * ((1u << kPrecision) - freq);
+      });
+      if (bad) return HYRES_ERR_ARG;
     }
   }
   for (int k = 0; k < NS; ++k) {
@@ -335,18 +353,19 @@ int decode_n(const uint8_t* const* in, const int64_t* in_len, const int32_t* con
     src[k].p += 4;
     x[k] = lo | (static_cast<uint64_t>(hi) << 32);
   }
-  const int n_cdfs = T.n_cdfs, stride = T.stride;
+  const int n_cdfs = T.n_cdfs;
   const RowInfo* rows = T.rows.data();
   const uint32_t* sf = T.sf.data();
   const uint16_t* lut = T.lut.data();
   for (int64_t i = 0; i < n; ++i) {
-#pragma GCC unroll 4
-    for (int k = 0; k < NS; ++k) {
+    int bad = 0;
+    unrolled<NS>([&](auto kc) __attribute__((always_inline)) {
+      constexpr int k = decltype(kc)::value;
       const int32_t ci = indexes[k][i];
-      if (static_cast<uint32_t>(ci) >= static_cast<uint32_t>(n_cdfs)) return HYRES_ERR_ARG;
+      if (static_cast<uint32_t>(ci) >= static_cast<uint32_t>(n_cdfs)) { bad = 1; return; }
       const RowInfo ri = rows[ci];
-      if (!ri.dec_ok) return HYRES_ERR_ARG;
-      const uint32_t* row = sf + static_cast<size_t>(ci) * stride;
+      if (!ri.dec_ok) { bad = 1; return; }
+      const uint32_t* row = sf + ri.base;
       const int32_t last_bin = ri.last_bin;  // == max_value: the escape bin
       const uint32_t cum = static_cast<uint32_t>(x[k] & ((1u << kPrecision) - 1));
       // last bin whose start is <= cum (strictly increasing CDF => the reference's linear scan finds the same one)
@@ -357,12 +376,10 @@ int decode_n(const uint8_t* const* in, const int64_t* in_len, const int32_t* con
       x[k] = static_cast<uint64_t>(freq) * (x[k] >> kPrecision) + cum - start;
       dec_renorm(x[k], src[k]);
       int32_t value = s;
-      if (s == last_bin) {
-        const int rc = dec_escape(x[k], src[k], last_bin, value);
-        if (rc != HYRES_OK) return rc;
-      }
+      if (s == last_bin && dec_escape(x[k], src[k], last_bin, value) != HYRES_OK) { bad = 1; return; }
       out[k][i] = value + ri.offset;
-    }
+    });
+    if (bad) return HYRES_ERR_ARG;
   }
   return HYRES_OK;
 }

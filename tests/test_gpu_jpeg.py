@@ -96,7 +96,8 @@ def test_model_forward_runs_the_stage_on_the_device(stage, oracle_net):
     pnet = hyres_b200.ResidualJPEGCompression()
     pnet.load_state_dict(oracle_net.state_dict())
     pnet = pnet.cuda().eval()
-    x = hyres_b200.synthetic.synthetic_image(2, 64, 96, seed=9)
+    from hyres_b200 import synthetic
+    x = synthetic.synthetic_image(2, 64, 96, seed=9)
     odec, obpp, _ = J.stage_forward(x.numpy(), 1)
     with torch.no_grad():
         out = pnet(x.cuda())
