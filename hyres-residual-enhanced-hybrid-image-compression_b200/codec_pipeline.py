@@ -13,6 +13,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 import torch
 
+from . import ops
+
 
 class CodecPipeline:
     def __init__(self, model, workers=3, reuse_host_buffers=False):
@@ -81,7 +83,7 @@ class CodecPipeline:
                 self._count(h2d=x.numel() * x.element_size())
                 x = x.to(self.dev, non_blocking=True)
             c = self.model.compress(x)
-            torch.cuda.current_stream().synchronize()
+            ops.stream_wait_blocking(self.dev)
         return c
 
     @torch.no_grad()
@@ -95,7 +97,7 @@ class CodecPipeline:
                 host.copy_(x_hat, non_blocking=True)
                 self._count(d2h=x_hat.numel() * x_hat.element_size())
                 x_hat = host
-            torch.cuda.current_stream().synchronize()
+            ops.stream_wait_blocking(self.dev)
         return x_hat
 
     def _roundtrip_job(self, x, to_host):

@@ -295,43 +295,61 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const uint32_t t_item = t_lane + buf * p.acc_cols;
       if (p.split_epi) {
         // split-precision layer: v = sum of the tile's accumulators (cross products first, fp32 round to nearest)
-        // + bias, the fp32 element-wise stage (skip / gate / GDN), ReLU -> fp32 row and / or its bf16 parts.
+        // + bias, the fp32 element-wise stage (skip / gate / GDN), ReLU -> fp32 row and / or its 16-bit parts.
         // TMEM hands every thread one position (row) of 32 channels; global memory wants a warp to touch few
         // 128-byte lines per instruction.  Each epilogue warp therefore owns a 4.5 KB shared-memory tile through
         // which operands and results are transposed: global accesses use the "line layout" (instruction j, lane l ->
         // row 4j + l/8, 16-byte piece l%8: four rows of 128 B per instruction instead of 32 scattered pieces).
+        // The layer's few MMAs leave this epilogue as the critical path (ncu: issue-bound on 8 warps), so every
+        // address below is a per-sub-tile base plus compile-time multiples of two strides -- no per-piece 64-bit
+        // index arithmetic.
         const float lo = p.act == HYRES_ACT_RELU ? 0.f : -3.402823466e38f;
         const int nch = it.bn >> 5;
         const int steps = nsub * nch;
         const uint32_t mask = static_cast<uint32_t>(p.acc_mask[it.phase]);
         float* stg = reinterpret_cast<float*>(smem_raw + (bar_base + 512 - hy::smem_u32(smem_raw))) + warp * (32 * 36);
+        const int wq = warp & 3;
         const int qrow = lane >> 3, qpc = lane & 7;  // line layout
+        const int prow = lane >> 2, ppc = lane & 3;  // parts layout: instruction j -> row 8j + l/4, 16-byte piece l%4
         const bool coalesced = p.f32_sc == 1 && (p.cout & 31) == 0;
-        // output pixel of local row `rl` (0..31) of this warp, sub-tile `sub`
-        auto rowpix = [&](int sub, int rl, long long& opix) -> bool {
-          const int r = (warp & 3) * 32 + rl;
-          const int hv = it.h0 + sub * kSubH + (r >> 3), wv = it.w0 + (r & 7);
-          opix = (static_cast<long long>(it.b_img) * p.OH + (hv * p.out_mul + ph_p)) * p.OW + (wv * p.out_mul + ph_q);
-          return hv < p.OHv && wv < p.OWv;
+        const bool has_aux = p.split_mode != HYRES_SPLIT_COPY;
+        const bool aux_staged = has_aux && coalesced;
+        const int om = p.out_mul;
+        const long long row_px = static_cast<long long>(om) * p.OW;  // output pixels between two tile rows
+        // tile row `tr` (0..15 within the sub-tile), tile column `tc` -> output pixel index
+        auto pixel = [&](int sub, int tr, int tc) -> long long {
+          const int hv = it.h0 + sub * kSubH + tr, wv = it.w0 + tc;
+          return (static_cast<long long>(it.b_img) * p.OH + (hv * om + ph_p)) * p.OW + (wv * om + ph_q);
+        };
+        // line layout of sub-tile `sub`: piece j sits at pixel  pix0 + (j >> 1) * row_px + (j & 1) * 4 * om ;
+        // bit j of the mask says whether that pixel exists
+        auto line_base = [&](int sub, long long& pix0, uint32_t& ok) {
+          const int tr0 = wq * 4;
+          pix0 = pixel(sub, tr0, qrow);
+          const int rows_ok = min(max(p.OHv - (it.h0 + sub * kSubH + tr0), 0), 4);
+          const uint32_t cols = (it.w0 + qrow < p.OWv ? 0x55u : 0u) | (it.w0 + 4 + qrow < p.OWv ? 0xaau : 0u);
+          ok = ((1u << (2 * rows_ok)) - 1u) & cols;
         };
         auto chunk_of = [&](int q, int& sub, int& cb) {
           const int si = q / nch;
           sub = sub0 + si * sub_step;
           cb = (q - si * nch) << 5;
         };
-        const bool has_aux = p.split_mode != HYRES_SPLIT_COPY;
+        const int aux_row_e = static_cast<int>(row_px) * p.cout, aux_col_e = 4 * om * p.cout;  // element strides
         // operand of chunk q in the line layout; chunk q + 1 is requested before chunk q's accumulators are read
         auto fetch = [&](const float* src, int q, float4 (&dst)[8]) {
           if (q >= steps) return;
           int sub, cb;
           chunk_of(q, sub, cb);
           if (it.n0 + cb >= p.cout) return;
+          long long pix0;
+          uint32_t ok;
+          line_base(sub, pix0, ok);
+          const float* s0 = src + pix0 * p.cout + (it.n0 + cb + qpc * 4);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            long long opix;
             dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rowpix(sub, 4 * j + qrow, opix))
-              dst[j] = __ldg(reinterpret_cast<const float4*>(src + opix * p.cout + it.n0 + cb) + qpc);
+            if ((ok >> j) & 1u) dst[j] = __ldg(reinterpret_cast<const float4*>(s0 + (j >> 1) * aux_row_e + (j & 1) * aux_col_e));
           }
         };
         // line layout -> the warp's tile; every thread then reads its own row (8 float4 = 32 channels) from there
@@ -344,23 +362,38 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         float4 an[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (has_aux && coalesced) fetch(p.aux0_f32, 0, an);
+        if (aux_staged) fetch(p.aux0_f32, 0, an);
         hy::mbar_wait(acc_full + 8 * buf, use & 1u);
         hy::tc_fence_after();
+        const int f32_row_e = static_cast<int>(row_px * p.f32_sw), f32_col_e = static_cast<int>(4 * om * p.f32_sw);
+        const int nparts = p.out_nsplit;
+        const int sp_px = nparts * p.cout;  // elements per pixel of the parts tensor
+        const int sp_row_e = static_cast<int>(row_px) * sp_px;
+        int cur_sub = -1;
+        long long pix_line = 0, pix_own = 0, pix_parts = 0;
+        uint32_t ok_line = 0, ok_parts = 0;
+        bool valid_row = false;
         for (int q = 0; q < steps; ++q) {
           int sub, cb;
           chunk_of(q, sub, cb);
-          long long opix;
-          const bool valid_row = rowpix(sub, lane, opix);
+          if (sub != cur_sub) {  // per sub-tile: the three pixel bases and their validity
+            cur_sub = sub;
+            line_base(sub, pix_line, ok_line);
+            const int tr_own = wq * 4 + (lane >> 3), tc_own = lane & 7;
+            pix_own = pixel(sub, tr_own, tc_own);
+            valid_row = it.h0 + sub * kSubH + tr_own < p.OHv && it.w0 + tc_own < p.OWv;
+            pix_parts = pixel(sub, wq * 4, prow);
+            const int rows_ok = min(max(p.OHv - (it.h0 + sub * kSubH + wq * 4), 0), 4);
+            ok_parts = it.w0 + prow < p.OWv ? ((1u << rows_ok) - 1u) : 0u;
+          }
           const int n = it.n0 + cb;
-          const bool aux_staged = has_aux && coalesced;
           if (aux_staged) {
             stage(an);
             fetch(p.aux0_f32, q + 1, an);
           }
           const bool row_ok = valid_row && n < p.cout;
-          const float4* g0 = reinterpret_cast<const float4*>(p.aux0_f32 + opix * p.cout + n);  // used when !aux_staged
-          const float4* g1 = reinterpret_cast<const float4*>(p.aux1_f32 + opix * p.cout + n);  // gate only
+          const float4* g0 = reinterpret_cast<const float4*>(p.aux0_f32 + pix_own * p.cout + n);  // used when !aux_staged
+          const float4* g1 = reinterpret_cast<const float4*>(p.aux1_f32 + pix_own * p.cout + n);  // gate only
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
@@ -411,15 +444,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               for (int i = 0; i < 8; ++i)
                 *reinterpret_cast<float4*>(stg + lane * 36 + i * 4) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
               __syncwarp();
+              float* o0 = p.out_f32 + pix_line * p.f32_sw + (n + qpc * 4);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                long long op;
-                if (rowpix(sub, 4 * j + qrow, op))
-                  reinterpret_cast<float4*>(p.out_f32 + op * p.f32_sw + n)[qpc] =
+              for (int j = 0; j < 8; ++j)
+                if ((ok_line >> j) & 1u)
+                  *reinterpret_cast<float4*>(o0 + (j >> 1) * f32_row_e + (j & 1) * f32_col_e) =
                       *reinterpret_cast<const float4*>(stg + (4 * j + qrow) * 36 + qpc * 4);
-              }
             } else if (valid_row) {
-              float* o = p.out_f32 + it.b_img * p.f32_sb + (opix / p.OW % p.OH) * p.f32_sh + (opix % p.OW) * p.f32_sw + n * p.f32_sc;
+              float* o = p.out_f32 + it.b_img * p.f32_sb + (pix_own / p.OW % p.OH) * p.f32_sh + (pix_own % p.OW) * p.f32_sw + n * p.f32_sc;
 #pragma unroll
               for (int i = 0; i < 32; ++i)
                 if (n + i < p.cout) o[i * p.f32_sc] = v[i];
@@ -431,37 +463,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
               for (int i = 0; i < 32; ++i) v[i] *= v[i];
             }
             uint4* stg4 = reinterpret_cast<uint4*>(stg);
-            for (int part = 0; part < p.out_nsplit; ++part) {
+            __nv_bfloat16* sp0 = p.out_split + pix_parts * sp_px + (n + ppc * 8);
+            for (int part = 0; part < nparts; ++part) {
               uint32_t w[16];
               if (p.out_f16) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  const __half h0 = __float2half_rn(v[2 * i]), h1 = __float2half_rn(v[2 * i + 1]);
-                  v[2 * i] = (v[2 * i] - __half2float(h0)) * hy::kF16LoScale;  // exact residual, back in p0's range
-                  v[2 * i + 1] = (v[2 * i + 1] - __half2float(h1)) * hy::kF16LoScale;
-                  w[i] = static_cast<uint32_t>(__half_as_ushort(h0)) | (static_cast<uint32_t>(__half_as_ushort(h1)) << 16);
+                  const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+                  const float2 f = __half22float2(h);
+                  v[2 * i] = (v[2 * i] - f.x) * hy::kF16LoScale;  // exact residual, back in p0's range
+                  v[2 * i + 1] = (v[2 * i + 1] - f.y) * hy::kF16LoScale;
+                  w[i] = *reinterpret_cast<const uint32_t*>(&h);
                 }
               } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                  const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-                  v[2 * i] -= __bfloat162float(h0);      // exact: the residual of a round-to-nearest bf16
-                  v[2 * i + 1] -= __bfloat162float(h1);
-                  w[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                  const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+                  w[i] = *reinterpret_cast<const uint32_t*>(&h);
+                  v[2 * i] -= __uint_as_float(w[i] << 16);          // exact: the residual of a round-to-nearest bf16
+                  v[2 * i + 1] -= __uint_as_float(w[i] & 0xffff0000u);
                 }
               }
               __syncwarp();
 #pragma unroll
               for (int i = 0; i < 4; ++i) stg4[lane * 5 + i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
               __syncwarp();
+              __nv_bfloat16* sp = sp0 + part * p.cout;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {  // instruction j, lane l -> row 8j + l/4, 16-byte piece l%4: 8 rows of 64 B
-                const int rl = 8 * j + (lane >> 2), pc = lane & 3;
-                long long op;
-                if (rowpix(sub, rl, op))
-                  reinterpret_cast<uint4*>(p.out_split + op * (static_cast<long long>(p.out_nsplit) * p.cout) +
-                                           static_cast<long long>(part) * p.cout + n)[pc] = stg4[rl * 5 + pc];
-              }
+              for (int j = 0; j < 4; ++j)  // instruction j, lane l -> row 8j + l/4 (tile row wq*4 + j), piece l%4: 8 rows of 64 B
+                if ((ok_parts >> j) & 1u)
+                  *reinterpret_cast<uint4*>(sp + j * sp_row_e) = stg4[(8 * j + prow) * 5 + ppc];
             }
           }
         }

@@ -111,7 +111,7 @@ class EntropyModel(nn.Module):
             buf = pinned[key] = torch.empty(t.numel(), dtype=torch.int32).pin_memory()
         view = buf.view(B, -1)
         view.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(t.device).synchronize()
+        ops.stream_wait_blocking(t.device)
         return view.numpy()
 
     def encode_symbols(self, symbols, indexes):

@@ -40,6 +40,24 @@ PACKED_CACHE = None
 PACKED_STATS = {"imported": 0, "packed": 0}  # layers filled from exported operands / packed from fp32 weights
 
 
+_SYNC_TLS = __import__("threading").local()
+
+
+def stream_wait_blocking(device=None):
+    """Wait for the current stream's work without spinning: a blocking-sync event lets the calling thread sleep
+    (``Stream.synchronize`` busy-waits, and a codec pipeline has several worker threads waiting on the GPU while the
+    host cores are needed by the range coder)."""
+    ev = getattr(_SYNC_TLS, "ev", None)
+    if ev is None:
+        ev = _SYNC_TLS.ev = {}
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    e = ev.get(dev)
+    if e is None:
+        e = ev[dev] = torch.cuda.Event(blocking=True)
+    e.record(torch.cuda.current_stream(dev))
+    e.synchronize()
+
+
 def split_parts(code):
     """Number of 16-bit parts per fp32 value of an nsplit code (1..3 bf16 parts, or 2 | SPLIT_F16: two half parts)."""
     return int(code) & 15

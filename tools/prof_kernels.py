@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Launch one hot layer at its bench shape a few times (target of `ncu --set full`, or a quick timer).
 
-    python tools/prof_kernels.py --case gate|gdn|c3x3|c1x1|ru|head0|head1|ctx|deconv|s2|gs8|fus0 [--n 3] [--time]
+    python tools/prof_kernels.py --case gate|gdn|c3x3|c1x1|ru|head0|head1|ctx|deconv|s2|gs8|fus0|p_ru1|p_ru2|p_ru3|p_s2 [--n 3] [--time] [--code 18]
 """
 import argparse
 import json
@@ -17,6 +17,7 @@ from hyres_b200.ops import (ACT_NONE, ACT_PRELU, ACT_RELU, EPI_ADD, EPI_GATE, EP
 
 B = 16
 MT = 0
+CODE = 18  # nsplit code of the p_* cases: 18 = two half parts (fp32h2), 3 = three bf16 parts
 
 
 def rnd(*shape):
@@ -169,6 +170,38 @@ def make(case):
         out = torch.empty(B, 256, 384, 128, device="cuda", dtype=torch.bfloat16)
         return (lambda: ops.conv3ch(L, 5, 2, a, b2, sign=-1, out=out),
                 2.0 * B * 256 * 384 * 128 * 75, a.numel() * 12 + out.numel() * 2)
+    if case.startswith("p_"):
+        # split-precision (fp32-equivalent) layers of g_a at the codec bench shape: 8 tiles of 704x512 -> 8 x 352 x 256
+        # positions.  p_ru1 / p_ru2 / p_ru3: the three layers of a ResidualUnit; p_gdn: conv -> x^2 parts, gamma GEMM
+        code = CODE
+        P = ops.split_parts(code)
+        Bc, Hc, Wc = 8, 352, 256
+        pos = Bc * Hc * Wc
+
+        def parts(c):
+            _, sp = ops.split_f32(torch.randn(Bc, Hc, Wc, c, device="cuda"), nsplit=code)
+            return sp
+        if case == "p_ru1":
+            L = ops.ConvLayer(w(64, 128, 1), bias(64), nsplit=code)
+            x = parts(128)
+            return (lambda: L(x, act=ACT_RELU, out_bf16=False, out_split=True), 2.0 * pos * 128 * 64,
+                    pos * (128 + 64) * 2 * P)
+        if case == "p_ru2":
+            L = ops.ConvLayer(w(64, 64, 3), bias(64), pad=1, nsplit=code)
+            x = parts(64)
+            return (lambda: L(x, act=ACT_RELU, out_bf16=False, out_split=True), 2.0 * pos * 576 * 64,
+                    pos * (64 + 64) * 2 * P)
+        if case == "p_ru3":
+            L = ops.ConvLayer(w(128, 64, 1), bias(128), nsplit=code)
+            x = parts(64)
+            skip = torch.randn(Bc, Hc, Wc, 128, device="cuda")
+            return (lambda: L(x, out_bf16=False, out_f32="nhwc", split_mode=ops.SPLIT_ADD, aux0_f32=skip, out_split=True),
+                    2.0 * pos * 64 * 128, pos * (64 * 2 * P + 128 * 4 * 2 + 128 * 2 * P))
+        if case == "p_s2":
+            L = ops.ConvLayer(w(128, 128, 5), bias(128), stride=2, pad=2, nsplit=code)
+            x = parts(128)
+            return (lambda: L(x, out_bf16=False, out_f32="nhwc", out_split=True, split_square=True, out_code=3),
+                    2.0 * pos / 4 * 128 * 25 * 128, pos * 128 * 2 * P + pos // 4 * 128 * (4 + 6))
     raise SystemExit(f"unknown case {case}")
 
 
@@ -178,9 +211,11 @@ def main():
     ap.add_argument("--n", type=int, default=3)
     ap.add_argument("--time", action="store_true")
     ap.add_argument("--mt", type=int, default=0)
+    ap.add_argument("--code", type=int, default=18)
     a = ap.parse_args()
-    global MT
+    global MT, CODE
     MT = a.mt
+    CODE = a.code
     for case in a.case.split(","):
         fn, flops, byts = make(case)
         for _ in range(a.n):
