@@ -65,7 +65,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 20 ms while the timed region runs."""
     Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,utilization.gpu")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
@@ -113,7 +113,8 @@ class ClockSampler:
                 continue
             try:
                 ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f")
-                rows.append((ts, float(c[1]), float(c[2]), [n for n, v in zip(names, c[5:9]) if v.lower().startswith("active")]))
+                util = float(c[9]) if len(c) > 9 and c[9].replace(".", "").isdigit() else None
+                rows.append((ts, float(c[1]), float(c[2]), [n for n, v in zip(names, c[5:9]) if v.lower().startswith("active")], util))
             except ValueError:
                 continue
         os.unlink(self.f.name)
@@ -121,8 +122,10 @@ class ClockSampler:
             return None
         inside = [r for r in rows if t0 is not None and t0 <= r[0] <= t1]
         use, window = (inside, "timed region") if len(inside) >= 3 else (rows, "timed region + the idle wait before it")
+        utils = [r[4] for r in use if r[4] is not None]
         return {"sm_mhz": statistics.median(r[1] for r in use), "sm_max_mhz": max(r[2] for r in use),
-                "reasons": sorted({n for r in use for n in r[3]}), "samples": len(use), "window": window}
+                "reasons": sorted({n for r in use for n in r[3]}), "samples": len(use), "window": window,
+                "gpu_util_pct": statistics.median(utils) if utils else None}
 
 
 def oracle_step_factory(sample_images, threads):
@@ -364,10 +367,26 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
             conv_ms, conv_n = ops.ConvLayer.profile_end()
             rows = ops.ConvLayer.last_profile
             split = [r for r in rows if r.get("nsplit", 1) > 1]
+            # the single most expensive layer geometry of the step and its algorithmic HBM traffic (fp32 tensors of the
+            # reference's own formulation: input, output, and the skip / gate operands the layer adds)
+            geo = {}
+            for r in split:
+                key = (r["cin"], r["cout"], r["k"], r["stride"], r["kind"], r["OH"], r["OW"], r["split_mode"])
+                g = geo.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, macs=0.0, r=r))
+                extra = {0: 0, 1: 1, 2: 2, 3: 1, 4: 1}.get(r["split_mode"], 0)
+                g["ms"] += r["ms"]
+                g["n"] += 1
+                g["bytes"] += 4.0 * r["B"] * (r["H"] * r["W"] * r["cin"] + r["OH"] * r["OW"] * r["cout"] * (1 + extra))
+                g["macs"] += r["alg_macs"]
+            top = max(geo.values(), key=lambda g: g["ms"])
             prof = dict(enc_ms=(t1 - t0) * 1e3, dec_ms=(t2 - t1) * 1e3, conv_ms=conv_ms, conv_n=conv_n,
                         split_ms=sum(r["ms"] for r in split), split_n=len(split),
                         split_flops=2.0 * sum(r["alg_macs"] for r in split),
-                        split_executed=2.0 * sum(r["alg_macs"] * r["products"] for r in split))
+                        split_executed=2.0 * sum(r["alg_macs"] * r["products"] for r in split),
+                        top=dict(ms=top["ms"], n=top["n"], bytes=top["bytes"], flops=2.0 * top["macs"],
+                                 what="%dx%d %d->%d%s at %dx%dx%d" % (top["r"]["k"], top["r"]["k"], top["r"]["cin"], top["r"]["cout"],
+                                                                    {1: " + skip", 2: " + gate", 3: " + GDN"}.get(top["r"]["split_mode"], ""),
+                                                                    top["r"]["B"], top["r"]["OH"], top["r"]["OW"])))
     pipe.close()
     if rank != 0:
         return None
@@ -401,6 +420,15 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
                              "tensor-core products (6 bf16 ones in the three GDN gamma layers) so that symbols equal the "
                              "fp32 reference's; `executed` is what the tensor pipe sustains.  Most of these layers are "
                              "HBM-bound at this tile size (1x1 / 3x3 layers of 64-128 channels carrying fp32 activations)",
+                     "dominant_layer": {"layer": prof["top"]["what"], "launches_per_step": prof["top"]["n"],
+                                        "ms_per_step": prof["top"]["ms"], "bound": "hbm",
+                                        "achieved": prof["top"]["bytes"] / (prof["top"]["ms"] * 1e-3) / 1e9, "peak": peaks["hbm"],
+                                        "unit": "GB/s", "frac": prof["top"]["bytes"] / (prof["top"]["ms"] * 1e-3) / 1e9 / peaks["hbm"],
+                                        "tflops_algorithmic": prof["top"]["flops"] / (prof["top"]["ms"] * 1e-3) / 1e12,
+                                        "traffic": 1_237_650_000 if prof["top"]["what"].startswith("1x1 64->128 + skip") else None,
+                                        "note": "the layer geometry with the largest share of the step's GPU time; achieved = "
+                                                "algorithmic fp32 bytes (input + output + added operands) / CUDA-event time; "
+                                                "traffic = dram bytes of one launch, profiles/r02_ncu_conv_tc.md"},
                      "all_tensor_kernels": {"launches": prof["conv_n"], "ms_per_step": prof["conv_ms"],
                                             "achieved": 2.0 * MAC_PER_PX_ENCDEC * px_step / (prof["conv_ms"] * 1e-3) / 1e12},
                      "step_tflops": 2.0 * MAC_PER_PX_ENCDEC * px_step / (ms * 1e-3) / 1e12},
@@ -632,7 +660,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="codec", choices=["codec", "forward", "train"])
-    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("HYRES_CODEC_IN_FLIGHT", "4")),
+    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("HYRES_CODEC_IN_FLIGHT", "6")),
                     help="images in flight in the codec pipeline (worker threads / CUDA streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="codec workload: skip the forward sub-benchmark")

@@ -39,8 +39,15 @@ namespace {
 
 constexpr int kTileW = 8;     // output columns per tile
 constexpr int kSubH = 16;     // output rows per 128-row accumulator
-constexpr int kThreads = 320; // warps 0-3 / 4-7: epilogue groups 0 / 1; warp 8: TMA producer; warp 9: MMA issuer
-constexpr int kWarpProd = 8, kWarpMma = 9;
+// Warp roles.  Plain layers: warps 0-3 / 4-7 = epilogue groups 0 / 1, warp 8 = TMA producer, warp 9 = MMA issuer.
+// Split-precision layers (kSplit): their fp32 epilogue is the critical path and latency-bound (ncu: 2.5 warps per
+// scheduler active, 0.4 eligible), so each group has EIGHT warps -- warps w and w + 4 of a group read the same TMEM
+// lane quarter and take alternate 32-column chunks -- 16 epilogue warps, warp 16 = producer, warp 17 = MMA issuer.
+template <bool kSplit> struct Roles {
+  static constexpr int kEpiWarps = kSplit ? 16 : 8;
+  static constexpr int kWarpProd = kEpiWarps, kWarpMma = kEpiWarps + 1;
+  static constexpr int kThreads = (kEpiWarps + 2) * 32;
+};
 constexpr int kMaxNBlocks = 8;
 constexpr int kSmemLimit = 227 * 1024;
 
@@ -114,7 +121,9 @@ struct Item {
 // The A patches and the weight tiles stream through two deep TMA rings that keep filling across
 // item boundaries; the accumulators are double buffered in TMEM whenever 2 * MT * BN <= 512 columns,
 // and two epilogue warp groups drain them while the next item's MMAs are issued.
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+template <bool kSplit>
+__global__ void __launch_bounds__(Roles<kSplit>::kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int kWarpProd = Roles<kSplit>::kWarpProd, kWarpMma = Roles<kSplit>::kWarpMma;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (hy::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = base;
@@ -268,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // epilogue operands (skip / gate / GDN inputs) of chunk c+1 are in flight while chunk c is
     // finished and stored, and the first chunk's operands are requested before the
     // accumulator is complete, so one global-load latency is exposed per item, not per chunk.
-    const int grp = warp >> 2;
+    const int grp = kSplit ? (warp >> 3) : (warp >> 2);
     const int row = (warp & 3) * 32 + lane;  // TMEM lane == tile row
     const int ti = row >> 3;
     const int tj = row & 7;
@@ -293,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const int nsub = (p.MT - sub0 + sub_step - 1) / sub_step;
       const int total = nsub * nchunk;
       const uint32_t t_item = t_lane + buf * p.acc_cols;
-      if (p.split_epi) {
+      if constexpr (kSplit) {
         // split-precision layer: v = sum of the tile's accumulators (cross products first, fp32 round to nearest)
         // + bias, the fp32 element-wise stage (skip / gate / GDN), ReLU -> fp32 row and / or its 16-bit parts.
         // TMEM hands every thread one position (row) of 32 channels; global memory wants a warp to touch few
@@ -362,9 +371,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         float4 an[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) an[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (aux_staged) fetch(p.aux0_f32, 0, an);
+        // the two warps of a lane quarter take alternate chunks: this one q = half, half + 2, ...
+        const int half = (warp >> 2) & 1;
+        if (aux_staged) fetch(p.aux0_f32, half, an);
         hy::mbar_wait(acc_full + 8 * buf, use & 1u);
         hy::tc_fence_after();
+        if (half >= steps) {  // a single-chunk item: nothing to read for this warp, release the accumulator at once
+          hy::tc_fence_before();
+          hy::mbar_arrive(acc_empty + 8 * buf);
+        }
         const int f32_row_e = static_cast<int>(row_px * p.f32_sw), f32_col_e = static_cast<int>(4 * om * p.f32_sw);
         const int nparts = p.out_nsplit;
         const int sp_px = nparts * p.cout;  // elements per pixel of the parts tensor
@@ -373,7 +388,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         long long pix_line = 0, pix_own = 0, pix_parts = 0;
         uint32_t ok_line = 0, ok_parts = 0;
         bool valid_row = false;
-        for (int q = 0; q < steps; ++q) {
+        for (int q = half; q < steps; q += 2) {
           int sub, cb;
           chunk_of(q, sub, cb);
           if (sub != cur_sub) {  // per sub-tile: the three pixel bases and their validity
@@ -389,7 +404,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const int n = it.n0 + cb;
           if (aux_staged) {
             stage(an);
-            fetch(p.aux0_f32, q + 1, an);
+            fetch(p.aux0_f32, q + 2, an);
           }
           const bool row_ok = valid_row && n < p.cout;
           const float4* g0 = reinterpret_cast<const float4*>(p.aux0_f32 + pix_own * p.cout + n);  // used when !aux_staged
@@ -407,7 +422,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = fmaf(__uint_as_float(r[i]), sc, v[i]);
           }
-          if (q + 1 == steps) {
+          if (q + 2 >= steps) {  // this warp's last chunk
             hy::tc_fence_before();
             hy::mbar_arrive(acc_empty + 8 * buf);
           }
@@ -498,6 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
         continue;
       }
+      if constexpr (!kSplit) {
       if (p.fast_epi) {
         // bias (+ReLU) -> bf16 / fp32 rows: 32 accumulator columns per step, TMEM loads double buffered
         const float lo = p.act == HYRES_ACT_RELU ? 0.f : -3.402823466e38f;
@@ -722,6 +738,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           a0c[0] = a0n[0]; a0c[1] = a0n[1]; a1c[0] = a1n[0]; a1c[1] = a1n[1];
         }
       }
+      }  // !kSplit
     }
   }
 
@@ -1260,7 +1277,7 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   p.acc_stride = mt * p.bn_max;
   p.acc_cols = nacc * p.acc_stride;
   p.nbuf = 2 * p.acc_cols <= 512 ? 2 : 1;
-  p.acc_empty_count = (p.nbuf == 2 || mt == 1) ? 128 : 256;
+  p.acc_empty_count = ((p.nbuf == 2 || mt == 1) ? 128 : 256) * (split ? 2 : 1);  // split layers: 8 warps per group
   for (int i = 0; i < 4; ++i) p.acc_mask[i] = c->acc_mask[i];
   int cols = 32;
   while (cols < p.nbuf * p.acc_cols) cols <<= 1;
@@ -1276,7 +1293,7 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
     for (int g = 0; g < c->ph_count[ph]; ++g) total_btiles += c->groups[c->ph_begin[ph] + g].ntaps;
   }
   // split layers: eight 4.5 KB transposition tiles for the epilogue warps behind the barrier block
-  const int fixed = 512 /*barriers*/ + 1024 /*alignment*/ + (split ? 8 * 32 * 36 * 4 : 0);
+  const int fixed = 512 /*barriers*/ + 1024 /*alignment*/ + (split ? Roles<true>::kEpiWarps * 32 * 36 * 4 : 0);
   const double taps_per_group = static_cast<double>(total_btiles) / total_groups;
   p.NA = 2; p.NB = 2;
   auto smem_need = [&]() { return p.NA * p.a_stage_bytes + p.NB * p.b_stage_bytes + fixed; };
@@ -1331,12 +1348,14 @@ int hyres_conv_run(hyres_conv* c, const hyres_conv_io* io, void* stream_v) {
   const int smem = smem_need();
   static HyPerDevice attr;
   if (!attr.done()) {
-    HY_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    HY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    HY_CUDA(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr.mark();
   }
   const int grid = std::min(p.nitems, io->cta_limit > 0 ? std::min(io->cta_limit, num_sms()) : num_sms());
   hy_count_launch();
-  HY_CUDA(hy_launch_pdl(conv_tc_kernel, grid, kThreads, smem, stream, p));
+  if (split) HY_CUDA(hy_launch_pdl(conv_tc_kernel<true>, grid, Roles<true>::kThreads, smem, stream, p));
+  else HY_CUDA(hy_launch_pdl(conv_tc_kernel<false>, grid, Roles<false>::kThreads, smem, stream, p));
   return HYRES_OK;
 }
 

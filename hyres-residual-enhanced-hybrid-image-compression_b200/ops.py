@@ -303,7 +303,8 @@ class ConvLayer:
             ConvLayer._prof_info.append(dict(kind=self.kind, cin=self.cin0 + self.cin1, cout=self.cout, k=self.R,
                                              stride=self.stride, dil=self.dil, B=B, H=H, W=W, OH=OH, OW=OW,
                                              epi=epi, f32=o32 is not None, sq=osq is not None, nsplit=self.nsplit,
-                                             products=(1, 1, 3, 6)[self.nsplit],
+                                             products=(1, 1, 3, 6)[self.nsplit], split_mode=int(split_mode),
+                                             split_out=osq is not None and self.nsplit > 1,
                                              alg_macs=self.alg_macs_per_out * B * OH * OW))
         else:
             L.check(L.lib().hyres_conv_run(self._h, C.byref(io), _stream()), "hyres_conv_run")

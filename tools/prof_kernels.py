@@ -197,6 +197,18 @@ def make(case):
             skip = torch.randn(Bc, Hc, Wc, 128, device="cuda")
             return (lambda: L(x, out_bf16=False, out_f32="nhwc", split_mode=ops.SPLIT_ADD, aux0_f32=skip, out_split=True),
                     2.0 * pos * 64 * 128, pos * (64 * 2 * P + 128 * 4 * 2 + 128 * 2 * P))
+        if case in ("p_ru3_nof32", "p_ru3_noparts", "p_ru3_noskip"):  # sensitivity of p_ru3 to each of its streams
+            L = ops.ConvLayer(w(128, 64, 1), bias(128), nsplit=code)
+            x = parts(64)
+            skip = torch.randn(Bc, Hc, Wc, 128, device="cuda")
+            kw = dict(out_bf16=False, out_f32="nhwc", split_mode=ops.SPLIT_ADD, aux0_f32=skip, out_split=True)
+            if case == "p_ru3_nof32":
+                kw["out_f32"] = None
+            elif case == "p_ru3_noparts":
+                kw["out_split"] = None
+            else:
+                kw["split_mode"], kw["aux0_f32"] = ops.SPLIT_COPY, None
+            return (lambda: L(x, **kw), 2.0 * pos * 64 * 128, pos * (64 * 2 * P + 128 * 4 * 2 + 128 * 2 * P))
         if case == "p_s2":
             L = ops.ConvLayer(w(128, 128, 5), bias(128), stride=2, pad=2, nsplit=code)
             x = parts(128)
