@@ -372,13 +372,13 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
             geo = {}
             for r in split:
                 key = (r["cin"], r["cout"], r["k"], r["stride"], r["kind"], r["OH"], r["OW"], r["split_mode"])
-                g = geo.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, macs=0.0, r=r))
+                gg = geo.setdefault(key, dict(ms=0.0, n=0, bytes=0.0, macs=0.0, r=r))
                 extra = {0: 0, 1: 1, 2: 2, 3: 1, 4: 1}.get(r["split_mode"], 0)
-                g["ms"] += r["ms"]
-                g["n"] += 1
-                g["bytes"] += 4.0 * r["B"] * (r["H"] * r["W"] * r["cin"] + r["OH"] * r["OW"] * r["cout"] * (1 + extra))
-                g["macs"] += r["alg_macs"]
-            top = max(geo.values(), key=lambda g: g["ms"])
+                gg["ms"] += r["ms"]
+                gg["n"] += 1
+                gg["bytes"] += 4.0 * r["B"] * (r["H"] * r["W"] * r["cin"] + r["OH"] * r["OW"] * r["cout"] * (1 + extra))
+                gg["macs"] += r["alg_macs"]
+            top = max(geo.values(), key=lambda e: e["ms"])
             prof = dict(enc_ms=(t1 - t0) * 1e3, dec_ms=(t2 - t1) * 1e3, conv_ms=conv_ms, conv_n=conv_n,
                         split_ms=sum(r["ms"] for r in split), split_n=len(split),
                         split_flops=2.0 * sum(r["alg_macs"] for r in split),
