@@ -329,10 +329,13 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
         sampler.wait_ready()
         barrier()
         t_start = datetime.datetime.now()
+        cpu0 = os.times()
         t0 = time.perf_counter()
         g = run(args.steps, True)
         barrier()
         ms_local = (time.perf_counter() - t0) * 1e3 / args.steps
+        cpu1 = os.times()
+        host_cpu_ms = ((cpu1.user - cpu0.user) + (cpu1.system - cpu0.system)) * 1e3 / args.steps
         t_end = datetime.datetime.now()
         clocks = sampler.stop(t_start, t_end)
         launches = lib.hyres_launch_count() - l0
@@ -405,6 +408,9 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
                 "note": "h2d / d2h count the image in and the reconstruction out; the symbol / index tensors cross PCIe "
                         "on top of that in both arms (resident and e2e), because the entropy coder runs on the host"},
         "gpu_launches": int(launches), "gpu_launches_per_step": int(launches) // max(1, args.steps),
+        "host": {"cores": os.cpu_count(), "cpu_ms_per_step": host_cpu_ms,
+                 "note": "process CPU time (user + system, all threads: range coder, JPEG file decode, launches) per step "
+                         "on rank 0; divided by the core count it is the floor the host puts under ms_per_step"},
         "clocks": clocks,
         "global_stats": {"bpp": 8.0 * gbytes / gpx, "mse_255": gse / (gpx * 3) * 255 ** 2, "images": gimg,
                          "note": "last step, all-reduced over ranks (NCCL) inside the timed loop"},

@@ -81,9 +81,10 @@ SIGNATURES = {
     "hyres_final_clamp": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hyres_gc_quant_pass": (_i, [_vp, _vp, _i, _i, _u64, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_gc_merge_likelihood": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _u64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "hyres_gc_symbols": (_i, [_vp, _vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_gc_symbols": (_i, [_vp, _vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "hyres_gc_codes": (_i, [_vp, _i, _vp, _i, _f, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "hyres_gc_indexes": (_i, [_vp, _vp, _i, _f, _vp, _i, _i, _i, _i, _vp]),
-    "hyres_gc_dequant": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "hyres_gc_dequant": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "hyres_add_to_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "hyres_split_f32": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _i, _vp]),
     "hyres_residual_im2col5s2_split": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
@@ -113,6 +114,9 @@ SIGNATURES = {
     "hyres_rans_decode": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp, _vp, _vp]),
     "hyres_rans_encode_batch": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "hyres_rans_decode_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
+    "hyres_rans_table_layout": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "hyres_rans_encode_slots_batch": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
+    "hyres_rans_decode_codes_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
 }
 
 

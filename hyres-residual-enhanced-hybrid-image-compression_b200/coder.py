@@ -77,9 +77,20 @@ def _threads(n):
     return max(1, min(n, os.cpu_count() or 1))
 
 
-def encode_batch(symbols, indexes, tables, threads=None):
+def table_layout(tables):
+    """-> int32 [3, n_cdfs]: first packed entry, offset and escape bin of every CDF row (hyres_rans_table_layout): what
+    the device-side front-end needs to emit coder slots / codes instead of (symbol, index) pairs."""
+    t = tables
+    out = np.zeros((3, t.cdf.shape[0]), dtype=np.int32)
+    L.check(L.lib().hyres_rans_table_layout(t.cdf.ctypes.data, t.cdf.shape[0], t.cdf.shape[1], t.sizes.ctypes.data,
+                                            t.offsets.ctypes.data, out.ctypes.data), "hyres_rans_table_layout")
+    return out
+
+
+def encode_batch(symbols, indexes, tables, threads=None, slots=False):
     """symbols / indexes: int32 arrays [count, n] (rows = independent strings), or equally long lists of such
-    arrays (their rows are coded as one batch, without concatenating them) -> list of bytes."""
+    arrays (their rows are coded as one batch, without concatenating them) -> list of bytes.
+    ``slots=True``: ``indexes`` holds coder slots (see ``table_layout`` / hyres_rans_encode_slots_batch); same bytes."""
     if isinstance(symbols, (list, tuple)):
         s_list, ix_list = [_i32(a) for a in symbols], [_i32(a) for a in indexes]
     else:
@@ -105,9 +116,10 @@ def encode_batch(symbols, indexes, tables, threads=None):
         ip = (C.c_void_p * count)(*[r.ctypes.data for r in rows_i])
         op = (C.c_void_p * count)(*[o.ctypes.data for o in outs])
         lens = np.zeros(count, dtype=np.int64)
-        rc = lib.hyres_rans_encode_batch(count, sp, ip, ns.ctypes.data, t.cdf.ctypes.data, t.cdf.shape[0],
-                                         t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data, op,
-                                         caps.ctypes.data, lens.ctypes.data, _threads(threads or count))
+        fn = lib.hyres_rans_encode_slots_batch if slots else lib.hyres_rans_encode_batch
+        rc = fn(count, sp, ip, ns.ctypes.data, t.cdf.ctypes.data, t.cdf.shape[0],
+                t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data, op,
+                caps.ctypes.data, lens.ctypes.data, _threads(threads or count))
         if rc != 0 and (lens > caps).any():
             caps = np.maximum(caps, lens)
             continue
@@ -115,8 +127,10 @@ def encode_batch(symbols, indexes, tables, threads=None):
         return [outs[i][: lens[i]].tobytes() for i in range(count)]
 
 
-def decode_batch(strings, indexes, tables, threads=None, out=None):
-    """strings: list of bytes; indexes int32 [count, n] -> int32 [count, n] (``out``: preallocated result)."""
+def decode_batch(strings, indexes, tables, threads=None, out=None, codes=False):
+    """strings: list of bytes; indexes int32 [count, n] -> int32 [count, n] (``out``: preallocated result).
+    ``codes=True``: ``indexes`` holds decoder codes (hyres_rans_decode_codes_batch): entries of known symbols only
+    advance the coder and leave ``out`` untouched there."""
     ix = _i32(indexes)
     count, n = ix.shape
     if len(strings) != count:
@@ -134,7 +148,7 @@ def decode_batch(strings, indexes, tables, threads=None, out=None):
     lens = np.array([b.size for b in bufs], dtype=np.int64)
     ns = np.full(count, n, dtype=np.int64)
     t = tables
-    L.check(L.lib().hyres_rans_decode_batch(count, bp, lens.ctypes.data, ip, ns.ctypes.data, t.cdf.ctypes.data,
-                                            t.cdf.shape[0], t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data,
-                                            op, _threads(threads or count)), "hyres_rans_decode_batch")
+    fn = L.lib().hyres_rans_decode_codes_batch if codes else L.lib().hyres_rans_decode_batch
+    L.check(fn(count, bp, lens.ctypes.data, ip, ns.ctypes.data, t.cdf.ctypes.data, t.cdf.shape[0], t.cdf.shape[1],
+               t.sizes.ctypes.data, t.offsets.ctypes.data, op, _threads(threads or count)), "hyres_rans_decode_batch")
     return out

@@ -169,13 +169,24 @@ __global__ void gc_merge_likelihood_kernel(const float* __restrict__ y, const fl
 // ---------------------------------------------------------------------------
 // symbols / indexes (compress) -- integer outputs in (B,M,h,w) order
 // ---------------------------------------------------------------------------
+// `rows` (optional): the host coder's packed-table layout [3][n_scales] = first entry, offset, escape bin of every CDF
+// row (hyres_rans_table_layout).  With it the kernel also writes, in the indexes' order,
+//   encoder (y given):  `slots`  -- base + (symbol - offset) for a value inside the table, -(row + 1) otherwise;
+//   decoder (y == NULL): `slots` holds CODES -- at the structurally zero positions of pass `pass` the symbol is
+//     round(-mean), known without decoding: bit 30 | packed entry when it is inside the table; the plain row index
+//     at every other position.
 __global__ void gc_symbols_kernel(const float* __restrict__ y, const float* __restrict__ params, int pass,
                                   const float* __restrict__ table, int n_scales, float scale_bound,
                                   int32_t* __restrict__ symbols, int32_t* __restrict__ indexes,
                                   float* __restrict__ yq_f32, __nv_bfloat16* __restrict__ yq_bf16, int h, int w,
-                                  int M) {
-  extern __shared__ int32_t itile[];  // [2][kPix][M+1]
+                                  int M, const int32_t* __restrict__ rows, int32_t* __restrict__ slots) {
+  extern __shared__ int32_t itile[];  // [2 or 3][kPix][M+1]
   __shared__ float s_table[64];
+  __shared__ int32_t s_rows[3 * 64];
+  if (rows && threadIdx.x < 3 * 64) {
+    const int k = threadIdx.x / 64, r = threadIdx.x - k * 64;
+    s_rows[threadIdx.x] = r < n_scales ? rows[k * n_scales + r] : 0;
+  }
   const int hw = h * w;
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * kPix;
@@ -183,6 +194,7 @@ __global__ void gc_symbols_kernel(const float* __restrict__ y, const float* __re
   const int ld = M + 1;
   int32_t* t_sym = itile;
   int32_t* t_idx = itile + kPix * ld;
+  int32_t* t_slot = itile + 2 * kPix * ld;  // only there (and only touched) when `slots` is given
   if (threadIdx.x < 64) s_table[threadIdx.x] = threadIdx.x < n_scales ? table[threadIdx.x] : 3.4e38f;
   __syncthreads();
   for (int t = threadIdx.x; t < np * M; t += kThreads) {
@@ -196,8 +208,18 @@ __global__ void gc_symbols_kernel(const float* __restrict__ y, const float* __re
     const float sc = __ldg(params + pix * 2 * M + c);
     const float mu = __ldg(params + pix * 2 * M + M + c);
     const float q = rintf(yv - mu);
-    t_sym[px * ld + c] = static_cast<int32_t>(q);
-    t_idx[px * ld + c] = scale_index(sc, scale_bound, s_table, n_scales);
+    const int32_t sym = static_cast<int32_t>(q);
+    const int32_t ci = scale_index(sc, scale_bound, s_table, n_scales);
+    if (slots) {
+      const int32_t value = sym - s_rows[64 + ci];
+      const bool inside = value >= 0 && value < s_rows[128 + ci];
+      int32_t sl;
+      if (y != nullptr) sl = inside ? s_rows[ci] + value : -(ci + 1);
+      else sl = ((pass == 0) != is_anchor(i, j) && inside) ? ((1 << 30) | (s_rows[ci] + value)) : ci;
+      t_slot[px * ld + c] = sl;
+    }
+    t_sym[px * ld + c] = sym;
+    t_idx[px * ld + c] = ci;
     const float deq = q + mu;  // dequantize: float(symbol) + mean
     if (yq_f32) yq_f32[e] = deq;
     if (yq_bf16) yq_bf16[e] = __float2bfloat16_rn(deq);
@@ -208,12 +230,16 @@ __global__ void gc_symbols_kernel(const float* __restrict__ y, const float* __re
     const int64_t o = (static_cast<int64_t>(b) * M + c) * hw + p0 + px;
     if (symbols) symbols[o] = t_sym[px * ld + c];
     if (indexes) indexes[o] = t_idx[px * ld + c];
+    if (slots) slots[o] = t_slot[px * ld + c];
   }
 }
 
 // decoder: yq = float(symbol) + mean, symbols in (B,M,h,w) order -> NHWC
+// pass >= 0: the symbols at the structurally zero positions of that checkerboard pass are not read (the decoder
+// does not produce them, hyres_gc_codes): they are round(-mean) by construction (models/checkerboard.py:106-110, Q1).
 __global__ void gc_dequant_kernel(const int32_t* __restrict__ symbols, const float* __restrict__ params,
-                                  float* __restrict__ yq_f32, __nv_bfloat16* __restrict__ yq_bf16, int hw, int M) {
+                                  float* __restrict__ yq_f32, __nv_bfloat16* __restrict__ yq_bf16, int hw, int M,
+                                  int pass, int w) {
   extern __shared__ int32_t itile[];  // [kPix][M+1]
   const int b = blockIdx.y;
   const int p0 = blockIdx.x * kPix;
@@ -228,7 +254,14 @@ __global__ void gc_dequant_kernel(const int32_t* __restrict__ symbols, const flo
     const int px = t / M, c = t - px * M;
     const int64_t pix = static_cast<int64_t>(b) * hw + p0 + px;
     const int64_t e = pix * M + c;
-    const float deq = static_cast<float>(itile[px * ld + c]) + __ldg(params + pix * 2 * M + M + c);
+    const float mu = __ldg(params + pix * 2 * M + M + c);
+    float q = static_cast<float>(itile[px * ld + c]);
+    if (pass >= 0) {
+      const int p = p0 + px;
+      const int i = p / w, j = p - i * w;
+      if ((pass == 0) != is_anchor(i, j)) q = rintf(0.f - mu);
+    }
+    const float deq = q + mu;
     if (yq_f32) yq_f32[e] = deq;
     if (yq_bf16) yq_bf16[e] = __float2bfloat16_rn(deq);
   }
@@ -393,17 +426,36 @@ int hyres_gc_merge_likelihood(const float* y, const float* params_a, const float
 
 int hyres_gc_symbols(const float* y, const float* params, int pass, const float* scale_table, int n_scales,
                      float scale_bound, int32_t* symbols, int32_t* indexes, float* yq_f32, void* yq_bf16, int B,
-                     int h, int w, int M, void* stream_v) {
+                     int h, int w, int M, const int32_t* coder_rows, int32_t* slots, void* stream_v) {
   if (!y || !params || !scale_table || n_scales < 2 || n_scales > 64 || B <= 0 || h <= 0 || w <= 0 || M <= 0)
     return hy_fail(HYRES_ERR_ARG, "gc_symbols: bad argument");
-  const int smem = 2 * kPix * (M + 1) * 4;
+  if ((slots != nullptr) != (coder_rows != nullptr)) return hy_fail(HYRES_ERR_ARG, "gc_symbols: slots and coder_rows go together");
+  const int smem = (slots ? 3 : 2) * kPix * (M + 1) * 4;
   int rc = set_smem(reinterpret_cast<const void*>(gc_symbols_kernel), smem);
   if (rc) return rc;
   dim3 grid((h * w + kPix - 1) / kPix, B);
   hy_count_launch();
   gc_symbols_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
       y, params, pass, scale_table, n_scales, scale_bound, symbols, indexes, yq_f32,
-      static_cast<__nv_bfloat16*>(yq_bf16), h, w, M);
+      static_cast<__nv_bfloat16*>(yq_bf16), h, w, M, coder_rows, slots);
+  HY_CUDA(cudaGetLastError());
+  return HYRES_OK;
+}
+
+int hyres_gc_codes(const float* params, int pass, const float* scale_table, int n_scales, float scale_bound,
+                   const int32_t* coder_rows, int32_t* indexes, int32_t* codes, int B, int h, int w, int M,
+                   void* stream_v) {
+  if (!params || !scale_table || !coder_rows || !codes || n_scales < 2 || n_scales > 64 || B <= 0 || h <= 0 || w <= 0 ||
+      M <= 0 || (pass != 0 && pass != 1))
+    return hy_fail(HYRES_ERR_ARG, "gc_codes: bad argument");
+  const int smem = 3 * kPix * (M + 1) * 4;
+  int rc = set_smem(reinterpret_cast<const void*>(gc_symbols_kernel), smem);
+  if (rc) return rc;
+  dim3 grid((h * w + kPix - 1) / kPix, B);
+  hy_count_launch();
+  gc_symbols_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
+      nullptr, params, pass, scale_table, n_scales, scale_bound, nullptr, indexes, nullptr, nullptr, h, w, M, coder_rows,
+      codes);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }
@@ -418,13 +470,14 @@ int hyres_gc_indexes(const float* params, const float* scale_table, int n_scales
   dim3 grid((h * w + kPix - 1) / kPix, B);
   hy_count_launch();
   gc_symbols_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
-      nullptr, params, 0, scale_table, n_scales, scale_bound, nullptr, indexes, nullptr, nullptr, h, w, M);
+      nullptr, params, 0, scale_table, n_scales, scale_bound, nullptr, indexes, nullptr, nullptr, h, w, M, nullptr,
+      nullptr);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }
 
 int hyres_gc_dequant(const int32_t* symbols, const float* params, float* yq_f32, void* yq_bf16, int B, int h,
-                     int w, int M, void* stream_v) {
+                     int w, int M, int pass, void* stream_v) {
   if (!symbols || !params || B <= 0 || h <= 0 || w <= 0 || M <= 0)
     return hy_fail(HYRES_ERR_ARG, "gc_dequant: bad argument");
   const int smem = kPix * (M + 1) * 4;
@@ -433,7 +486,7 @@ int hyres_gc_dequant(const int32_t* symbols, const float* params, float* yq_f32,
   dim3 grid((h * w + kPix - 1) / kPix, B);
   hy_count_launch();
   gc_dequant_kernel<<<grid, kThreads, smem, static_cast<cudaStream_t>(stream_v)>>>(
-      symbols, params, yq_f32, static_cast<__nv_bfloat16*>(yq_bf16), h * w, M);
+      symbols, params, yq_f32, static_cast<__nv_bfloat16*>(yq_bf16), h * w, M, pass, w);
   HY_CUDA(cudaGetLastError());
   return HYRES_OK;
 }

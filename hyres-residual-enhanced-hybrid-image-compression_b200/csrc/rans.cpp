@@ -228,8 +228,16 @@ inline void enc_escape(uint64_t& x, WordSink& sink, uint32_t raw) {
   for (int32_t k = 0; k < full; ++k) enc_put_bits(x, sink.p, kMaxBypass, kBypassBits);
 }
 
+// Device-side front-end (hyres_gc_symbols with coder rows): instead of a CDF row index the coder receives, per
+// symbol, a SLOT -- slot >= 0: the entry row.base + value of the packed tables (the value is inside the table);
+// slot < 0: row index -(slot + 1) of a value outside it, coded through the escape path from symbols[i].  The
+// decoder's CODES: bit 30 set = the symbol is known to the caller (a structurally zero position of the checkerboard
+// pass: round(-mean)), low bits = its packed entry, only the range-coder state is advanced and nothing is written;
+// otherwise a plain row index.
+constexpr int32_t kKnownBit = 1 << 30;
+
 // NS strings of n symbols each, coded in lock step
-template <int NS>
+template <int NS, bool kSlots = false>
 int encode_n(const int32_t* const* symbols, const int32_t* const* indexes, int64_t n, const Prepared& T,
              std::vector<uint8_t>* const* out_bytes) {
   WordSink* sinks[NS];
@@ -243,6 +251,7 @@ int encode_n(const int32_t* const* symbols, const int32_t* const* indexes, int64
   const int n_cdfs = T.n_cdfs;
   const RowInfo* rows = T.rows.data();
   const EncSym* enc = T.enc.data();
+  const uint32_t n_entries = static_cast<uint32_t>(T.enc.size());
   constexpr int64_t kBlock = 256;  // symbols between two capacity checks (one word per symbol at most + escapes)
   for (int64_t hi = n; hi > 0; hi -= kBlock) {
     const int64_t lo = std::max<int64_t>(hi - kBlock, 0);
@@ -251,18 +260,26 @@ int encode_n(const int32_t* const* symbols, const int32_t* const* indexes, int64
       int bad = 0;
       unrolled<NS>([&](auto kc) __attribute__((always_inline)) {
         constexpr int k = decltype(kc)::value;
-        const int32_t ci = indexes[k][i];
-        if (static_cast<uint32_t>(ci) >= static_cast<uint32_t>(n_cdfs)) { bad = 1; return; }
-        const RowInfo ri = rows[ci];
-        if (!ri.enc_ok) { bad = 1; return; }
-        int32_t value = symbols[k][i] - ri.offset;
-        if (static_cast<uint32_t>(value) >= static_cast<uint32_t>(ri.last_bin)) {  // negative, or at / beyond the escape bin
-          const uint32_t raw = value < 0 ? static_cast<uint32_t>(-2 * value - 1) : static_cast<uint32_t>(2 * (value - ri.last_bin));
-          enc_escape(x[k], *sinks[k], raw);
-          value = ri.last_bin;
-          sinks[k]->room(kBlock + 64);
+        int32_t ci = indexes[k][i];
+        uint32_t entry;
+        if (kSlots && ci >= 0) {  // in-table value: the packed entry itself
+          entry = static_cast<uint32_t>(ci);
+          if (entry >= n_entries) { bad = 1; return; }
+        } else {
+          if (kSlots) ci = -(ci + 1);
+          if (static_cast<uint32_t>(ci) >= static_cast<uint32_t>(n_cdfs)) { bad = 1; return; }
+          const RowInfo ri = rows[ci];
+          if (!ri.enc_ok) { bad = 1; return; }
+          int32_t value = symbols[k][i] - ri.offset;
+          if (static_cast<uint32_t>(value) >= static_cast<uint32_t>(ri.last_bin)) {  // negative, or at / beyond the escape bin
+            const uint32_t raw = value < 0 ? static_cast<uint32_t>(-2 * value - 1) : static_cast<uint32_t>(2 * (value - ri.last_bin));
+            enc_escape(x[k], *sinks[k], raw);
+            value = ri.last_bin;
+            sinks[k]->room(kBlock + 64);
+          }
+          entry = ri.base + static_cast<uint32_t>(value);
         }
-        const EncSym e = enc[ri.base + value];
+        const EncSym e = enc[entry];
         if (!e.valid) { bad = 1; return; }
         const uint32_t freq = static_cast<uint32_t>(e.freq_m1) + 1u;
         enc_renorm(x[k], sinks[k]->p, static_cast<uint64_t>(freq) << 47);  // ((L >> 16) << 32) * freq
@@ -339,7 +356,7 @@ inline int dec_escape(uint64_t& x, WordSource& src, int32_t max_value, int32_t& 
   return HYRES_OK;
 }
 
-template <int NS>
+template <int NS, bool kCodes = false>
 int decode_n(const uint8_t* const* in, const int64_t* in_len, const int32_t* const* indexes, int64_t n,
              const Prepared& T, int32_t* const* out) {
   WordSource src[NS];
@@ -357,11 +374,20 @@ int decode_n(const uint8_t* const* in, const int64_t* in_len, const int32_t* con
   const RowInfo* rows = T.rows.data();
   const uint32_t* sf = T.sf.data();
   const uint16_t* lut = T.lut.data();
+  const uint32_t n_entries = static_cast<uint32_t>(T.sf.size());
   for (int64_t i = 0; i < n; ++i) {
     int bad = 0;
     unrolled<NS>([&](auto kc) __attribute__((always_inline)) {
       constexpr int k = decltype(kc)::value;
       const int32_t ci = indexes[k][i];
+      if (kCodes && (ci & kKnownBit)) {  // known symbol: advance the state by its (start, frequency), nothing to find
+        const uint32_t entry = static_cast<uint32_t>(ci & (kKnownBit - 1));
+        if (entry >= n_entries) { bad = 1; return; }
+        const uint32_t e = sf[entry];
+        x[k] = static_cast<uint64_t>((e >> 16) + 1) * (x[k] >> kPrecision) + (x[k] & ((1u << kPrecision) - 1)) - (e & 0xffffu);
+        dec_renorm(x[k], src[k]);
+        return;
+      }
       if (static_cast<uint32_t>(ci) >= static_cast<uint32_t>(n_cdfs)) { bad = 1; return; }
       const RowInfo ri = rows[ci];
       if (!ri.dec_ok) { bad = 1; return; }
@@ -384,10 +410,12 @@ int decode_n(const uint8_t* const* in, const int64_t* in_len, const int32_t* con
   return HYRES_OK;
 }
 
+inline int host_cores();
+
 template <typename F>
 int run_pool(int count, int threads, F&& job) {
   if (count <= 0) return HYRES_OK;
-  int nt = std::max(1, std::min(threads > 0 ? threads : static_cast<int>(std::thread::hardware_concurrency()), count));
+  int nt = std::max(1, std::min(std::min(threads > 0 ? threads : host_cores(), host_cores()), count));
   std::atomic<int> next{0};
   std::atomic<int> status{HYRES_OK};
   auto worker = [&]() {
@@ -423,9 +451,22 @@ struct ActiveStrings {
   explicit ActiveStrings(int k) : n(k) { g_active_strings.fetch_add(n); }
   ~ActiveStrings() { g_active_strings.fetch_sub(n); }
 };
-inline int dec_group_for(int count) {
-  const int hw = std::max(1u, std::thread::hardware_concurrency());
-  return g_active_strings.load() + count > hw ? 2 : 1;
+// Host cores this process may count on: all of them, divided by the number of processes torchrun started on this
+// node (one per GPU share the box's cores); HYRES_HOST_CORES overrides.
+inline int host_cores() {
+  static const int n = [] {
+    if (const char* e = getenv("HYRES_HOST_CORES")) return std::max(1, atoi(e));
+    int hw = static_cast<int>(std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) hw = std::max(1, hw / std::max(1, atoi(e)));
+    return hw;
+  }();
+  return n;
+}
+// lock-step group size for a batch of `count` strings: 1 while the cores are free, 2 when oversubscribed, 4 when
+// oversubscribed four times over (fewer, longer jobs: 12.7 / 6.9 / 5.9 ns per decoded symbol and core)
+inline int group_for(int count) {
+  const int load = g_active_strings.load() + count, hw = host_cores();
+  return load > 4 * hw ? 4 : load > hw ? 2 : 1;
 }
 struct Job { int id[kMaxGroup]; int count; };
 std::vector<Job> make_jobs(int count, const int64_t* n, int dflt) {
@@ -445,17 +486,17 @@ std::vector<Job> make_jobs(int count, const int64_t* n, int dflt) {
   return jobs;
 }
 
-template <int NS>
+template <int NS, bool kSlots>
 int encode_group(const Job& j, const int32_t* const* symbols, const int32_t* const* indexes, int64_t n, const Prepared& T,
                  std::vector<uint8_t>* bytes) {
   const int32_t* sy[NS];
   const int32_t* ix[NS];
   std::vector<uint8_t>* o[NS];
   for (int k = 0; k < NS; ++k) { sy[k] = symbols[j.id[k]]; ix[k] = indexes[j.id[k]]; o[k] = &bytes[k]; }
-  return encode_n<NS>(sy, ix, n, T, o);
+  return encode_n<NS, kSlots>(sy, ix, n, T, o);
 }
 
-template <int NS>
+template <int NS, bool kCodes>
 int decode_group(const Job& j, const uint8_t* const* in, const int64_t* in_len, const int32_t* const* indexes, int64_t n,
                  const Prepared& T, int32_t* const* out) {
   const uint8_t* ins[NS];
@@ -463,7 +504,65 @@ int decode_group(const Job& j, const uint8_t* const* in, const int64_t* in_len, 
   const int32_t* ix[NS];
   int32_t* o[NS];
   for (int k = 0; k < NS; ++k) { ins[k] = in[j.id[k]]; lens[k] = in_len[j.id[k]]; ix[k] = indexes[j.id[k]]; o[k] = out[j.id[k]]; }
-  return decode_n<NS>(ins, lens, ix, n, T, o);
+  return decode_n<NS, kCodes>(ins, lens, ix, n, T, o);
+}
+
+}  // namespace
+
+namespace {
+
+template <bool kSlots>
+int encode_batch_impl(int count, const int32_t* const* symbols, const int32_t* const* indexes, const int64_t* n,
+                      const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                      uint8_t* const* out, const int64_t* out_cap, int64_t* out_len, int threads) {
+  if (count < 0 || (count > 0 && (!symbols || !indexes || !n || !out || !out_cap || !out_len)))
+    return hy_fail(HYRES_ERR_ARG, "rans_encode_batch: bad argument");
+  if (count == 0) return HYRES_OK;
+  if (n_cdfs <= 0 || cdf_stride <= 0 || !cdfs || !cdf_sizes || !offsets)
+    return hy_fail(HYRES_ERR_ARG, "rans_encode_batch: bad tables");
+  const auto T = prepare(cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets);
+  const auto jobs = make_jobs(count, n, group_for(count));  // fewer threads when the cores are oversubscribed
+  const ActiveStrings active(count);
+  const int rc = run_pool(static_cast<int>(jobs.size()), threads, [&](int ji) {
+    const Job& j = jobs[ji];
+    std::vector<uint8_t> bytes[kMaxGroup];
+    const int64_t len = n[j.id[0]];
+    int r = j.count == 4   ? encode_group<4, kSlots>(j, symbols, indexes, len, *T, bytes)
+            : j.count == 2 ? encode_group<2, kSlots>(j, symbols, indexes, len, *T, bytes)
+                           : encode_group<1, kSlots>(j, symbols, indexes, len, *T, bytes);
+    if (r != HYRES_OK) return r;
+    for (int k = 0; k < j.count; ++k) {
+      const int i = j.id[k];
+      out_len[i] = static_cast<int64_t>(bytes[k].size());
+      if (out_cap[i] < out_len[i]) { r = HYRES_ERR_ARG; continue; }
+      std::memcpy(out[i], bytes[k].data(), bytes[k].size());
+    }
+    return r;
+  });
+  if (rc != HYRES_OK) return hy_fail(rc, "rans_encode_batch: a string failed (bad tables or buffer too small)");
+  return HYRES_OK;
+}
+
+template <bool kCodes>
+int decode_batch_impl(int count, const uint8_t* const* in, const int64_t* in_len, const int32_t* const* indexes,
+                      const int64_t* n, const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                      const int32_t* offsets, int32_t* const* symbols_out, int threads) {
+  if (count < 0 || (count > 0 && (!in || !in_len || !indexes || !n || !symbols_out)))
+    return hy_fail(HYRES_ERR_ARG, "rans_decode_batch: bad argument");
+  if (n_cdfs <= 0 || cdf_stride <= 0 || !cdfs || !cdf_sizes || !offsets) return hy_fail(HYRES_ERR_ARG, "rans_decode_batch: bad tables");
+  if (count == 0) return HYRES_OK;
+  const auto T = prepare(cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets);
+  const auto jobs = make_jobs(count, n, group_for(count));
+  const ActiveStrings active(count);
+  const int rc = run_pool(static_cast<int>(jobs.size()), threads, [&](int ji) {
+    const Job& j = jobs[ji];
+    const int64_t len = n[j.id[0]];
+    return j.count == 4   ? decode_group<4, kCodes>(j, in, in_len, indexes, len, *T, symbols_out)
+           : j.count == 2 ? decode_group<2, kCodes>(j, in, in_len, indexes, len, *T, symbols_out)
+                          : decode_group<1, kCodes>(j, in, in_len, indexes, len, *T, symbols_out);
+  });
+  if (rc != HYRES_OK) return hy_fail(rc, "rans_decode_batch: a string failed");
+  return HYRES_OK;
 }
 
 }  // namespace
@@ -539,53 +638,46 @@ int hyres_rans_encode_batch(int count, const int32_t* const* symbols, const int3
                             const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
                             const int32_t* offsets, uint8_t* const* out, const int64_t* out_cap, int64_t* out_len,
                             int threads) {
-  if (count < 0 || (count > 0 && (!symbols || !indexes || !n || !out || !out_cap || !out_len)))
-    return hy_fail(HYRES_ERR_ARG, "rans_encode_batch: bad argument");
-  if (count == 0) return HYRES_OK;
-  if (n_cdfs <= 0 || cdf_stride <= 0 || !cdfs || !cdf_sizes || !offsets)
-    return hy_fail(HYRES_ERR_ARG, "rans_encode_batch: bad tables");
-  const auto T = prepare(cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets);
-  const auto jobs = make_jobs(count, n, dec_group_for(count));  // same policy: halves the threads when crowded
-  const ActiveStrings active(count);
-  const int rc = run_pool(static_cast<int>(jobs.size()), threads, [&](int ji) {
-    const Job& j = jobs[ji];
-    std::vector<uint8_t> bytes[kMaxGroup];
-    const int64_t len = n[j.id[0]];
-    int r = j.count == 4   ? encode_group<4>(j, symbols, indexes, len, *T, bytes)
-            : j.count == 2 ? encode_group<2>(j, symbols, indexes, len, *T, bytes)
-                           : encode_group<1>(j, symbols, indexes, len, *T, bytes);
-    if (r != HYRES_OK) return r;
-    for (int k = 0; k < j.count; ++k) {
-      const int i = j.id[k];
-      out_len[i] = static_cast<int64_t>(bytes[k].size());
-      if (out_cap[i] < out_len[i]) { r = HYRES_ERR_ARG; continue; }
-      std::memcpy(out[i], bytes[k].data(), bytes[k].size());
-    }
-    return r;
-  });
-  if (rc != HYRES_OK) return hy_fail(rc, "rans_encode_batch: a string failed (bad tables or buffer too small)");
-  return HYRES_OK;
+  return encode_batch_impl<false>(count, symbols, indexes, n, cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets, out, out_cap,
+                                  out_len, threads);
+}
+
+int hyres_rans_encode_slots_batch(int count, const int32_t* const* symbols, const int32_t* const* slots, const int64_t* n,
+                                  const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                                  const int32_t* offsets, uint8_t* const* out, const int64_t* out_cap, int64_t* out_len,
+                                  int threads) {
+  return encode_batch_impl<true>(count, symbols, slots, n, cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets, out, out_cap,
+                                 out_len, threads);
 }
 
 int hyres_rans_decode_batch(int count, const uint8_t* const* in, const int64_t* in_len, const int32_t* const* indexes,
                             const int64_t* n, const int32_t* cdfs, int n_cdfs, int cdf_stride,
                             const int32_t* cdf_sizes, const int32_t* offsets, int32_t* const* symbols_out,
                             int threads) {
-  if (count < 0 || (count > 0 && (!in || !in_len || !indexes || !n || !symbols_out)))
-    return hy_fail(HYRES_ERR_ARG, "rans_decode_batch: bad argument");
-  if (n_cdfs <= 0 || cdf_stride <= 0 || !cdfs || !cdf_sizes || !offsets) return hy_fail(HYRES_ERR_ARG, "rans_decode_batch: bad tables");
-  if (count == 0) return HYRES_OK;
+  return decode_batch_impl<false>(count, in, in_len, indexes, n, cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets, symbols_out,
+                                  threads);
+}
+
+int hyres_rans_decode_codes_batch(int count, const uint8_t* const* in, const int64_t* in_len, const int32_t* const* codes,
+                                  const int64_t* n, const int32_t* cdfs, int n_cdfs, int cdf_stride,
+                                  const int32_t* cdf_sizes, const int32_t* offsets, int32_t* const* symbols_out,
+                                  int threads) {
+  return decode_batch_impl<true>(count, in, in_len, codes, n, cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets, symbols_out,
+                                 threads);
+}
+
+int hyres_rans_table_layout(const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                            const int32_t* offsets, int32_t* rows_out) {
+  if (!cdfs || !cdf_sizes || !offsets || !rows_out || n_cdfs <= 0 || cdf_stride <= 0)
+    return hy_fail(HYRES_ERR_ARG, "rans_table_layout: bad argument");
   const auto T = prepare(cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets);
-  const auto jobs = make_jobs(count, n, dec_group_for(count));
-  const ActiveStrings active(count);
-  const int rc = run_pool(static_cast<int>(jobs.size()), threads, [&](int ji) {
-    const Job& j = jobs[ji];
-    const int64_t len = n[j.id[0]];
-    return j.count == 4   ? decode_group<4>(j, in, in_len, indexes, len, *T, symbols_out)
-           : j.count == 2 ? decode_group<2>(j, in, in_len, indexes, len, *T, symbols_out)
-                          : decode_group<1>(j, in, in_len, indexes, len, *T, symbols_out);
-  });
-  if (rc != HYRES_OK) return hy_fail(rc, "rans_decode_batch: a string failed");
+  for (int r = 0; r < n_cdfs; ++r) {
+    const RowInfo& ri = T->rows[r];
+    const bool ok = ri.enc_ok && ri.dec_ok;
+    rows_out[r] = static_cast<int32_t>(ri.base);
+    rows_out[n_cdfs + r] = ri.offset;
+    rows_out[2 * n_cdfs + r] = ok ? ri.last_bin : 0;  // 0: no in-table value, every symbol takes the plain path
+  }
   return HYRES_OK;
 }
 

@@ -89,6 +89,17 @@ class EntropyModel(nn.Module):
             self._tables_cache = (key, t)
         return self._tables_cache[1]
 
+    def coder_rows(self, device):
+        """int32 [3, n_cdfs] on ``device``: the host coder's packed-table layout (``coder.table_layout``), what the
+        device front-end needs to emit coder slots / codes (cached with the tables)."""
+        t = self.tables()
+        cache = getattr(self, "_rows_cache", None)
+        key = (id(t), str(device))
+        if cache is None or cache[0] != key:
+            rows = torch.from_numpy(coder.table_layout(t)).to(device)
+            self._rows_cache = cache = (key, rows)
+        return cache[1]
+
     # -- coding of already-quantised symbols --
     _tls = threading.local()  # pinned staging buffers are per thread: CodecPipeline runs one batch per worker thread
 
@@ -118,10 +129,11 @@ class EntropyModel(nn.Module):
         """symbols / indexes: int32 tensors [B, ...] (any device) -> list of B byte strings."""
         return self.encode_symbol_groups([(symbols, indexes)])[0]
 
-    def encode_symbol_groups(self, groups):
+    def encode_symbol_groups(self, groups, slots=False):
         """groups: list of (symbols, indexes) pairs of equal shape -> list (per group) of lists of B byte strings.
         All strings of all groups are coded in ONE batch, so e.g. the anchor and non-anchor passes of a batch of
-        8 tiles keep 16 host threads busy instead of 8 twice."""
+        8 tiles keep 16 host threads busy instead of 8 twice.  ``slots=True``: the second tensor of every pair holds
+        coder slots from the device front-end (``ops.gc_symbols(..., rows=...)``) instead of CDF indexes; same bytes."""
         syms, idxs = [], []
         for g, (symbols, indexes) in enumerate(groups):
             if symbols.dim() < 2:
@@ -130,7 +142,7 @@ class EntropyModel(nn.Module):
                 raise ValueError("`inputs` and `indexes` should have the same size.")
             syms.append(self._host_i32(symbols, ("s", g)))
             idxs.append(self._host_i32(indexes, ("i", g)))
-        out = coder.encode_batch(syms, idxs, self.tables())
+        out = coder.encode_batch(syms, idxs, self.tables(), slots=slots)
         res, k = [], 0
         for a in syms:
             res.append(out[k:k + a.shape[0]])
@@ -148,10 +160,12 @@ class EntropyModel(nn.Module):
             buf = pinned[key] = torch.empty(n, dtype=torch.int32).pin_memory()
         return buf
 
-    def decode_symbols(self, strings, indexes, slot=None):
+    def decode_symbols(self, strings, indexes, slot=None, codes=False):
         """-> int32 CPU tensor shaped like ``indexes`` (pinned when the indexes came from the GPU).  ``slot``: decode
         into this thread's cached pinned buffer of that name instead of a fresh allocation (pinning 35 MB per pass
-        costs milliseconds); the result is then only valid until the same thread decodes into the slot again."""
+        costs milliseconds); the result is then only valid until the same thread decodes into the slot again.
+        ``codes=True``: ``indexes`` holds decoder codes (``ops.gc_codes``); the entries of known symbols are then
+        unspecified in the result (``ops.gc_dequant(..., pass_id)`` does not read them)."""
         if not isinstance(strings, (tuple, list)):
             raise ValueError("Invalid `strings` parameter type.")
         if len(strings) != indexes.size(0):
@@ -161,9 +175,10 @@ class EntropyModel(nn.Module):
         ix = self._host_i32(indexes, ("d", 0))
         if slot is not None and indexes.is_cuda:
             buf = self._pinned_i32(("o", slot), ix.size)
-            coder.decode_batch(list(strings), ix, self.tables(), out=buf.numpy().reshape(ix.shape))
+            coder.decode_batch(list(strings), ix, self.tables(), out=buf.numpy().reshape(ix.shape), codes=codes)
             return buf.view(indexes.shape)
-        out = coder.decode_batch(list(strings), ix, self.tables())
+        out = coder.decode_batch(list(strings), ix, self.tables(), codes=codes,
+                                 out=np.zeros(ix.shape, dtype=np.int32) if codes else None)
         res = torch.from_numpy(out).reshape(indexes.shape)
         return res.pin_memory() if indexes.is_cuda else res
 

@@ -267,12 +267,14 @@ class LightWeightCheckerboard(CompressionModel):
             zhat32, _ = ops.split_f32(z32, mode=ops.SPLIT_ROUND_CHAN, chan=med, want_f32=True, want_split=False)
             latent = pt.h_s(zhat32)
             pa = pt.head(latent)
-            sym_a, idx_a, yqa32, _ = ops.gc_symbols(y.f32, pa, 0, table, bound, want_bf16=False)
+            rows = self.gaussian_conditional.coder_rows(x.device)
+            sym_a, idx_a, yqa32, _, slot_a = ops.gc_symbols(y.f32, pa, 0, table, bound, want_bf16=False, rows=rows)
             ctx = pt.context(yqa32)
             pna = pt.head(latent, ctx)
-            sym_na, idx_na, _, _ = ops.gc_symbols(y.f32, pna, 1, table, bound, want_f32=False, want_bf16=False)
+            sym_na, idx_na, _, _, slot_na = ops.gc_symbols(y.f32, pna, 1, table, bound, want_f32=False, want_bf16=False,
+                                                           rows=rows)
             out = {"sym_z": eb["symbols"], "sym_a": sym_a, "idx_a": idx_a, "sym_na": sym_na, "idx_na": idx_na,
-                   "y": y.f32, "z": z32, "params_a": pa, "params_na": pna}
+                   "slot_a": slot_a, "slot_na": slot_na, "y": y.f32, "z": z32, "params_a": pa, "params_na": pna}
             if self.codec_precision == "fp32h2":
                 # half parts overflow at |activation| >= 65 520: that shows as NaN in y or in the second-pass
                 # parameters (every layer of the trunk feeds one of the two); compress() refuses such a result
@@ -284,12 +286,14 @@ class LightWeightCheckerboard(CompressionModel):
         eb = ops.eb_forward(z32, ebp, med, want_lik=False, want_symbols=True)
         latent = eng.h_s(eb["zhat_bf16"])
         pa = eng.head(latent)
-        sym_a, idx_a, _, yqa16 = ops.gc_symbols(y32, pa, 0, table, bound, want_f32=False)
+        rows = self.gaussian_conditional.coder_rows(x.device)
+        sym_a, idx_a, _, yqa16, slot_a = ops.gc_symbols(y32, pa, 0, table, bound, want_f32=False, rows=rows)
         ctx = eng.context(yqa16)
         pna = eng.head(latent, ctx)
-        sym_na, idx_na, _, _ = ops.gc_symbols(y32, pna, 1, table, bound, want_f32=False, want_bf16=False)
+        sym_na, idx_na, _, _, slot_na = ops.gc_symbols(y32, pna, 1, table, bound, want_f32=False, want_bf16=False,
+                                                       rows=rows)
         return {"sym_z": eb["symbols"], "sym_a": sym_a, "idx_a": idx_a, "sym_na": sym_na, "idx_na": idx_na,
-                "y": y32, "z": z32, "params_a": pa, "params_na": pna}
+                "slot_a": slot_a, "slot_na": slot_na, "y": y32, "z": z32, "params_a": pa, "params_na": pna}
 
     # -- compress (models/checkerboard.py:167-198) --
     def compress(self, x, _jpeg=None):
@@ -298,8 +302,10 @@ class LightWeightCheckerboard(CompressionModel):
         _check_finite(s)
         gc, ebm = self.gaussian_conditional, self.entropy_bottleneck
         z_strings = ebm.encode_symbols(s["sym_z"], ebm._build_indexes(s["sym_z"].size()))
-        anchor_strings, non_anchor_strings = gc.encode_symbol_groups([(s["sym_a"], s["idx_a"]),
-                                                                      (s["sym_na"], s["idx_na"])])
+        # the device front-end hands the coder one slot per symbol (packed table entry, or an escape marker):
+        # the same bytes as coding (symbol, index) pairs, at ~2/3 of the host work per symbol
+        anchor_strings, non_anchor_strings = gc.encode_symbol_groups([(s["sym_a"], s["slot_a"]),
+                                                                      (s["sym_na"], s["slot_na"])], slots=True)
         return {"strings": [[anchor_strings, non_anchor_strings], z_strings],
                 "shape": torch.Size(s["sym_z"].shape[-2:]), "time": time.time() - start_time}
 
@@ -325,18 +331,21 @@ class LightWeightCheckerboard(CompressionModel):
             latent = eng.h_s(ops.eb_dequant(sym_z.contiguous(), med))
             head, context = eng.head, eng.context
             ctx_in = 1  # ... or their bf16 copy
+        # decoder codes: at the structurally zero half of each pass the symbol is round(-mean) (Q1) -- the coder only
+        # advances its state there, and gc_dequant recomputes the value instead of reading it
+        rows = gc.coder_rows(dev)
         pa = head(latent)
-        idx_a = ops.gc_indexes(pa, table, self.M, bound)
-        sym_a = gc.decode_symbols(strings[0][0], idx_a, slot=slot).to(dev, non_blocking=True)
-        yqa = ops.gc_dequant(sym_a.contiguous(), pa, want_bf16=bool(ctx_in))
+        code_a = ops.gc_codes(pa, 0, table, self.M, rows, bound)
+        sym_a = gc.decode_symbols(strings[0][0], code_a, slot=slot, codes=True).to(dev, non_blocking=True)
+        yqa = ops.gc_dequant(sym_a.contiguous(), pa, want_bf16=bool(ctx_in), pass_id=0)
         yqa32 = yqa[0]
         ctx = context(yqa[ctx_in])
         pna = head(latent, ctx)
         if self.codec_precision == "fp32h2":
             _check_finite({"finite": torch.isfinite(pna).all()})
-        idx_na = ops.gc_indexes(pna, table, self.M, bound)
-        sym_na = gc.decode_symbols(strings[0][1], idx_na, slot=slot).to(dev, non_blocking=True)
-        yqna32, _ = ops.gc_dequant(sym_na.contiguous(), pna, want_bf16=False)
+        code_na = ops.gc_codes(pna, 1, table, self.M, rows, bound)
+        sym_na = gc.decode_symbols(strings[0][1], code_na, slot=slot, codes=True).to(dev, non_blocking=True)
+        yqna32, _ = ops.gc_dequant(sym_na.contiguous(), pna, want_bf16=False, pass_id=1)
         y_hat16 = ops.add_to_bf16(yqa32, yqna32)
         x_hat = eng.g_s(y_hat16, clamp=True)  # Q3
         return {"x_hat": x_hat, "time": time.time() - start_time}

@@ -519,18 +519,42 @@ def gc_merge_likelihood(y, params_a, params_na, yq_a, yq_na, noise=False, seed=0
     return y_hat, lik
 
 
-def gc_symbols(y, params, pass_id, scale_table, scale_bound=0.11, want_f32=True, want_bf16=True):
-    """-> (symbols int32 [B,M,h,w], indexes int32 [B,M,h,w], yq fp32 NHWC, yq bf16 NHWC)"""
+def _chk_rows(rows, scale_table):
+    if rows.dtype != torch.int32 or not rows.is_cuda or not rows.is_contiguous() or tuple(rows.shape) != (3, scale_table.numel()):
+        raise ValueError("rows: expected the contiguous int32 CUDA tensor [3, n_scales] of EntropyModel.coder_rows()")
+
+
+def gc_symbols(y, params, pass_id, scale_table, scale_bound=0.11, want_f32=True, want_bf16=True, rows=None):
+    """-> (symbols int32 [B,M,h,w], indexes int32 [B,M,h,w], yq fp32 NHWC, yq bf16 NHWC); with ``rows`` (the host
+    coder's table layout, ``EntropyModel.coder_rows``) a fifth result: the coder slots int32 [B,M,h,w]."""
     _f32c(y, "y"), _f32c(params, "params"), _f32c(scale_table, "scale_table")
     B, h, w, M = y.shape
     sym = torch.empty((B, M, h, w), dtype=torch.int32, device=y.device)
     idx = torch.empty((B, M, h, w), dtype=torch.int32, device=y.device)
     o32 = torch.empty_like(y) if want_f32 else None
     o16 = torch.empty(y.shape, dtype=torch.bfloat16, device=y.device) if want_bf16 else None
+    slots = None
+    if rows is not None:
+        _chk_rows(rows, scale_table)
+        slots = torch.empty((B, M, h, w), dtype=torch.int32, device=y.device)
     L.check(L.lib().hyres_gc_symbols(_ptr(y), _ptr(params), pass_id, _ptr(scale_table), scale_table.numel(),
                                      float(scale_bound), _ptr(sym), _ptr(idx), _ptr(o32), _ptr(o16), B, h, w, M,
-                                     _stream()), "hyres_gc_symbols")
+                                     _ptr(rows), _ptr(slots), _stream()), "hyres_gc_symbols")
+    if rows is not None:
+        return sym, idx, o32, o16, slots
     return sym, idx, o32, o16
+
+
+def gc_codes(params, pass_id, scale_table, M, rows, scale_bound=0.11):
+    """Decoder front-end of checkerboard pass ``pass_id``: -> decoder codes int32 [B,M,h,w] (CDF row index, or
+    bit 30 | packed entry at the structurally zero positions, whose symbol round(-mean) needs no decoding)."""
+    _f32c(params, "params")
+    _chk_rows(rows, scale_table)
+    B, h, w, _ = params.shape
+    codes = torch.empty((B, M, h, w), dtype=torch.int32, device=params.device)
+    L.check(L.lib().hyres_gc_codes(_ptr(params), int(pass_id), _ptr(scale_table), scale_table.numel(), float(scale_bound),
+                                   _ptr(rows), C.c_void_p(0), _ptr(codes), B, h, w, M, _stream()), "hyres_gc_codes")
+    return codes
 
 
 def gc_indexes(params, scale_table, M, scale_bound=0.11):
@@ -542,14 +566,15 @@ def gc_indexes(params, scale_table, M, scale_bound=0.11):
     return idx
 
 
-def gc_dequant(symbols, params, want_f32=True, want_bf16=True):
-    """symbols int32 [B,M,h,w] (+ means from params NHWC) -> (yq fp32 NHWC, yq bf16 NHWC)"""
+def gc_dequant(symbols, params, want_f32=True, want_bf16=True, pass_id=-1):
+    """symbols int32 [B,M,h,w] (+ means from params NHWC) -> (yq fp32 NHWC, yq bf16 NHWC).  ``pass_id`` 0 / 1: the
+    symbols at that pass's structurally zero positions are recomputed as round(-mean), not read (``gc_codes``)."""
     B, M, h, w = symbols.shape
     dev = symbols.device
     o32 = torch.empty((B, h, w, M), dtype=torch.float32, device=dev) if want_f32 else None
     o16 = torch.empty((B, h, w, M), dtype=torch.bfloat16, device=dev) if want_bf16 else None
-    L.check(L.lib().hyres_gc_dequant(_ptr(symbols), _ptr(params), _ptr(o32), _ptr(o16), B, h, w, M, _stream()),
-            "hyres_gc_dequant")
+    L.check(L.lib().hyres_gc_dequant(_ptr(symbols), _ptr(params), _ptr(o32), _ptr(o16), B, h, w, M, int(pass_id),
+                                     _stream()), "hyres_gc_dequant")
     return o32, o16
 
 

@@ -250,13 +250,23 @@ int hyres_gc_merge_likelihood(const float* y, const float* params_a, const float
  * models/checkerboard.py:159-161 */
 int hyres_gc_symbols(const float* y, const float* params, int pass, const float* scale_table,
                      int n_scales, float scale_bound, int32_t* symbols, int32_t* indexes,
-                     float* yq_f32, void* yq_bf16, int B, int h, int w, int M, void* stream);
+                     float* yq_f32, void* yq_bf16, int B, int h, int w, int M,
+                     const int32_t* coder_rows, int32_t* slots, void* stream);
+/* coder_rows / slots (both or neither): the host coder's table layout (hyres_rans_table_layout, on the device) and,
+ * in the indexes' order, the coder SLOT of every symbol (see hyres_rans_encode_slots_batch).
+ * hyres_gc_codes is the decoder's counterpart for checkerboard pass `pass`: indexes (optional) and the decoder CODES --
+ * at the structurally zero positions of the pass the symbol is round(-mean) and the code carries its packed entry
+ * (hyres_rans_decode_codes_batch); hyres_gc_dequant with the same `pass` then recomputes those symbols instead of
+ * reading them (pass = -1: every symbol is read). */
+int hyres_gc_codes(const float* params, int pass, const float* scale_table, int n_scales, float scale_bound,
+                   const int32_t* coder_rows, int32_t* indexes, int32_t* codes, int B, int h, int w, int M,
+                   void* stream);
 /* decoder side: indexes from scales only. models/checkerboard.py:163-165 */
 int hyres_gc_indexes(const float* params, const float* scale_table, int n_scales,
                      float scale_bound, int32_t* indexes, int B, int h, int w, int M, void* stream);
 /* decoder side: yq = float(symbol) + mean; symbols in (B,M,h,w) order. */
 int hyres_gc_dequant(const int32_t* symbols, const float* params, float* yq_f32, void* yq_bf16,
-                     int B, int h, int w, int M, void* stream);
+                     int B, int h, int w, int M, int pass, void* stream);
 /* y_hat = a + b (fp32 NHWC in, bf16 NHWC out). models/checkerboard.py:234 */
 int hyres_add_to_bf16(const float* a, const float* b, void* out_bf16, int64_t n, void* stream);
 
@@ -390,6 +400,25 @@ int hyres_rans_decode_batch(int count, const uint8_t* const* in, const int64_t* 
                             const int32_t* const* indexes, const int64_t* n, const int32_t* cdfs,
                             int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
                             const int32_t* offsets, int32_t* const* symbols_out, int threads);
+/* Device-side coder front-end ("GPU emits compact streams per (image, pass)").
+ * hyres_rans_table_layout: rows_out[3 * n_cdfs] = for every CDF row the first entry of the row in the coder's packed
+ * tables, its offset, and its escape bin (number of in-table values; 0 for an unusable row).  With these three vectors
+ * on the device, hyres_gc_symbols emits per symbol a SLOT (>= 0: packed entry = base + value of an in-table value;
+ * < 0: -(row + 1), the value is outside the table and is coded through the escape path from symbols[i]) and
+ * hyres_gc_codes emits per symbol a CODE for the decoder (bit 30 set: the symbol is known to the caller -- a
+ * structurally zero position of the checkerboard pass, models/checkerboard.py:106-110 -- low bits = its packed entry:
+ * the decoder only advances the range-coder state and leaves symbols_out[i] untouched; otherwise a plain row index).
+ * The byte strings are identical to hyres_rans_encode_batch / consumed exactly like hyres_rans_decode_batch. */
+int hyres_rans_table_layout(const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                            const int32_t* offsets, int32_t* rows_out);
+int hyres_rans_encode_slots_batch(int count, const int32_t* const* symbols, const int32_t* const* slots,
+                                  const int64_t* n, const int32_t* cdfs, int n_cdfs, int cdf_stride,
+                                  const int32_t* cdf_sizes, const int32_t* offsets, uint8_t* const* out,
+                                  const int64_t* out_cap, int64_t* out_len, int threads);
+int hyres_rans_decode_codes_batch(int count, const uint8_t* const* in, const int64_t* in_len,
+                                  const int32_t* const* codes, const int64_t* n, const int32_t* cdfs, int n_cdfs,
+                                  int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
+                                  int32_t* const* symbols_out, int threads);
 
 #ifdef __cplusplus
 }

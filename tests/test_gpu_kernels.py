@@ -45,11 +45,36 @@ def test_symbols_indexes_strings_bit_exact_vs_reference_fixture(pcodec, golden_w
         M = pcodec.M
         want = got_sym.permute(0, 2, 3, 1).float() + prm[..., M:]
         assert torch.equal(yq32, want)
+        # device front-end of the coder: slots (encoder) and codes (decoder) against their definition
+        gcm = pcodec.gaussian_conditional
+        rows = gcm.coder_rows("cuda")
+        base, off, last = (r.long() for r in rows.cpu())
+        r5 = ops.gc_symbols(y, prm, ps, table, 0.11, rows=rows)
+        assert torch.equal(r5[0], got_sym) and torch.equal(r5[1], got_idx) and torch.equal(r5[2], yq32)
+        ci, sv = got_idx.cpu().long(), got_sym.cpu().long()
+        value = sv - off[ci]
+        inside = (value >= 0) & (value < last[ci])
+        assert torch.equal(r5[4].cpu().long(), torch.where(inside, base[ci] + value, -(ci + 1)))
+        codes = ops.gc_codes(prm, ps, table, M := pcodec.M, rows, 0.11).cpu().long()
+        hh, ww = ci.shape[-2:]
+        anchor = ((torch.arange(hh).view(-1, 1) + torch.arange(ww).view(1, -1)) % 2 == 0).expand_as(ci)
+        structural = anchor != (ps == 0)
+        mu = prm[..., M:].permute(0, 3, 1, 2).cpu()
+        known_val = torch.round(-mu).long() - off[ci]
+        known = structural & (known_val >= 0) & (known_val < last[ci])
+        assert torch.equal(codes, torch.where(known, (1 << 30) | (base[ci] + known_val), ci))
+        assert torch.equal(sv[structural], torch.round(-mu).long()[structural])  # Q1: what the encoder coded there
+        junk = torch.where(structural.cuda(), torch.full_like(got_sym, 777), got_sym)
+        dq_pass, _ = ops.gc_dequant(junk, prm, pass_id=ps)
+        assert torch.equal(dq_pass, yq32)  # structural symbols are recomputed, not read
         if golden_weights_ok:  # the CDF tables come from the regenerated weights / scale table
             strings = pcodec.gaussian_conditional.encode_symbols(got_sym, got_idx)
             assert strings[0] == g[s].tobytes()
+            assert gcm.encode_symbol_groups([(got_sym, r5[4])], slots=True)[0][0] == g[s].tobytes()
             back = pcodec.gaussian_conditional.decode_symbols(strings, got_idx)
             assert torch.equal(back, got_sym.cpu())
+            back2 = gcm.decode_symbols(strings, ops.gc_codes(prm, ps, table, M, rows, 0.11), codes=True)
+            assert torch.equal(back2[~known], got_sym.cpu()[~known])
     if golden_weights_ok:
         z = _nhwc(g["z"])
         ebp, med = pcodec.engine().eb_params()

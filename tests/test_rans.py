@@ -168,3 +168,35 @@ def test_entropy_model_string_api(build_lib, oracle_net):
     assert torch.equal(gc.decode_symbols(strings, idx), sym)
     with pytest.raises(ValueError):
         gc.decode_symbols(strings[:1], idx)
+
+
+def test_slots_and_codes_front_end(build_lib, tables):
+    """The device front-end's streams (csrc/rans.cpp: slots for the encoder, codes with known symbols for the decoder),
+    built here with numpy from (symbol, index): the same bytes as the plain encoder, and a decoder that skips the search
+    for known symbols stays in step and returns every unknown symbol."""
+    from hyres_b200 import coder
+    rng = np.random.default_rng(21)
+    count, n = 4, 6000
+    idx = rng.integers(0, 64, size=(count, n)).astype(np.int32)
+    sym = np.round(rng.standard_normal((count, n)) * rng.choice([0.4, 3.0, 40.0], size=(count, 1))).astype(np.int32)
+    sym[0, ::41] += 70000  # escapes
+    sym[2, ::53] -= 70000
+    base, off, last = coder.table_layout(tables)
+    assert (off == tables.offsets).all() and (last == tables.sizes - 2).all() and (np.diff(base) > 0).all()
+    value = sym - off[idx]
+    inside = (value >= 0) & (value < last[idx])
+    slots = np.where(inside, base[idx] + value, -(idx + 1)).astype(np.int32)
+    plain = coder.encode_batch(sym, idx, tables)
+    assert coder.encode_batch(sym, slots, tables, slots=True) == plain
+    # decoder: every second position is "known" (when its value is inside the table)
+    known = inside & (np.arange(n)[None, :] % 2 == 0)
+    codes = np.where(known, (1 << 30) | (base[idx] + value), idx).astype(np.int32)
+    out = np.full((count, n), -12345, dtype=np.int32)
+    coder.decode_batch(plain, codes, tables, out=out, codes=True)
+    assert (out[~known] == sym[~known]).all() and (out[known] == -12345).all()
+    # malformed slot / code
+    from hyres_b200 import _lib
+    bad = slots.copy()
+    bad[1, 5] = 2 ** 29
+    with pytest.raises(_lib.HyresError):
+        coder.encode_batch(sym, bad, tables, slots=True)
