@@ -7,6 +7,7 @@ in flight, each on its own worker thread and CUDA stream: the coder calls (ctype
 overlap the kernels and PCIe copies of the others.  Every batch still goes through the model's public
 ``compress`` / ``decompress``, so the strings are exactly what single calls return.
 """
+import queue
 import threading
 from collections import deque
 from concurrent.futures import ThreadPoolExecutor
@@ -17,10 +18,13 @@ from . import ops
 
 
 class CodecPipeline:
-    def __init__(self, model, workers=3, reuse_host_buffers=False):
+    def __init__(self, model, workers=3, reuse_host_buffers=False, use_graphs=True):
         """model: ``ResidualJPEGCompression`` (or ``LightWeightCheckerboard``) on a CUDA sm_100 device.
         ``reuse_host_buffers``: decoded images come back in a per-worker ring of pinned buffers (no 35 MB
-        ``pin_memory`` per batch); a yielded ``x_hat`` is then valid until the next result is taken from the iterator."""
+        ``pin_memory`` per batch); a yielded ``x_hat`` is then valid until the next result is taken from the iterator.
+        ``use_graphs``: every worker replays the GPU phases of compress / decompress (the launches between two host
+        steps) from CUDA graphs captured on its second batch of a shape -- identical kernels and results, but one
+        launch per phase instead of 20 - 80 issued under the interpreter lock that all workers share."""
         self.model = model
         self.dev = next(model.parameters()).device
         if self.dev.type != "cuda":
@@ -28,6 +32,10 @@ class CodecPipeline:
         self.workers = max(1, int(workers))
         self._pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="hyres-codec")
         self._tls = threading.local()
+        # one context per image in flight: its CUDA stream and the CUDA graphs captured on it; a job checks one out
+        self._contexts = queue.LifoQueue()
+        for _ in range(self.workers):
+            self._contexts.put({"stream": torch.cuda.Stream(device=self.dev), "graphs": {}})
         self._lock = threading.Lock()
         self.h2d_bytes = 0
         self.d2h_bytes = 0
@@ -35,6 +43,9 @@ class CodecPipeline:
         self.reuse_host_buffers = bool(reuse_host_buffers)
         # build the packed layers (and their weight uploads) once, outside the worker threads
         codec = model.residual_model if self._wrapper else model
+        self._codec = codec
+        self._graphs_before = codec.graph_phases
+        codec.graph_phases = bool(use_graphs)
         codec.engine()
         if codec.codec_precision != "bf16":
             codec.precise(codec.codec_precision)
@@ -43,12 +54,41 @@ class CodecPipeline:
 
     def close(self):
         self._pool.shutdown(wait=True)
+        self._codec.graph_phases = self._graphs_before
 
-    def _stream(self):
-        s = getattr(self._tls, "stream", None)
-        if s is None:
-            s = self._tls.stream = torch.cuda.Stream(device=self.dev)
-        return s
+    class _Checkout:
+        """``with pipe._checkout() as ctx``: a free context, installed as this thread's graph cache for the model."""
+
+        def __init__(self, pipe):
+            self.pipe, self.ctx = pipe, None
+
+        def __enter__(self):
+            self.ctx = self.pipe._contexts.get()
+            self.pipe._codec._phase_tls.graphs = self.ctx["graphs"]
+            return self.ctx
+
+        def __exit__(self, *exc):
+            self.pipe._codec._phase_tls.graphs = {}
+            self.pipe._contexts.put(self.ctx)
+
+    def _checkout(self):
+        return CodecPipeline._Checkout(self)
+
+    def warm(self, x, rounds=3):
+        """Run ``rounds`` compress + decompress round trips of ``x`` on every context (eager pass, graph capture,
+        first replay), so that no capture happens inside a measured or latency-critical region."""
+        n = self._contexts.qsize()
+        held = [self._contexts.get() for _ in range(n)]
+        try:
+            for ctx in held:
+                self._contexts.put(ctx)
+                for _ in range(rounds):
+                    self._roundtrip_job(x, False)  # checks out the only free context: this one
+                assert self._contexts.get() is ctx
+        finally:
+            for ctx in held:
+                self._contexts.put(ctx)
+        torch.cuda.synchronize(self.dev)
 
     def _host_buffer(self, like):
         if not self.reuse_host_buffers:
@@ -78,7 +118,7 @@ class CodecPipeline:
     @torch.no_grad()
     def _compress_job(self, x):
         torch.cuda.set_device(self.dev)
-        with torch.cuda.stream(self._stream()):
+        with self._checkout() as ctx, torch.cuda.stream(ctx["stream"]):
             if not x.is_cuda:
                 self._count(h2d=x.numel() * x.element_size())
                 x = x.to(self.dev, non_blocking=True)
@@ -89,9 +129,11 @@ class CodecPipeline:
     @torch.no_grad()
     def _decompress_job(self, c, to_host):
         torch.cuda.set_device(self.dev)
-        with torch.cuda.stream(self._stream()):
+        with self._checkout() as ctx, torch.cuda.stream(ctx["stream"]):
             d = self.model.decompress(c) if self._wrapper else self.model.decompress(c["strings"], c["shape"])
             x_hat = d["x_hat"]
+            if not to_host and self._codec.graph_phases:
+                x_hat = x_hat.clone()  # a graph's output buffer is overwritten by this worker's next batch
             if to_host:
                 host = self._host_buffer(x_hat)
                 host.copy_(x_hat, non_blocking=True)

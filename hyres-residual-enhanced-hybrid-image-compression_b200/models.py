@@ -18,6 +18,7 @@ before loading the refine block (the reference passes the prefixed keys through,
 for any checkpoint that contains them -- models/hyres.py:150-162).
 """
 import math
+import threading
 import time
 
 import torch
@@ -98,12 +99,46 @@ class CompressionModel(nn.Module):
         return nn.Module.load_state_dict(self, state_dict, strict=strict)
 
 
+def _as_latent(t, precise):
+    """The hyper-synthesis output as the parameter head takes it: the parts of the split-precision trunk wrapped
+    back into their activation record, or the bf16 tensor itself."""
+    if precise:
+        from .engine import _PT
+        return _PT(None, t)
+    return t
+
+
 def _check_finite(s):
     """Raise if the half-part trunk ("fp32h2") overflowed (``encode_symbols`` sets ``finite``; one scalar read)."""
     f = s.get("finite")
     if f is not None and not bool(f):
         raise FloatingPointError("the fp32h2 trunk produced non-finite values: an activation left the IEEE half range "
                                  "(|v| >= 65 520); use codec_precision = 'fp32x3' for this model")
+
+
+_CAPTURE_LOCK = threading.Lock()
+
+
+class _PhaseGraph:
+    """One GPU phase of compress / decompress (a run of kernel launches between two host steps) captured into a CUDA
+    graph on static input buffers; calling it copies the inputs in and replays.  The outputs are the capture's own
+    tensors: valid until the same graph is replayed again."""
+
+    def __init__(self, fn, tensors):
+        self.inputs = [None if t is None else t.detach().clone() for t in tensors]
+        cur = torch.cuda.current_stream()
+        with _CAPTURE_LOCK:  # one capture at a time; other threads keep launching (thread-local capture mode)
+            cur.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=cur, capture_error_mode="thread_local"):
+                self.outputs = fn(*self.inputs)
+
+    def __call__(self, *tensors):
+        for s, t in zip(self.inputs, tensors):
+            if s is not None and s.data_ptr() != t.data_ptr():
+                s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        return self.outputs
 
 
 # nsplit codes of the split-precision trunks (ops.ConvLayer / hyres_conv_create_split)
@@ -145,6 +180,12 @@ class LightWeightCheckerboard(CompressionModel):
         # tests/test_gpu_precise.py; "fp32x3" is the one that also reproduces both reference fixtures byte for byte).
         self.precision = "bf16"
         self.codec_precision = "fp32h2"
+        # GPU phases of compress / decompress replayed from per-thread CUDA graphs (CodecPipeline turns this on: a
+        # phase is 20 - 80 launches of 20 - 300 us kernels, and with several images in flight the Python threads that
+        # issue them contend for the interpreter lock while the GPU runs dry).  Same kernels, same results.
+        self.graph_phases = False
+        self._phase_tls = threading.local()
+        self._bound_cache = None
 
     # -- engine plumbing --
     def engine(self):
@@ -248,16 +289,62 @@ class LightWeightCheckerboard(CompressionModel):
             out["_residual"] = residual
         return out
 
+    def _scale_bound(self):
+        """The scale lower bound as a Python float (a device buffer: read once, not once per call)."""
+        sb = self.gaussian_conditional.scale_bound
+        key = (sb.data_ptr(), sb._version)
+        if self._bound_cache is None or self._bound_cache[0] != key:
+            self._bound_cache = (key, float(sb.item()))
+        return self._bound_cache[1]
+
+    def _phase(self, name, fn, *tensors):
+        """``fn(*tensors)`` -> tuple of tensors.  With ``graph_phases`` on: the first call of a (thread, phase, shapes,
+        weights) combination runs eagerly (it builds layers and caches), the second captures a CUDA graph, later ones
+        replay it."""
+        if not self.graph_phases or torch.cuda.current_stream() == torch.cuda.default_stream():
+            return fn(*tensors)  # (a graph cannot be captured on the default stream)
+        cache = self._phase_tls.__dict__.setdefault("graphs", {})
+        key = (name, self.codec_precision, sum(p._version for p in self.parameters()),
+               tuple(None if t is None else (tuple(t.shape), t.dtype) for t in tensors))
+        ent = cache.get(key)
+        if ent is None:
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = "warm"
+            return fn(*tensors)
+        if ent == "warm":
+            try:
+                ent = cache[key] = _PhaseGraph(fn, tensors)
+            except Exception as exc:  # noqa: BLE001 -- a capture that fails leaves eager launches, which stay correct
+                import warnings
+                warnings.warn(f"CUDA-graph capture of codec phase {name!r} failed ({type(exc).__name__}: {exc}); "
+                              "running it eagerly")
+                ent = cache[key] = "eager"
+        if ent == "eager":
+            return fn(*tensors)
+        return ent(*tensors)
+
     # -- symbols of both passes (GPU part of compress) --
     def encode_symbols(self, x, _jpeg=None):
         """GPU front-end of ``compress``: returns the integer streams the entropy coder consumes,
         all int32 CUDA tensors in (B,C,h,w) order, plus the shapes."""
         _require_cuda(x, "compress")
         self._check_input(x)
-        eng = self.engine()
+        self.engine()
         x = x.contiguous().float()
+        names = ("sym_z", "sym_a", "idx_a", "sym_na", "idx_na", "slot_a", "slot_na", "y", "z", "params_a", "params_na",
+                 "finite")
+
+        def run(xx, jj):
+            d = self._encode_symbols_impl(xx, jj)
+            return tuple(d.get(k) for k in names)
+        vals = self._phase("encode", run, x, _jpeg)
+        return {k: v for k, v in zip(names, vals) if v is not None}
+
+    def _encode_symbols_impl(self, x, _jpeg):
+        eng = self.engine()
         table = self._scale_table(x.device)
-        bound = float(self.gaussian_conditional.scale_bound.item())
+        bound = self._scale_bound()
         if self.codec_precision != "bf16":
             pt = self.precise(self.codec_precision)
             y, _ = pt.g_a(x, _jpeg)
@@ -316,38 +403,51 @@ class LightWeightCheckerboard(CompressionModel):
         dev = next(self.parameters()).device
         gc, ebm = self.gaussian_conditional, self.entropy_bottleneck
         table = self._scale_table(dev)
-        bound = float(gc.scale_bound.item())
+        bound = self._scale_bound()
         B = len(strings[1])
         out_size = (B, ebm._quantized_cdf.size(0), int(shape[0]), int(shape[1]))
         sym_z = ebm.decode_symbols(strings[1], ebm._build_indexes(out_size)).to(dev)
         slot = "y" if dev.type == "cuda" else None  # both passes decode into one cached pinned buffer per thread
         _, med = eng.eb_params()
-        if self.codec_precision != "bf16":
+        precise = self.codec_precision != "bf16"
+        if precise:
             pt = self.precise(self.codec_precision)
-            latent = pt.h_s(ops.symbols_to_nhwc_f32(sym_z.contiguous(), med))
             head, context = pt.head, pt.context
             ctx_in = 0  # the context conv reads the fp32 dequantised anchors
         else:
-            latent = eng.h_s(ops.eb_dequant(sym_z.contiguous(), med))
             head, context = eng.head, eng.context
             ctx_in = 1  # ... or their bf16 copy
         # decoder codes: at the structurally zero half of each pass the symbol is round(-mean) (Q1) -- the coder only
         # advances its state there, and gc_dequant recomputes the value instead of reading it
         rows = gc.coder_rows(dev)
-        pa = head(latent)
-        code_a = ops.gc_codes(pa, 0, table, self.M, rows, bound)
+        M = self.M
+
+        # three GPU phases, separated by the two host decoding passes
+        def phase1(sz):
+            if precise:
+                latent = pt.h_s(ops.symbols_to_nhwc_f32(sz, med)).sp
+            else:
+                latent = eng.h_s(ops.eb_dequant(sz, med))
+            pa = head(_as_latent(latent, precise))
+            return latent, pa, ops.gc_codes(pa, 0, table, M, rows, bound)
+
+        def phase2(sa, pa, latent):
+            yqa = ops.gc_dequant(sa, pa, want_bf16=bool(ctx_in), pass_id=0)
+            ctx = context(yqa[ctx_in])
+            pna = head(_as_latent(latent, precise), ctx)
+            finite = torch.isfinite(pna).all() if self.codec_precision == "fp32h2" else None
+            return yqa[0], pna, ops.gc_codes(pna, 1, table, M, rows, bound), finite
+
+        def phase3(sna, pna, yqa32):
+            yqna32, _ = ops.gc_dequant(sna, pna, want_bf16=False, pass_id=1)
+            return (eng.g_s(ops.add_to_bf16(yqa32, yqna32), clamp=True),)  # Q3
+
+        latent, pa, code_a = self._phase("dec1", phase1, sym_z.contiguous())
         sym_a = gc.decode_symbols(strings[0][0], code_a, slot=slot, codes=True).to(dev, non_blocking=True)
-        yqa = ops.gc_dequant(sym_a.contiguous(), pa, want_bf16=bool(ctx_in), pass_id=0)
-        yqa32 = yqa[0]
-        ctx = context(yqa[ctx_in])
-        pna = head(latent, ctx)
-        if self.codec_precision == "fp32h2":
-            _check_finite({"finite": torch.isfinite(pna).all()})
-        code_na = ops.gc_codes(pna, 1, table, self.M, rows, bound)
+        yqa32, pna, code_na, finite = self._phase("dec2", phase2, sym_a.contiguous(), pa, latent)
         sym_na = gc.decode_symbols(strings[0][1], code_na, slot=slot, codes=True).to(dev, non_blocking=True)
-        yqna32, _ = ops.gc_dequant(sym_na.contiguous(), pna, want_bf16=False, pass_id=1)
-        y_hat16 = ops.add_to_bf16(yqa32, yqna32)
-        x_hat = eng.g_s(y_hat16, clamp=True)  # Q3
+        _check_finite({"finite": finite})  # the code tensor's copy has synchronised the stream already
+        (x_hat,) = self._phase("dec3", phase3, sym_na.contiguous(), pna, yqa32)
         return {"x_hat": x_hat, "time": time.time() - start_time}
 
     def inference(self, x):
@@ -452,7 +552,8 @@ class ResidualJPEGCompression(CompressionModel):
         device = next(self.parameters()).device
         jpeg_decoded = self.jpeg.decompress(jpeg_buffers, device).float().contiguous()
         result = self.residual_model.decompress(strings, shape)
-        result["x_hat"] = self._reconstruct(jpeg_decoded, result["x_hat"])
+        (result["x_hat"],) = self.residual_model._phase("refine", lambda jd, rh: (self._reconstruct(jd, rh),),
+                                                        jpeg_decoded, result["x_hat"])
         return result
 
     def load_state_dict(self, state_dict, **kwargs):
