@@ -47,6 +47,7 @@ RU_DRAM_BYTES_PER_LAUNCH = 761_778_944  # dram__bytes_read.sum + dram__bytes_wri
 
 
 CODEC_TILES, CODEC_H, CODEC_W = 8, 704, 512  # one 2048x1408 image as a 2x4 grid of tiles
+CODEC_IMAGES = 4  # images per GPU per step (each goes through the public compress / decompress on its own)
 # canonical algorithmic work of compress + decompress, SURVEY.md section 8d: encode 215 488 + decode 322 642 MAC/px
 MAC_PER_PX_ENCDEC = 538_130
 
@@ -256,8 +257,10 @@ def run_reference(args, rank):
 def codec_config(n, workers=None):
     c = {"workload": "BASELINE.json configs[2]: ResidualJPEGCompression.compress + .decompress (JPEG q=1 stage, residual "
                      "codec N=128 M=192 with checkerboard two-pass symbols + CDF indexes, rANS strings, MultiScaleRefine) of "
-                     "one 2048x1408 synthetic image per GPU per step as eight 704x512 tiles (tier T-A)",
-         "tiles_per_gpu": CODEC_TILES, "height": CODEC_H, "width": CODEC_W, "global_tiles": CODEC_TILES * n,
+                     "%d 2048x1408 synthetic images per GPU per step, each as eight 704x512 tiles (tier T-A) through its own "
+                     "compress / decompress call" % CODEC_IMAGES,
+         "images_per_gpu_per_step": CODEC_IMAGES, "tiles_per_image": CODEC_TILES, "height": CODEC_H, "width": CODEC_W,
+         "global_tiles": CODEC_IMAGES * CODEC_TILES * n,
          "trunk_precision": "fp32h2 (fp32 activations carried as two IEEE half parts, 3 tensor-core products per MAC: "
                             "fp32-equivalent) for g_a/h_a/h_s/context/parameter head; bf16 for g_s/refine",
          "sharding": "by image (tile set) per rank, no data-path collective; per-step NCCL all-reduce of 4 doubles "
@@ -289,9 +292,14 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
     import hyres_b200
     from hyres_b200 import dist as D, ops, synthetic
 
-    workers = args.in_flight
+    net.residual_model.coder = args.coder
+    device_coder = net.residual_model.uses_device_coder()
+    # images in flight: the host coder is fed by ~6; a coder warp runs a string's chain ~10x slower than a host core, so
+    # the device coder needs more images resident to keep the convolution kernels busy (they only cost memory)
+    workers = args.in_flight if args.in_flight > 0 else (16 if device_coder else 6)
     tiles, h, w = CODEC_TILES, CODEC_H, CODEC_W
-    px_step = tiles * h * w
+    px_img = tiles * h * w
+    px_step = CODEC_IMAGES * px_img
     # a few distinct images per rank, cycled (the JPEG stage and the coder see different data every step)
     hosts = [synthetic.synthetic_image(tiles, h, w, seed=7 + 17 * rank + k).pin_memory() for k in range(4)]
     devs = [t.to(dev) for t in hosts]
@@ -304,26 +312,31 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
         torch.cuda.synchronize()
 
     def run(n, resident):
-        """n steps; every result is consumed (its stream size and reconstruction error enter the step statistics,
-        which are all-reduced across ranks: the bpp / MSE a multi-GPU job reports)."""
+        """n steps of CODEC_IMAGES images; every result is consumed (its stream size and reconstruction error enter the
+        step statistics, which are all-reduced across ranks once per step: the bpp / MSE a multi-GPU job reports)."""
         src = devs if resident else hosts
         last = None
-        for k, (c, x_hat) in enumerate(pipe.roundtrip((src[i % len(src)] for i in range(n)), to_host=not resident)):
+        acc = torch.zeros(4, dtype=torch.float64, device=dev)
+        images = n * CODEC_IMAGES
+        for k, (c, x_hat) in enumerate(pipe.roundtrip((src[i % len(src)] for i in range(images)), to_host=not resident)):
             nbytes = pipe._stream_bytes(c)
             ref = devs[k % len(devs)]
             xh = x_hat if resident else x_hat.to(dev, non_blocking=True)
             se = (xh - ref).double().pow(2).sum()
-            stats.copy_(torch.stack([torch.tensor(float(nbytes), dtype=torch.float64, device=dev), se,
-                                     torch.tensor(float(px_step), dtype=torch.float64, device=dev),
-                                     torch.tensor(1.0, dtype=torch.float64, device=dev)]))
-            D.reduce_stats(stats)
-            last = stats.clone()
+            acc += torch.stack([torch.tensor(float(nbytes), dtype=torch.float64, device=dev), se,
+                                torch.tensor(float(px_img), dtype=torch.float64, device=dev),
+                                torch.tensor(1.0, dtype=torch.float64, device=dev)])
+            if (k + 1) % CODEC_IMAGES == 0:
+                stats.copy_(acc)
+                acc.zero_()
+                D.reduce_stats(stats)
+                last = stats.clone()
         torch.cuda.synchronize()
         return last
 
     with torch.no_grad():
         pipe.warm(devs[0])  # every context: eager pass, CUDA-graph capture of its GPU phases, first replay
-        run(max(args.warmup, workers + 1), True)
+        run(max(args.warmup, (workers + CODEC_IMAGES) // CODEC_IMAGES), True)
         l0 = lib.hyres_launch_count()
         sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else dev.index)
         sampler.start()
@@ -343,7 +356,7 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
         ms = D.max_over_ranks(ms_local, dev)
 
         # ---- end to end: pinned host images in, x_hat back in pinned host memory ----
-        run(workers + 1, False)
+        run((workers + CODEC_IMAGES) // CODEC_IMAGES, False)
         barrier()
         pipe.h2d_bytes = pipe.d2h_bytes = 0
         t0 = time.perf_counter()
@@ -406,15 +419,22 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f16 / bf16 tensor-core products, fp32 accumulation; the entropy-critical trunk carries "
                                       "fp32 activations as 2 half parts (fp32-equivalent); symbols int32",
-        "data": "synthetic", "config": codec_config(world, workers),
+        "data": "synthetic", "config": dict(codec_config(world, workers), coder=(
+            "device: every rANS string coded by one warp beside the convolution kernels (csrc/rans_dev.cu), no host work "
+            "per symbol" if device_coder else "host: rANS strings coded on the box's cores (csrc/rans.cpp)") +
+            " [--coder %s, %d host cores for this process]" % (args.coder, hyres_b200.coder.host_cores_per_process())),
         "e2e": {"value": world * px_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "note": "h2d / d2h count the image in and the reconstruction out; the symbol / index tensors cross PCIe "
-                        "on top of that in both arms (resident and e2e), because the entropy coder runs on the host"},
-        "gpu_launches": prof["eager_launches"] * args.steps, "gpu_launches_per_step": prof["eager_launches"],
+                "note": "h2d / d2h count the image in and the reconstruction out; " + (
+                    "the byte strings cross PCIe on top of that in both arms (resident and e2e): they are the product"
+                    if device_coder else
+                    "the symbol / index tensors cross PCIe on top of that in both arms (resident and e2e), because the "
+                    "entropy coder runs on the host")},
+        "gpu_launches": prof["eager_launches"] * CODEC_IMAGES * args.steps,
+        "gpu_launches_per_step": prof["eager_launches"] * CODEC_IMAGES,
         "launch": "the library's kernels of one compress + decompress (counted on an eager pass); in the timed steps the "
-                  "launches between two host steps are replayed from CUDA graphs, one graph per GPU phase and image in "
-                  "flight (%d counted eager launches per step remain: JPEG stage, copies)" % (int(launches) // max(1, args.steps)),
+                  "launches of a GPU phase are replayed from CUDA graphs, one graph per phase and image in "
+                  "flight (%d counted eager launches per step remain: JPEG stage, coder, copies)" % (int(launches) // max(1, args.steps)),
         "host": {"cores": os.cpu_count(), "cpu_ms_per_step": host_cpu_ms,
                  "note": "process CPU time (user + system, all threads: range coder, JPEG file decode, launches) per step "
                          "on rank 0; divided by the core count it is the floor the host puts under ms_per_step"},
@@ -422,19 +442,19 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
         "global_stats": {"bpp": 8.0 * gbytes / gpx, "mse_255": gse / (gpx * 3) * 255 ** 2, "images": gimg,
                          "note": "last step, all-reduced over ranks (NCCL) inside the timed loop"},
         "single_call_latency": {"compress_ms": prof["enc_ms"], "decompress_ms": prof["dec_ms"],
-                                "note": "one un-pipelined public compress() / decompress() of the 8-tile image"},
+                                "note": "one un-pipelined public compress() / decompress() of one 8-tile image"},
         "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel on the %d split-precision (%s) layers of one compress + "
                                                   "decompress" % (prof["split_n"], net.residual_model.codec_precision),
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                      "traffic": None, "executed": executed,
                      "executed_frac": executed / peaks["tflops"],
-                     "ms_per_step": prof["split_ms"], "peak_source": peaks["source"],
+                     "ms_per_step": prof["split_ms"] * CODEC_IMAGES, "peak_source": peaks["source"],
                      "note": "achieved counts ALGORITHMIC FLOPs (one MAC per weight tap); each is executed as 3 half-precision "
                              "tensor-core products (6 bf16 ones in the three GDN gamma layers) so that symbols equal the "
                              "fp32 reference's; `executed` is what the tensor pipe sustains.  Most of these layers are "
                              "HBM-bound at this tile size (1x1 / 3x3 layers of 64-128 channels carrying fp32 activations)",
-                     "dominant_layer": {"layer": prof["top"]["what"], "launches_per_step": prof["top"]["n"],
-                                        "ms_per_step": prof["top"]["ms"], "bound": "hbm",
+                     "dominant_layer": {"layer": prof["top"]["what"], "launches_per_step": prof["top"]["n"] * CODEC_IMAGES,
+                                        "ms_per_step": prof["top"]["ms"] * CODEC_IMAGES, "bound": "hbm",
                                         "achieved": prof["top"]["bytes"] / (prof["top"]["ms"] * 1e-3) / 1e9, "peak": peaks["hbm"],
                                         "unit": "GB/s", "frac": prof["top"]["bytes"] / (prof["top"]["ms"] * 1e-3) / 1e9 / peaks["hbm"],
                                         "tflops_algorithmic": prof["top"]["flops"] / (prof["top"]["ms"] * 1e-3) / 1e12,
@@ -442,8 +462,9 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
                                         "note": "the layer geometry with the largest share of the step's GPU time; achieved = "
                                                 "algorithmic fp32 bytes (input + output + added operands) / CUDA-event time; "
                                                 "traffic = dram bytes of one launch, profiles/r02_ncu_conv_tc.md"},
-                     "all_tensor_kernels": {"launches": prof["conv_n"], "ms_per_step": prof["conv_ms"],
-                                            "achieved": 2.0 * MAC_PER_PX_ENCDEC * px_step / (prof["conv_ms"] * 1e-3) / 1e12},
+                     "all_tensor_kernels": {"launches": prof["conv_n"] * CODEC_IMAGES,
+                                            "ms_per_step": prof["conv_ms"] * CODEC_IMAGES,
+                                            "achieved": 2.0 * MAC_PER_PX_ENCDEC * px_img / (prof["conv_ms"] * 1e-3) / 1e12},
                      "step_tflops": 2.0 * MAC_PER_PX_ENCDEC * px_step / (ms * 1e-3) / 1e12},
     }
     return line
@@ -673,7 +694,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="codec", choices=["codec", "forward", "train"])
-    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("HYRES_CODEC_IN_FLIGHT", "6")),
+    ap.add_argument("--coder", default=os.environ.get("HYRES_CODER", "auto"), choices=["auto", "host", "device"],
+                    help="codec: where the rANS strings are coded (auto: on the device when this process has fewer than "
+                         "16 host cores to itself)")
+    ap.add_argument("--in-flight", type=int, default=int(os.environ.get("HYRES_CODEC_IN_FLIGHT", "0")),
                     help="images in flight in the codec pipeline (worker threads / CUDA streams)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="codec workload: skip the forward sub-benchmark")

@@ -49,6 +49,14 @@ class RuIO(C.Structure):
     ]
 
 
+class RansGroup(C.Structure):
+    _fields_ = [
+        ("symbols", C.c_void_p), ("index", C.c_void_p), ("enc", C.c_void_p), ("rows", C.c_void_p),
+        ("scratch", C.c_void_p), ("n", C.c_int64), ("cap_words", C.c_int64), ("n_entries", C.c_int64),
+        ("n_rows", C.c_int32), ("count", C.c_int32), ("slots", C.c_int32),
+    ]
+
+
 _lib = None
 
 _vp, _i, _i64, _f, _u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
@@ -117,6 +125,11 @@ SIGNATURES = {
     "hyres_rans_table_layout": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "hyres_rans_encode_slots_batch": (_i, [_i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i]),
     "hyres_rans_decode_codes_batch": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i]),
+    "hyres_rans_table_entries": (_i64, [_vp, _i, _i, _vp, _vp]),
+    "hyres_rans_table_export": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "hyres_rans_dev_encode": (_i, [_i, _vp, _vp, _i64, _vp, _i, _vp]),
+    "hyres_set_reserved_sms": (_i, [_i]),
+    "hyres_rans_dev_decode": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _i, _i64, _vp, _vp, _vp]),
 }
 
 

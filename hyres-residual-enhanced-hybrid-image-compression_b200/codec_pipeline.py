@@ -14,7 +14,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 class CodecPipeline:
@@ -46,6 +46,15 @@ class CodecPipeline:
         self._codec = codec
         self._graphs_before = codec.graph_phases
         codec.graph_phases = bool(use_graphs)
+        # Device coder: every image in flight keeps one coder launch resident for tens of milliseconds (a warp per
+        # string, eight warps per block, each block holding a whole SM).  The convolution kernels take a whole SM per
+        # CTA with a fixed share of the tiles, so a CTA that had to wait for -- or share -- a coder block's SM would hold
+        # up its launch: leave SMs to the coder.  How many does not grow with the images in flight: at the throughput the
+        # convolutions allow (~22 ms per 8-tile image) the coder blocks of one image (3 x ~70 ms encoding, 1 x ~110 ms
+        # decoding) keep ~13 blocks resident on average, whatever the depth of the pipeline.
+        self._reserved_before = None
+        if codec.uses_device_coder():
+            self._reserved_before = _lib.lib().hyres_set_reserved_sms(min((3 * self.workers + 1) // 2, 16))
         codec.engine()
         if codec.codec_precision != "bf16":
             codec.precise(codec.codec_precision)
@@ -55,6 +64,9 @@ class CodecPipeline:
     def close(self):
         self._pool.shutdown(wait=True)
         self._codec.graph_phases = self._graphs_before
+        if self._reserved_before is not None:
+            _lib.lib().hyres_set_reserved_sms(self._reserved_before)
+            self._reserved_before = None
 
     class _Checkout:
         """``with pipe._checkout() as ctx``: a free context, installed as this thread's graph cache for the model."""

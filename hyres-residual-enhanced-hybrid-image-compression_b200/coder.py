@@ -152,3 +152,36 @@ def decode_batch(strings, indexes, tables, threads=None, out=None, codes=False):
     L.check(fn(count, bp, lens.ctypes.data, ip, ns.ctypes.data, t.cdf.ctypes.data, t.cdf.shape[0], t.cdf.shape[1],
                t.sizes.ctypes.data, t.offsets.ctypes.data, op, _threads(threads or count)), "hyres_rans_decode_batch")
     return out
+
+
+def host_cores_per_process():
+    """Host cores this process can count on: all of them divided by the processes torchrun started on this node (one
+    per GPU); ``HYRES_HOST_CORES`` overrides (the same rule as the coder's thread pool, csrc/rans.cpp)."""
+    env = os.environ.get("HYRES_HOST_CORES")
+    if env:
+        return max(1, int(env))
+    hw = os.cpu_count() or 1
+    return max(1, hw // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)))
+
+
+class DeviceTables:
+    """The coder's packed tables on a CUDA device (hyres_rans_table_export), for the device-resident coder
+    (csrc/rans_dev.cu): ``enc`` 16-byte encoder entries, ``sf`` decoder words, ``rows`` int32 [4, n_cdfs]."""
+
+    def __init__(self, tables, device):
+        import torch
+        t = tables
+        lib = L.lib()
+        args = (t.cdf.ctypes.data, t.cdf.shape[0], t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data)
+        n = int(lib.hyres_rans_table_entries(*args))
+        if n <= 0:
+            raise L.HyresError("hyres_rans_table_entries failed: " + lib.hyres_last_error().decode())
+        enc = np.zeros(n * 16, dtype=np.uint8)
+        sf = np.zeros(n, dtype=np.uint32)
+        rows = np.zeros((4, t.cdf.shape[0]), dtype=np.int32)
+        L.check(lib.hyres_rans_table_export(*args, enc.ctypes.data, sf.ctypes.data, rows.ctypes.data),
+                "hyres_rans_table_export")
+        self.n_entries, self.n_rows = n, int(t.cdf.shape[0])
+        self.enc = torch.from_numpy(enc).to(device)
+        self.sf = torch.from_numpy(sf.view(np.int32)).to(device)
+        self.rows = torch.from_numpy(rows).to(device)

@@ -1004,6 +1004,14 @@ int encode_w_map(CUtensorMap* m, const void* ptr, int ktot, int cout_pad, int bn
   return HYRES_OK;
 }
 
+// SMs the persistent kernels leave alone (hyres_set_reserved_sms): grids are sized to the rest
+static std::atomic<int> g_reserved_sms{0};
+
+extern "C" int hyres_set_reserved_sms(int n) {
+  if (n < 0) return hy_fail(HYRES_ERR_ARG, "set_reserved_sms: negative count");
+  return g_reserved_sms.exchange(n);
+}
+
 int num_sms() {
   static std::atomic<int> cache[64];  // per device
   int dev = 0;
@@ -1015,7 +1023,7 @@ int num_sms() {
     if (n <= 0) n = 148;
     slot.store(n, std::memory_order_relaxed);
   }
-  return n;
+  return std::max(n / 2, n - g_reserved_sms.load(std::memory_order_relaxed));
 }
 
 extern "C" {

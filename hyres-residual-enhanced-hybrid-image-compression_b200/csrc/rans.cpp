@@ -681,4 +681,31 @@ int hyres_rans_table_layout(const int32_t* cdfs, int n_cdfs, int cdf_stride, con
   return HYRES_OK;
 }
 
+int64_t hyres_rans_table_entries(const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                                 const int32_t* offsets) {
+  if (!cdfs || !cdf_sizes || !offsets || n_cdfs <= 0 || cdf_stride <= 0) {
+    hy_fail(HYRES_ERR_ARG, "rans_table_entries: bad argument");
+    return -1;
+  }
+  return static_cast<int64_t>(prepare(cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets)->enc.size());
+}
+
+int hyres_rans_table_export(const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                            const int32_t* offsets, void* enc_out, uint32_t* sf_out, int32_t* rows_out) {
+  if (!cdfs || !cdf_sizes || !offsets || !enc_out || !sf_out || !rows_out || n_cdfs <= 0 || cdf_stride <= 0)
+    return hy_fail(HYRES_ERR_ARG, "rans_table_export: bad argument");
+  static_assert(sizeof(EncSym) == 16, "the device coder reads encoder entries as 16-byte words");
+  const auto T = prepare(cdfs, n_cdfs, cdf_stride, cdf_sizes, offsets);
+  std::memcpy(enc_out, T->enc.data(), T->enc.size() * sizeof(EncSym));
+  std::memcpy(sf_out, T->sf.data(), T->sf.size() * sizeof(uint32_t));
+  for (int r = 0; r < n_cdfs; ++r) {
+    const RowInfo& ri = T->rows[r];
+    rows_out[r] = static_cast<int32_t>(ri.base);
+    rows_out[n_cdfs + r] = ri.offset;
+    rows_out[2 * n_cdfs + r] = ri.last_bin;
+    rows_out[3 * n_cdfs + r] = (ri.enc_ok && ri.dec_ok) ? 1 : 0;
+  }
+  return HYRES_OK;
+}
+
 }  // extern "C"

@@ -100,6 +100,16 @@ class EntropyModel(nn.Module):
             self._rows_cache = cache = (key, rows)
         return cache[1]
 
+    def device_tables(self, device):
+        """The coder's packed tables on ``device`` for the device-resident coder (``coder.DeviceTables``, cached with
+        the host tables)."""
+        t = self.tables()
+        cache = getattr(self, "_dev_tables_cache", None)
+        key = (id(t), str(device))
+        if cache is None or cache[0] != key:
+            self._dev_tables_cache = cache = (key, coder.DeviceTables(t, device))
+        return cache[1]
+
     # -- coding of already-quantised symbols --
     _tls = threading.local()  # pinned staging buffers are per thread: CodecPipeline runs one batch per worker thread
 
@@ -287,6 +297,17 @@ class EntropyBottleneck(EntropyModel):
         view = [1] * len(size)
         view[1] = -1
         return torch.arange(Cc, dtype=torch.int32, device=device).view(*view).repeat(N, 1, *size[2:])
+
+    def device_indexes(self, size, device):
+        """``_build_indexes(size)`` as a cached CUDA tensor (the device coder reads the CDF row of every symbol)."""
+        key = (tuple(int(v) for v in size), str(device))
+        cache = self.__dict__.setdefault("_dev_index_cache", {})
+        ix = cache.get(key)
+        if ix is None:
+            if len(cache) > 8:
+                cache.clear()
+            ix = cache[key] = self._build_indexes(size, device=device).contiguous()
+        return ix
 
     def compress(self, x):
         """(B,C,H,W) -> list of strings (symbols = round(x - median))."""

@@ -24,7 +24,7 @@ import time
 import torch
 import torch.nn as nn
 
-from . import _lib, ops
+from . import _lib, coder, ops
 from .engine import CodecEngine, PreciseTrunk, RefineEngine
 from .entropy import EntropyBottleneck, GaussianConditional
 from .jpeg import TurboJPEGCompression
@@ -184,6 +184,12 @@ class LightWeightCheckerboard(CompressionModel):
         # phase is 20 - 80 launches of 20 - 300 us kernels, and with several images in flight the Python threads that
         # issue them contend for the interpreter lock while the GPU runs dry).  Same kernels, same results.
         self.graph_phases = False
+        # Where the rANS strings are coded: "host" (csrc/rans.cpp on the box's cores: ~5 ns per symbol and core, the
+        # shortest single call), "device" (csrc/rans_dev.cu: one warp per string beside the convolution kernels, no host
+        # work per symbol -- throughput then scales with the GPUs of a box, not with its cores), or "auto": the device
+        # coder when this process can count on fewer than 16 host cores (torchrun with several GPUs per box).  The
+        # bytes are the same either way.
+        self.coder = "auto"
         self._phase_tls = threading.local()
         self._bound_cache = None
 
@@ -382,12 +388,31 @@ class LightWeightCheckerboard(CompressionModel):
         return {"sym_z": eb["symbols"], "sym_a": sym_a, "idx_a": idx_a, "sym_na": sym_na, "idx_na": idx_na,
                 "slot_a": slot_a, "slot_na": slot_na, "y": y32, "z": z32, "params_a": pa, "params_na": pna}
 
+    def uses_device_coder(self):
+        c = self.coder
+        if c not in ("auto", "host", "device"):
+            raise ValueError(f"unknown coder {c!r}: expected 'auto', 'host' or 'device'")
+        if c == "auto":
+            c = "device" if coder.host_cores_per_process() < 16 else "host"
+        return c == "device"
+
     # -- compress (models/checkerboard.py:167-198) --
     def compress(self, x, _jpeg=None):
         start_time = time.time()
         s = self.encode_symbols(x, _jpeg=_jpeg)
-        _check_finite(s)
         gc, ebm = self.gaussian_conditional, self.entropy_bottleneck
+        if self.uses_device_coder():
+            # all strings of the batch (z, anchors, non-anchors) are coded by warps on this stream; the finite flag
+            # comes back with the strings
+            dev = s["sym_z"].device
+            ty, tz = gc.device_tables(dev), ebm.device_tables(dev)
+            z_strings, anchor_strings, non_anchor_strings = ops.rans_encode_device([
+                (s["sym_z"], ebm.device_indexes(s["sym_z"].size(), dev), tz, False),
+                (s["sym_a"], s["slot_a"], ty, True), (s["sym_na"], s["slot_na"], ty, True)])
+            _check_finite(s)
+            return {"strings": [[anchor_strings, non_anchor_strings], z_strings],
+                    "shape": torch.Size(s["sym_z"].shape[-2:]), "time": time.time() - start_time}
+        _check_finite(s)
         z_strings = ebm.encode_symbols(s["sym_z"], ebm._build_indexes(s["sym_z"].size()))
         # the device front-end hands the coder one slot per symbol (packed table entry, or an escape marker):
         # the same bytes as coding (symbol, index) pairs, at ~2/3 of the host work per symbol
@@ -406,7 +431,18 @@ class LightWeightCheckerboard(CompressionModel):
         bound = self._scale_bound()
         B = len(strings[1])
         out_size = (B, ebm._quantized_cdf.size(0), int(shape[0]), int(shape[1]))
-        sym_z = ebm.decode_symbols(strings[1], ebm._build_indexes(out_size)).to(dev)
+        device_coder = self.uses_device_coder()
+        if device_coder:
+            if len(strings[0][0]) != B or len(strings[0][1]) != B:
+                raise ValueError("Invalid strings or indexes parameters")
+            # one upload for the three string sets; every pass is then decoded by warps on this stream, so the whole
+            # call is a single run of launches with no host step between the GPU phases
+            ty, tz = gc.device_tables(dev), ebm.device_tables(dev)
+            words, str_table = ops.rans_upload([strings[1], strings[0][0], strings[0][1]], dev)
+            coder_status = torch.zeros(1, dtype=torch.int32, device=dev)
+            sym_z = ops.rans_decode_device(words, str_table, 0, ebm.device_indexes(out_size, dev), tz, False, coder_status)
+        else:
+            sym_z = ebm.decode_symbols(strings[1], ebm._build_indexes(out_size)).to(dev)
         slot = "y" if dev.type == "cuda" else None  # both passes decode into one cached pinned buffer per thread
         _, med = eng.eb_params()
         precise = self.codec_precision != "bf16"
@@ -442,6 +478,20 @@ class LightWeightCheckerboard(CompressionModel):
             yqna32, _ = ops.gc_dequant(sna, pna, want_bf16=False, pass_id=1)
             return (eng.g_s(ops.add_to_bf16(yqa32, yqna32), clamp=True),)  # Q3
 
+        if device_coder:
+            latent, pa, code_a = self._phase("dec1", phase1, sym_z)
+            sym_a = ops.rans_decode_device(words, str_table, B, code_a, ty, True, coder_status)
+            yqa32, pna, code_na, finite = self._phase("dec2", phase2, sym_a, pa, latent)
+            sym_na = ops.rans_decode_device(words, str_table, 2 * B, code_na, ty, True, coder_status)
+            (x_hat,) = self._phase("dec3", phase3, sym_na, pna, yqa32)
+            # the last phase is already in the stream; wait for it asleep (the scalar reads below would spin on a
+            # core for the whole decode, and every image in flight has a thread here)
+            flags = torch.stack([coder_status[0] != 0, ~finite if finite is not None else coder_status[0] != 0])
+            hflags = ops.read_small(flags)
+            if hflags[0]:
+                raise ValueError("decompress: malformed rANS stream")
+            _check_finite({"finite": not hflags[1]} if finite is not None else {})
+            return {"x_hat": x_hat, "time": time.time() - start_time}
         latent, pa, code_a = self._phase("dec1", phase1, sym_z.contiguous())
         sym_a = gc.decode_symbols(strings[0][0], code_a, slot=slot, codes=True).to(dev, non_blocking=True)
         yqa32, pna, code_na, finite = self._phase("dec2", phase2, sym_a.contiguous(), pa, latent)

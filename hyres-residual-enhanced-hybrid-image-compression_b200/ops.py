@@ -58,6 +58,16 @@ def stream_wait_blocking(device=None):
     e.synchronize()
 
 
+def read_small(t):
+    """A small CUDA tensor -> list of Python scalars, through pinned memory and a blocking event wait (``.item()`` /
+    ``.tolist()`` spin on a host core until the stream drains)."""
+    nbytes = t.numel() * t.element_size()
+    host = _pinned_bytes("small", nbytes)[:nbytes].view(t.dtype).view(t.shape)
+    host.copy_(t, non_blocking=True)
+    stream_wait_blocking(t.device)
+    return host.tolist()
+
+
 def split_parts(code):
     """Number of 16-bit parts per fp32 value of an nsplit code (1..3 bf16 parts, or 2 | SPLIT_F16: two half parts)."""
     return int(code) & 15
@@ -749,3 +759,157 @@ def jpeg_assemble(words_host, nbits, H, W, quality):
     L.check(L.lib().hyres_jpeg_assemble(C.c_void_p(w.ctypes.data), int(nbits), H, W, int(quality),
                                         C.c_void_p(out.ctypes.data), cap, C.byref(n)), "hyres_jpeg_assemble")
     return out[:n.value].tobytes()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Device-resident entropy coder (csrc/rans_dev.cu): the host coder's byte strings, one warp per string
+# ---------------------------------------------------------------------------------------------------------------
+_CODER_TLS = __import__("threading").local()
+
+
+def _pinned_bytes(slot, nbytes):
+    """This thread's cached pinned uint8 staging buffer ``slot`` with at least ``nbytes`` bytes."""
+    bufs = _CODER_TLS.__dict__.setdefault("pinned", {})
+    buf = bufs.get(slot)
+    if buf is None or buf.numel() < nbytes:
+        buf = bufs[slot] = torch.empty(max(int(nbytes * 1.25) + 4096, 1 << 16), dtype=torch.uint8).pin_memory()
+    return buf
+
+
+class _coder_stream:
+    """``with _coder_stream(dev):`` -- launches inside go to this thread's HIGH-PRIORITY side stream, ordered after the
+    work already in the current stream; the current stream continues after them.  A coder block needs most of an SM to
+    itself; while convolution kernels of other streams keep the SMs full, the block scheduler hands an SM that frees
+    up to the highest-priority pending block -- without the priority a coder launch can wait behind a long chain of
+    convolution CTAs."""
+
+    def __init__(self, device):
+        self.dev = torch.device(device)
+
+    def __enter__(self):
+        side = _CODER_TLS.__dict__.setdefault("side", {})
+        st = side.get(self.dev.index)
+        if st is None:
+            st = side[self.dev.index] = torch.cuda.Stream(device=self.dev, priority=-1)
+        self.cur = torch.cuda.current_stream(self.dev)
+        self.side = st
+        st.wait_stream(self.cur)
+        self.ctx = torch.cuda.stream(st)
+        self.ctx.__enter__()
+        return st
+
+    def __exit__(self, *exc):
+        self.ctx.__exit__(*exc)
+        self.cur.wait_stream(self.side)
+
+
+def rans_encode_device(groups, escape_room=False):
+    """groups: list of ``(symbols, index, tables, slots)`` -- int32 CUDA tensors ``[B, ...]`` of equal shape (``index`` =
+    CDF row per symbol, or coder slots from ``gc_symbols`` when ``slots``), ``tables`` a ``coder.DeviceTables`` ->
+    list (per group) of lists of B byte strings, identical to ``coder.encode_batch``'s.  One kernel launch per group on
+    the current stream (every string is coded by one warp), then two small device -> host copies: the string table
+    and the bytes.  ``escape_room``: size the working space for streams made of escapes (the retry after an
+    overflow)."""
+    dev = groups[0][1].device
+    n_str = sum(int(g[1].size(0)) for g in groups)
+    meta = torch.zeros(2 + 2 * n_str, dtype=torch.int32, device=dev)
+    plans, dst_cap = [], 0
+    for symbols, index, tables, slots in groups:
+        B = int(index.size(0))
+        n = index.numel() // max(B, 1)
+        if symbols is not None and symbols.shape != index.shape:
+            raise ValueError("`symbols` and `indexes` should have the same size.")
+        for t in (symbols, index):
+            if t is not None and (t.dtype != torch.int32 or not t.is_cuda or not t.is_contiguous()):
+                raise ValueError("rans_encode_device: expected contiguous int32 CUDA tensors")
+        cap = (3 * n + 256) if escape_room else (n // 2 + 4096)
+        plans.append((B, n, cap))
+        dst_cap += B * cap
+    dst = torch.empty(dst_cap, dtype=torch.int32, device=dev)
+    keep = []
+    for first in range(0, len(groups), 4):  # one launch per four groups: their strings are coded side by side
+        part = list(zip(groups, plans))[first:first + 4]
+        arr = (L.RansGroup * len(part))()
+        for k, ((symbols, index, tables, slots), (B, n, cap)) in enumerate(part):
+            scratch = torch.empty(B * cap, dtype=torch.int32, device=dev)
+            keep.append(scratch)
+            g = arr[k]
+            g.symbols, g.index = symbols.data_ptr() if symbols is not None else None, index.data_ptr()
+            g.enc, g.rows, g.scratch = tables.enc.data_ptr(), tables.rows.data_ptr(), scratch.data_ptr()
+            g.n, g.cap_words, g.n_entries = n, cap, tables.n_entries
+            g.n_rows, g.count, g.slots = tables.n_rows, B, int(bool(slots))
+        base = sum(pl[0] for pl in plans[:first])
+        with _coder_stream(dev):
+            L.check(L.lib().hyres_rans_dev_encode(len(part), C.cast(arr, C.c_void_p), _ptr(dst), dst_cap, _ptr(meta),
+                                                  base, _stream()), "hyres_rans_dev_encode")
+    hmeta = _pinned_bytes("meta", meta.numel() * 4)[: meta.numel() * 4].view(torch.int32)
+    hmeta.copy_(meta, non_blocking=True)
+    stream_wait_blocking(dev)
+    m = hmeta.numpy()
+    total, status = int(m[0]), int(m[1])
+    if status == 2 and not escape_room:
+        return rans_encode_device(groups, escape_room=True)
+    if status != 0:
+        raise L.HyresError("hyres_rans_dev_encode: " + ("output buffer too small" if status == 2 else
+                                                        "symbol / index outside the CDF tables"))
+    hbytes = _pinned_bytes("bytes", total * 4)[: total * 4]
+    hbytes.view(torch.int32).copy_(dst[:total], non_blocking=True)
+    stream_wait_blocking(dev)
+    raw = hbytes.numpy()
+    out, k = [], 0
+    for B, _, _ in plans:
+        grp = []
+        for _ in range(B):
+            off, ln = int(m[2 + 2 * k]), int(m[3 + 2 * k])
+            grp.append(raw[off * 4:(off + ln) * 4].tobytes())
+            k += 1
+        out.append(grp)
+    return out
+
+
+def rans_upload(string_groups, device):
+    """list of lists of byte strings -> (words int32 CUDA tensor with every string back to back, string table int64
+    CUDA ``[2, S]`` = first word and word count of each): one host -> device copy for all passes of a decompress."""
+    import numpy as np
+    strings = [s for grp in string_groups for s in grp]
+    S = len(strings)
+    lens = [len(s) for s in strings]
+    for n in lens:
+        if n % 4 or n < 8:
+            raise ValueError("Invalid strings: a rANS64 stream is a whole number (>= 2) of 32-bit words")
+    head = 16 * S
+    total = head + sum(lens)
+    buf = _pinned_bytes("up", total)[:total]
+    arr = buf.numpy()
+    table = arr[:head].view(np.int64).reshape(2, S)
+    pos = 0
+    for k, s in enumerate(strings):
+        table[0, k] = pos // 4
+        table[1, k] = lens[k] // 4
+        arr[head + pos: head + pos + lens[k]] = np.frombuffer(s, dtype=np.uint8)
+        pos += lens[k]
+    d = torch.empty(total, dtype=torch.uint8, device=device)
+    d.copy_(buf, non_blocking=True)
+    # the pinned buffer is reused by this thread's next upload: the copy must have left it
+    stream_wait_blocking(device)
+    return d[head:].view(torch.int32), d[:head].view(torch.int64).view(2, S)
+
+
+def rans_decode_device(words, table, first, codes, tables, has_codes, status):
+    """Decode strings ``first .. first + B`` of an uploaded set (``rans_upload``) -> int32 CUDA tensor shaped like
+    ``codes`` ``[B, ...]`` (CDF row per symbol, or decoder codes from ``gc_codes`` when ``has_codes``: the entries of
+    known symbols are then left unwritten).  ``status``: int32 CUDA tensor [1], zeroed by the caller; non-zero after
+    a malformed stream.  One launch on the current stream, no synchronisation."""
+    if codes.dtype != torch.int32 or not codes.is_cuda or not codes.is_contiguous():
+        raise ValueError("rans_decode_device: expected a contiguous int32 CUDA tensor of codes")
+    B = int(codes.size(0))
+    n = codes.numel() // max(B, 1)
+    if first + B > table.size(1):
+        raise ValueError("Invalid strings or indexes parameters")
+    out = torch.empty_like(codes)
+    off, ln = table[0, first:first + B], table[1, first:first + B]
+    with _coder_stream(codes.device):
+        L.check(L.lib().hyres_rans_dev_decode(_ptr(words), _ptr(off), _ptr(ln), _ptr(codes), B, n, int(bool(has_codes)),
+                                              _ptr(tables.sf), _ptr(tables.rows), tables.n_rows, tables.n_entries,
+                                              _ptr(out), _ptr(status), _stream()), "hyres_rans_dev_decode")
+    return out

@@ -420,6 +420,48 @@ int hyres_rans_decode_codes_batch(int count, const uint8_t* const* in, const int
                                   int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets,
                                   int32_t* const* symbols_out, int threads);
 
+/* ------------------------------------------------------------------------- */
+/* Entropy coder (device): the same byte strings, coded on the GPU.           */
+/* ------------------------------------------------------------------------- */
+/* A string is one dependency chain, so each is coded by one warp (csrc/rans_dev.cu); dozens of strings (all images in
+ * flight) run beside the convolution kernels and no host core is involved -- compress + decompress then scale with the
+ * number of GPUs of a box instead of with its host cores.  Same format as hyres_rans_encode / hyres_rans_decode
+ * (RansEncoder.encode_with_indexes / RansDecoder.decode_with_indexes of compressai 1.2.6).
+ * hyres_rans_table_entries / _export: the host coder's packed tables for upload -- enc_out: 16 bytes per entry,
+ * sf_out: one uint32 per entry, rows_out: [4][n_cdfs] = first entry, offset, escape bin, usable (0 / 1).
+ * hyres_rans_dev_encode: ONE launch for up to four groups (e.g. the z strings and both y passes of a batch), a group
+ * = `count` strings of n symbols with one table set; one warp per string, all warps in as few blocks as possible.
+ * scratch: n / 2 + 192 words per string always suffice without escapes; 3 n + 192 with.  The strings land back to back,
+ * in no particular order, in dst; meta (int32, zeroed by the caller before the first launch that shares it): [0] words
+ * used in dst, [1] status (0 ok, 1 bad table / symbol, 2 buffer too small), [2 + 2 k] first word and [3 + 2 k] word
+ * count of string k = meta_base + (index of the string in this launch, groups in order).
+ * hyres_set_reserved_sms(n): every persistent kernel of the library sizes its grid to (SMs - n) from now on (returns
+ * the previous value).  The convolution kernels take a whole SM per CTA with a fixed share of the tiles each, so a CTA
+ * that has to wait for an SM held by a (long-running) coder block delays its whole launch: a pipeline that keeps n
+ * coder launches resident reserves n SMs for them.
+ * hyres_rans_dev_decode: words = all strings in one device buffer, str_off / str_len = first word and word count of
+ * each; codes = [count][n] CDF rows, or decoder CODES from hyres_gc_codes when has_codes != 0 (symbols_out is left
+ * untouched at known symbols); *status (device int32, zeroed by the caller) receives 1 for a malformed stream. */
+int64_t hyres_rans_table_entries(const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                                 const int32_t* offsets);
+int hyres_rans_table_export(const int32_t* cdfs, int n_cdfs, int cdf_stride, const int32_t* cdf_sizes,
+                            const int32_t* offsets, void* enc_out, uint32_t* sf_out, int32_t* rows_out);
+typedef struct hyres_rans_group {
+  const int32_t* symbols;  /* [count][n] device int32 (may be NULL with slots when no slot is negative) */
+  const int32_t* index;    /* [count][n] CDF row per symbol, or coder SLOTS (hyres_gc_symbols) when slots != 0 */
+  const void* enc;         /* packed encoder entries (hyres_rans_table_export), 16 bytes each */
+  const int32_t* rows;     /* [4][n_rows] */
+  uint32_t* scratch;       /* [count][cap_words] working space */
+  int64_t n, cap_words, n_entries;
+  int32_t n_rows, count, slots;
+} hyres_rans_group;
+int hyres_rans_dev_encode(int n_groups, const hyres_rans_group* groups, uint32_t* dst, int64_t dst_cap_words,
+                          int32_t* meta, int meta_base, void* stream);
+int hyres_set_reserved_sms(int n);
+int hyres_rans_dev_decode(const uint32_t* words, const int64_t* str_off, const int64_t* str_len, const int32_t* codes,
+                          int count, int64_t n, int has_codes, const uint32_t* sf, const int32_t* rows, int n_rows,
+                          int64_t n_entries, int32_t* symbols_out, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

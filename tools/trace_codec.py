@@ -18,6 +18,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workers", type=int, default=4)
     ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--coder", default="auto", choices=["auto", "host", "device"])
     a = ap.parse_args()
     import torch
     import hyres_b200
@@ -54,11 +55,19 @@ def main():
     net = hyres_b200.ResidualJPEGCompression(jpeg_quality=1)
     net.update(force=True)
     net = net.cuda().eval()
+    net.residual_model.coder = a.coder
+    from hyres_b200 import ops
+    wrap(ops, "rans_encode_device", "dev_encode(incl. wait)")
+    wrap(ops, "rans_upload", "dev_upload")
+    wrap(ops, "read_small", "dev_decode_wait")
+    wrap(net.jpeg, "decompress", "jpeg_decode")
+    wrap(net.jpeg, "compress_device", "jpeg_encode")
     wrap(net, "compress", "compress_job")
     wrap(net, "decompress", "decompress_job")
     xs = [synthetic.synthetic_image(8, 704, 512, seed=7 + k).cuda() for k in range(4)]
     pipe = hyres_b200.CodecPipeline(net, workers=a.workers, reuse_host_buffers=True)
     with torch.no_grad():
+        pipe.warm(xs[0])
         for _ in pipe.roundtrip((xs[i % 4] for i in range(a.workers + 2)), to_host=False):
             pass
         torch.cuda.synchronize()
