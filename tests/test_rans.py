@@ -200,3 +200,62 @@ def test_slots_and_codes_front_end(build_lib, tables):
     bad[1, 5] = 2 ** 29
     with pytest.raises(_lib.HyresError):
         coder.encode_batch(sym, bad, tables, slots=True)
+
+
+def test_device_table_export_is_the_host_coders_tables(build_lib, tables):
+    """hyres_rans_table_export (what the device-resident coder uploads): rows agree with hyres_rans_table_layout, the
+    decoder words are (start, freq - 1) of every bin, and the encoder entries divide exactly: for random states x,
+    x + bias + (mulhi(x, rcp) >> shift) * (2^16 - freq) == ((x // freq) << 16) + x % freq + start."""
+    from hyres_b200 import _lib, coder
+    t = tables
+    lib = _lib.lib()
+    args = (t.cdf.ctypes.data, t.cdf.shape[0], t.cdf.shape[1], t.sizes.ctypes.data, t.offsets.ctypes.data)
+    n = int(lib.hyres_rans_table_entries(*args))
+    assert n == int(np.maximum(1, np.minimum(t.sizes, t.cdf.shape[1])).sum())
+    enc = np.zeros(n * 16, dtype=np.uint8)
+    sf = np.zeros(n, dtype=np.uint32)
+    rows = np.zeros((4, t.cdf.shape[0]), dtype=np.int32)
+    assert lib.hyres_rans_table_export(*args, enc.ctypes.data, sf.ctypes.data, rows.ctypes.data) == 0
+    lay = coder.table_layout(t)
+    assert (rows[3] == 1).all() and (rows[:3] == lay).all()
+    e = enc.view(np.dtype([("rcp", "<u8"), ("bias", "<u4"), ("freq_m1", "<u2"), ("shift", "u1"), ("valid", "u1")]))
+    rng = np.random.default_rng(0)
+    for r in (0, 7, 31, 63):
+        base, last = int(rows[0, r]), int(rows[2, r])
+        cdf = t.cdf[r].astype(np.int64)
+        for v in sorted({0, 1, last // 2, last - 1, last}):
+            start, freq = int(cdf[v]), int(cdf[v + 1] - cdf[v])
+            assert int(sf[base + v]) == start | ((freq - 1) << 16)
+            ent = e[base + v]
+            assert ent["valid"] == 1 and int(ent["freq_m1"]) + 1 == freq
+            for x in [1 << 31, (freq << 47) - 1] + [int(rng.integers(1 << 31, freq << 47)) for _ in range(50)]:
+                q = ((x * int(ent["rcp"])) >> 64) >> int(ent["shift"])
+                got = x + int(ent["bias"]) + q * (65536 - freq)
+                assert got == ((x // freq) << 16) + x % freq + start, (r, v, x)
+    assert lib.hyres_rans_table_export(*args, None, sf.ctypes.data, rows.ctypes.data) != 0
+
+
+def test_coder_choice_follows_the_host_cores_of_the_process(build_lib, monkeypatch):
+    """coder = "auto": the device coder when this process can count on fewer than 16 host cores (one process per GPU
+    under torchrun share the box), the host coder otherwise; explicit choices are respected; nonsense is refused."""
+    import hyres_b200
+    from hyres_b200 import coder
+    net = hyres_b200.LightWeightCheckerboard()
+    monkeypatch.setenv("HYRES_HOST_CORES", "32")
+    assert coder.host_cores_per_process() == 32 and not net.uses_device_coder()
+    monkeypatch.setenv("HYRES_HOST_CORES", "4")
+    assert net.uses_device_coder()
+    monkeypatch.delenv("HYRES_HOST_CORES")
+    monkeypatch.setattr("os.cpu_count", lambda: 32)
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert coder.host_cores_per_process() == 4 and net.uses_device_coder()
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "1")
+    assert not net.uses_device_coder()
+    net.coder = "device"
+    assert net.uses_device_coder()
+    net.coder = "host"
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert not net.uses_device_coder()
+    net.coder = "gpu"
+    with pytest.raises(ValueError):
+        net.uses_device_coder()
