@@ -294,9 +294,9 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
 
     net.residual_model.coder = args.coder
     device_coder = net.residual_model.uses_device_coder()
-    # images in flight: the host coder is fed by ~6; a coder warp runs a string's chain ~10x slower than a host core, so
+    # images in flight: the host coder is fed by ~8; a coder warp runs a string's chain ~10x slower than a host core, so
     # the device coder needs more images resident to keep the convolution kernels busy (they only cost memory)
-    workers = args.in_flight if args.in_flight > 0 else (16 if device_coder else 6)
+    workers = args.in_flight if args.in_flight > 0 else (16 if device_coder else 8)
     tiles, h, w = CODEC_TILES, CODEC_H, CODEC_W
     px_img = tiles * h * w
     px_step = CODEC_IMAGES * px_img
