@@ -398,10 +398,12 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
                 gg["bytes"] += 4.0 * r["B"] * (r["H"] * r["W"] * r["cin"] + r["OH"] * r["OW"] * r["cout"] * (1 + extra))
                 gg["macs"] += r["alg_macs"]
             top = max(geo.values(), key=lambda e: e["ms"])
+            split_bytes = sum(e["bytes"] for e in geo.values())
             prof = dict(enc_ms=(t1 - t0) * 1e3, dec_ms=(t2 - t1) * 1e3, conv_ms=conv_ms, conv_n=conv_n,
                         split_ms=sum(r["ms"] for r in split), split_n=len(split),
                         split_flops=2.0 * sum(r["alg_macs"] for r in split),
                         split_executed=2.0 * sum(r["alg_macs"] * r["products"] for r in split),
+                        split_bytes=split_bytes,
                         eager_launches=int(eager_launches),
                         top=dict(ms=top["ms"], n=top["n"], bytes=top["bytes"], flops=2.0 * top["macs"],
                                  what="%dx%d %d->%d%s at %dx%dx%d" % (top["r"]["k"], top["r"]["k"], top["r"]["cin"], top["r"]["cout"],
@@ -414,6 +416,7 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
     gbytes, gse, gpx, gimg = [float(v) for v in g.tolist()]
     achieved = prof["split_flops"] / (prof["split_ms"] * 1e-3) / 1e12
     executed = prof["split_executed"] / (prof["split_ms"] * 1e-3) / 1e12
+    hbm_gbs = prof["split_bytes"] / (prof["split_ms"] * 1e-3) / 1e9
     line = {
         "metric": "hyres_encdec_mpixel_per_s", "value": value, "unit": "Mpixel/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -448,6 +451,11 @@ def bench_codec(args, net, dev, rank, world, lib, peaks):
                      "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                      "traffic": None, "executed": executed,
                      "executed_frac": executed / peaks["tflops"],
+                     "hbm": {"achieved": hbm_gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": hbm_gbs / peaks["hbm"],
+                             "note": "the same launches against the HBM roof: algorithmic fp32 bytes of every layer (input + "
+                                     "output + added operands, as the reference formulates it) / their summed CUDA-event "
+                                     "time; the kernel is about as far from this roof as from the tensor one: the fused fp32 epilogue "
+                                     "(instruction issue) bounds most launches, profiles/r02_ncu_conv_tc.md"},
                      "ms_per_step": prof["split_ms"] * CODEC_IMAGES, "peak_source": peaks["source"],
                      "note": "achieved counts ALGORITHMIC FLOPs (one MAC per weight tap); each is executed as 3 half-precision "
                              "tensor-core products (6 bf16 ones in the three GDN gamma layers) so that symbols equal the "
