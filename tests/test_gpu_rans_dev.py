@@ -91,6 +91,40 @@ def test_device_coder_wide_rows_take_the_search_path(gc_tables):
     assert int(status.item()) == 0 and np.array_equal(dec.cpu().numpy(), sym)
 
 
+def test_device_coder_many_strings_and_groups(gc_tables):
+    """More strings than one block holds (8 warps per block) and more groups than one launch takes (4): strings of
+    different lengths and table sets side by side, every one byte-identical to the host coder's."""
+    from hyres_b200 import coder, entropy, ops
+    torch.manual_seed(5)
+    eb = entropy.EntropyBottleneck(16)
+    eb.update(force=True)
+    t, dt = gc_tables.tables(), gc_tables.device_tables("cuda")
+    tz, dtz = eb.tables(), eb.device_tables("cuda")
+    rng = np.random.default_rng(9)
+    groups, want = [], []
+    for g, (B, n) in enumerate([(20, 333), (1, 70), (9, 1024), (3, 5), (11, 640), (2, 4097)]):
+        if g % 3 == 1:
+            idx = rng.integers(0, 16, size=(B, n)).astype(np.int32)
+            sym = rng.integers(-30, 31, size=(B, n)).astype(np.int32)
+            tab, dtab = tz, dtz
+        else:
+            syms, idxs = zip(*[_symbols(t, t.cdf.shape[0], n, rng, 0.01) for _ in range(B)])
+            sym, idx = np.stack(syms), np.stack(idxs)
+            tab, dtab = t, dt
+        want.append(coder.encode_batch(sym, idx, tab))
+        groups.append((torch.from_numpy(sym).cuda(), torch.from_numpy(idx).cuda(), dtab, False))
+    got = ops.rans_encode_device(groups)
+    assert got == want
+    words, table = ops.rans_upload(want, "cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    first = 0
+    for (sym, idx, dtab, _), strings in zip(groups, want):
+        dec = ops.rans_decode_device(words, table, first, idx, dtab, False, status)
+        assert torch.equal(dec, sym)
+        first += len(strings)
+    assert int(status.item()) == 0
+
+
 def test_device_coder_entropy_bottleneck_tables(build_lib):
     """The factorised prior's tables (one row per channel, short rows, non-symmetric offsets) and mixed groups."""
     from hyres_b200 import coder, entropy, ops
