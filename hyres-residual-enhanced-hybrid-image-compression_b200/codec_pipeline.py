@@ -7,6 +7,7 @@ in flight, each on its own worker thread and CUDA stream: the coder calls (ctype
 overlap the kernels and PCIe copies of the others.  Every batch still goes through the model's public
 ``compress`` / ``decompress``, so the strings are exactly what single calls return.
 """
+import os
 import queue
 import threading
 from collections import deque
@@ -54,7 +55,8 @@ class CodecPipeline:
         # decoding) keep ~13 blocks resident on average, whatever the depth of the pipeline.
         self._reserved_before = None
         if codec.uses_device_coder():
-            self._reserved_before = _lib.lib().hyres_set_reserved_sms(min((3 * self.workers + 1) // 2, 16))
+            reserve = int(os.environ.get("HYRES_CODER_SMS", "0")) or min((3 * self.workers + 1) // 2, 16)
+            self._reserved_before = _lib.lib().hyres_set_reserved_sms(reserve)
         codec.engine()
         if codec.codec_precision != "bf16":
             codec.precise(codec.codec_precision)
