@@ -212,6 +212,26 @@ def test_model_strings_and_reconstruction_do_not_depend_on_the_coder(pnet, oracl
         codec.coder = "auto"
 
 
+@pytest.mark.parametrize("shape", [(1, 32, 32), (2, 64, 32), (1, 32, 96)])
+def test_smallest_shapes_through_the_device_coder(pnet, oracle, shape):
+    """The smallest legal inputs (H, W multiples of 32: one hyper-latent position per channel, strings shorter than a
+    32-symbol chunk for z): device-coded strings and reconstruction equal the host coder's."""
+    codec = pnet.residual_model
+    B, H, W = shape
+    x = oracle.synthetic_residual(B, H, W, seed=H + W).cuda()
+    try:
+        res = {}
+        for c in ("host", "device"):
+            codec.coder = c
+            with torch.no_grad():
+                cc = codec.compress(x)
+                res[c] = (cc["strings"], cc["shape"], codec.decompress(cc["strings"], cc["shape"])["x_hat"])
+        assert res["host"][0] == res["device"][0] and res["host"][1] == res["device"][1]
+        assert torch.equal(res["host"][2], res["device"][2])
+    finally:
+        codec.coder = "auto"
+
+
 def test_codec_pipeline_with_the_device_coder(pnet, oracle):
     """Several images in flight, CUDA-graph phases and coder warps on every worker's stream: same strings and pixels
     as single host-coder calls."""
