@@ -6,15 +6,16 @@
 // one GPU has the box's cores to itself and becomes the limit of compress + decompress when eight GPUs share them
 // (34 M state updates per 2048x1408 image).  Here every string is coded by ONE WARP: the chain runs redundantly in all
 // 32 lanes (no divergence), while the lanes share everything that is not on the chain --
-//   * 32 symbols' slots / codes and table entries are fetched coalesced and ahead of the chain, and handed to the chain
-//     by warp shuffles;
+//   * 32 symbols' slots / codes are resolved at once, one per lane, and their table entries gathered a chunk ahead of the
+//     chain; the chain reads them back as shared-memory broadcasts issued ahead of their use;
 //   * the decoder first tries the row's MODE (value 0), whose start and frequency were fetched before the state was
 //     known: one compare and one multiply-add; another symbol is found with a ballot over the 32 bins around the
 //     centre (one bin per lane) and, rarely, a warp-parallel search of the row;
 //   * renormalisation words are gathered in lane registers and stored / loaded 32 at a time.
-// A warp runs the chain at tens of ns per symbol -- slower than a host core -- but a coder warp needs no shared memory
-// and no tensor memory, so dozens of them (all strings of all images in flight) run beside the persistent convolution
-// kernels of other streams, and the host cores are not involved at all: the strings scale with the number of GPUs.
+// A warp runs the chain at ~60 ns per symbol -- ten times slower than a host core -- but the warps of a launch sit in a
+// few blocks that hold whole SMs (see kHogBytes), dozens of strings (all images in flight) are coded beside the
+// persistent convolution kernels of other streams, and the host cores are not involved at all: compress + decompress
+// scale with the number of GPUs of a box (profiles/r02_scaling.md, profiles/r02_ncu_rans_dev.md).
 //
 // Table formats are the host coder's (hyres_rans_table_export): 16-byte encoder entries (64-bit reciprocal, bias,
 // freq - 1, shift, valid), decoder words start | (freq - 1) << 16, rows = [4][n_rows] (first entry, offset, escape

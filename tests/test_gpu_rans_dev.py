@@ -91,6 +91,27 @@ def test_device_coder_wide_rows_take_the_search_path(gc_tables):
     assert int(status.item()) == 0 and np.array_equal(dec.cpu().numpy(), sym)
 
 
+def test_device_coder_streams_made_of_escapes(gc_tables):
+    """Every symbol outside its table: the stream outgrows the encoder's first working-space estimate (half a word per
+    symbol), the wrapper retries with room for escapes, and the bytes are still the host coder's."""
+    from hyres_b200 import coder, ops
+    t, dt = gc_tables.tables(), gc_tables.device_tables("cuda")
+    rng = np.random.default_rng(13)
+    B, n = 3, 20000
+    idx = rng.integers(0, 64, size=(B, n)).astype(np.int32)
+    last = t.sizes[idx] - 2
+    far = rng.integers(1, 1 << 20, size=(B, n))
+    sym = np.where(rng.random((B, n)) < 0.5, last - last // 2 + far, -(last // 2) - 1 - far).astype(np.int32)
+    want = coder.encode_batch(sym, idx, t)
+    assert min(len(w) for w in want) > 4 * (n // 2 + 4096)
+    (got,) = ops.rans_encode_device([(torch.from_numpy(sym).cuda(), torch.from_numpy(idx).cuda(), dt, False)])
+    assert got == want
+    words, table = ops.rans_upload([want], "cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dec = ops.rans_decode_device(words, table, 0, torch.from_numpy(idx).cuda(), dt, False, status)
+    assert int(status.item()) == 0 and np.array_equal(dec.cpu().numpy(), sym)
+
+
 def test_device_coder_many_strings_and_groups(gc_tables):
     """More strings than one block holds (8 warps per block) and more groups than one launch takes (4): strings of
     different lengths and table sets side by side, every one byte-identical to the host coder's."""
