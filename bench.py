@@ -47,7 +47,7 @@ RU_DRAM_BYTES_PER_LAUNCH = 761_778_944  # dram__bytes_read.sum + dram__bytes_wri
 
 
 CODEC_TILES, CODEC_H, CODEC_W = 8, 704, 512  # one 2048x1408 image as a 2x4 grid of tiles
-CODEC_IMAGES = 4  # images per GPU per step (each goes through the public compress / decompress on its own)
+CODEC_IMAGES = 8  # images per GPU per step (each goes through the public compress / decompress on its own)
 # canonical algorithmic work of compress + decompress, SURVEY.md section 8d: encode 215 488 + decode 322 642 MAC/px
 MAC_PER_PX_ENCDEC = 538_130
 
