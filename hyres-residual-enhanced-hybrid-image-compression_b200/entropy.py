@@ -89,26 +89,34 @@ class EntropyModel(nn.Module):
             self._tables_cache = (key, t)
         return self._tables_cache[1]
 
+    @staticmethod
+    def _device_key(device):
+        d = torch.device(device)
+        if d.type == "cuda" and d.index is None:
+            d = torch.device("cuda", torch.cuda.current_device())
+        return str(d)
+
     def coder_rows(self, device):
         """int32 [3, n_cdfs] on ``device``: the host coder's packed-table layout (``coder.table_layout``), what the
         device front-end needs to emit coder slots / codes (cached with the tables)."""
         t = self.tables()
         cache = getattr(self, "_rows_cache", None)
-        key = (id(t), str(device))
-        if cache is None or cache[0] != key:
+        # (the cache holds the table object itself: an id() alone could be reused by the tables of a later update())
+        key = self._device_key(device)
+        if cache is None or cache[0] is not t or cache[1] != key:
             rows = torch.from_numpy(coder.table_layout(t)).to(device)
-            self._rows_cache = cache = (key, rows)
-        return cache[1]
+            self._rows_cache = cache = (t, key, rows)
+        return cache[2]
 
     def device_tables(self, device):
         """The coder's packed tables on ``device`` for the device-resident coder (``coder.DeviceTables``, cached with
         the host tables)."""
         t = self.tables()
         cache = getattr(self, "_dev_tables_cache", None)
-        key = (id(t), str(device))
-        if cache is None or cache[0] != key:
-            self._dev_tables_cache = cache = (key, coder.DeviceTables(t, device))
-        return cache[1]
+        key = self._device_key(device)
+        if cache is None or cache[0] is not t or cache[1] != key:
+            self._dev_tables_cache = cache = (t, key, coder.DeviceTables(t, device))
+        return cache[2]
 
     # -- coding of already-quantised symbols --
     _tls = threading.local()  # pinned staging buffers are per thread: CodecPipeline runs one batch per worker thread
